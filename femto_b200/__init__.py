@@ -1,0 +1,315 @@
+"""femto_b200 -- B200-native FM-index query engine behind femto's count/locate/extract API.
+
+This package is a thin ctypes mirror of the C ABI in ``include/femto_b200.h`` (the product is the
+shared library ``libfemto_b200.so`` built from ``femto_b200/csrc``).  Names follow the reference:
+``Index.count`` == ``parallel_count`` (reference src/main/femto.c:275), ``Index.locate`` ==
+``parallel_locate`` (:331), ``Index.locate_range`` == ``parallel_locate_range`` (:481),
+``Index.extract`` == the extract-document query (src/main/server.c:6364).
+
+Symbols are ``alpha_t`` values: ``5 + byte`` for text bytes (src/main/index_types.h:64-68).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import FmInfo
+
+CHARACTER_OFFSET = 5
+ALPHA_SIZE = 261
+ESCAPE_CODE_SEOF = 2
+
+ERR_NAMES = {0: "OK", 1: "MEM", 2: "IO", 3: "PARAM", 4: "FORMAT", 5: "BZ_DATA", 6: "INVALID", 7: "PTHREADS",
+             8: "MISSING", 9: "CANCELED", 10: "FULL", 11: "OVERWORKED", 12: "UNKNOWN"}
+
+
+class FemtoError(RuntimeError):
+    def __init__(self, code: int, where: str, msg: str = ""):
+        self.code = code
+        super().__init__(f"{where}: ERR_{ERR_NAMES.get(code, code)} {msg}".strip())
+
+
+def _check(rc: int, where: str) -> None:
+    if rc:
+        msg = _lib.load().fm_last_error()
+        raise FemtoError(rc, where, msg.decode(errors="replace") if msg else "")
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def bytes_to_alpha(b: bytes) -> np.ndarray:
+    """strtoalpha (src/main/index_types.h:85-97)."""
+    return np.frombuffer(b, dtype=np.uint8).astype(np.uint16) + CHARACTER_OFFSET
+
+
+def flatten_patterns(pats: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    plen = np.array([len(p) for p in pats], dtype=np.int32)
+    offs = np.zeros(len(pats), dtype=np.int64)
+    if len(pats) > 1:
+        offs[1:] = np.cumsum(plen[:-1], dtype=np.int64)
+    total = int(plen.sum()) if len(pats) else 0
+    flat = (np.concatenate([np.asarray(p, dtype=np.uint16) for p in pats]) if total
+            else np.zeros(1, dtype=np.uint16))
+    return plen, np.ascontiguousarray(flat), offs
+
+
+class Index:
+    """An index resident in one GPU's HBM (``fm_open`` ... ``fm_close``)."""
+
+    def __init__(self, path: str, device: int = 0, shard: int = 0, nshards: int = 1):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        if nshards == 1:
+            rc = self.lib.fm_open(os.fsencode(path), device, C.byref(h))
+        else:
+            rc = self.lib.fm_open_shard(os.fsencode(path), device, shard, nshards, C.byref(h))
+        _check(rc, "fm_open")
+        self.h = h
+        info = FmInfo()
+        _check(self.lib.fm_info(self.h, C.byref(info)), "fm_info")
+        self.info = info
+
+    # -- lifecycle -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.fm_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def total_length(self) -> int:
+        return int(self.info.total_length)
+
+    @property
+    def num_documents(self) -> int:
+        return int(self.info.num_documents)
+
+    def set_lanes_per_query(self, lanes: int) -> None:
+        _check(self.lib.fm_set_lanes_per_query(self.h, lanes), "fm_set_lanes_per_query")
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.fm_kernel_launches(self.h))
+
+    # -- count -----------------------------------------------------------------------------
+    def count_flat(self, plen: np.ndarray, flat: np.ndarray, offs: np.ndarray,
+                   first: Optional[np.ndarray] = None, last: Optional[np.ndarray] = None):
+        n = len(plen)
+        if first is None:
+            first = np.empty(max(n, 1), dtype=np.int64)
+        if last is None:
+            last = np.empty(max(n, 1), dtype=np.int64)
+        rc = self.lib.fm_count_flat(self.h, n, _ptr(plen, C.c_int32), _ptr(flat, C.c_uint16), _ptr(offs, C.c_int64),
+                                    _ptr(first, C.c_int64), _ptr(last, C.c_int64))
+        _check(rc, "fm_count_flat")
+        return first[:n], last[:n]
+
+    def count(self, pats: Sequence[np.ndarray]):
+        """[first,last] BWT row range per pattern, through the reference-shaped pointer-array call."""
+        n = len(pats)
+        arrs = [np.ascontiguousarray(p, dtype=np.uint16) for p in pats]
+        plen = (C.c_int * max(n, 1))(*[len(a) for a in arrs])
+        ptrs = (C.POINTER(C.c_uint16) * max(n, 1))(*[_ptr(a, C.c_uint16) for a in arrs])
+        first = np.empty(max(n, 1), dtype=np.int64)
+        last = np.empty(max(n, 1), dtype=np.int64)
+        _check(self.lib.fm_count(self.h, n, plen, ptrs, _ptr(first, C.c_int64), _ptr(last, C.c_int64)), "fm_count")
+        return first[:n], last[:n]
+
+    def count_device(self, npats: int, d_plen: int, d_flat: int, d_offs: int, d_first: int, d_last: int,
+                     stream: int = 0) -> None:
+        """Device-pointer form (integers are raw device addresses, e.g. ``tensor.data_ptr()``)."""
+        _check(self.lib.fm_count_device(self.h, npats, d_plen, d_flat, d_offs, d_first, d_last, stream),
+               "fm_count_device")
+
+    # -- locate ----------------------------------------------------------------------------
+    def locate(self, pats: Sequence[np.ndarray], max_occs: int) -> List[np.ndarray]:
+        n = len(pats)
+        arrs = [np.ascontiguousarray(p, dtype=np.uint16) for p in pats]
+        plen = (C.c_int * max(n, 1))(*[len(a) for a in arrs])
+        ptrs = (C.POINTER(C.c_uint16) * max(n, 1))(*[_ptr(a, C.c_uint16) for a in arrs])
+        noccs = (C.c_int * max(n, 1))()
+        outs = (C.POINTER(C.c_int64) * max(n, 1))()
+        _check(self.lib.fm_locate(self.h, n, plen, ptrs, int(max_occs), noccs, outs), "fm_locate")
+        res = []
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        for i in range(n):
+            k = noccs[i]
+            if k > 0:
+                res.append(np.ctypeslib.as_array(outs[i], shape=(k,)).copy())
+                libc.free(C.cast(outs[i], C.c_void_p))
+            else:
+                res.append(np.zeros(0, dtype=np.int64))
+        return res
+
+    def locate_flat(self, plen, flat, offs, max_occs: int, cap: int):
+        n = len(plen)
+        noccs = np.zeros(max(n, 1), dtype=np.int32)
+        start = np.zeros(max(n, 1), dtype=np.int64)
+        out = np.zeros(max(cap, 1), dtype=np.int64)
+        rc = self.lib.fm_locate_flat(self.h, n, _ptr(plen, C.c_int32), _ptr(flat, C.c_uint16), _ptr(offs, C.c_int64),
+                                     int(max_occs), _ptr(noccs, C.c_int32), _ptr(start, C.c_int64),
+                                     _ptr(out, C.c_int64), cap)
+        _check(rc, "fm_locate_flat")
+        return noccs[:n], start[:n], out
+
+    def locate_range(self, first: int, last: int) -> np.ndarray:
+        n = max(last - first + 1, 0)
+        out = np.zeros(max(n, 1), dtype=np.int64)
+        _check(self.lib.fm_locate_range(self.h, first, last, _ptr(out, C.c_int64)), "fm_locate_range")
+        return out[:n]
+
+    def locate_rows(self, rows: np.ndarray) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros(max(len(rows), 1), dtype=np.int64)
+        _check(self.lib.fm_locate_rows(self.h, len(rows), _ptr(rows, C.c_int64), _ptr(out, C.c_int64)),
+               "fm_locate_rows")
+        return out[:len(rows)]
+
+    # -- leaf interface --------------------------------------------------------------------
+    def back_step(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        n = len(rows)
+        ch = np.zeros(max(n, 1), dtype=np.int32)
+        nxt = np.zeros(max(n, 1), dtype=np.int64)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        _check(self.lib.fm_back_step(self.h, n, _ptr(rows, C.c_int64), _ptr(ch, C.c_int32), _ptr(nxt, C.c_int64),
+                                     _ptr(off, C.c_int64)), "fm_back_step")
+        return ch[:n], nxt[:n], off[:n]
+
+    def occ(self, ch: np.ndarray, rows: np.ndarray) -> np.ndarray:
+        ch = np.ascontiguousarray(ch, dtype=np.uint16)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros(max(len(rows), 1), dtype=np.int64)
+        _check(self.lib.fm_occ(self.h, len(rows), _ptr(ch, C.c_uint16), _ptr(rows, C.c_int64), _ptr(out, C.c_int64)),
+               "fm_occ")
+        return out[:len(rows)]
+
+    # -- documents -------------------------------------------------------------------------
+    def doc_info(self, doc: int) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _check(self.lib.fm_doc_info(self.h, doc, C.byref(a), C.byref(b)), "fm_doc_info")
+        return a.value, b.value
+
+    def resolve(self, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets)
+        doc = np.zeros(max(n, 1), dtype=np.int64)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        _check(self.lib.fm_resolve(self.h, n, _ptr(offsets, C.c_int64), _ptr(doc, C.c_int64), _ptr(off, C.c_int64)),
+               "fm_resolve")
+        return doc[:n], off[:n]
+
+    def extract(self, doc: int) -> np.ndarray:
+        ln, _ = self.doc_info(doc)
+        out = np.zeros(max(ln, 1), dtype=np.uint16)
+        n = C.c_int64()
+        _check(self.lib.fm_extract(self.h, doc, _ptr(out, C.c_uint16), ln, C.byref(n)), "fm_extract")
+        return out[:n.value]
+
+
+# ---------------------------------------------------------------------------------------------
+# index construction (host side)
+
+def prepare_text(docs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """The reference's prepared text for documents without headers: each document's bytes as
+    5+byte followed by one SEOF symbol (append_file_mem, src/main/bwt_prepare.c:231-311).
+    Returns (text uint16, doc_ends int64)."""
+    parts = []
+    ends = []
+    total = 0
+    for d in docs:
+        a = np.empty(len(d) + 1, dtype=np.uint16)
+        a[:-1] = np.frombuffer(d, dtype=np.uint8).astype(np.uint16) + CHARACTER_OFFSET
+        a[-1] = ESCAPE_CODE_SEOF
+        parts.append(a)
+        total += len(a)
+        ends.append(total)
+    return np.concatenate(parts), np.array(ends, dtype=np.int64)
+
+
+def suffix_sort_host(text: np.ndarray) -> np.ndarray:
+    lib = _lib.load()
+    text = np.ascontiguousarray(text, dtype=np.uint16)
+    sa = np.empty(len(text), dtype=np.int64)
+    _check(lib.fm_suffix_sort_host(_ptr(text, C.c_uint16), len(text), _ptr(sa, C.c_int64)), "fm_suffix_sort_host")
+    return sa
+
+
+def bwt_from_sa(text: np.ndarray, sa: np.ndarray) -> np.ndarray:
+    """L[r] = text[sa[r]-1], SEOF for sa[r]==0 (get_L_char_from_offsets, src/main/bwt_qsufsort.c:63-84)."""
+    L = text[sa - 1].copy()  # sa==0 wraps to the last symbol, which is the final document's SEOF
+    return L
+
+
+class IndexBuilder:
+    """Streams BWT rows into femto's on-disk format (``fm_builder_*``)."""
+
+    def __init__(self, out_dir: str, doc_ends: np.ndarray, block_size: int = 128 << 20, bucket_size: int = 1 << 20,
+                 chunk_size: int = 2048, mark_period: int = 20, nthreads: int = 0):
+        self.lib = _lib.load()
+        doc_ends = np.ascontiguousarray(doc_ends, dtype=np.int64)
+        b = C.c_void_p()
+        _check(self.lib.fm_builder_create(os.fsencode(out_dir), int(doc_ends[-1]), len(doc_ends),
+                                          _ptr(doc_ends, C.c_int64), block_size, bucket_size, chunk_size,
+                                          mark_period, nthreads, C.byref(b)), "fm_builder_create")
+        self.b = b
+
+    def set_doc_info(self, doc: int, info: bytes) -> None:
+        _check(self.lib.fm_builder_set_doc_info(self.b, doc, info, len(info)), "fm_builder_set_doc_info")
+
+    def append(self, L: np.ndarray, sa: np.ndarray) -> None:
+        L = np.ascontiguousarray(L, dtype=np.uint16)
+        sa = np.ascontiguousarray(sa, dtype=np.int64)
+        assert len(L) == len(sa)
+        _check(self.lib.fm_builder_append(self.b, len(L), _ptr(L, C.c_uint16), _ptr(sa, C.c_int64)),
+               "fm_builder_append")
+
+    def finish(self) -> None:
+        b, self.b = self.b, None
+        _check(self.lib.fm_builder_finish(b), "fm_builder_finish")
+
+    def abort(self) -> None:
+        if self.b:
+            self.lib.fm_builder_abort(self.b)
+            self.b = None
+
+    def __del__(self):
+        try:
+            self.abort()
+        except Exception:
+            pass
+
+
+def build_index_host(docs: Sequence[bytes], out_dir: str, doc_infos: Optional[Sequence[bytes]] = None,
+                     **params) -> None:
+    """Small-corpus builder: host suffix sort + the format-identical emitter."""
+    text, ends = prepare_text(docs)
+    sa = suffix_sort_host(text)
+    L = bwt_from_sa(text, sa)
+    b = IndexBuilder(out_dir, ends, **params)
+    if doc_infos is not None:
+        for i, info in enumerate(doc_infos):
+            b.set_doc_info(i, info)
+    b.append(L, sa)
+    b.finish()
+
+
+def flatten(index_dir: str, out_file: str) -> None:
+    _check(_lib.load().fm_flatten(os.fsencode(index_dir), os.fsencode(out_file)), "fm_flatten")

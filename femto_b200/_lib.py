@@ -1,0 +1,92 @@
+"""Loads libfemto_b200.so (the C ABI of include/femto_b200.h) and declares its prototypes.
+
+There is deliberately no fallback: if the shared library is missing the import fails loudly and
+tells the user how to build it.  The library itself has no CPU query path either.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfemto_b200.so")
+
+i32, i64, u16, u8 = C.c_int32, C.c_int64, C.c_uint16, C.c_uint8
+P = C.POINTER
+vp = C.c_void_p
+
+
+class FmInfo(C.Structure):
+    _fields_ = [
+        ("total_length", i64), ("num_documents", i64), ("num_blocks", i64),
+        ("block_size", i32), ("bucket_size", i32), ("mark_period", i32), ("chunk_size", i32),
+        ("first_row", i64), ("end_row", i64), ("hbm_bytes", i64), ("rank_block_bytes", i64),
+        ("device", i32), ("max_code_len", i32),
+    ]
+
+
+# name -> (restype, argtypes); exactly the symbols declared in include/femto_b200.h
+PROTOTYPES = {
+    "fm_open": (C.c_int, [C.c_char_p, C.c_int, P(vp)]),
+    "fm_open_shard": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, P(vp)]),
+    "fm_close": (None, [vp]),
+    "fm_info": (C.c_int, [vp, P(FmInfo)]),
+    "fm_last_error": (C.c_char_p, []),
+    "fm_count": (C.c_int, [vp, C.c_int, P(C.c_int), P(P(u16)), P(i64), P(i64)]),
+    "fm_count_flat": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), P(i64), P(i64)]),
+    "fm_count_device": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
+    "fm_locate": (C.c_int, [vp, C.c_int, P(C.c_int), P(P(u16)), C.c_int, P(C.c_int), P(P(i64))]),
+    "fm_locate_flat": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), C.c_int, P(i32), P(i64), P(i64), i64]),
+    "fm_locate_range": (C.c_int, [vp, i64, i64, P(i64)]),
+    "fm_locate_rows": (C.c_int, [vp, i64, P(i64), P(i64)]),
+    "fm_locate_rows_device": (C.c_int, [vp, i64, vp, vp, vp]),
+    "fm_back_step": (C.c_int, [vp, i64, P(i64), P(i32), P(i64), P(i64)]),
+    "fm_occ": (C.c_int, [vp, i64, P(u16), P(i64), P(i64)]),
+    "fm_doc_info": (C.c_int, [vp, i64, P(i64), P(i64)]),
+    "fm_resolve": (C.c_int, [vp, i64, P(i64), P(i64), P(i64)]),
+    "fm_extract": (C.c_int, [vp, i64, P(u16), i64, P(i64)]),
+    "fm_host_alloc": (vp, [C.c_size_t]),
+    "fm_host_free": (None, [vp]),
+    "fm_kernel_launches": (i64, [vp]),
+    "fm_set_lanes_per_query": (C.c_int, [vp, C.c_int]),
+    "fm_builder_create": (C.c_int, [C.c_char_p, i64, i64, P(i64), i32, i32, i32, i32, C.c_int, P(vp)]),
+    "fm_builder_append": (C.c_int, [vp, i64, P(u16), P(i64)]),
+    "fm_builder_set_doc_info": (C.c_int, [vp, i64, vp, i64]),
+    "fm_builder_finish": (C.c_int, [vp]),
+    "fm_builder_abort": (None, [vp]),
+    "fm_flatten": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "fm_suffix_sort_host": (C.c_int, [P(u16), i64, P(i64)]),
+}
+
+# loader/builder inspection hooks used by the CPU test-suite (not part of the public header)
+DEBUG_PROTOTYPES = {
+    "fm_debug_bseq_encode": (C.c_int, [C.c_char_p, i64, C.c_int, P(vp), P(i64)]),
+    "fm_debug_bseq_expand": (C.c_int, [C.c_char_p, i64, C.c_char_p, i64, P(i64)]),
+    "fm_debug_free": (None, [vp]),
+    "fm_debug_image_open": (vp, [C.c_char_p, C.c_int, C.c_int, C.c_int, P(C.c_int)]),
+    "fm_debug_image_close": (None, [vp]),
+    "fm_debug_image_stats": (None, [vp, P(i64)]),
+    "fm_debug_image_occ": (i64, [vp, C.c_int, i64]),
+    "fm_debug_image_back_step": (C.c_int, [vp, i64, P(i32), P(i64), P(i64)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C femto_b200/csrc`). "
+            "femto_b200 has no pure-Python or CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for table in (PROTOTYPES, DEBUG_PROTOTYPES):
+        for name, (res, args) in table.items():
+            fn = getattr(lib, name)  # AttributeError here == a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+    _lib = lib
+    return lib

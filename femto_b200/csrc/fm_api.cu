@@ -1,0 +1,608 @@
+// fm_api.cu -- the C ABI of include/femto_b200.h: index lifecycle, host<->device staging and the
+// entry points that mirror the reference's parallel_count / parallel_locate / parallel_locate_range
+// (src/main/femto.c:275-536).  Query work is done only by the kernels in fm_kernels.cu; there is no
+// CPU fallback on any query path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/femto_b200.h"
+#include "fm_format.hpp"
+#include "fm_image.hpp"
+#include "fm_kernels.cuh"
+#include "fm_loader.hpp"
+
+using namespace fmb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+struct CudaFail : std::runtime_error {
+  explicit CudaFail(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define CK(expr)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      throw CudaFail(std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+  } while (0)
+
+// A growable device buffer (freed with the index).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) CK(cudaFree(p));
+      p = nullptr;
+      cap = 0;
+      const size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+      CK(cudaMalloc(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HostBuf {  // pinned staging
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) CK(cudaFreeHost(p));
+      p = nullptr;
+      cap = 0;
+      const size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+      CK(cudaMallocHost(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct fm_index {
+  int device = 0;
+  int sm_count = 148;
+  int lanes_per_query = 4;
+  fm_info_t info{};
+  DevImage im;
+  // device allocations of the image
+  void* d_blocks = nullptr;
+  void* d_nodes = nullptr;
+  void* d_occ = nullptr;
+  void* d_mark = nullptr;
+  void* d_buckets = nullptr;
+  void* d_markvals = nullptr;
+  void* d_C = nullptr;
+  unsigned long long* d_work = nullptr;  // work-queue counters (one per concurrent launch slot)
+  int32_t* d_status = nullptr;
+  // host-side header tables
+  std::vector<int64_t> doc_ends, doc_eof_rows;
+  // per-call scratch, serialised by mu
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  DevBuf d_in[4], d_out[4];
+  HostBuf h_stage[2];
+  int64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    CK(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+void upload(void** dptr, const T* src, size_t count, int64_t* total) {
+  const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+  CK(cudaMalloc(dptr, bytes));
+  if (count) CK(cudaMemcpy(*dptr, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *total += int64_t(bytes);
+}
+
+void destroy(fm_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  for (void* p : {ix->d_blocks, ix->d_nodes, ix->d_occ, ix->d_mark, ix->d_buckets, ix->d_markvals, ix->d_C,
+                  static_cast<void*>(ix->d_work), static_cast<void*>(ix->d_status)})
+    if (p) cudaFree(p);
+  for (auto& b : ix->d_in) b.release();
+  for (auto& b : ix->d_out) b.release();
+  for (auto& b : ix->h_stage) b.release();
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+}
+
+int open_impl(const char* path, int device, int shard, int nshards, fm_index_t** out) {
+  if (!path || !out) return fail(FM_ERR_PARAM, "fm_open: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return fail(FM_ERR_IO, std::string("fm_open: no usable CUDA device (") + cudaGetErrorString(ce) +
+                               "); this library has no CPU query path");
+  if (device < 0 || device >= ndev) return fail(FM_ERR_PARAM, "fm_open: no such CUDA device");
+  std::unique_ptr<HostImage> host;
+  try {
+    host = build_host_image(path, shard, nshards, 0);
+  } catch (const Error& e) {
+    return fail(e.code, std::string("fm_open: ") + e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(FM_ERR_MEM, "fm_open: out of host memory");
+  }
+  fm_index* ix = new fm_index();
+  try {
+    ix->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ix->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    int64_t total = 0;
+    upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * kBlockWords, &total);
+    upload(&ix->d_nodes, host->nodes.data(), host->nodes.size(), &total);
+    upload(&ix->d_occ, host->occ.data(), host->occ.size(), &total);
+    upload(&ix->d_mark, host->mark.data(), host->mark.size(), &total);
+    upload(&ix->d_buckets, host->buckets.data(), host->buckets.size(), &total);
+    upload(&ix->d_markvals, host->markvals.data(), host->markvals.size(), &total);
+    upload(&ix->d_C, host->C.data(), host->C.size(), &total);
+    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 64));
+    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_status), 64));
+    CK(cudaMemset(ix->d_status, 0, 64));
+
+    const BlockHeader& h = host->hdr;
+    ix->im.blocks = static_cast<const uint4*>(ix->d_blocks);
+    ix->im.nodes = static_cast<const NodeRec*>(ix->d_nodes);
+    ix->im.occ = static_cast<const OccRec*>(ix->d_occ);
+    ix->im.mark = static_cast<const MarkRec*>(ix->d_mark);
+    ix->im.buckets = static_cast<const BucketRec*>(ix->d_buckets);
+    ix->im.markvals = static_cast<const int64_t*>(ix->d_markvals);
+    ix->im.C = static_cast<const int64_t*>(ix->d_C);
+    ix->im.total_length = h.total_length;
+    ix->im.first_row = host->first_row;
+    ix->im.end_row = host->end_row;
+    ix->im.first_bucket = host->first_bucket;
+    ix->im.bucket_size = h.bucket_size;
+    ix->im.bucket_shift = (h.bucket_size & (h.bucket_size - 1)) == 0 ? __builtin_ctz(unsigned(h.bucket_size)) : -1;
+
+    ix->info.total_length = h.total_length;
+    ix->info.num_documents = h.ndocs;
+    ix->info.num_blocks = h.nblocks;
+    ix->info.block_size = h.block_size;
+    ix->info.bucket_size = h.bucket_size;
+    ix->info.mark_period = h.mark_period;
+    ix->info.chunk_size = h.chunk_size;
+    ix->info.first_row = host->first_row;
+    ix->info.end_row = host->end_row;
+    ix->info.hbm_bytes = total;
+    ix->info.rank_block_bytes = host->n_rank_blocks * int64_t(kBlockWords) * 4;
+    ix->info.device = device;
+    ix->info.max_code_len = host->max_code_len;
+    ix->doc_ends = std::move(host->doc_ends);
+    ix->doc_eof_rows = std::move(host->doc_eof_rows);
+  } catch (const CudaFail& e) {
+    destroy(ix);
+    return fail(FM_ERR_IO, std::string("fm_open: ") + e.what());
+  }
+  *out = ix;
+  return FM_OK;
+}
+
+// Run `body` with the handle locked, its device current, CUDA failures mapped to FM_ERR_IO.
+template <typename F>
+int guarded(fm_index* ix, const char* what, F&& body) {
+  if (!ix) return fail(FM_ERR_PARAM, std::string(what) + ": null index");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  try {
+    DeviceGuard guard(ix->device);
+    return body();
+  } catch (const CudaFail& e) {
+    return fail(FM_ERR_IO, std::string(what) + ": " + e.what());
+  } catch (const Error& e) {
+    return fail(e.code, std::string(what) + ": " + e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(FM_ERR_MEM, std::string(what) + ": out of memory");
+  }
+}
+
+// Validate a flat pattern batch on the host and return the number of symbols referenced.
+int check_patterns(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t* flat_len) {
+  int64_t end = 0;
+  for (int64_t i = 0; i < npats; i++) {
+    if (plen[i] < 0 || offs[i] < 0) return FM_ERR_PARAM;
+    end = std::max(end, offs[i] + plen[i]);
+  }
+  *flat_len = end;
+  return FM_OK;
+}
+
+int walk_status(fm_index* ix) {
+  int32_t st = 0;
+  CK(cudaMemcpyAsync(&st, ix->d_status, sizeof(st), cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  if (st) CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), ix->stream));
+  return st;
+}
+
+// count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
+int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, int64_t flat_len,
+               const int64_t* offs, int64_t* first, int64_t* last) {
+  if (npats == 0) return FM_OK;
+  cudaStream_t s = ix->stream;
+  int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
+  uint16_t* d_flat = static_cast<uint16_t*>(ix->d_in[1].get(size_t(std::max<int64_t>(flat_len, 1)) * 2));
+  int64_t* d_offs = static_cast<int64_t*>(ix->d_in[2].get(size_t(npats) * 8));
+  int64_t* d_first = static_cast<int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
+  int64_t* d_last = last ? static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8)) : nullptr;
+  CK(cudaMemcpyAsync(d_plen, plen, size_t(npats) * 4, cudaMemcpyHostToDevice, s));
+  if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * 2, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
+  CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
+  CK(launch_count(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+  CK(cudaMemcpyAsync(first, d_first, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
+  if (last) CK(cudaMemcpyAsync(last, d_last, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return FM_OK;
+}
+
+int locate_rows_host(fm_index* ix, int64_t nrows, const int64_t* rows, int64_t* offsets) {
+  if (nrows == 0) return FM_OK;
+  cudaStream_t s = ix->stream;
+  int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(nrows) * 8));
+  int64_t* d_off = static_cast<int64_t*>(ix->d_out[2].get(size_t(nrows) * 8));
+  CK(cudaMemcpyAsync(d_rows, rows, size_t(nrows) * 8, cudaMemcpyHostToDevice, s));
+  WalkArgs w{};
+  w.nrows = nrows;
+  w.rows = d_rows;
+  w.out_offset = d_off;
+  w.status = ix->d_status;
+  CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+  CK(cudaMemcpyAsync(offsets, d_off, size_t(nrows) * 8, cudaMemcpyDeviceToHost, s));
+  const int st = walk_status(ix);
+  if (st) return fail(st == 1 ? FM_ERR_PARAM : FM_ERR_INVALID, "locate: malformed walk (status " + std::to_string(st) + ")");
+  return FM_OK;
+}
+
+// Gather the reference-style pointer array into one pinned flat buffer.
+void gather_patterns(fm_index* ix, int64_t npats, const int* plen, const uint16_t* const* pats,
+                     std::vector<int64_t>* offs, uint16_t** flat, int64_t* flat_len) {
+  offs->resize(size_t(npats));
+  int64_t total = 0;
+  for (int64_t i = 0; i < npats; i++) {
+    if (plen[i] < 0) throw Error(FM_ERR_PARAM, "negative pattern length");
+    (*offs)[size_t(i)] = total;
+    total += plen[i];
+  }
+  uint16_t* dst = static_cast<uint16_t*>(ix->h_stage[0].get(size_t(std::max<int64_t>(total, 1)) * 2));
+  const int nthreads = int(std::min<int64_t>(8, std::max<int64_t>(1, npats / 65536)));
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; i++)
+      if (plen[i]) std::memcpy(dst + (*offs)[size_t(i)], pats[i], size_t(plen[i]) * 2);
+  };
+  if (nthreads <= 1) {
+    work(0, npats);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(work, npats * t / nthreads, npats * (t + 1) / nthreads);
+    for (auto& t : th) t.join();
+  }
+  *flat = dst;
+  *flat_len = total;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* fm_last_error(void) { return g_last_error.c_str(); }
+
+int fm_open(const char* path, int device, fm_index_t** out) { return open_impl(path, device, 0, 1, out); }
+
+int fm_open_shard(const char* path, int device, int shard, int nshards, fm_index_t** out) {
+  return open_impl(path, device, shard, nshards, out);
+}
+
+void fm_close(fm_index_t* ix) { destroy(ix); }
+
+int fm_info(const fm_index_t* ix, fm_info_t* out) {
+  if (!ix || !out) return fail(FM_ERR_PARAM, "fm_info: null argument");
+  *out = ix->info;
+  return FM_OK;
+}
+
+int64_t fm_kernel_launches(const fm_index_t* ix) { return ix ? ix->launches : 0; }
+
+int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
+  if (!ix || (lanes != 4 && lanes != 8)) return fail(FM_ERR_PARAM, "fm_set_lanes_per_query: lanes must be 4 or 8");
+  ix->lanes_per_query = lanes;
+  return FM_OK;
+}
+
+void* fm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, std::max<size_t>(bytes, 1)) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void fm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                  int64_t* first, int64_t* last) {
+  return guarded(ix, "fm_count_flat", [&]() -> int {
+    if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
+    int64_t flat_len = 0;
+    if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
+    if (flat_len && !flat) return fail(FM_ERR_PARAM, "fm_count_flat: null pattern buffer");
+    if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
+      return fail(FM_ERR_MISSING, "fm_count_flat: index is a shard; use the sharded driver");
+    return count_host(ix, npats, plen, flat, flat_len, offs, first, last);
+  });
+}
+
+int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* pats, int64_t* first,
+             int64_t* last) {
+  return guarded(ix, "fm_count", [&]() -> int {
+    if (npats < 0 || (npats && (!plen || !pats || !first))) return fail(FM_ERR_PARAM, "fm_count: bad argument");
+    if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
+      return fail(FM_ERR_MISSING, "fm_count: index is a shard; use the sharded driver");
+    std::vector<int64_t> offs;
+    uint16_t* flat = nullptr;
+    int64_t flat_len = 0;
+    gather_patterns(ix, npats, plen, pats, &offs, &flat, &flat_len);
+    return count_host(ix, npats, reinterpret_cast<const int32_t*>(plen), flat, flat_len, offs.data(), first, last);
+  });
+}
+
+int fm_count_device(fm_index_t* ix, int64_t npats, const int32_t* d_plen, const uint16_t* d_flat,
+                    const int64_t* d_offs, int64_t* d_first, int64_t* d_last, void* stream) {
+  return guarded(ix, "fm_count_device", [&]() -> int {
+    if (npats < 0) return fail(FM_ERR_PARAM, "fm_count_device: negative npats");
+    CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
+    CK(launch_count(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, static_cast<cudaStream_t>(stream),
+                    &ix->launches));
+    return FM_OK;
+  });
+}
+
+int fm_locate_rows(fm_index_t* ix, int64_t nrows, const int64_t* rows, int64_t* offsets) {
+  return guarded(ix, "fm_locate_rows", [&]() -> int {
+    if (nrows < 0 || (nrows && (!rows || !offsets))) return fail(FM_ERR_PARAM, "fm_locate_rows: bad argument");
+    return locate_rows_host(ix, nrows, rows, offsets);
+  });
+}
+
+int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, int64_t* d_offsets, void* stream) {
+  return guarded(ix, "fm_locate_rows_device", [&]() -> int {
+    if (nrows < 0) return fail(FM_ERR_PARAM, "fm_locate_rows_device: negative nrows");
+    WalkArgs w{};
+    w.nrows = nrows;
+    w.rows = d_rows;
+    w.out_offset = d_offsets;
+    w.status = ix->d_status;
+    CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work + 1, ix->lanes_per_query, ix->sm_count,
+                   static_cast<cudaStream_t>(stream), &ix->launches));
+    return FM_OK;
+  });
+}
+
+int fm_locate_range(fm_index_t* ix, int64_t first, int64_t last, int64_t* offsets) {
+  return guarded(ix, "fm_locate_range", [&]() -> int {
+    if (last < first) return FM_OK;
+    if (first < 0 || last >= ix->info.total_length || !offsets)
+      return fail(FM_ERR_PARAM, "fm_locate_range: rows out of range");
+    const int64_t n = last - first + 1;
+    int64_t* rows = static_cast<int64_t*>(ix->h_stage[1].get(size_t(n) * 8));
+    for (int64_t i = 0; i < n; i++) rows[i] = first + i;
+    return locate_rows_host(ix, n, rows, offsets);
+  });
+}
+
+int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                   int max_occs_each, int32_t* noccs, int64_t* out_start, int64_t* out, int64_t out_cap) {
+  return guarded(ix, "fm_locate_flat", [&]() -> int {
+    if (npats < 0 || (npats && (!plen || !offs || !noccs || !out_start)))
+      return fail(FM_ERR_PARAM, "fm_locate_flat: bad argument");
+    int64_t flat_len = 0;
+    if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_locate_flat: negative length/offset");
+    std::vector<int64_t> first(size_t(npats) + 1), last(size_t(npats) + 1);
+    int rc = count_host(ix, npats, plen, flat, flat_len, offs, first.data(), last.data());
+    if (rc) return rc;
+    // clip as do_locate_query (server.c:4407-4415)
+    int64_t total = 0;
+    for (int64_t i = 0; i < npats; i++) {
+      int64_t f = first[size_t(i)], l = last[size_t(i)];
+      out_start[i] = total;
+      if (f > l) { noccs[i] = 0; continue; }
+      if (l - f > int64_t(max_occs_each)) l = f + int64_t(max_occs_each) - 1;
+      last[size_t(i)] = l;
+      noccs[i] = int32_t(l - f + 1);
+      total += l - f + 1;
+    }
+    if (total > out_cap) return fail(FM_ERR_FULL, "fm_locate_flat: output buffer too small");
+    if (total == 0) return FM_OK;
+    if (!out) return fail(FM_ERR_PARAM, "fm_locate_flat: null output");
+    int64_t* rows = static_cast<int64_t*>(ix->h_stage[1].get(size_t(total) * 8));
+    for (int64_t i = 0; i < npats; i++)
+      for (int32_t j = 0; j < noccs[i]; j++) rows[out_start[i] + j] = first[size_t(i)] + j;
+    return locate_rows_host(ix, total, rows, out);
+  });
+}
+
+int fm_locate(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* pats, int max_occs_each,
+              int* noccs, int64_t** offsets) {
+  if (!ix) return fail(FM_ERR_PARAM, "fm_locate: null index");
+  if (npats < 0 || (npats && (!plen || !pats || !noccs || !offsets))) return fail(FM_ERR_PARAM, "fm_locate: bad argument");
+  std::vector<int64_t> offs(size_t(npats) + 1), start(size_t(npats) + 1);
+  std::vector<uint16_t> flat;
+  int64_t total = 0;
+  for (int i = 0; i < npats; i++) {
+    if (plen[i] < 0) return fail(FM_ERR_PARAM, "fm_locate: negative pattern length");
+    offs[size_t(i)] = total;
+    total += plen[i];
+  }
+  flat.resize(size_t(std::max<int64_t>(total, 1)));
+  for (int i = 0; i < npats; i++)
+    if (plen[i]) std::memcpy(flat.data() + offs[size_t(i)], pats[i], size_t(plen[i]) * 2);
+  // two passes: sizes first, then results
+  std::vector<int64_t> tmp(1);
+  int rc = fm_locate_flat(ix, npats, reinterpret_cast<const int32_t*>(plen), flat.data(), offs.data(), max_occs_each,
+                          noccs, start.data(), tmp.data(), 0);
+  int64_t need = 0;
+  for (int i = 0; i < npats; i++) need += noccs[i];
+  if (rc != FM_OK && !(rc == FM_ERR_FULL)) return rc;
+  std::vector<int64_t> outv(static_cast<size_t>(std::max<int64_t>(need, 1)));
+  if (need > 0) {
+    rc = fm_locate_flat(ix, npats, reinterpret_cast<const int32_t*>(plen), flat.data(), offs.data(), max_occs_each,
+                        noccs, start.data(), outv.data(), need);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < npats; i++) {
+    offsets[i] = nullptr;
+    if (noccs[i] > 0) {
+      offsets[i] = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * size_t(noccs[i])));
+      if (!offsets[i]) {
+        for (int j = 0; j < i; j++) { std::free(offsets[j]); offsets[j] = nullptr; }
+        return fail(FM_ERR_MEM, "fm_locate: out of memory");
+      }
+      std::memcpy(offsets[i], outv.data() + start[size_t(i)], sizeof(int64_t) * size_t(noccs[i]));
+    }
+  }
+  return FM_OK;
+}
+
+int fm_back_step(fm_index_t* ix, int64_t nrows, const int64_t* rows, int32_t* ch, int64_t* next, int64_t* offset) {
+  return guarded(ix, "fm_back_step", [&]() -> int {
+    if (nrows < 0 || (nrows && (!rows || !ch || !next || !offset))) return fail(FM_ERR_PARAM, "fm_back_step: bad argument");
+    if (nrows == 0) return FM_OK;
+    cudaStream_t s = ix->stream;
+    int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(nrows) * 8));
+    int64_t* d_off = static_cast<int64_t*>(ix->d_out[2].get(size_t(nrows) * 8));
+    int64_t* d_next = static_cast<int64_t*>(ix->d_out[3].get(size_t(nrows) * 8));
+    int32_t* d_ch = static_cast<int32_t*>(ix->d_out[1].get(size_t(nrows) * 4));
+    CK(cudaMemcpyAsync(d_rows, rows, size_t(nrows) * 8, cudaMemcpyHostToDevice, s));
+    WalkArgs w{};
+    w.nrows = nrows;
+    w.rows = d_rows;
+    w.out_offset = d_off;
+    w.out_next = d_next;
+    w.out_ch = d_ch;
+    w.status = ix->d_status;
+    CK(launch_walk(ix->im, w, kWalkStep, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(offset, d_off, size_t(nrows) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(next, d_next, size_t(nrows) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ch, d_ch, size_t(nrows) * 4, cudaMemcpyDeviceToHost, s));
+    const int st = walk_status(ix);
+    if (st) return fail(st == 1 ? FM_ERR_PARAM : FM_ERR_INVALID, "fm_back_step: bad row (status " + std::to_string(st) + ")");
+    return FM_OK;
+  });
+}
+
+int fm_occ(fm_index_t* ix, int64_t n, const uint16_t* ch, const int64_t* rows, int64_t* c_plus_occ) {
+  return guarded(ix, "fm_occ", [&]() -> int {
+    if (n < 0 || (n && (!ch || !rows || !c_plus_occ))) return fail(FM_ERR_PARAM, "fm_occ: bad argument");
+    if (n == 0) return FM_OK;
+    cudaStream_t s = ix->stream;
+    uint16_t* d_ch = static_cast<uint16_t*>(ix->d_in[1].get(size_t(n) * 2));
+    int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(n) * 8));
+    int64_t* d_out = static_cast<int64_t*>(ix->d_out[2].get(size_t(n) * 8));
+    CK(cudaMemcpyAsync(d_ch, ch, size_t(n) * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_rows, rows, size_t(n) * 8, cudaMemcpyHostToDevice, s));
+    OccArgs a{n, d_ch, d_rows, d_out};
+    CK(launch_occ(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(c_plus_occ, d_out, size_t(n) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; i++)
+      if (c_plus_occ[i] < 0) return fail(FM_ERR_PARAM, "fm_occ: symbol or row out of range");
+    return FM_OK;
+  });
+}
+
+int fm_doc_info(const fm_index_t* ix, int64_t doc, int64_t* doc_len, int64_t* eof_row) {
+  if (!ix || !doc_len || !eof_row) return fail(FM_ERR_PARAM, "fm_doc_info: null argument");
+  if (doc < 0 || doc >= ix->info.num_documents) return fail(FM_ERR_PARAM, "fm_doc_info: no such document");
+  const int64_t e = ix->doc_ends[size_t(doc)];
+  *doc_len = doc == 0 ? e : e - ix->doc_ends[size_t(doc - 1)];
+  *eof_row = ix->doc_eof_rows[size_t(doc)];
+  return FM_OK;
+}
+
+int fm_resolve(const fm_index_t* ix, int64_t n, const int64_t* offsets, int64_t* doc, int64_t* doc_off) {
+  if (!ix || n < 0 || (n && (!offsets || !doc || !doc_off))) return fail(FM_ERR_PARAM, "fm_resolve: bad argument");
+  for (int64_t i = 0; i < n; i++) {
+    // previous document = last d with doc_ends[d] <= offset (bsearch_int64_ntoh_arr, src/utils/util.c:346)
+    const auto it = std::upper_bound(ix->doc_ends.begin(), ix->doc_ends.end(), offsets[i]);
+    const int64_t prev = int64_t(it - ix->doc_ends.begin()) - 1;
+    if (prev < 0) { doc[i] = 0; doc_off[i] = offsets[i]; }
+    else { doc[i] = prev + 1; doc_off[i] = offsets[i] - ix->doc_ends[size_t(prev)]; }
+  }
+  return FM_OK;
+}
+
+int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int64_t* out_len) {
+  return guarded(ix, "fm_extract", [&]() -> int {
+    if (!out_len) return fail(FM_ERR_PARAM, "fm_extract: null argument");
+    if (doc < 0 || doc >= ix->info.num_documents) return fail(FM_ERR_PARAM, "fm_extract: no such document");
+    const int64_t e = ix->doc_ends[size_t(doc)];
+    const int64_t len = (doc == 0 ? e : e - ix->doc_ends[size_t(doc - 1)]) - 1;
+    *out_len = len;
+    if (len > out_cap) return fail(FM_ERR_FULL, "fm_extract: output buffer too small");
+    if (len <= 0) return FM_OK;
+    if (!out) return fail(FM_ERR_PARAM, "fm_extract: null output");
+    cudaStream_t s = ix->stream;
+    int64_t hrow[3] = {ix->doc_eof_rows[size_t(doc)], len, 0};
+    int64_t* d_par = static_cast<int64_t*>(ix->d_in[3].get(3 * 8));
+    uint16_t* d_sym = static_cast<uint16_t*>(ix->d_out[0].get(size_t(len) * 2));
+    CK(cudaMemcpyAsync(d_par, hrow, sizeof(hrow), cudaMemcpyHostToDevice, s));
+    WalkArgs w{};
+    w.nrows = 1;
+    w.rows = d_par;
+    w.nsteps = d_par + 1;
+    w.sym_off = d_par + 2;
+    w.out_sym = d_sym;
+    w.status = ix->d_status;
+    CK(launch_walk(ix->im, w, kWalkExtract, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(out, d_sym, size_t(len) * 2, cudaMemcpyDeviceToHost, s));
+    const int st = walk_status(ix);
+    if (st) return fail(FM_ERR_INVALID, "fm_extract: malformed walk (status " + std::to_string(st) + ")");
+    return FM_OK;
+  });
+}
+
+}  // extern "C"

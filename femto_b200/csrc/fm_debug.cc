@@ -1,0 +1,109 @@
+// fm_debug.cc -- host-side inspection hooks for the rank image (tests of the LOADER only).
+//
+// These walk the host copy of the image (fm_loader.hpp) with plain loops so that the decoding of
+// the on-disk format into rank blocks / node records can be verified on a machine without a GPU.
+// They are not part of the query API: nothing in fm_api.cu calls them, they are not declared in
+// include/femto_b200.h, and the fm_* query entry points fail when no CUDA device is present.
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "fm_loader.hpp"
+
+using namespace fmb;
+
+namespace {
+struct DebugImage {
+  std::unique_ptr<HostImage> im;
+};
+
+bool split(const HostImage& im, int64_t row, int64_t* g, uint32_t* rb) {
+  if (row < im.first_row || row >= im.end_row) return false;
+  *g = row / im.hdr.bucket_size - im.first_bucket;
+  *rb = uint32_t(row % im.hdr.bucket_size);
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+void* fm_debug_image_open(const char* path, int shard, int nshards, int nthreads, int* err) {
+  try {
+    auto* d = new DebugImage();
+    d->im = build_host_image(path, shard, nshards, nthreads);
+    if (err) *err = 0;
+    return d;
+  } catch (const Error& e) {
+    if (err) *err = e.code;
+    return nullptr;
+  }
+}
+
+void fm_debug_image_close(void* h) { delete static_cast<DebugImage*>(h); }
+
+// out[0..7] = n_rank_blocks, n_wtree_blocks, nodes, buckets, markvals, first_row, end_row, max_code_len
+void fm_debug_image_stats(void* h, int64_t* out) {
+  const HostImage& im = *static_cast<DebugImage*>(h)->im;
+  out[0] = im.n_rank_blocks;
+  out[1] = im.n_wtree_blocks;
+  out[2] = int64_t(im.nodes.size());
+  out[3] = im.nbuckets;
+  out[4] = int64_t(im.markvals.size());
+  out[5] = im.first_row;
+  out[6] = im.end_row;
+  out[7] = im.max_code_len;
+}
+
+// C[ch] + Occ(ch,row) through the image tables; -1 if out of range
+int64_t fm_debug_image_occ(void* h, int ch, int64_t row) {
+  const HostImage& im = *static_cast<DebugImage*>(h)->im;
+  int64_t g;
+  uint32_t rb;
+  if (ch < 0 || ch >= kAlpha || !split(im, row, &g, &rb)) return -1;
+  const OccRec& o = im.occ[size_t(g) * kAlphaStride + size_t(ch)];
+  if (!o.leaf) return o.occ_base;
+  const BucketRec& br = im.buckets[size_t(g)];
+  uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1;
+  const int L = 31 - __builtin_clz(o.leaf);
+  for (int lvl = 1; lvl <= L; lvl++) {
+    const HostRank r = host_rank(im.rank_words, base, idx1);
+    const uint32_t b = (o.leaf >> (L - lvl)) & 1u;
+    idx1 = b ? r.ones : idx1 - r.ones;
+    if (idx1 == 0) break;
+    if (lvl < L) {
+      const NodeRec& nr = im.nodes[node];
+      if (nr.child_info[b] & kChildLeaf) return -2;  // image inconsistent with the leaf code
+      base = nr.child_base[b];
+      node = nr.child_info[b];
+    }
+  }
+  return o.occ_base + idx1;
+}
+
+// one LF step with mark test; returns 0 or a negative error
+int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* next, int64_t* offset) {
+  const HostImage& im = *static_cast<DebugImage*>(h)->im;
+  int64_t g;
+  uint32_t rb;
+  if (!split(im, row, &g, &rb)) return -1;
+  const BucketRec& br = im.buckets[size_t(g)];
+  uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1, ch = 0;
+  for (int guard = 0; guard < 64; guard++) {
+    const HostRank r = host_rank(im.rank_words, base, idx1);
+    idx1 = r.bit ? r.ones : idx1 - r.ones;
+    const NodeRec& nr = im.nodes[node];
+    const uint32_t info = nr.child_info[r.bit];
+    if (info & kChildLeaf) { ch = info & 0xffffu; break; }
+    base = nr.child_base[r.bit];
+    node = info;
+  }
+  if (ch >= uint32_t(kAlpha) || idx1 == 0) return -2;
+  const size_t rec = size_t(g) * kAlphaStride + ch;
+  const HostRank m = host_rank(im.rank_words, im.mark[rec].mark_base, idx1);
+  *ch_out = int32_t(ch);
+  *offset = m.bit ? im.markvals[size_t(br.markval_base) + im.mark[rec].markval_off + m.ones - 1] : -1;
+  *next = ch <= uint32_t(kEscSeof) ? -1 : im.occ[rec].occ_base + idx1 - 1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// fm_image.hpp -- the HBM-resident rank image derived from a femto index at load time.
+//
+// The on-disk format (big-endian, 8-byte aligned, RLE-gamma / raw 512-bit segments behind
+// three dependent searches per wavelet-tree level) is hostile to SIMT, so fm_open() decodes it
+// ONCE into the layout below; queries never touch the file bytes again.  The layout keeps the
+// reference's structure -- one Huffman-shaped wavelet tree per bucket, one mark bit-vector and
+// one sampled-SA array per (bucket, symbol) -- so every quantity the reference computes
+// (Occ, L[row], mark bit, SA sample) has a one-to-one counterpart here:
+//
+//   rank block (128 B, 128-B aligned)   word 0      = ones in the node's bit sequence before this block
+//                                        words 1..31 = 992 bits of the sequence, MSB-first per word
+//     -> one rank = ONE 128-byte line; replaces bseq header + A0/A1 bsearch + AP + S scan +
+//        64-B segment decode (reference src/main/wtree.c:635-763)
+//   NodeRec  (16 B)  per internal wavelet-tree node: rank-block base and identity of both children
+//     -> replaces the per-level bsearch of the node directory (wtree_funcs.h:583-626)
+//   OccRec   (16 B)  per (bucket, symbol): C[ch]+block_occs[ch][blk]+bucket_occs[ch][bucket] folded
+//                    into one int64, and the symbol's leaf code in this bucket (0 = not in use)
+//     -> replaces get_C + get_block_occs + get_bucket_occs + cached Huffman code
+//        (src/main/index.c:1538-1569, 1828-1843, 2078-2084)
+//   MarkRec  (8 B)   per (bucket, symbol): rank-block base of the mark bit-vector and offset of its
+//                    sampled-SA values (src/main/index.c:2102-2140)
+//   BucketRec(16 B)  per bucket: root node, root rank-block base, base of the bucket's SA samples
+//
+// All indices are relative to the shard resident on this device.
+#pragma once
+
+#include <cstdint>
+#include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
+
+namespace fmb {
+
+constexpr int kBlockWords = 32;                 // 128-byte rank block
+constexpr int kBitsPerBlock = 31 * 32;          // 992 payload bits
+constexpr uint32_t kChildLeaf = 0x80000000u;    // NodeRec::child_info flag
+constexpr int kAlphaStride = 261;               // records per bucket in OccRec / MarkRec tables
+
+struct alignas(16) NodeRec {
+  uint32_t child_base[2];  // first rank block of child b (internal children only)
+  uint32_t child_info[2];  // kChildLeaf | symbol   or   node index of the internal child
+};
+
+struct alignas(16) OccRec {
+  int64_t occ_base;  // C[ch] + occurrences of ch before this bucket
+  uint32_t leaf;     // wavelet-tree leaf id (1<<len | code) of ch in this bucket, 0 = absent
+  uint32_t pad;
+};
+
+struct alignas(8) MarkRec {
+  uint32_t mark_base;    // first rank block of the mark bit-vector
+  uint32_t markval_off;  // index of the first SA sample of (bucket, ch) within the bucket's samples
+};
+
+struct alignas(16) BucketRec {
+  uint32_t root_base;
+  uint32_t root_node;
+  uint64_t markval_base;
+};
+
+// Device view handed to kernels by value.
+struct DevImage {
+  const uint4* blocks = nullptr;        // rank blocks, 8 x uint4 each
+  const NodeRec* nodes = nullptr;
+  const OccRec* occ = nullptr;          // [nbuckets][kAlphaStride]
+  const MarkRec* mark = nullptr;        // [nbuckets][kAlphaStride]
+  const BucketRec* buckets = nullptr;   // [nbuckets]
+  const int64_t* markvals = nullptr;    // sampled SA values
+  const int64_t* C = nullptr;           // [262]; C[261] = total_length (get_C, index.c:1545)
+  int64_t total_length = 0;
+  int64_t first_row = 0, end_row = 0;   // rows resident here
+  int64_t first_bucket = 0;             // global index of buckets[0]
+  int32_t bucket_size = 0;
+  int32_t bucket_shift = -1;            // log2(bucket_size) when it is a power of two, else -1
+};
+
+}  // namespace fmb

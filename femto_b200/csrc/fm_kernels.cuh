@@ -1,0 +1,55 @@
+// fm_kernels.cuh -- launch interface of the sm_100a query kernels (fm_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "fm_image.hpp"
+
+namespace fmb {
+
+// Work-queue counters live in device memory owned by the caller (one uint64 per launch).
+struct CountArgs {
+  int64_t npats;
+  const int32_t* plen;
+  const uint16_t* flat;
+  const int64_t* offs;
+  int64_t* first;
+  int64_t* last;   // may be NULL: first[i] receives the count
+};
+
+enum WalkMode : int {
+  kWalkLocate = 0,  // follow LF until a marked row; out_offset[i] = SA[rows[i]]
+  kWalkStep = 1,    // one LF step: out_ch, out_next, out_offset (mark of the row itself or -1)
+  kWalkExtract = 2  // nsteps[i] LF steps writing L right-to-left into out_sym[sym_off[i] + nsteps[i]-1-t]
+};
+
+struct WalkArgs {
+  int64_t nrows;
+  const int64_t* rows;
+  int64_t* out_offset;   // locate / step
+  int32_t* out_ch;       // step
+  int64_t* out_next;     // step
+  const int64_t* nsteps; // extract
+  const int64_t* sym_off;
+  uint16_t* out_sym;
+  int32_t* status;       // device int: set non-zero on malformed walk (unmarked document start, bad row)
+};
+
+struct OccArgs {
+  int64_t n;
+  const uint16_t* ch;
+  const int64_t* rows;
+  int64_t* out;  // C[ch] + Occ(ch,row)
+};
+
+// lanes_per_query: 4 or 8.  Each launch bumps *launch_counter (host) by the number of kernels launched.
+cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long long* d_work_counter,
+                         int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
+cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work_counter,
+                        int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
+cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* d_work_counter,
+                       int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
+
+}  // namespace fmb

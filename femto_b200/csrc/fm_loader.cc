@@ -1,0 +1,375 @@
+// fm_loader.cc -- decode a femto index into the host copy of the rank image.
+//
+// Replaces, as a one-time load step, what the reference does lazily per query:
+// open_data_block / b_fault (src/main/index.c:1419-1468, 1222-1342) and the per-rank
+// decoding inside bseq_rank (src/main/wtree.c:635-763).
+#include "fm_loader.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+
+namespace fmb {
+
+HostImage::~HostImage() { std::free(rank_words); }
+
+namespace {
+
+struct BucketPlan {
+  BucketTables tab;
+  std::vector<uint32_t> node_ids;   // internal node ids (heap numbering), sorted
+  std::vector<uint32_t> node_offs;  // bseq offset of each from the wtree start (0 = no data)
+  std::vector<int64_t> node_bits;
+  std::vector<uint32_t> mark_offs;  // per in-use seq: offset of the mark-table bseq from off_marktab
+  std::vector<int64_t> mark_bits;
+  std::vector<uint32_t> markarr_offs;
+  int64_t n_blocks = 0, n_wtree_blocks = 0;
+  // assigned bases
+  int64_t node_base = 0, block_base = 0, markval_base = 0;
+  int64_t n_markvals = 0;  // total ones over the bucket's mark tables
+};
+
+inline int64_t blocks_for_bits(int64_t nbits) { return std::max<int64_t>(1, (nbits + kBitsPerBlock - 1) / kBitsPerBlock); }
+
+void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p) {
+  parse_bucket_tables(blk, bh, bpb, bucket, &p->tab);
+  const BucketTables& t = p->tab;
+  // wavelet tree directory
+  const uint8_t* wt = blk.at(t.off_wtree, 4);
+  const size_t wt_avail = size_t(t.off_marktab) - size_t(t.off_wtree);
+  const uint32_t n_int = be32(wt);
+  if (4 + 8 * size_t(n_int) > wt_avail) throw Error(FM_ERR_FORMAT, "wavelet tree directory truncated");
+  if (n_int == 0 || n_int > uint32_t(kAlpha + 1)) throw Error(FM_ERR_FORMAT, "bad wavelet tree node count");
+  p->node_ids.resize(n_int);
+  p->node_offs.resize(n_int);
+  p->node_bits.resize(n_int);
+  p->n_blocks = 0;
+  for (uint32_t k = 0; k < n_int; k++) {
+    p->node_ids[k] = be32(wt + 4 + 8 * size_t(k));
+    p->node_offs[k] = be32(wt + 8 + 8 * size_t(k));
+    if (k && p->node_ids[k] <= p->node_ids[k - 1]) throw Error(FM_ERR_FORMAT, "wavelet tree directory not sorted");
+    int64_t nbits = 0;
+    if (p->node_offs[k] != 0) {
+      if (p->node_offs[k] >= wt_avail || (p->node_offs[k] & 7u)) throw Error(FM_ERR_FORMAT, "bad bseq offset");
+      nbits = bseq_length(open_bseq(wt + p->node_offs[k], wt_avail - p->node_offs[k]));
+    }
+    p->node_bits[k] = nbits;
+    p->n_blocks += blocks_for_bits(nbits);
+  }
+  if (p->node_ids[0] != 1) throw Error(FM_ERR_FORMAT, "wavelet tree has no root");
+  p->n_wtree_blocks = p->n_blocks;
+  // mark tables / arrays: u32 offsets per in-use symbol, relative to the section start
+  const int n = t.n_in_use;
+  const size_t mt_avail = size_t(t.off_markarr) - size_t(t.off_marktab);
+  const uint8_t* mt = blk.at(t.off_marktab, mt_avail);
+  const size_t ma_end = t.off_end > t.off_markarr ? t.off_end : blk.size();
+  const size_t ma_avail = ma_end - size_t(t.off_markarr);
+  const uint8_t* ma = blk.at(t.off_markarr, ma_avail);
+  if (4 * size_t(n) > mt_avail || 4 * size_t(n) > ma_avail) throw Error(FM_ERR_FORMAT, "mark offsets truncated");
+  p->mark_offs.resize(size_t(n));
+  p->mark_bits.resize(size_t(n));
+  p->markarr_offs.resize(size_t(n));
+  int64_t mark_ones_total = 0;
+  for (int s = 0; s < n; s++) {
+    p->mark_offs[size_t(s)] = be32(mt + 4 * size_t(s));
+    p->markarr_offs[size_t(s)] = be32(ma + 4 * size_t(s));
+    if (p->mark_offs[size_t(s)] >= mt_avail || (p->mark_offs[size_t(s)] & 7u))
+      throw Error(FM_ERR_FORMAT, "bad mark table offset");
+    if (p->markarr_offs[size_t(s)] > ma_avail) throw Error(FM_ERR_FORMAT, "bad mark array offset");
+    int64_t ones = 0;
+    const int64_t nbits = bseq_length(open_bseq(mt + p->mark_offs[size_t(s)], mt_avail - p->mark_offs[size_t(s)]), &ones);
+    p->mark_bits[size_t(s)] = nbits;
+    p->n_blocks += blocks_for_bits(nbits);
+    mark_ones_total += ones;
+  }
+  p->n_markvals = mark_ones_total;
+}
+
+// Fill rank blocks for one expanded bit sequence. bits: MSB-first words (zero padded).
+// Returns the number of ones.
+int64_t fill_blocks(const uint32_t* bits, int64_t nbits, uint32_t* dst_blocks) {
+  const int64_t nb = blocks_for_bits(nbits);
+  const int64_t nwords = (nbits + 31) / 32;
+  uint32_t ones = 0;
+  for (int64_t k = 0; k < nb; k++) {
+    uint32_t* w = dst_blocks + k * kBlockWords;
+    w[0] = ones;
+    const int64_t w0 = k * 31;
+    for (int j = 0; j < 31; j++) {
+      const uint32_t v = (w0 + j < nwords) ? bits[w0 + j] : 0u;
+      w[1 + j] = v;
+      ones += uint32_t(__builtin_popcount(v));
+    }
+  }
+  return ones;
+}
+
+struct Scratch {
+  std::vector<uint32_t> bits;
+  uint32_t* get(int64_t nbits) {
+    const size_t words = size_t((nbits + 31) / 32) + 1;
+    if (bits.size() < words) bits.resize(words);
+    std::fill(bits.begin(), bits.begin() + words, 0u);
+    return bits.data();
+  }
+};
+
+void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh, int64_t blk_num, int bucket,
+                 const BucketPlan& p, HostImage* im, int64_t local_bucket, Scratch* scratch,
+                 std::atomic<int64_t>* markval_used) {
+  const BucketTables& t = p.tab;
+  const int bpb = files.buckets_per_block();
+  const uint8_t* wt = blk.at(t.off_wtree, 4);
+  const size_t wt_avail = size_t(t.off_marktab) - size_t(t.off_wtree);
+  const size_t n_int = p.node_ids.size();
+
+  // leaf id -> symbol
+  std::unordered_map<uint32_t, uint32_t> leaf_sym;
+  leaf_sym.reserve(size_t(t.n_in_use) * 2 + 2);
+  for (int s = 0; s <= t.n_in_use; s++) leaf_sym[t.leaf[s]] = t.seq_to_ch[s];
+
+  // rank blocks of every internal node, in directory order
+  std::vector<int64_t> node_block(n_int);
+  int64_t cursor = p.block_base;
+  for (size_t k = 0; k < n_int; k++) {
+    node_block[k] = cursor;
+    const int64_t nbits = p.node_bits[k];
+    if (nbits > 0) {
+      uint32_t* bits = scratch->get(nbits);
+      const int64_t got = bseq_expand(open_bseq(wt + p.node_offs[k], wt_avail - p.node_offs[k]), bits, nbits);
+      if (got != nbits) throw Error(FM_ERR_FORMAT, "bseq expansion length mismatch");
+      fill_blocks(bits, nbits, im->rank_words + cursor * kBlockWords);
+    }
+    cursor += blocks_for_bits(nbits);
+  }
+
+  // node records
+  for (size_t k = 0; k < n_int; k++) {
+    NodeRec& nr = im->nodes[size_t(p.node_base) + k];
+    for (uint32_t b = 0; b < 2; b++) {
+      const uint32_t child = p.node_ids[k] * 2 + b;
+      auto it = std::lower_bound(p.node_ids.begin(), p.node_ids.end(), child);
+      if (it != p.node_ids.end() && *it == child) {
+        const size_t ci = size_t(it - p.node_ids.begin());
+        nr.child_base[b] = uint32_t(node_block[ci]);
+        nr.child_info[b] = uint32_t(p.node_base + int64_t(ci));
+      } else {
+        auto ls = leaf_sym.find(child);
+        nr.child_base[b] = 0;
+        nr.child_info[b] = kChildLeaf | (ls == leaf_sym.end() ? kEndOfBucketSym : ls->second);
+      }
+    }
+  }
+
+  BucketRec& br = im->buckets[size_t(local_bucket)];
+  br.root_base = uint32_t(node_block[0]);
+  br.root_node = uint32_t(p.node_base);
+  br.markval_base = uint64_t(p.markval_base);
+
+  // per-symbol records
+  const size_t rec0 = size_t(local_bucket) * kAlphaStride;
+  for (int ch = 0; ch < kAlpha; ch++) {
+    OccRec& o = im->occ[rec0 + size_t(ch)];
+    o.occ_base = files.C(ch) + files.block_occs(ch, blk_num) + int64_t(bucket_occs(blk, bh, bpb, ch, bucket));
+    o.leaf = t.in_use[ch] ? t.leaf[t.ch_to_seq[ch]] : 0u;
+    o.pad = 0;
+    MarkRec& m = im->mark[rec0 + size_t(ch)];
+    m.mark_base = 0;
+    m.markval_off = 0;
+  }
+
+  // mark bit-vectors and sampled SA values
+  const size_t mt_avail = size_t(t.off_markarr) - size_t(t.off_marktab);
+  const uint8_t* mt = blk.at(t.off_marktab, mt_avail);
+  const size_t ma_end = t.off_end > t.off_markarr ? t.off_end : blk.size();
+  const size_t ma_avail = ma_end - size_t(t.off_markarr);
+  const uint8_t* ma = blk.at(t.off_markarr, ma_avail);
+  const int vbits = num_bits64(uint64_t(bh.total_length));  // text_size_bits, index.c:1445
+  int64_t val_cursor = 0;
+  for (int s = 0; s < t.n_in_use; s++) {
+    const int ch = t.seq_to_ch[s];
+    const int64_t nbits = p.mark_bits[size_t(s)];
+    uint32_t* bits = scratch->get(nbits);
+    const uint32_t off = p.mark_offs[size_t(s)];
+    const int64_t got = bseq_expand(open_bseq(mt + off, mt_avail - off), bits, nbits);
+    if (got != nbits) throw Error(FM_ERR_FORMAT, "mark table expansion length mismatch");
+    const int64_t ones = fill_blocks(bits, nbits, im->rank_words + cursor * kBlockWords);
+    MarkRec& m = im->mark[rec0 + size_t(ch)];
+    m.mark_base = uint32_t(cursor);
+    m.markval_off = uint32_t(val_cursor);
+    cursor += blocks_for_bits(nbits);
+    // values: `ones` fields of vbits bits, MSB-first (bsW64, buffer_funcs.h:118-127)
+    const uint32_t aoff = p.markarr_offs[size_t(s)];
+    const size_t need_bytes = size_t((ones * vbits + 7) / 8);
+    if (size_t(aoff) + need_bytes > ma_avail) throw Error(FM_ERR_FORMAT, "mark array truncated");
+    const uint8_t* src = ma + aoff;
+    int64_t* dst = im->markvals.data() + p.markval_base + val_cursor;
+    size_t bitpos = 0;
+    for (int64_t j = 0; j < ones; j++) {
+      uint64_t v = 0;
+      int left = vbits;
+      while (left > 0) {
+        const int o = int(bitpos & 7);
+        const int take = std::min(8 - o, left);
+        const uint32_t byte = src[bitpos >> 3];
+        v = (v << take) | ((byte >> (8 - o - take)) & ((1u << take) - 1u));
+        bitpos += size_t(take);
+        left -= take;
+      }
+      dst[j] = int64_t(v);
+    }
+    val_cursor += ones;
+  }
+  if (cursor != p.block_base + p.n_blocks) throw Error(FM_ERR_INVALID, "rank block accounting error");
+  if (val_cursor != p.n_markvals) throw Error(FM_ERR_FORMAT, "mark table ones do not match their S sums");
+  markval_used->fetch_add(val_cursor);
+}
+
+template <typename F>
+void parallel_for(int64_t n, int nthreads, F&& fn) {
+  std::atomic<int64_t> next{0};
+  std::mutex err_mu;
+  std::unique_ptr<Error> first_err;
+  auto worker = [&](int tid) {
+    try {
+      for (;;) {
+        const int64_t i = next.fetch_add(1);
+        if (i >= n) break;
+        fn(i, tid);
+      }
+    } catch (const Error& e) {
+      std::lock_guard<std::mutex> g(err_mu);
+      if (!first_err) first_err.reset(new Error(e));
+      next.store(n);
+    } catch (const std::exception& e) {
+      std::lock_guard<std::mutex> g(err_mu);
+      if (!first_err) first_err.reset(new Error(FM_ERR_UNKNOWN, e.what()));
+      next.store(n);
+    }
+  };
+  nthreads = int(std::max<int64_t>(1, std::min<int64_t>(nthreads, n)));
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& t : th) t.join();
+  if (first_err) throw *first_err;
+}
+
+}  // namespace
+
+HostRank host_rank(const uint32_t* rank_words, uint32_t base_block, uint32_t index1) {
+  const uint32_t p = index1 - 1;
+  const uint32_t k = p / kBitsPerBlock, off = p % kBitsPerBlock;
+  const uint32_t* w = rank_words + (size_t(base_block) + k) * kBlockWords;
+  uint32_t ones = w[0];
+  const uint32_t full = off / 32, rem = off % 32;
+  for (uint32_t j = 0; j < full; j++) ones += uint32_t(__builtin_popcount(w[1 + j]));
+  const uint32_t last = w[1 + full];
+  ones += uint32_t(__builtin_popcount(last >> (31 - rem)));
+  return HostRank{ones, (last >> (31 - rem)) & 1u};
+}
+
+std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads) {
+  if (nshards < 1 || shard < 0 || shard >= nshards) throw Error(FM_ERR_PARAM, "bad shard");
+  if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
+  auto files = IndexFiles::open(path);
+  const BlockHeader& h = files->header();
+  const int bpb = files->buckets_per_block();
+  std::unique_ptr<HostImage> im(new HostImage());
+  im->hdr = h;
+
+  // data blocks of this shard: b with b*nshards/nblocks == shard
+  int64_t b0 = h.nblocks, b1 = 0;
+  for (int64_t b = 0; b < h.nblocks; b++) {
+    if (b * nshards / std::max<int64_t>(1, h.nblocks) == shard) { b0 = std::min(b0, b); b1 = std::max(b1, b + 1); }
+  }
+  if (b0 >= b1) { b0 = b1 = 0; }
+  im->first_block = b0;
+  im->end_block = b1;
+  im->first_row = b0 * int64_t(h.block_size);
+  im->end_row = std::min<int64_t>(h.total_length, b1 * int64_t(h.block_size));
+  if (b0 == b1) im->end_row = im->first_row;
+  im->first_bucket = b0 * bpb;
+
+  im->C.resize(262);
+  for (int c = 0; c < 262; c++) im->C[size_t(c)] = files->C(c);
+  im->doc_ends.resize(size_t(h.ndocs));
+  im->doc_eof_rows.resize(size_t(h.ndocs));
+  for (int64_t d = 0; d < h.ndocs; d++) {
+    im->doc_ends[size_t(d)] = files->doc_end(d);
+    im->doc_eof_rows[size_t(d)] = files->doc_eof_row(d);
+  }
+
+  // map blocks, validate headers
+  std::vector<Blob> blobs;
+  std::vector<BlockHeader> bhs;
+  std::vector<int64_t> bucket0;  // local index of each block's first bucket
+  int64_t nb = 0;
+  for (int64_t b = b0; b < b1; b++) {
+    blobs.push_back(files->map_block(b));
+    BlockHeader bh = parse_block_header(blobs.back(), kMagicDataBlock);
+    if (bh.block_number != b || bh.block_size != h.block_size || bh.bucket_size != h.bucket_size ||
+        bh.total_length != h.total_length)
+      throw Error(FM_ERR_FORMAT, "data block header does not match the header block");
+    const int64_t expect_rows = std::min<int64_t>(h.block_size, h.total_length - b * int64_t(h.block_size));
+    if (bh.size != expect_rows) throw Error(FM_ERR_FORMAT, "data block has an unexpected number of rows");
+    if (bh.num_buckets != (bh.size + h.bucket_size - 1) / h.bucket_size)
+      throw Error(FM_ERR_FORMAT, "data block has an unexpected number of buckets");
+    if (b + 1 < h.nblocks && bh.num_buckets != bpb) throw Error(FM_ERR_FORMAT, "short block in the middle of the index");
+    blobs.back().at(0, size_t(kBlockHeaderBytes) + 4 * (size_t(bpb) + 1) + 4 * size_t(kAlpha) * size_t(bh.num_buckets));
+    bhs.push_back(bh);
+    bucket0.push_back(nb);
+    nb += bh.num_buckets;
+  }
+  im->nbuckets = nb;
+
+  // pass 1: plan every bucket
+  std::vector<BucketPlan> plans{size_t(nb)};
+  std::vector<std::pair<int32_t, int32_t>> where{size_t(nb)};  // (local block, bucket in block)
+  for (size_t lb = 0; lb < blobs.size(); lb++)
+    for (int k = 0; k < bhs[lb].num_buckets; k++) where[size_t(bucket0[lb] + k)] = {int32_t(lb), int32_t(k)};
+  parallel_for(nb, nthreads, [&](int64_t g, int) {
+    const auto [lb, k] = where[size_t(g)];
+    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)]);
+  });
+
+  int64_t nodes = 0, blocks = 0, vals = 0, wt_blocks = 0;
+  int max_len = 0;
+  for (auto& p : plans) {
+    p.node_base = nodes;
+    p.block_base = blocks;
+    p.markval_base = vals;
+    nodes += int64_t(p.node_ids.size());
+    blocks += p.n_blocks;
+    wt_blocks += p.n_wtree_blocks;
+    vals += p.n_markvals;
+    max_len = std::max(max_len, p.tab.max_len);
+  }
+  if (blocks >= (int64_t(1) << 32) || nodes >= (int64_t(1) << 31))
+    throw Error(FM_ERR_FULL, "shard too large for 32-bit rank block indices; use more shards");
+  im->max_code_len = max_len;
+  im->n_rank_blocks = blocks;
+  im->n_wtree_blocks = wt_blocks;
+  im->rank_words = static_cast<uint32_t*>(std::calloc(size_t(std::max<int64_t>(blocks, 1)) * kBlockWords, 4));
+  if (!im->rank_words) throw Error(FM_ERR_MEM, "out of host memory for the rank image");
+  im->nodes.resize(size_t(nodes));
+  im->occ.resize(size_t(nb) * kAlphaStride);
+  im->mark.resize(size_t(nb) * kAlphaStride);
+  im->buckets.resize(size_t(nb));
+  im->markvals.resize(size_t(vals));
+
+  // pass 2: decode
+  std::atomic<int64_t> used{0};
+  std::vector<Scratch> scratch{size_t(std::max(1, nthreads))};
+  parallel_for(nb, nthreads, [&](int64_t g, int tid) {
+    const auto [lb, k] = where[size_t(g)];
+    fill_bucket(*files, blobs[size_t(lb)], bhs[size_t(lb)], b0 + lb, k, plans[size_t(g)], im.get(), g,
+                &scratch[size_t(tid)], &used);
+  });
+  return im;
+}
+
+}  // namespace fmb

@@ -1,0 +1,196 @@
+/* femto_b200.h -- C ABI of the B200-native FM-index query engine.
+ *
+ * Drop-in boundary for the backward-search hot path of femto-dev/femto: the batch
+ * functions of the reference's src/main/femto_internal.h:63-74 (parallel_count,
+ * parallel_locate, parallel_locate_range), the server/index lifecycle around them
+ * (src/main/femto.c:54-81, 269-272) and document extraction
+ * (src/main/server.c:6364-6437), over the reference's UNCHANGED on-disk index
+ * (directory of block files or flattened single file).
+ *
+ * Plain pointers and sizes only: no C++, CUDA or torch types cross this boundary.
+ * Every entry point returns an fm_err_t whose numbering equals the reference's
+ * err_code_t (src/utils/error.h:25-39); fm_last_error() returns a thread-local
+ * message (the reference's error ring, src/utils/error.c:30-57, is process-global
+ * and not thread-safe, so it is not reproduced).
+ *
+ * Symbols are alpha_t-compatible: uint16_t holding 5+byte for text bytes, 1..4 for
+ * the escape codes (src/main/index_types.h:42-68).  Rows and offsets are int64_t.
+ * "No match" is first > last, not an error (src/main/server.c:832-841).
+ *
+ * The library has NO CPU fallback for the query path: without a usable CUDA device
+ * fm_open() fails with FM_ERR_IO and says why.
+ */
+#ifndef FEMTO_B200_H
+#define FEMTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_ALPHA_SIZE 261        /* src/main/index_types.h:64-65 */
+#define FM_CHARACTER_OFFSET 5
+
+typedef enum {                   /* == err_code_t, src/utils/error.h:25-39 */
+  FM_OK = 0,
+  FM_ERR_MEM = 1,
+  FM_ERR_IO = 2,
+  FM_ERR_PARAM = 3,
+  FM_ERR_FORMAT = 4,
+  FM_ERR_BZ_DATA = 5,
+  FM_ERR_INVALID = 6,
+  FM_ERR_PTHREADS = 7,
+  FM_ERR_MISSING = 8,
+  FM_ERR_CANCELED = 9,
+  FM_ERR_FULL = 10,
+  FM_ERR_OVERWORKED = 11,
+  FM_ERR_UNKNOWN = 12
+} fm_err_t;
+
+typedef struct fm_index fm_index_t;   /* replaces (femto_server_t, index_locator_t) */
+
+typedef struct {
+  int64_t total_length;      /* rows of the BWT = indexed symbols incl. one SEOF per document */
+  int64_t num_documents;
+  int64_t num_blocks;        /* data blocks in the index (all of them, not only this shard's) */
+  int32_t block_size;        /* rows per block   (index_block_param_t, src/main/index.h:103-121) */
+  int32_t bucket_size;       /* rows per bucket */
+  int32_t mark_period;
+  int32_t chunk_size;
+  int64_t first_row;         /* rows [first_row, end_row) are resident on this device */
+  int64_t end_row;
+  int64_t hbm_bytes;         /* device memory held by the index image */
+  int64_t rank_block_bytes;  /* of which wavelet-tree rank blocks */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t max_code_len;      /* deepest wavelet-tree leaf over all resident buckets */
+} fm_info_t;
+
+/* --------------------------------------------------------------------------
+ * Lifecycle.  fm_open == femto_start_server_err + femto_loc_for_path_err
+ * (src/main/femto.c:54-69, 269-272): parses the index at `path`, validates the
+ * block headers exactly as read_block_header (src/main/index.c:1348-1404), decodes
+ * every bucket's map/Huffman tables (b_fault, index.c:1222-1342) and wavelet-tree
+ * segments once, and uploads the rank image to `device`'s HBM.
+ * fm_close == femto_stop_server (femto.c:77-81).
+ * fm_open_shard loads only the data blocks whose index b satisfies
+ * b*nshards/num_blocks == shard (BWT row range sharding). */
+int fm_open(const char* path, int device, fm_index_t** out);
+int fm_open_shard(const char* path, int device, int shard, int nshards, fm_index_t** out);
+void fm_close(fm_index_t* ix);
+int fm_info(const fm_index_t* ix, fm_info_t* out);
+const char* fm_last_error(void);
+
+/* --------------------------------------------------------------------------
+ * count: backward search.  Mirrors parallel_count (src/main/femto.c:275-329):
+ * for pattern i, [first[i], last[i]] is the BWT row range of its occurrences
+ * (first > last when there is none); if last == NULL, first[i] receives the count
+ * (femto.c:313-318).  plen[i] == 0 yields [0, total_length-1] (server.c:782-808).
+ * Host buffers; the call blocks until results are in first/last.  Re-entrant. */
+int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* pats,
+             int64_t* first, int64_t* last);
+
+/* Same operation with the patterns in one flat buffer: pattern i is
+ * flat[offs[i] .. offs[i]+plen[i]).  This is the form the engine works on;
+ * fm_count() gathers into it. */
+int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
+                  const int64_t* offs, int64_t* first, int64_t* last);
+
+/* Device-resident form: all pointers are device pointers on ix's device, `stream`
+ * is a cudaStream_t (NULL = default stream).  Asynchronous: returns after enqueueing.
+ * flat_len = number of symbols in d_flat. */
+int fm_count_device(fm_index_t* ix, int64_t npats, const int32_t* d_plen, const uint16_t* d_flat,
+                    const int64_t* d_offs, int64_t* d_first, int64_t* d_last, void* stream);
+
+/* --------------------------------------------------------------------------
+ * locate.  Mirrors parallel_locate (src/main/femto.c:331-399): for pattern i,
+ * noccs[i] offsets are returned in BWT row order first..; offsets[i] is malloc()ed
+ * by the callee and freed by the caller with free() (NULL when noccs[i]==0).
+ * The max_occs clip reproduces do_locate_query (src/main/server.c:4411-4415):
+ * all rows when last-first <= max_occs, else the first max_occs rows. */
+int fm_locate(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* pats,
+              int max_occs_each, int* noccs, int64_t** offsets);
+
+/* Flat form: results of pattern i are out[out_start[i] .. out_start[i]+noccs[i]).
+ * Fails with FM_ERR_FULL (noccs/out_start still filled) when out_cap is too small. */
+int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
+                   const int64_t* offs, int max_occs_each, int32_t* noccs, int64_t* out_start,
+                   int64_t* out, int64_t out_cap);
+
+/* parallel_locate_range (src/main/femto.c:481-536): text offsets SA[first..last];
+ * offsets must have room for last-first+1 entries. */
+int fm_locate_range(fm_index_t* ix, int64_t first, int64_t last, int64_t* offsets);
+
+/* Arbitrary rows (host buffers): offsets[i] = SA[rows[i]]. */
+int fm_locate_rows(fm_index_t* ix, int64_t nrows, const int64_t* rows, int64_t* offsets);
+int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, int64_t* d_offsets,
+                          void* stream);
+
+/* --------------------------------------------------------------------------
+ * Single LF step with mark test = do_back_query (src/main/server.c:2228-2359):
+ * ch[i] = L[rows[i]], next[i] = LF(rows[i]) or -1 when ch <= ESCAPE_CODE_SEOF,
+ * offset[i] = SA[rows[i]] when the row is marked, else -1.  Host buffers. */
+int fm_back_step(fm_index_t* ix, int64_t nrows, const int64_t* rows, int32_t* ch, int64_t* next,
+                 int64_t* offset);
+
+/* C[ch] + Occ(ch,row) for each (ch,row): one half of a backward-search step, i.e.
+ * header_occs_request(HDR_BACK...) + block_request(BLOCK_REQUEST_OCCS)
+ * (src/main/index.c:1698-1765, 1973-2100).  Host buffers. */
+int fm_occ(fm_index_t* ix, int64_t n, const uint16_t* ch, const int64_t* rows, int64_t* c_plus_occ);
+
+/* --------------------------------------------------------------------------
+ * Documents.  fm_doc_info: length (incl. its SEOF) and EOF row (header tables,
+ * src/main/index.c:1668-1696).  fm_resolve: text offset -> (document, offset in
+ * document) as resolve_location (index.c:1587-1611).  fm_extract: the doc_len-1
+ * symbols of the document, as do_extract_document_query's backward context
+ * (src/main/server.c:6364-6437). */
+int fm_doc_info(const fm_index_t* ix, int64_t doc, int64_t* doc_len, int64_t* eof_row);
+int fm_resolve(const fm_index_t* ix, int64_t n, const int64_t* offsets, int64_t* doc, int64_t* doc_off);
+int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int64_t* out_len);
+
+/* --------------------------------------------------------------------------
+ * Pinned host memory for callers that want zero-staging transfers. */
+void* fm_host_alloc(size_t bytes);
+void fm_host_free(void* p);
+
+/* Counters of the engine's own kernel launches since fm_open (all entry points). */
+int64_t fm_kernel_launches(const fm_index_t* ix);
+
+/* Tuning knob: lanes cooperating on one rank query (4 or 8; default 4). */
+int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
+
+/* --------------------------------------------------------------------------
+ * Index construction (host side; "next" row f-1 of the scope table).  Emits an
+ * index byte-identical to what the reference's compress_bucket / constructor_*
+ * path (src/main/index.c:309-738, src/main/construct.c:146-566) writes for the
+ * same BWT rows.  Input per row r of the BWT, in row order:
+ *   L[r]       alpha_t symbol preceding the suffix (SEOF for a document start)
+ *   sa[r]      suffix array value, i.e. text offset of the suffix
+ * and the document ends (exclusive prefix sums of document lengths incl. SEOF).
+ * The marking rule should_mark() (src/main/index_types.h:134-144) is applied
+ * here.  chunk_size <= 0 writes no document chunks (header chunk_size = -1, as
+ * index_documents with map == NULL, construct.c:606).
+ * out_dir is created if needed and receives "00", "01", ... and "_femto_index". */
+typedef struct fm_builder fm_builder_t;
+int fm_builder_create(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                      int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                      int nthreads, fm_builder_t** out);
+/* Append the next `nrows` BWT rows (any granularity; rows must arrive in order). */
+int fm_builder_append(fm_builder_t* b, int64_t nrows, const uint16_t* L, const int64_t* sa);
+/* Document information strings stored in the header block (may be NULL => "doc<i>"). */
+int fm_builder_set_doc_info(fm_builder_t* b, int64_t doc, const void* info, int64_t len);
+int fm_builder_finish(fm_builder_t* b);       /* writes the header block; frees b */
+void fm_builder_abort(fm_builder_t* b);
+/* Convert a directory index into the flattened single-file form (flatten_index,
+ * src/main/index.c:2260-2365). */
+int fm_flatten(const char* index_dir, const char* out_file);
+
+/* Suffix array of a prepared text (symbols 1..260, no zeros) by prefix doubling on the
+ * host; for tests and small corpora.  sa must hold n entries. */
+int fm_suffix_sort_host(const uint16_t* text, int64_t n, int64_t* sa);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMTO_B200_H */
