@@ -290,9 +290,7 @@ int ref_build_index(int ndocs, const int64_t* doc_lens, const unsigned char* con
   prepared_text_t p;
   index_block_param_t param;
   bwt_reader_t bwt;
-  bwt_document_map_reader_t map;
   FILE* bwt_f = NULL;
-  FILE* map_f = NULL;
   error_t err;
   char info_path[4096];
   int i;
@@ -300,7 +298,12 @@ int ref_build_index(int ndocs, const int64_t* doc_lens, const unsigned char* con
   set_default_param(&param);
   if (block_size > 0) param.block_size = block_size;
   if (bucket_size > 0) param.b_size = bucket_size;
-  if (chunk_size >= 0) param.chunk_size = chunk_size;
+  /* No document map is passed to index_documents (as the reference's own test_construct does,
+   * src/main/index_test.c:566): its map branch (construct.c:663-679) never advances the map reader
+   * and indexes chunks[] by block, not bucket.  Document chunks are pinned through femto_index
+   * (oracle/_ref/femto_index) instead.  chunk_size is therefore ignored here. */
+  (void) chunk_size;
+  param.chunk_size = 0;
   if (mark_period >= 0) param.mark_period = mark_period;
   err = calculate_params(&param);
   if (err) return code_of(err);
@@ -323,25 +326,19 @@ int ref_build_index(int ndocs, const int64_t* doc_lens, const unsigned char* con
     if (err) goto fail;
   }
   bwt_f = tmpfile();
-  map_f = tmpfile();
-  if (!bwt_f || !map_f) { err = ERR_IO_UNK; goto fail; }
+  if (!bwt_f) { err = ERR_IO_UNK; goto fail; }
   start_clock(); /* save_prepared_bwt ends with one stop_clock() more than it starts (bwt_creator.c:135) */
-  err = save_prepared_bwt(&p, param.mark_period, bwt_f, param.chunk_size, map_f, 0);
+  err = save_prepared_bwt(&p, param.mark_period, bwt_f, 0, NULL, 0);
   if (err) goto fail;
   rewind(bwt_f);
-  rewind(map_f);
   err = bwt_reader_open(&bwt, bwt_f);
   if (err) goto fail;
-  err = bwt_document_map_reader_open(&map, map_f);
-  if (err) goto fail;
-  err = index_documents(&bwt, &map, &p.info_reader, &param, index_path, NULL);
+  err = index_documents(&bwt, NULL, &p.info_reader, &param, index_path, NULL);
   bwt_reader_close(&bwt);
-  bwt_document_map_reader_close(&map);
   if (err) goto fail;
   err = free_prepared_text(&p);
   unlink(info_path);
   if (bwt_f) fclose(bwt_f);
-  if (map_f) fclose(map_f);
   return code_of(err);
 fail:
   {
@@ -349,7 +346,6 @@ fail:
     free_prepared_text(&p);
     unlink(info_path);
     if (bwt_f) fclose(bwt_f);
-    if (map_f) fclose(map_f);
     return rc;
   }
 }

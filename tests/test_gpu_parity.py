@@ -1,0 +1,215 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle on the same index and
+the same seeded inputs.  Bit-exact: every first/last row, every located offset (in row order),
+every L symbol, LF target and SA sample.  Run on the B200 box with `-m gpu`."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import corpus
+import femto_b200 as fb
+from conftest import GOLDEN_DIR
+from oracle.bindings import Oracle, Reference, have_reference
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["two_docs", "gen400_big_buckets", "gen400_small_buckets", "gen400_small_blocks", "gen13_small_blocks",
+       "gen3", "single_symbol", "multi_doc_mixed", "acgt_64k", "bytes_200k", "skewed_deep", "english_100k"]
+
+
+@pytest.fixture(scope="module")
+def gpu_indexes(built_indexes):
+    opened = {name: fb.Index(path, device=0) for name, path in built_indexes.items()}
+    yield opened
+    for ix in opened.values():
+        ix.close()
+
+
+def edge_patterns():
+    return [np.zeros(0, dtype=np.uint16),                      # plen == 0 -> [0, n-1]
+            np.array([2], dtype=np.uint16),                    # the SEOF symbol itself
+            np.array([1], dtype=np.uint16), np.array([3, 4], dtype=np.uint16),   # unused escape codes
+            np.array([260], dtype=np.uint16), np.array([260, 260], dtype=np.uint16),
+            np.array([5], dtype=np.uint16), np.array([5, 5, 5], dtype=np.uint16)]
+
+
+@pytest.mark.parametrize("lanes", [4, 8])
+@pytest.mark.parametrize("name", ALL)
+def test_count_matches_oracle(name, lanes, gpu_indexes, built_indexes, corpora):
+    docs, _ = corpora[name]
+    ix = gpu_indexes[name]
+    ix.set_lanes_per_query(lanes)
+    pats = corpus.sample_patterns(docs, 1500, [1, 2, 3, 4, 5, 6, 8, 12, 16, 24, 32, 64], seed=31) + edge_patterns()
+    with Oracle(built_indexes[name]) as o:
+        of, ol = o.count(pats)
+    f, l = ix.count(pats)                                    # reference-shaped pointer-array call
+    assert (f == of).all() and (l == ol).all()
+    plen, flat, offs = fb.flatten_patterns(pats)
+    f2, l2 = ix.count_flat(plen, flat, offs)                 # flat host-buffer call
+    assert (f2 == of).all() and (l2 == ol).all()
+    for i in range(0, len(pats), 97):
+        c = corpus.brute_count(docs, pats[i])
+        if c >= 0:
+            assert max(l[i] - f[i] + 1, 0) == c
+    ix.set_lanes_per_query(4)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_occ_and_back_step_match_oracle(name, gpu_indexes, built_indexes):
+    ix = gpu_indexes[name]
+    with Oracle(built_indexes[name]) as o:
+        n = o.header_info()["total_length"]
+        rng = np.random.default_rng(4)
+        if n <= 500:
+            rows = np.repeat(np.arange(n), 261)
+            chs = np.tile(np.arange(261), n)
+        else:
+            rows = rng.integers(0, n, 5000)
+            chs = rng.integers(0, 261, 5000)
+        got = ix.occ(chs, rows)
+        want = np.array([o.occ(int(c), int(r))[0] for c, r in zip(chs, rows)], dtype=np.int64)
+        assert (got == want).all()
+        srows = np.arange(n) if n <= 3000 else np.concatenate([rng.integers(0, n, 3000), [0, n - 1]])
+        ch, nxt, off = ix.back_step(srows)
+        for i, r in enumerate(srows):
+            assert (int(ch[i]), int(nxt[i]), int(off[i])) == o.back_step(int(r)), r
+
+
+@pytest.mark.parametrize("lanes", [4, 8])
+@pytest.mark.parametrize("name", ALL)
+def test_locate_matches_oracle(name, lanes, gpu_indexes, built_indexes, corpora):
+    docs, _ = corpora[name]
+    ix = gpu_indexes[name]
+    ix.set_lanes_per_query(lanes)
+    pats = corpus.sample_patterns(docs, 300, [1, 2, 3, 4, 6, 8, 16, 32], seed=41) + edge_patterns()[1:]
+    with Oracle(built_indexes[name]) as o:
+        n = o.header_info()["total_length"]
+        for max_occs in (1, 2, 7, 100000):                   # incl. the '>' clip quirk (server.c:4411)
+            want = o.locate(pats, max_occs)
+            got = ix.locate(pats, max_occs)
+            assert all((a == b).all() for a, b in zip(got, want)), max_occs
+        if n <= 70000:
+            assert (ix.locate_range(0, n - 1) == o.locate_range(0, n - 1)).all()
+        else:
+            assert (ix.locate_range(1000, 9000) == o.locate_range(1000, 9000)).all()
+    # every located offset really is an occurrence
+    got = ix.locate(pats[:60], 50)
+    for p, offs_ in zip(pats[:60], got):
+        truth = set(corpus.brute_locate(docs, p)) if (p >= 5).all() and len(p) else None
+        if truth is not None:
+            assert set(offs_.tolist()) <= truth
+    ix.set_lanes_per_query(4)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_extract_and_doc_tables(name, gpu_indexes, built_indexes, corpora):
+    docs, _ = corpora[name]
+    ix = gpu_indexes[name]
+    with Oracle(built_indexes[name]) as o:
+        n = o.header_info()["total_length"]
+        for d in range(len(docs)):
+            assert ix.doc_info(d) == o.doc_info(d)
+            got = bytes((ix.extract(d) - fb.CHARACTER_OFFSET).astype(np.uint8))
+            assert got == docs[d]
+        offs_ = np.arange(0, n, max(1, n // 200), dtype=np.int64)
+        doc, doff = ix.resolve(offs_)
+        for i, off in enumerate(offs_):
+            assert (int(doc[i]), int(doff[i])) == o.resolve(int(off))
+
+
+def test_golden_reference_outputs():
+    """Committed answers of the unmodified reference on indexes built by the reference."""
+    for case in sorted(os.listdir(GOLDEN_DIR)):
+        base = os.path.join(GOLDEN_DIR, case)
+        if not os.path.exists(os.path.join(base, "expected.json")):
+            continue
+        exp = json.load(open(os.path.join(base, "expected.json")))
+        with fb.Index(os.path.join(base, "index")) as ix:
+            pats = [np.array(p, dtype=np.uint16) for p in exp["patterns"]]
+            f, l = ix.count(pats)
+            assert f.tolist() == exp["first"] and l.tolist() == exp["last"]
+            assert [x.tolist() for x in ix.locate(pats, exp["max_occs"])] == exp["locate"]
+            n = exp["total_length"]
+            ch, nxt, off = ix.back_step(np.arange(n))
+            assert [[int(a), int(b), int(c)] for a, b, c in zip(ch, nxt, off)] == exp["back_step"]
+            assert ix.locate_range(0, n - 1).tolist() == exp["sa"]
+            occ = np.array(exp["occ_samples"])
+            assert ix.occ(occ[:, 0], occ[:, 1]).tolist() == occ[:, 2].tolist()
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref did not travel")
+def test_live_reference_on_gpu_box(gpu_indexes, built_indexes, corpora):
+    """The unmodified reference, run on this box, against the GPU on the same index."""
+    for name in ("multi_doc_mixed", "english_100k", "bytes_200k"):
+        docs, _ = corpora[name]
+        pats = corpus.sample_patterns(docs, 500, [2, 4, 8, 16, 32], seed=51)
+        with Reference(built_indexes[name]) as r:
+            rf, rl = r.count(pats)
+            rloc = r.locate(pats[:100], 20)
+        f, l = gpu_indexes[name].count(pats)
+        assert (f == rf).all() and (l == rl).all()
+        assert all((a == b).all() for a, b in zip(gpu_indexes[name].locate(pats[:100], 20), rloc))
+
+
+def test_flattened_container_and_reopen(built_indexes, corpora, tmp_path):
+    docs, _ = corpora["acgt_64k"]
+    flat = str(tmp_path / "acgt.femto")
+    fb.flatten(built_indexes["acgt_64k"], flat)
+    pats = corpus.sample_patterns(docs, 400, [4, 8, 12], seed=61)
+    with fb.Index(built_indexes["acgt_64k"]) as a, fb.Index(flat) as b:
+        fa, la = a.count(pats)
+        fbb, lb = b.count(pats)
+        assert (fa == fbb).all() and (la == lb).all()
+        assert a.kernel_launches() > 0
+
+
+def test_device_pointer_api_with_torch(built_indexes, corpora):
+    """fm_count_device: inputs and outputs stay in HBM (what bench.py's `value` times)."""
+    import torch
+    docs, _ = corpora["english_100k"]
+    pats = corpus.sample_patterns(docs, 5000, [8, 16, 32], seed=71)
+    plen, flat, offs = fb.flatten_patterns(pats)
+    with fb.Index(built_indexes["english_100k"]) as ix, Oracle(built_indexes["english_100k"]) as o:
+        d_plen = torch.from_numpy(plen).cuda()
+        d_flat = torch.from_numpy(flat.view(np.int16)).cuda()
+        d_offs = torch.from_numpy(offs).cuda()
+        d_first = torch.empty(len(pats), dtype=torch.int64, device="cuda")
+        d_last = torch.empty(len(pats), dtype=torch.int64, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        ix.count_device(len(pats), d_plen.data_ptr(), d_flat.data_ptr(), d_offs.data_ptr(), d_first.data_ptr(),
+                        d_last.data_ptr(), s)
+        torch.cuda.synchronize()
+        of, ol = o.count(pats)
+        assert (d_first.cpu().numpy() == of).all() and (d_last.cpu().numpy() == ol).all()
+
+
+def test_properties_at_scale(tmp_path):
+    """Size-independent properties on a corpus too large for the scalar oracle to sweep:
+    count == occurrences found by locate, every located offset matches the text, LF is a
+    permutation walk that reproduces the document (extract), ranges nest when a pattern grows."""
+    docs = [corpus.random_bytes(1 << 20, 101), corpus.random_acgt(1 << 20, 102)]
+    path = str(tmp_path / "scale")
+    fb.build_index_host(docs, path, block_size=1 << 20, bucket_size=1 << 16, chunk_size=0)
+    text = b"".join(d + b"\x00" for d in docs)    # offsets only; SEOF positions never match a pattern
+    pats = corpus.sample_patterns(docs, 20000, [3, 4, 6, 8, 12, 20, 32], seed=81, random_fraction=0.1)
+    with fb.Index(path) as ix:
+        f, l = ix.count(pats)
+        cnt = np.maximum(l - f + 1, 0)
+        loc = ix.locate(pats[:3000], 64)
+        for p, c, offs_ in zip(pats[:3000], cnt[:3000], loc):
+            assert len(offs_) == min(int(c), 64) or (int(c) == 65 and len(offs_) == 65)
+            pb = bytes((p - 5).astype(np.uint8))
+            for off in offs_:
+                assert text[off:off + len(pb)] == pb
+            assert len(set(offs_.tolist())) == len(offs_)
+        # nesting: the range of a suffix of the pattern contains ... (backward search narrows)
+        shorter = [p[1:] for p in pats[:2000]]
+        fs, ls = ix.count(shorter)
+        assert (np.maximum(ls - fs + 1, 0) >= cnt[:2000]).all()
+        # SA is a permutation on a sampled range, and offsets agree with the suffix order
+        sa = ix.locate_range(5000, 9000)
+        assert len(set(sa.tolist())) == len(sa)
+        for d in range(2):
+            got = bytes((ix.extract(d) - 5).astype(np.uint8))
+            assert got == docs[d]
