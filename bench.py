@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- patterns/sec of batched FM-index count() on a synthetic corpus (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU count()
+
+A "step" is one pass of the hot path over one batch of synthetic patterns: 1 Mi text-sampled
+length-32 patterns counted against the index of a 4 GiB i.i.d. uniform byte corpus
+(BASELINE.json configs[1]).  Per-GPU work is fixed as N grows (each rank holds a replica of the
+index and counts its own batch: weak scaling, no data-path collective).
+
+The index is femto's unchanged on-disk format.  It is built once per box into --cache-dir by
+femto_b200.build_gpu (GPU suffix sort + the byte-identical host emitter) -- the reference's own
+builder runs at ~1 MB/s and would need over an hour; both arms read the same files.
+
+Printed JSON (one line, rank 0):
+  value      whole-job patterns/s with the pattern batch already resident in HBM (CUDA events
+             around K launches of the count kernel through fm_count_device, max over ranks)
+  e2e        the same through the host-buffer C-ABI call fm_count_flat: pinned host patterns in,
+             host first/last out, copies inside the timed region
+  roofline   algorithmic HBM bytes per launch / kernel time, against MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference (oracle/_ref) counting a bounded sample of the same
+             batch on this box's host cores, 1 server thread as shipped; the sample doubles as
+             the in-run parity check (GPU first/last must equal the reference's)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PLEN_DEFAULT = 32
+
+
+# ------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--corpus-mib", type=int, default=4096, help="synthetic corpus size (MiB); 4096 = headline")
+    ap.add_argument("--kind", choices=["bytes", "acgt"], default="bytes")
+    ap.add_argument("--npats", type=int, default=1 << 20)
+    ap.add_argument("--plen", type=int, default=PLEN_DEFAULT)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per rank query (4 or 8); 0 = engine default")
+    ap.add_argument("--cache-dir", default=os.environ.get("FEMTO_B200_CACHE", "/tmp/femto_b200_cache"))
+    ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-worker", nargs=3, metavar=("INDEX", "PATS_NPZ", "OUT_NPZ"), help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+def log(msg):
+    print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+def index_name(args):
+    return f"{args.kind}_{args.corpus_mib}MiB_seed{args.seed}_v1"
+
+
+def corpus_tensor(args, device):
+    from femto_b200 import build_gpu
+    n = args.corpus_mib << 20
+    alphabet = b"ACGT" if args.kind == "acgt" else None
+    return build_gpu.synthetic_bytes(n, args.seed, device, alphabet)
+
+
+def ensure_index(args, device, rank, world):
+    """Rank 0 builds the index if the cache does not hold it; everyone returns its path."""
+    import torch
+    path = os.path.join(args.cache_dir, index_name(args))
+    done = os.path.join(path, "_femto_index")
+    info = {"built": False}
+    if rank == 0 and not os.path.exists(done):
+        from femto_b200 import build_gpu
+        os.makedirs(args.cache_dir, exist_ok=True)
+        tmp = path + ".building"
+        subprocess.run(["rm", "-rf", tmp, path], check=False)
+        log(f"building index {index_name(args)} (one-time, cached in {args.cache_dir})")
+        text = corpus_tensor(args, device)
+        t = build_gpu.build_index_gpu([text], tmp, log=log)
+        del text
+        torch.cuda.empty_cache()
+        os.rename(tmp, path)
+        info = {"built": True, **{k: round(v, 2) for k, v in t.items()}}
+        log(f"index built: {info}")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    return path, info
+
+
+def sample_patterns(args, text, batch_id, rank):
+    """Text-sampled patterns (every pattern occurs, so all plen-1 backward steps execute)."""
+    import torch
+    g = torch.Generator(device=text.device)
+    g.manual_seed((args.seed + 1) * 1000003 + batch_id * 9176 + rank * 131)
+    n = text.numel()
+    starts = torch.randint(0, n - args.plen + 1, (args.npats,), generator=g, device=text.device)
+    idx = starts[:, None] + torch.arange(args.plen, device=text.device)[None, :]
+    return (text[idx].to(torch.int16) + 5).contiguous()      # [npats, plen] alpha_t symbols
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.proc = None
+        self.file = None
+
+    def start(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.strip().split(", ") for r in open(self.file.name) if r.strip()]
+        os.unlink(self.file.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU runs (subprocess workers: the parent may hold a CUDA context)
+
+def ref_worker(index, pats_npz, out_npz):
+    from oracle.bindings import Reference
+    d = np.load(pats_npz)
+    with Reference(index) as r:
+        r.count_flat(d["plen"][:64], d["flat"], d["offs"][:64])          # touch the index / warm caches
+        t0 = time.perf_counter()
+        f, l = r.count_flat(d["plen"], d["flat"], d["offs"])
+        dt = time.perf_counter() - t0
+    np.savez(out_npz, first=f, last=l, seconds=dt)
+
+
+def run_reference(index, pats2d, nprocs):
+    """Count pats2d [n, plen] with the unmodified reference in nprocs processes; returns
+    (first, last, wall_seconds_of_slowest_worker)."""
+    n, m = pats2d.shape
+    nprocs = max(1, min(nprocs, n))
+    tmp = tempfile.mkdtemp(prefix="femto_ref_")
+    procs = []
+    bounds = [n * i // nprocs for i in range(nprocs + 1)]
+    for i in range(nprocs):
+        sl = pats2d[bounds[i]:bounds[i + 1]]
+        k = sl.shape[0]
+        np.savez(os.path.join(tmp, f"in{i}.npz"), plen=np.full(k, m, dtype=np.int32),
+                 flat=np.ascontiguousarray(sl.reshape(-1)).view(np.uint16),
+                 offs=np.arange(k, dtype=np.int64) * m)
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", index,
+                                       os.path.join(tmp, f"in{i}.npz"), os.path.join(tmp, f"out{i}.npz")]))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("reference worker failed")
+    outs = [np.load(os.path.join(tmp, f"out{i}.npz")) for i in range(nprocs)]
+    first = np.concatenate([o["first"] for o in outs])
+    last = np.concatenate([o["last"] for o in outs])
+    secs = max(float(o["seconds"]) for o in outs)
+    subprocess.run(["rm", "-rf", tmp], check=False)
+    return first, last, secs
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.ref_worker:
+        ref_worker(*args.ref_worker)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference" and rank != 0:
+        return                                     # rank 0 alone runs the CPU arm
+
+    import torch
+    import __graft_entry__ as entry
+    entry.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); run it on the B200 box")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and args.impl == "b200":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    index_path, build_info = ensure_index(args, device, rank, world if args.impl == "b200" else 1)
+    text = corpus_tensor(args, device)
+    workload = (f"count() of {args.npats} text-sampled length-{args.plen} patterns on a {args.corpus_mib} MiB "
+                f"synthetic {'uniform byte' if args.kind == 'bytes' else 'ACGT'} corpus (1 document), "
+                f"default index params (block 128Mi rows, bucket 1Mi, mark_period 20, chunk 2048)")
+
+    if args.impl == "reference":
+        run_reference_arm(args, index_path, text, workload)
+        return
+
+    import femto_b200 as fb
+    from femto_b200 import _lib
+    lib = _lib.load()
+
+    t0 = time.time()
+    ix = fb.Index(index_path, device=local)
+    load_s = time.time() - t0
+    if args.lanes:
+        ix.set_lanes_per_query(args.lanes)
+    log(f"index resident: {ix.info.hbm_bytes / 2**30:.2f} GiB HBM, loaded in {load_s:.1f}s, "
+        f"max code length {ix.info.max_code_len}")
+
+    # distinct pattern batches (cycled) -- each batch touches ~32 KB x npats of a multi-GB image,
+    # far beyond the 126 MB L2, so no L2 flush is needed between steps
+    nbatch = min(args.steps + args.warmup, 4)
+    batches = [sample_patterns(args, text, b, rank) for b in range(nbatch)]
+    del text
+    torch.cuda.empty_cache()
+    npats, m = args.npats, args.plen
+    d_plen = torch.full((npats,), m, dtype=torch.int32, device=device)
+    d_offs = torch.arange(npats, dtype=torch.int64, device=device) * m
+    d_first = torch.empty(npats, dtype=torch.int64, device=device)
+    d_last = torch.empty(npats, dtype=torch.int64, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(b):
+        ix.count_device(npats, d_plen.data_ptr(), batches[b % nbatch].data_ptr(), d_offs.data_ptr(),
+                        d_first.data_ptr(), d_last.data_ptr(), stream)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------
+    for w in range(args.warmup):
+        step_resident(w)
+    barrier()
+    launches0 = ix.kernel_launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(args.steps):
+        step_resident(args.warmup + s)
+    ev1.record()
+    barrier()
+    kernel_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    gpu_launches = ix.kernel_launches() - launches0
+    results_gpu = (d_first.cpu().numpy().copy(), d_last.cpu().numpy().copy())
+    last_batch = batches[(args.warmup + args.steps - 1) % nbatch]
+
+    # ---- e2e: host buffers through the C ABI (pinned in, pinned out) -------------------------
+    h_flat = [b.cpu().pin_memory() for b in batches]
+    h_plen = torch.full((npats,), m, dtype=torch.int32).pin_memory()
+    h_offs = (torch.arange(npats, dtype=torch.int64) * m).pin_memory()
+    h_first = torch.empty(npats, dtype=torch.int64).pin_memory()
+    h_last = torch.empty(npats, dtype=torch.int64).pin_memory()
+    import ctypes as C
+
+    def step_e2e(b):
+        rc = lib.fm_count_flat(ix.h, npats, C.cast(h_plen.data_ptr(), C.POINTER(C.c_int32)),
+                               C.cast(h_flat[b % nbatch].data_ptr(), C.POINTER(C.c_uint16)),
+                               C.cast(h_offs.data_ptr(), C.POINTER(C.c_int64)),
+                               C.cast(h_first.data_ptr(), C.POINTER(C.c_int64)),
+                               C.cast(h_last.data_ptr(), C.POINTER(C.c_int64)))
+        if rc:
+            raise RuntimeError(f"fm_count_flat rc={rc}: {lib.fm_last_error()}")
+
+    for w in range(args.warmup):
+        step_e2e(w)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(args.warmup + s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert (h_first.numpy() == results_gpu[0]).all() and (h_last.numpy() == results_gpu[1]).all(), \
+        "host-buffer and device-buffer paths disagree"
+    h2d = npats * 4 + npats * m * 2 + npats * 8
+    d2h = npats * 16
+
+    # ---- max over ranks ---------------------------------------------------------------------
+    times = torch.tensor([kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_ms = float(times[0]), float(times[1])
+    ms_per_step = kernel_ms / args.steps
+    value = npats * world / (ms_per_step / 1e3)
+    e2e_value = npats * world / (e2e_ms / args.steps / 1e3)
+
+    if rank != 0:
+        ix.close()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: algorithmic bytes of one launch (instrumented replay of the last batch) ----
+    hb = h_flat[(args.warmup + args.steps - 1) % nbatch].numpy().reshape(-1).view(np.uint16)
+    st = ix.count_stats(h_plen.numpy(), hb, h_offs.numpy())
+    # per distinct rank block: 128 B payload line + 16 B node record; per Occ evaluation:
+    # 16 B OccRec + 16 B BucketRec; per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
+    alg_bytes = (st["distinct_block_reads"] * (128 + 16) + st["occ_evals"] * 32 + npats * (m * 2 + 28))
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "kernel": "count_kernel",
+                "kernel_ms": round(ms_per_step, 4),
+                "rank_blocks_requested": st["block_reads"], "rank_blocks_distinct": st["distinct_block_reads"],
+                "occ_evals": st["occ_evals"], "backward_steps": st["steps"]}
+    traffic_file = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- cpu_baseline + in-run parity: the unmodified reference on a bounded sample ----------
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        from oracle.bindings import have_reference
+        pats_host = last_batch.cpu().numpy()
+        if have_reference():
+            probe = 256
+            _, _, ps = run_reference(index_path, pats_host[:probe], 1)
+            rate = probe / max(ps, 1e-6)
+            sample = int(max(probe, min(npats, rate * args.cpu_sample_seconds)))
+            rf, rl, secs = run_reference(index_path, pats_host[:sample], 1)
+            ok = bool((rf == results_gpu[0][:sample]).all() and (rl == results_gpu[1][:sample]).all())
+            parity = {"checked_patterns": sample, "bit_exact_vs_reference": ok}
+            cpu = {"value": round(sample / secs, 1), "unit": "patterns/s", "cores": 1, "kind": "reference",
+                   "sample": f"first {sample} patterns of the last timed batch, parallel_count via oracle/_ref "
+                             f"(1 server thread as shipped, src/main/server.c:3597), {secs:.1f}s"}
+            if not ok:
+                raise SystemExit("PARITY FAILURE: GPU first/last differ from the reference on the bench batch")
+        else:
+            from oracle.bindings import Oracle
+            sample = 2000
+            with Oracle(index_path) as o:
+                t0 = time.perf_counter()
+                of, ol = o.count_flat(np.full(sample, m, dtype=np.int32),
+                                      np.ascontiguousarray(pats_host[:sample].reshape(-1)).view(np.uint16),
+                                      np.arange(sample, dtype=np.int64) * m)
+                secs = time.perf_counter() - t0
+            ok = bool((of == results_gpu[0][:sample]).all() and (ol == results_gpu[1][:sample]).all())
+            parity = {"checked_patterns": sample, "bit_exact_vs_oracle": ok}
+            cpu = {"value": round(sample / secs, 1), "unit": "patterns/s", "cores": 1, "kind": "port",
+                   "sample": f"first {sample} patterns of the last timed batch, oracle/fm_oracle.c, {secs:.1f}s"}
+            if not ok:
+                raise SystemExit("PARITY FAILURE: GPU first/last differ from the oracle on the bench batch")
+
+    out = {
+        "metric": "patterns/sec (count)", "value": round(value, 1), "unit": "patterns/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u32 popcount",
+        "data": "synthetic", "impl": "b200",
+        "config": {"workload": workload, "patterns_per_gpu_per_step": npats, "pattern_length": m,
+                   "index": index_name(args), "index_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
+                   "index_load_s": round(load_s, 1), "index_build": build_info,
+                   "parallelism": f"replica x{world} (patterns split, no collective)",
+                   "lanes_per_query": args.lanes or 4,
+                   "l2_policy": "inputs larger than L2: each step reads ~%.1f GB of a %.1f GiB image; %d distinct batches cycled"
+                                % (alg_bytes / 1e9, ix.info.hbm_bytes / 2**30, nbatch)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "patterns/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms / args.steps, 4),
+                "api": "fm_count_flat (pinned host buffers in/out)"},
+        "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu, "parity": parity,
+    }
+    print(json.dumps(out), flush=True)
+    ix.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args, index_path, text, workload):
+    """--impl reference: the reference's own CPU count() on this box's host cores."""
+    from oracle.bindings import have_reference
+    nprocs = args.ref_procs or (os.cpu_count() or 1)
+    m = args.plen
+    if not have_reference():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfemto_ref.so did not travel"}))
+        return
+    pats = sample_patterns(args, text, 0, 0).cpu().numpy()
+    del text
+    # size the per-step sample so that warmup+steps finish within a few minutes
+    probe = 64 * nprocs
+    _, _, ps = run_reference(index_path, pats[:probe], nprocs)
+    rate = probe / max(ps, 1e-6)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    sample = int(max(probe, min(args.npats, rate * budget)))
+    log(f"reference probe: {rate:.0f} patterns/s with {nprocs} processes; {sample} patterns per step")
+    secs = []
+    for s in range(args.warmup + args.steps):
+        lo = (s * sample) % max(1, args.npats - sample + 1)
+        _, _, dt = run_reference(index_path, pats[lo:lo + sample], nprocs)
+        if s >= args.warmup:
+            secs.append(dt)
+    per_step = float(np.mean(secs))
+    value = sample / per_step
+    out = {
+        "metric": "patterns/sec (count)", "value": round(value, 1), "unit": "patterns/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(per_step * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload, "pattern_length": m, "index": index_name(args),
+                   "patterns_per_step": sample,
+                   "note": "bounded sample of the same batch; index built by femto_b200's byte-identical emitter "
+                           "(the reference's builder needs >1 h for this corpus) and opened by the reference reader"},
+        "cpu_baseline": {"value": round(value, 1), "unit": "patterns/s", "cores": nprocs, "kind": "reference",
+                         "sample": f"{sample} patterns per step; {nprocs} processes, each an unmodified "
+                                   f"femto server (1 worker thread, as shipped) on a slice of the batch"},
+        "e2e": {"value": round(value, 1), "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,14 @@ class Index:
         _check(self.lib.fm_count(self.h, n, plen, ptrs, _ptr(first, C.c_int64), _ptr(last, C.c_int64)), "fm_count")
         return first[:n], last[:n]
 
+    def count_stats(self, plen: np.ndarray, flat: np.ndarray, offs: np.ndarray) -> dict:
+        """Counters of one instrumented count launch (see fm_count_stats)."""
+        st = (C.c_uint64 * 4)()
+        _check(self.lib.fm_count_stats(self.h, len(plen), _ptr(plen, C.c_int32), _ptr(flat, C.c_uint16),
+                                       _ptr(offs, C.c_int64), st), "fm_count_stats")
+        return {"block_reads": int(st[0]), "distinct_block_reads": int(st[1]), "occ_evals": int(st[2]),
+                "steps": int(st[3])}
+
     def count_device(self, npats: int, d_plen: int, d_flat: int, d_offs: int, d_first: int, d_last: int,
                      stream: int = 0) -> None:
         """Device-pointer form (integers are raw device addresses, e.g. ``tensor.data_ptr()``)."""

@@ -111,6 +111,7 @@ struct fm_index {
   DevBuf d_in[4], d_out[4];
   HostBuf h_stage[2];
   int64_t launches = 0;
+  int dev_slot = 0;
 };
 
 namespace {
@@ -376,6 +377,33 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
   });
 }
 
+int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                   uint64_t* stats4) {
+  return guarded(ix, "fm_count_stats", [&]() -> int {
+    if (npats < 0 || !stats4 || (npats && (!plen || !offs))) return fail(FM_ERR_PARAM, "fm_count_stats: bad argument");
+    int64_t flat_len = 0;
+    if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_count_stats: negative length/offset");
+    std::memset(stats4, 0, 4 * sizeof(uint64_t));
+    if (npats == 0) return FM_OK;
+    cudaStream_t s = ix->stream;
+    int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
+    uint16_t* d_flat = static_cast<uint16_t*>(ix->d_in[1].get(size_t(std::max<int64_t>(flat_len, 1)) * 2));
+    int64_t* d_offs = static_cast<int64_t*>(ix->d_in[2].get(size_t(npats) * 8));
+    int64_t* d_first = static_cast<int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
+    int64_t* d_last = static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8));
+    unsigned long long* d_stats = static_cast<unsigned long long*>(ix->d_out[3].get(64));
+    CK(cudaMemcpyAsync(d_plen, plen, size_t(npats) * 4, cudaMemcpyHostToDevice, s));
+    if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_stats, 0, 64, s));
+    CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
+    CK(launch_count(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches, d_stats));
+    CK(cudaMemcpyAsync(stats4, d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return FM_OK;
+  });
+}
+
 int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* pats, int64_t* first,
              int64_t* last) {
   return guarded(ix, "fm_count", [&]() -> int {
@@ -395,8 +423,11 @@ int fm_count_device(fm_index_t* ix, int64_t npats, const int32_t* d_plen, const 
   return guarded(ix, "fm_count_device", [&]() -> int {
     if (npats < 0) return fail(FM_ERR_PARAM, "fm_count_device: negative npats");
     CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
-    CK(launch_count(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, static_cast<cudaStream_t>(stream),
-                    &ix->launches));
+    // caller-stream launches rotate over work-queue slots 1..7 (slot 0 belongs to the host-buffer calls),
+    // so up to 7 of them may be in flight on different streams
+    ix->dev_slot = ix->dev_slot % 7 + 1;
+    CK(launch_count(ix->im, a, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
+                    static_cast<cudaStream_t>(stream), &ix->launches));
     return FM_OK;
   });
 }
@@ -416,7 +447,8 @@ int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, 
     w.rows = d_rows;
     w.out_offset = d_offsets;
     w.status = ix->d_status;
-    CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work + 1, ix->lanes_per_query, ix->sm_count,
+    ix->dev_slot = ix->dev_slot % 7 + 1;
+    CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
                    static_cast<cudaStream_t>(stream), &ix->launches));
     return FM_OK;
   });

@@ -764,26 +764,40 @@ int fm_builder_append(fm_builder_t* b, int64_t nrows, const uint16_t* L, const i
       b->L.resize(at + size_t(take));
       b->off.resize(at + size_t(take));
       if (b->chunk_size > 0) b->docs.resize(at + size_t(take));
-      for (int64_t j = 0; j < take; j++) {
-        const int64_t s = sa[i + j];
-        if (s < 0 || s >= b->total_length) return bfail(FM_ERR_PARAM, "fm_builder_append: suffix array value out of range");
-        const int64_t doc = b->ndocs == 1 ? 0 : find_doc(b->doc_ends, s);
-        const int64_t start = doc ? b->doc_ends[size_t(doc - 1)] : 0;
-        const int64_t dlen = b->doc_ends[size_t(doc)] - start;
-        const int64_t doff = s - start;
-        bool mark = false;  // should_mark (index_types.h:134-144)
-        if (b->mark_period != 0) mark = doff == 0 || doff == dlen - 1 || doff % b->mark_period == 0;
-        b->L[at + size_t(j)] = L[i + j];
-        b->off[at + size_t(j)] = mark ? s : -1;
-        if (b->chunk_size > 0) b->docs[at + size_t(j)] = doc;
-        // the first ndocs rows are the suffixes starting with each document's SEOF
-        // (constructor_construct_header, construct.c:407-460)
-        const int64_t row = row0 + j;
-        if (row < b->ndocs) {
-          if (!mark) return bfail(FM_ERR_PARAM, "Final EOF character of each document must be marked");
-          b->eof_rows[size_t(doc)] = row;
+      std::atomic<int> bad{0};
+      auto mark_rows = [&](int64_t j0, int64_t j1) {
+        const int64_t period = b->mark_period;
+        for (int64_t j = j0; j < j1; j++) {
+          const int64_t s = sa[i + j];
+          if (s < 0 || s >= b->total_length) { bad.store(1); return; }
+          const int64_t doc = b->ndocs == 1 ? 0 : find_doc(b->doc_ends, s);
+          const int64_t start = doc ? b->doc_ends[size_t(doc - 1)] : 0;
+          const int64_t dlen = b->doc_ends[size_t(doc)] - start;
+          const int64_t doff = s - start;
+          bool mark = false;  // should_mark (index_types.h:134-144)
+          if (period != 0) mark = doff == 0 || doff == dlen - 1 || doff % period == 0;
+          b->L[at + size_t(j)] = L[i + j];
+          b->off[at + size_t(j)] = mark ? s : -1;
+          if (b->chunk_size > 0) b->docs[at + size_t(j)] = doc;
+          // the first ndocs rows are the suffixes starting with each document's SEOF
+          // (constructor_construct_header, construct.c:407-460)
+          const int64_t row = row0 + j;
+          if (row < b->ndocs) {
+            if (!mark) { bad.store(2); return; }
+            b->eof_rows[size_t(doc)] = row;
+          }
         }
+      };
+      const int nt = int(std::min<int64_t>(b->nthreads, take >> 18));
+      if (nt <= 1) {
+        mark_rows(0, take);
+      } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(mark_rows, take * t / nt, take * (t + 1) / nt);
+        for (auto& t : th) t.join();
       }
+      if (bad.load() == 1) return bfail(FM_ERR_PARAM, "fm_builder_append: suffix array value out of range");
+      if (bad.load() == 2) return bfail(FM_ERR_PARAM, "Final EOF character of each document must be marked");
       i += take;
       if (int64_t(b->L.size()) == block_rows) flush_block(b);
     }

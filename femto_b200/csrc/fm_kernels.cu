@@ -95,8 +95,13 @@ __device__ __forceinline__ void split_row(const DevImage& im, int64_t row, int64
 
 // C[c] + Occ(c,row) for the sub-group's query (uniform across its LPQ lanes).  Warp-collective:
 // every lane of the warp must call it; inactive sub-groups pass active=false and get 0.
-template <int LPQ>
-__device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, int c, int64_t row, int sub) {
+// STATS (instrumented launches only): n_reads counts rank blocks requested, n_distinct counts them
+// once when the partner sub-group (the other Occ of the same backward-search step) asks for the
+// same block at the same level -- the bytes the step needs by design.
+template <int LPQ, bool STATS = false>
+__device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, int c, int64_t row, int sub,
+                                               unsigned long long* n_reads = nullptr,
+                                               unsigned long long* n_distinct = nullptr) {
   int64_t occ_base = 0;
   uint32_t leaf = 0, base = 0, node = 0, idx1 = 0;
   int L = 0;
@@ -125,6 +130,15 @@ __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, 
     if (desc && lvl + 1 < L) nr = __ldg(reinterpret_cast<const uint4*>(im.nodes + node));
     uint32_t ones, bit;
     block_rank<LPQ, false>(im.blocks, base + k, off, desc, sub, ones, bit);
+    if (STATS) {
+      const uint32_t mine = desc ? base + k : 0xffffffffu;
+      const uint32_t partner = __shfl_xor_sync(kFull, mine, LPQ);
+      if (desc && sub == 0) {
+        ++*n_reads;
+        const bool second_of_pair = ((threadIdx.x & 31) / LPQ) & 1;
+        if (!(second_of_pair && partner == mine)) ++*n_distinct;
+      }
+    }
     if (desc) {
       lvl++;
       const uint32_t b = (leaf >> (L - lvl)) & 1u;
@@ -141,9 +155,11 @@ __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ>
+template <int LPQ, bool STATS>
 __global__ void __launch_bounds__(kThreads) count_kernel(const DevImage im, const CountArgs a,
-                                                          unsigned long long* __restrict__ work) {
+                                                          unsigned long long* __restrict__ work,
+                                                          unsigned long long* __restrict__ stats) {
+  unsigned long long n_reads = 0, n_distinct = 0, n_occ = 0, n_steps = 0;
   constexpr int GL = 2 * LPQ;  // lanes per pattern
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPQ - 1);
@@ -198,7 +214,11 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const DevImage im, cons
       row = which ? l : f - 1;
       q = !badc && row >= 0;  // first == 0: Occ(c,-1) = 0 without touching the index (server.c:847-851)
     }
-    int64_t r = occ_descend<LPQ>(im, q, c, row, sub);
+    int64_t r = occ_descend<LPQ, STATS>(im, q, c, row, sub, &n_reads, &n_distinct);
+    if (STATS && sub == 0) {
+      n_occ += q ? 1 : 0;
+      n_steps += (stepping && which == 0) ? 1 : 0;
+    }
     if (stepping && !q && !badc) r = __ldg(im.C + c);
     const int64_t other = __shfl_xor_sync(kFull, r, LPQ);
     if (stepping) {
@@ -209,6 +229,21 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const DevImage im, cons
         l = (which ? r : other) - 1;
       }
       i--;
+    }
+  }
+  if (STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      n_reads += __shfl_xor_sync(kFull, n_reads, o);
+      n_distinct += __shfl_xor_sync(kFull, n_distinct, o);
+      n_occ += __shfl_xor_sync(kFull, n_occ, o);
+      n_steps += __shfl_xor_sync(kFull, n_steps, o);
+    }
+    if (lane == 0) {
+      atomicAdd(stats + 0, n_reads);
+      atomicAdd(stats + 1, n_distinct);
+      atomicAdd(stats + 2, n_occ);
+      atomicAdd(stats + 3, n_steps);
     }
   }
 }
@@ -397,18 +432,26 @@ inline int grid_for(int64_t groups_needed, int groups_per_block, int sm_count, i
 }  // namespace
 
 cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long long* d_work, int lpq, int sm_count,
-                         cudaStream_t stream, int64_t* launch_counter) {
+                         cudaStream_t stream, int64_t* launch_counter, unsigned long long* d_stats) {
   if (a.npats <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  if (lpq == 8) {
-    static const int bps = blocks_per_sm(count_kernel<8>);
+  if (d_stats) {  // instrumented variant: same schedule, extra counters (never the timed path)
+    if (lpq == 8) {
+      static const int bps = blocks_per_sm(count_kernel<8, true>);
+      count_kernel<8, true><<<grid_for(a.npats, kThreads / 16, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work, d_stats);
+    } else {
+      static const int bps = blocks_per_sm(count_kernel<4, true>);
+      count_kernel<4, true><<<grid_for(a.npats, kThreads / 8, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work, d_stats);
+    }
+  } else if (lpq == 8) {
+    static const int bps = blocks_per_sm(count_kernel<8, false>);
     const int grid = grid_for(a.npats, kThreads / 16, sm_count, bps);
-    count_kernel<8><<<grid, kThreads, 0, stream>>>(im, a, d_work);
+    count_kernel<8, false><<<grid, kThreads, 0, stream>>>(im, a, d_work, nullptr);
   } else {
-    static const int bps = blocks_per_sm(count_kernel<4>);
+    static const int bps = blocks_per_sm(count_kernel<4, false>);
     const int grid = grid_for(a.npats, kThreads / 8, sm_count, bps);
-    count_kernel<4><<<grid, kThreads, 0, stream>>>(im, a, d_work);
+    count_kernel<4, false><<<grid, kThreads, 0, stream>>>(im, a, d_work, nullptr);
   }
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();

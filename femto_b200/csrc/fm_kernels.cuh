@@ -45,8 +45,12 @@ struct OccArgs {
 };
 
 // lanes_per_query: 4 or 8.  Each launch bumps *launch_counter (host) by the number of kernels launched.
+// d_stats (optional, 4 x uint64 zeroed by the caller) selects the instrumented kernel variant:
+// [0] rank blocks requested, [1] distinct rank blocks per step and level, [2] Occ evaluations,
+// [3] backward-search steps.
 cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long long* d_work_counter,
-                         int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
+                         int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter,
+                         unsigned long long* d_stats = nullptr);
 cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work_counter,
                         int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
 cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* d_work_counter,

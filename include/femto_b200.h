@@ -157,6 +157,13 @@ void fm_host_free(void* p);
 /* Counters of the engine's own kernel launches since fm_open (all entry points). */
 int64_t fm_kernel_launches(const fm_index_t* ix);
 
+/* Instrumented count (not a timed path): runs the same batch through a counter-carrying variant
+ * of the count kernel and returns stats4 = { rank blocks requested, distinct rank blocks per
+ * step and level (the two Occ of a step often share a block), Occ evaluations, backward-search
+ * steps }.  bench.py derives the kernel's algorithmic HBM bytes from these. */
+int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
+                   const int64_t* offs, uint64_t* stats4);
+
 /* Tuning knob: lanes cooperating on one rank query (4 or 8; default 4). */
 int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
 
