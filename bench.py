@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--npats", type=int, default=1 << 20)
     ap.add_argument("--plen", type=int, default=PLEN_DEFAULT)
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--lanes", type=int, default=0, help="lanes per rank query (4 or 8); 0 = engine default")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per pattern group (2, 4 or 8); 0 = engine default")
+    ap.add_argument("--sched", choices=["merged", "pair"], default="merged", help="count kernel schedule")
     ap.add_argument("--cache-dir", default=os.environ.get("FEMTO_B200_CACHE", "/tmp/femto_b200_cache"))
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
@@ -259,8 +260,7 @@ def main():
     t0 = time.time()
     ix = fb.Index(index_path, device=local)
     load_s = time.time() - t0
-    if args.lanes:
-        ix.set_lanes_per_query(args.lanes)
+    ix.set_count_schedule(args.sched == "merged", args.lanes or 4)
     log(f"index resident: {ix.info.hbm_bytes / 2**30:.2f} GiB HBM, loaded in {load_s:.1f}s, "
         f"max code length {ix.info.max_code_len}")
 
@@ -419,7 +419,7 @@ def main():
                    "index": index_name(args), "index_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
                    "index_load_s": round(load_s, 1), "index_build": build_info,
                    "parallelism": f"replica x{world} (patterns split, no collective)",
-                   "lanes_per_query": args.lanes or 4,
+                   "count_schedule": f"{args.sched}/{args.lanes or 4} lanes per pattern group",
                    "l2_policy": "inputs larger than L2: each step reads ~%.1f GB of a %.1f GiB image; %d distinct batches cycled"
                                 % (alg_bytes / 1e9, ix.info.hbm_bytes / 2**30, nbatch)},
         "e2e": {"value": round(e2e_value, 1), "unit": "patterns/s", "h2d_bytes_per_step": h2d,

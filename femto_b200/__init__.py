@@ -104,6 +104,9 @@ class Index:
     def set_lanes_per_query(self, lanes: int) -> None:
         _check(self.lib.fm_set_lanes_per_query(self.h, lanes), "fm_set_lanes_per_query")
 
+    def set_count_schedule(self, merged: bool, lanes: int) -> None:
+        _check(self.lib.fm_set_count_schedule(self.h, int(merged), lanes), "fm_set_count_schedule")
+
     def kernel_launches(self) -> int:
         return int(self.lib.fm_kernel_launches(self.h))
 

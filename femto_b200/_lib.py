@@ -49,6 +49,7 @@ PROTOTYPES = {
     "fm_host_free": (None, [vp]),
     "fm_kernel_launches": (i64, [vp]),
     "fm_set_lanes_per_query": (C.c_int, [vp, C.c_int]),
+    "fm_set_count_schedule": (C.c_int, [vp, C.c_int, C.c_int]),
     "fm_count_stats": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), P(C.c_uint64)]),
     "fm_builder_create": (C.c_int, [C.c_char_p, i64, i64, P(i64), i32, i32, i32, i32, C.c_int, P(vp)]),
     "fm_builder_append": (C.c_int, [vp, i64, P(u16), P(i64)]),

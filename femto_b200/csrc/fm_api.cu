@@ -90,7 +90,8 @@ struct HostBuf {  // pinned staging
 struct fm_index {
   int device = 0;
   int sm_count = 148;
-  int lanes_per_query = 4;
+  int lanes_per_query = 4;   // walk / occ kernels
+  int count_sched = 1045;    // count kernel: 1000 + 10*lanes + min blocks = merged-pair schedule, 4 / 8 = pair
   fm_info_t info{};
   DevImage im;
   // device allocations of the image
@@ -273,7 +274,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * 2, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
   CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
-  CK(launch_count(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+  CK(launch_count(ix->im, a, ix->d_work, ix->count_sched, ix->sm_count, s, &ix->launches));
   CK(cudaMemcpyAsync(first, d_first, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
   if (last) CK(cudaMemcpyAsync(last, d_last, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -354,6 +355,18 @@ int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
   return FM_OK;
 }
 
+int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
+  const bool ok = merged ? (lanes == 2 || lanes == 4 || lanes == 8) : (lanes == 4 || lanes == 8);
+  if (!ix || !ok) return fail(FM_ERR_PARAM, "fm_set_count_schedule: merged needs 2/4/8 lanes, pair needs 4/8");
+  // merged: 1000 + 10*lanes + resident blocks per SM the kernel variant is compiled for
+  ix->count_sched = merged ? 1000 + 10 * lanes + (lanes == 2 ? 4 : lanes == 4 ? 5 : 6) : lanes;
+  if (const char* e = std::getenv("FEMTO_B200_COUNT_SCHED")) {  // tuning experiments only
+    const int v = std::atoi(e);
+    if (v > 0) ix->count_sched = v;
+  }
+  return FM_OK;
+}
+
 void* fm_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, std::max<size_t>(bytes, 1)) != cudaSuccess) return nullptr;
@@ -397,7 +410,7 @@ int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
     CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(d_stats, 0, 64, s));
     CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
-    CK(launch_count(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches, d_stats));
+    CK(launch_count(ix->im, a, ix->d_work, ix->count_sched, ix->sm_count, s, &ix->launches, d_stats));
     CK(cudaMemcpyAsync(stats4, d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return FM_OK;
@@ -426,7 +439,7 @@ int fm_count_device(fm_index_t* ix, int64_t npats, const int32_t* d_plen, const 
     // caller-stream launches rotate over work-queue slots 1..7 (slot 0 belongs to the host-buffer calls),
     // so up to 7 of them may be in flight on different streams
     ix->dev_slot = ix->dev_slot % 7 + 1;
-    CK(launch_count(ix->im, a, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
+    CK(launch_count(ix->im, a, ix->d_work + ix->dev_slot, ix->count_sched, ix->sm_count,
                     static_cast<cudaStream_t>(stream), &ix->launches));
     return FM_OK;
   });

@@ -430,29 +430,41 @@ inline int grid_for(int64_t groups_needed, int groups_per_block, int sm_count, i
 }
 
 }  // namespace
+}  // namespace fmb
+
+#include "fm_count_merged.cuh"
+
+namespace fmb {
 
 cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long long* d_work, int lpq, int sm_count,
                          cudaStream_t stream, int64_t* launch_counter, unsigned long long* d_stats) {
   if (a.npats <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  if (d_stats) {  // instrumented variant: same schedule, extra counters (never the timed path)
-    if (lpq == 8) {
-      static const int bps = blocks_per_sm(count_kernel<8, true>);
-      count_kernel<8, true><<<grid_for(a.npats, kThreads / 16, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work, d_stats);
-    } else {
-      static const int bps = blocks_per_sm(count_kernel<4, true>);
-      count_kernel<4, true><<<grid_for(a.npats, kThreads / 8, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work, d_stats);
-    }
-  } else if (lpq == 8) {
-    static const int bps = blocks_per_sm(count_kernel<8, false>);
-    const int grid = grid_for(a.npats, kThreads / 16, sm_count, bps);
-    count_kernel<8, false><<<grid, kThreads, 0, stream>>>(im, a, d_work, nullptr);
-  } else {
-    static const int bps = blocks_per_sm(count_kernel<4, false>);
-    const int grid = grid_for(a.npats, kThreads / 8, sm_count, bps);
-    count_kernel<4, false><<<grid, kThreads, 0, stream>>>(im, a, d_work, nullptr);
+  // lpq encodes the schedule: 4/8 = "pair" (two sub-groups per pattern), 100+{2,4,8} = "merged pair"
+  // (fm_count_merged.cuh).  d_stats selects the instrumented twin (never the timed path).
+#define FM_LAUNCH_COUNT(KERNEL, LANES_PER_PATTERN)                                                      \
+  do {                                                                                                  \
+    static const int bps = blocks_per_sm(KERNEL);                                                       \
+    KERNEL<<<grid_for(a.npats, kThreads / (LANES_PER_PATTERN), sm_count, bps), kThreads, 0, stream>>>(   \
+        im, a, d_work, d_stats);                                                                        \
+  } while (0)
+  // merged schedule codes: 1000 + 10*lanes + min resident blocks per SM (register budget)
+#define FM_MERGED_CASE(LANES, MINB)                                                                      \
+    case 1000 + 10 * (LANES) + (MINB):                                                                   \
+      if (d_stats) FM_LAUNCH_COUNT((count_merged_kernel<LANES, MINB, true>), LANES);                     \
+      else FM_LAUNCH_COUNT((count_merged_kernel<LANES, MINB, false>), LANES);                            \
+      break;
+  switch (lpq) {
+    FM_MERGED_CASE(2, 3) FM_MERGED_CASE(2, 4)
+    FM_MERGED_CASE(4, 4) FM_MERGED_CASE(4, 5) FM_MERGED_CASE(4, 6)
+    FM_MERGED_CASE(8, 5) FM_MERGED_CASE(8, 6)
+    case 8: if (d_stats) FM_LAUNCH_COUNT((count_kernel<8, true>), 16); else FM_LAUNCH_COUNT((count_kernel<8, false>), 16); break;
+    case 4: if (d_stats) FM_LAUNCH_COUNT((count_kernel<4, true>), 8); else FM_LAUNCH_COUNT((count_kernel<4, false>), 8); break;
+    default: return cudaErrorInvalidValue;
   }
+#undef FM_MERGED_CASE
+#undef FM_LAUNCH_COUNT
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();
 }

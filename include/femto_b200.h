@@ -164,8 +164,14 @@ int64_t fm_kernel_launches(const fm_index_t* ix);
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
                    const int64_t* offs, uint64_t* stats4);
 
-/* Tuning knob: lanes cooperating on one rank query (4 or 8; default 4). */
+/* Tuning knob: lanes cooperating on one rank query in the locate/extract/occ kernels (4 or 8;
+ * default 4). */
 int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
+
+/* Tuning knob of the count kernel.  merged != 0 (default, lanes 4): one group of `lanes` (2, 4 or
+ * 8) lanes per pattern advances both Occ of a step together and reads a shared rank block once;
+ * merged == 0: two sub-groups of `lanes` (4 or 8) lanes per pattern, one per Occ. */
+int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes);
 
 /* --------------------------------------------------------------------------
  * Index construction (host side; "next" row f-1 of the scope table).  Emits an

@@ -34,12 +34,12 @@ def edge_patterns():
             np.array([5], dtype=np.uint16), np.array([5, 5, 5], dtype=np.uint16)]
 
 
-@pytest.mark.parametrize("lanes", [4, 8])
+@pytest.mark.parametrize("sched", [(1, 4), (1, 2), (1, 8), (0, 4), (0, 8)])
 @pytest.mark.parametrize("name", ALL)
-def test_count_matches_oracle(name, lanes, gpu_indexes, built_indexes, corpora):
+def test_count_matches_oracle(name, sched, gpu_indexes, built_indexes, corpora):
     docs, _ = corpora[name]
     ix = gpu_indexes[name]
-    ix.set_lanes_per_query(lanes)
+    ix.set_count_schedule(*sched)
     pats = corpus.sample_patterns(docs, 1500, [1, 2, 3, 4, 5, 6, 8, 12, 16, 24, 32, 64], seed=31) + edge_patterns()
     with Oracle(built_indexes[name]) as o:
         of, ol = o.count(pats)
@@ -52,7 +52,7 @@ def test_count_matches_oracle(name, lanes, gpu_indexes, built_indexes, corpora):
         c = corpus.brute_count(docs, pats[i])
         if c >= 0:
             assert max(l[i] - f[i] + 1, 0) == c
-    ix.set_lanes_per_query(4)
+    ix.set_count_schedule(1, 4)
 
 
 @pytest.mark.parametrize("name", ALL)
