@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per pattern group (2, 4 or 8); 0 = engine default")
     ap.add_argument("--sched", choices=["merged", "pair"], default="merged", help="count kernel schedule")
+    ap.add_argument("--block-bytes", type=int, default=0, help="rank block size of the HBM image (128/64/32)")
     ap.add_argument("--cache-dir", default=os.environ.get("FEMTO_B200_CACHE", "/tmp/femto_b200_cache"))
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
@@ -257,10 +258,14 @@ def main():
     from femto_b200 import _lib
     lib = _lib.load()
 
+    if args.block_bytes:
+        assert lib.fm_set_default_block_bytes(args.block_bytes) == 0
     t0 = time.time()
     ix = fb.Index(index_path, device=local)
     load_s = time.time() - t0
-    ix.set_count_schedule(args.sched == "merged", args.lanes or 4)
+    block_bytes = int(ix.info.rank_block_size)
+    if args.lanes or args.sched != "merged":
+        ix.set_count_schedule(args.sched == "merged", args.lanes or {128: 4, 64: 2, 32: 1}[block_bytes])
     log(f"index resident: {ix.info.hbm_bytes / 2**30:.2f} GiB HBM, loaded in {load_s:.1f}s, "
         f"max code length {ix.info.max_code_len}")
 
@@ -359,7 +364,7 @@ def main():
     st = ix.count_stats(h_plen.numpy(), hb, h_offs.numpy())
     # per distinct rank block: 128 B payload line + 16 B node record; per Occ evaluation:
     # 16 B OccRec + 16 B BucketRec; per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
-    alg_bytes = (st["distinct_block_reads"] * (128 + 16) + st["occ_evals"] * 32 + npats * (m * 2 + 28))
+    alg_bytes = (st["distinct_block_reads"] * (block_bytes + 16) + st["occ_evals"] * 32 + npats * (m * 2 + 28))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
@@ -419,7 +424,9 @@ def main():
                    "index": index_name(args), "index_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
                    "index_load_s": round(load_s, 1), "index_build": build_info,
                    "parallelism": f"replica x{world} (patterns split, no collective)",
-                   "count_schedule": f"{args.sched}/{args.lanes or 4} lanes per pattern group",
+                   "rank_block_bytes": block_bytes,
+                   "count_schedule": os.environ.get("FEMTO_B200_COUNT_SCHED") or
+                                     f"{args.sched}/{args.lanes or 'default'} lanes per pattern group",
                    "l2_policy": "inputs larger than L2: each step reads ~%.1f GB of a %.1f GiB image; %d distinct batches cycled"
                                 % (alg_bytes / 1e9, ix.info.hbm_bytes / 2**30, nbatch)},
         "e2e": {"value": round(e2e_value, 1), "unit": "patterns/s", "h2d_bytes_per_step": h2d,

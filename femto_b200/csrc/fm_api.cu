@@ -117,6 +117,24 @@ struct fm_index {
 
 namespace {
 
+// count schedule codes understood by launch_count: pair = lanes per Occ query;
+// sync = 1000 + 10*lanes + resident blocks per SM the variant is compiled for.
+int sync_sched(int block_words, int lanes) {
+  const int minb = block_words == 32 ? (lanes == 8 ? 5 : lanes == 4 ? 5 : 4)
+                 : block_words == 16 ? (lanes == 4 ? 6 : lanes == 2 ? 5 : 4)
+                                     : (lanes == 2 ? 6 : 5);
+  return 1000 + 10 * lanes + minb;
+}
+
+int default_count_sched(int block_words) {
+  int sched = sync_sched(block_words, block_words == 32 ? 4 : block_words == 16 ? 2 : 1);
+  if (const char* e = std::getenv("FEMTO_B200_COUNT_SCHED")) {  // tuning experiments only
+    const int v = std::atoi(e);
+    if (v > 0) sched = v;
+  }
+  return sched;
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -175,7 +193,7 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     int64_t total = 0;
-    upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * kBlockWords, &total);
+    upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * size_t(host->block_words), &total);
     upload(&ix->d_nodes, host->nodes.data(), host->nodes.size(), &total);
     upload(&ix->d_occ, host->occ.data(), host->occ.size(), &total);
     upload(&ix->d_mark, host->mark.data(), host->mark.size(), &total);
@@ -211,9 +229,12 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->info.first_row = host->first_row;
     ix->info.end_row = host->end_row;
     ix->info.hbm_bytes = total;
-    ix->info.rank_block_bytes = host->n_rank_blocks * int64_t(kBlockWords) * 4;
+    ix->info.rank_block_bytes = host->n_rank_blocks * int64_t(host->block_words) * 4;
+    ix->im.block_words = host->block_words;
+    ix->count_sched = default_count_sched(host->block_words);
     ix->info.device = device;
     ix->info.max_code_len = host->max_code_len;
+    ix->info.rank_block_size = host->block_words * 4;
     ix->doc_ends = std::move(host->doc_ends);
     ix->doc_eof_rows = std::move(host->doc_eof_rows);
   } catch (const CudaFail& e) {
@@ -356,14 +377,21 @@ int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
 }
 
 int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
-  const bool ok = merged ? (lanes == 2 || lanes == 4 || lanes == 8) : (lanes == 4 || lanes == 8);
-  if (!ix || !ok) return fail(FM_ERR_PARAM, "fm_set_count_schedule: merged needs 2/4/8 lanes, pair needs 4/8");
-  // merged: 1000 + 10*lanes + resident blocks per SM the kernel variant is compiled for
-  ix->count_sched = merged ? 1000 + 10 * lanes + (lanes == 2 ? 4 : lanes == 4 ? 5 : 6) : lanes;
-  if (const char* e = std::getenv("FEMTO_B200_COUNT_SCHED")) {  // tuning experiments only
-    const int v = std::atoi(e);
-    if (v > 0) ix->count_sched = v;
-  }
+  if (!ix) return fail(FM_ERR_PARAM, "fm_set_count_schedule: null index");
+  const int bw = ix->im.block_words;
+  // each lane must own at least 2 words of the block (sync) / 4 words (pair)
+  const bool ok = merged ? ((bw == 32 && (lanes == 2 || lanes == 4 || lanes == 8)) ||
+                            (bw == 16 && (lanes == 1 || lanes == 2 || lanes == 4)) ||
+                            (bw == 8 && (lanes == 1 || lanes == 2)))
+                         : ((bw == 32 && (lanes == 4 || lanes == 8)) || (bw == 16 && (lanes == 2 || lanes == 4)) ||
+                            (bw == 8 && lanes == 2));
+  if (!ok) return fail(FM_ERR_PARAM, "fm_set_count_schedule: lane count not available for this rank block size");
+  ix->count_sched = merged ? sync_sched(bw, lanes) : lanes;
+  return FM_OK;
+}
+
+int fm_set_default_block_bytes(int bytes) {
+  if (!set_default_block_words(bytes / 4) || bytes % 4) return fail(FM_ERR_PARAM, "fm_set_default_block_bytes: 32, 64 or 128");
   return FM_OK;
 }
 

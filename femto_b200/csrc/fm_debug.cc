@@ -66,7 +66,7 @@ int64_t fm_debug_image_occ(void* h, int ch, int64_t row) {
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1;
   const int L = 31 - __builtin_clz(o.leaf);
   for (int lvl = 1; lvl <= L; lvl++) {
-    const HostRank r = host_rank(im.rank_words, base, idx1);
+    const HostRank r = host_rank(im.rank_words, im.block_words, base, idx1);
     const uint32_t b = (o.leaf >> (L - lvl)) & 1u;
     idx1 = b ? r.ones : idx1 - r.ones;
     if (idx1 == 0) break;
@@ -89,7 +89,7 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
   const BucketRec& br = im.buckets[size_t(g)];
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1, ch = 0;
   for (int guard = 0; guard < 64; guard++) {
-    const HostRank r = host_rank(im.rank_words, base, idx1);
+    const HostRank r = host_rank(im.rank_words, im.block_words, base, idx1);
     idx1 = r.bit ? r.ones : idx1 - r.ones;
     const NodeRec& nr = im.nodes[node];
     const uint32_t info = nr.child_info[r.bit];
@@ -99,7 +99,7 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
   }
   if (ch >= uint32_t(kAlpha) || idx1 == 0) return -2;
   const size_t rec = size_t(g) * kAlphaStride + ch;
-  const HostRank m = host_rank(im.rank_words, im.mark[rec].mark_base, idx1);
+  const HostRank m = host_rank(im.rank_words, im.block_words, im.mark[rec].mark_base, idx1);
   *ch_out = int32_t(ch);
   *offset = m.bit ? im.markvals[size_t(br.markval_base) + im.mark[rec].markval_off + m.ones - 1] : -1;
   *next = ch <= uint32_t(kEscSeof) ? -1 : im.occ[rec].occ_base + idx1 - 1;

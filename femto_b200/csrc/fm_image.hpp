@@ -29,8 +29,9 @@
 
 namespace fmb {
 
-constexpr int kBlockWords = 32;                 // 128-byte rank block
-constexpr int kBitsPerBlock = 31 * 32;          // 992 payload bits
+// Rank block size is chosen at load time: 32, 16 or 8 words (128 / 64 / 32 bytes); word 0 is the
+// header, the other block_words-1 words are payload.
+constexpr int kDefaultBlockWords = 32;
 constexpr uint32_t kChildLeaf = 0x80000000u;    // NodeRec::child_info flag
 constexpr int kAlphaStride = 261;               // records per bucket in OccRec / MarkRec tables
 
@@ -70,6 +71,7 @@ struct DevImage {
   int64_t first_bucket = 0;             // global index of buckets[0]
   int32_t bucket_size = 0;
   int32_t bucket_shift = -1;            // log2(bucket_size) when it is a power of two, else -1
+  int32_t block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
 };
 
 }  // namespace fmb

@@ -1,23 +1,28 @@
 // fm_kernels.cu -- hand-written sm_100a kernels of the FM-index query engine.
 //
 // What runs here, per reference function (paths relative to the reference tree):
-//   count_kernel  : do_string_query's backward search loop (src/main/server.c:713-946) with both
-//                   Occ evaluations of a step -- header_occs_request(HDR_BACK) + block_request(OCCS)
-//                   (src/main/index.c:1698-1765, 1973-2100) -> wtree_occs (src/main/wtree.c:1081-1115)
-//                   -> bseq_rank (wtree.c:635-763) -- as one rank-block read per wavelet-tree level.
-//   walk_kernel   : do_back_query (server.c:2228-2359) = wtree_rank (wtree.c:1117-1148) + mark test +
-//                   sampled-SA read (index.c:2037-2140) + LF; iterated for locate
-//                   (do_context_query, server.c:2627-2795, backward half) and document extract
-//                   (do_extract_document_query, server.c:6364-6437).
-//   occ_kernel    : a batch of single C[ch]+Occ(ch,row) evaluations (leaf interface cross-check).
+//   count_*_kernel : do_string_query's backward search loop (src/main/server.c:713-946) with both
+//                    Occ evaluations of a step -- header_occs_request(HDR_BACK) + block_request(OCCS)
+//                    (src/main/index.c:1698-1765, 1973-2100) -> wtree_occs (src/main/wtree.c:1081-1115)
+//                    -> bseq_rank (wtree.c:635-763) -- as one rank-block read per wavelet-tree level.
+//   walk_kernel    : do_back_query (server.c:2228-2359) = wtree_rank (wtree.c:1117-1148) + mark test +
+//                    sampled-SA read (index.c:2037-2140) + LF; iterated for locate
+//                    (do_context_query, server.c:2627-2795, backward half) and document extract
+//                    (do_extract_document_query, server.c:6364-6437).
+//   occ_kernel     : a batch of single C[ch]+Occ(ch,row) evaluations (leaf interface cross-check).
 //
-// Execution model: a rank query is served by LPQ (4 or 8) adjacent lanes that together read ONE
-// 128-byte rank block with 128-bit loads (ld.global.nc.v4), popcount their words under a position
-// mask and combine with __shfl_xor_sync.  A pattern owns 2*LPQ lanes: one sub-group evaluates
-// Occ(c, first-1), the other Occ(c, last), concurrently -- so a warp carries 32/(2*LPQ) patterns and
-// 32/LPQ independent 128-byte HBM reads per step.  Warps are persistent: finished pattern groups pull
-// the next pattern from a global atomic queue, so early-dying patterns and mixed lengths do not idle
-// lanes for the rest of the batch.  No tensor cores: this is HBM-latency/bandwidth-bound integer work.
+// Execution model.  A rank block (BW 32-bit words: word 0 = ones before the block, then (BW-1)*32
+// payload bits) is read by a group of LPQ adjacent lanes, each lane loading BW/LPQ words with one or
+// more 128-bit (or 64-bit) ld.global.nc, popcounting them under a position mask built with a funnel
+// shift, and combining with __shfl_xor_sync.  Warps are persistent: a lane group that finishes its
+// pattern pulls the next one from a global atomic queue, so dead patterns and mixed lengths do not
+// idle lanes for the rest of the batch.  No tensor cores: this is HBM-latency / issue-bound integer work.
+//
+// Two schedules of the count kernel:
+//   pair : a pattern owns 2*LPQ lanes; one sub-group evaluates Occ(c, first-1), the other Occ(c, last).
+//   sync : a pattern owns LPQ lanes that advance BOTH ranks together, warp-synchronously per
+//          backward-search step; when both positions fall into the same rank block (93% of the
+//          levels on the 4 GiB byte corpus) the block is read once and popcounted under two masks.
 #include "fm_kernels.cuh"
 
 namespace fmb {
@@ -25,57 +30,80 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kThreads = 256;
-constexpr int kEscSeofDev = 2;       // ESCAPE_CODE_SEOF, src/main/index_types.h:42-48
+constexpr int kEscSeofDev = 2;  // ESCAPE_CODE_SEOF, src/main/index_types.h:42-48
 constexpr int kAlphaDev = 261;
 
-__device__ __forceinline__ uint32_t popc_top(uint32_t w, int n) {
-  // ones among the n (0..32) most significant bits of w
-  const uint32_t mask = static_cast<uint32_t>(0xFFFFFFFF00000000ull >> n);
-  return __popc(w & mask);
+__device__ __forceinline__ uint32_t top_mask(int n) {
+  // the n (>= 0) most significant bits set; n >= 32 gives all ones (the funnel shift clamps at 32)
+  return __funnelshift_rc(0u, 0xFFFFFFFFu, static_cast<uint32_t>(n));
 }
 
-// Rank inside one 128-byte block, cooperatively by the LPQ lanes of a sub-group.
-//   blk : rank block index, off : 0-based bit offset inside the block payload (0..991)
-// Returns ones in the node's sequence up to and including the addressed bit (header + in-block),
-// and optionally the bit itself.  Inactive sub-groups issue no loads but take part in the shuffles.
-template <int LPQ, bool WANT_BIT>
-__device__ __forceinline__ void block_rank(const uint4* __restrict__ blocks, uint32_t blk, uint32_t off,
-                                           bool active, int sub, uint32_t& ones_incl, uint32_t& bit) {
-  constexpr int WPL = 32 / LPQ;  // 32-bit words per lane
-  constexpr int VPL = WPL / 4;   // 128-bit loads per lane
+// The WPL words of rank block `blk` that belong to lane `sub` of its group.
+template <int LPQ, int BW>
+struct BlockWords {
+  static constexpr int WPL = BW / LPQ;
   uint32_t w[WPL];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int t = 0; t < WPL; t++) w[t] = 0;
-  if (active) {
-    const uint4* p = blocks + static_cast<size_t>(blk) * 8 + sub * VPL;
+    for (int t = 0; t < WPL; t++) w[t] = 0;
+  }
+  __device__ __forceinline__ void load(const uint4* __restrict__ blocks, uint32_t blk, int sub) {
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(blocks) + static_cast<size_t>(blk) * BW + sub * WPL;
+    if (WPL >= 4) {
 #pragma unroll
-    for (int v = 0; v < VPL; v++) {
-      const uint4 x = __ldg(p + v);
-      w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+      for (int v = 0; v < WPL / 4; v++) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(base) + v);
+        w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+      }
+    } else {
+      const uint2 x = __ldg(reinterpret_cast<const uint2*>(base));
+      w[0] = x.x; w[1] = x.y;
     }
   }
-  // block bit space: word 0 is the header, payload bit `off` sits at position 32+off
-  const int upto = static_cast<int>(off) + 33;  // number of block bit positions up to and incl. the bit
-  uint32_t cnt = 0;
+  // ones among this lane's payload bits at or before payload offset `off` (header word excluded)
+  __device__ __forceinline__ uint32_t count_upto(uint32_t off, int sub) const {
+    const int nb = static_cast<int>(off) + 33 - 32 * WPL * sub;
+    uint32_t c = 0;
 #pragma unroll
-  for (int t = 0; t < WPL; t++) {
-    const int wi = sub * WPL + t;
-    int n = upto - 32 * wi;
-    n = max(0, min(32, n));
-    const uint32_t word = (t == 0 && sub == 0) ? 0u : w[t];
-    cnt += popc_top(word, n);
+    for (int t = 0; t < WPL; t++) {
+      const uint32_t word = (t == 0 && sub == 0) ? 0u : w[t];
+      c += __popc(word & top_mask(max(nb - 32 * t, 0)));
+    }
+    return c;
   }
+};
+
+template <int LPQ>
+__device__ __forceinline__ uint32_t group_sum(uint32_t v) {
 #pragma unroll
-  for (int o = LPQ / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
-  const uint32_t hdr = __shfl_sync(kFull, w[0], 0, LPQ);
-  ones_incl = hdr + cnt;
+  for (int o = LPQ / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+template <int LPQ>
+__device__ __forceinline__ uint32_t group_lane0(uint32_t v) {
+  return LPQ == 1 ? v : __shfl_sync(kFull, v, 0, LPQ);
+}
+
+// Rank at one offset of one block, cooperatively by the LPQ lanes of a group (warp-collective).
+//   blk : rank block index, off : 0-based bit offset inside the block payload
+// Returns ones in the node's sequence up to and including the addressed bit, optionally the bit.
+template <int LPQ, int BW, bool WANT_BIT>
+__device__ __forceinline__ void block_rank(const uint4* __restrict__ blocks, uint32_t blk, uint32_t off,
+                                           bool active, int sub, uint32_t& ones_incl, uint32_t& bit) {
+  constexpr int WPL = BW / LPQ;
+  BlockWords<LPQ, BW> b;
+  b.clear();
+  if (active) b.load(blocks, blk, sub);
+  const uint32_t cnt = group_sum<LPQ>(b.count_upto(off, sub));
+  ones_incl = group_lane0<LPQ>(b.w[0]) + cnt;
   if (WANT_BIT) {
-    const int wq = (static_cast<int>(off) + 32) >> 5;
+    const int wq = (static_cast<int>(off) + 32) >> 5;  // block word holding the bit
     const int t_sel = wq % WPL;
     uint32_t mine = 0;
 #pragma unroll
-    for (int t = 0; t < WPL; t++) mine = (t == t_sel) ? w[t] : mine;
-    const uint32_t word = __shfl_sync(kFull, mine, wq / WPL, LPQ);
+    for (int t = 0; t < WPL; t++) mine = (t == t_sel) ? b.w[t] : mine;
+    const uint32_t word = LPQ == 1 ? mine : __shfl_sync(kFull, mine, wq / WPL, LPQ);
     bit = (word >> (31 - (off & 31))) & 1u;
   } else {
     bit = 0;
@@ -93,15 +121,20 @@ __device__ __forceinline__ void split_row(const DevImage& im, int64_t row, int64
   g -= im.first_bucket;
 }
 
-// C[c] + Occ(c,row) for the sub-group's query (uniform across its LPQ lanes).  Warp-collective:
-// every lane of the warp must call it; inactive sub-groups pass active=false and get 0.
+__device__ __forceinline__ int64_t rec_occ_base(const int4& rv) {
+  return static_cast<int64_t>(static_cast<uint32_t>(rv.x)) | (static_cast<int64_t>(rv.y) << 32);
+}
+
+// C[c] + Occ(c,row) for the group's query (uniform across its LPQ lanes).  Warp-collective:
+// every lane of the warp must call it; inactive groups pass active=false and get 0.
 // STATS (instrumented launches only): n_reads counts rank blocks requested, n_distinct counts them
 // once when the partner sub-group (the other Occ of the same backward-search step) asks for the
-// same block at the same level -- the bytes the step needs by design.
-template <int LPQ, bool STATS = false>
+// same block at the same level.
+template <int LPQ, int BW, bool STATS = false>
 __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, int c, int64_t row, int sub,
                                                unsigned long long* n_reads = nullptr,
                                                unsigned long long* n_distinct = nullptr) {
+  constexpr uint32_t BITS = (BW - 1) * 32;
   int64_t occ_base = 0;
   uint32_t leaf = 0, base = 0, node = 0, idx1 = 0;
   int L = 0;
@@ -110,7 +143,7 @@ __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, 
     uint32_t rb;
     split_row(im, row, g, rb);
     const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-    occ_base = static_cast<int64_t>(static_cast<uint32_t>(rv.x)) | (static_cast<int64_t>(rv.y) << 32);
+    occ_base = rec_occ_base(rv);
     leaf = static_cast<uint32_t>(rv.z);
     if (leaf) {
       const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
@@ -124,12 +157,12 @@ __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, 
   int lvl = 0;
   while (__any_sync(kFull, desc)) {
     const uint32_t p = desc ? idx1 - 1 : 0u;
-    const uint32_t k = p / kBitsPerBlock;
-    const uint32_t off = p - k * kBitsPerBlock;
+    const uint32_t k = p / BITS;
+    const uint32_t off = p - k * BITS;
     uint4 nr = make_uint4(0, 0, 0, 0);
     if (desc && lvl + 1 < L) nr = __ldg(reinterpret_cast<const uint4*>(im.nodes + node));
     uint32_t ones, bit;
-    block_rank<LPQ, false>(im.blocks, base + k, off, desc, sub, ones, bit);
+    block_rank<LPQ, BW, false>(im.blocks, base + k, off, desc, sub, ones, bit);
     if (STATS) {
       const uint32_t mine = desc ? base + k : 0xffffffffu;
       const uint32_t partner = __shfl_xor_sync(kFull, mine, LPQ);
@@ -154,67 +187,95 @@ __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, 
   return occ_base + static_cast<int64_t>(leaf ? idx1 : 0u);
 }
 
+// Shared by both count schedules: retire a finished pattern, pull the next one from the queue.
+// "first > last || i == 0" ends the reference's while loop (server.c:832-841).
+struct PatternState {
+  int64_t f = 0, l = -1, pid = -1;
+  int i = 0;
+  const uint16_t* pat = nullptr;
+  bool have = false, exhausted = false;
+};
+
+__device__ __forceinline__ void retire_and_fetch(PatternState& s, bool can_retire, const DevImage& im,
+                                                 const CountArgs& a, unsigned long long* work, int lane,
+                                                 int gleader) {
+  if (s.have && can_retire && (s.f > s.l || s.i == 0)) {
+    if (lane == gleader) {
+      if (a.last) { a.first[s.pid] = s.f; a.last[s.pid] = s.l; }
+      else a.first[s.pid] = s.l - s.f + 1;  // parallel_count with last==NULL (femto.c:313-318)
+    }
+    s.have = false;
+  }
+  const bool need = !s.have && !s.exhausted;
+  unsigned long long idx = 0;
+  if (need && lane == gleader) idx = atomicAdd(work, 1ull);
+  idx = __shfl_sync(kFull, idx, gleader);
+  if (need) {
+    if (static_cast<int64_t>(idx) < a.npats) {
+      s.pid = static_cast<int64_t>(idx);
+      const int m = a.plen[s.pid];
+      s.pat = a.flat + a.offs[s.pid];
+      if (m <= 0) {  // empty pattern: every row (server.c:782-808)
+        s.f = 0; s.l = im.total_length - 1; s.i = 0;
+      } else {
+        const int c = s.pat[m - 1];
+        if (c >= kAlphaDev) { s.f = im.total_length; s.l = s.f - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
+        else { s.f = __ldg(im.C + c); s.l = __ldg(im.C + c + 1) - 1; }
+        s.i = m - 1;
+      }
+      s.have = true;
+    } else {
+      s.exhausted = true;
+    }
+  }
+}
+
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, int lane, unsigned long long a,
+                                            unsigned long long b, unsigned long long c, unsigned long long d) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(kFull, a, o);
+    b += __shfl_xor_sync(kFull, b, o);
+    c += __shfl_xor_sync(kFull, c, o);
+    d += __shfl_xor_sync(kFull, d, o);
+  }
+  if (lane == 0) {
+    atomicAdd(stats + 0, a);
+    atomicAdd(stats + 1, b);
+    atomicAdd(stats + 2, c);
+    atomicAdd(stats + 3, d);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, bool STATS>
-__global__ void __launch_bounds__(kThreads) count_kernel(const DevImage im, const CountArgs a,
-                                                          unsigned long long* __restrict__ work,
-                                                          unsigned long long* __restrict__ stats) {
+// count, "pair" schedule
+template <int LPQ, int BW, bool STATS>
+__global__ void __launch_bounds__(kThreads) count_pair_kernel(const DevImage im, const CountArgs a,
+                                                               unsigned long long* __restrict__ work,
+                                                               unsigned long long* __restrict__ stats) {
   unsigned long long n_reads = 0, n_distinct = 0, n_occ = 0, n_steps = 0;
   constexpr int GL = 2 * LPQ;  // lanes per pattern
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPQ - 1);
   const int which = (lane / LPQ) & 1;  // 0: Occ(c, first-1)   1: Occ(c, last)
   const int gleader = lane & ~(GL - 1);
-
-  int64_t f = 0, l = -1, pid = -1;
-  int i = 0;
-  const uint16_t* pat = nullptr;
-  bool have = false, exhausted = false;
+  PatternState s;
 
   for (;;) {
-    // retire: "first > last || i == 0" ends the reference's while loop (server.c:832-841)
-    if (have && (f > l || i == 0)) {
-      if (lane == gleader) {
-        if (a.last) { a.first[pid] = f; a.last[pid] = l; }
-        else a.first[pid] = l - f + 1;  // parallel_count with last==NULL (femto.c:313-318)
-      }
-      have = false;
-    }
-    const bool need = !have && !exhausted;
-    unsigned long long idx = 0;
-    if (need && lane == gleader) idx = atomicAdd(work, 1ull);
-    idx = __shfl_sync(kFull, idx, gleader);
-    if (need) {
-      if (static_cast<int64_t>(idx) < a.npats) {
-        pid = static_cast<int64_t>(idx);
-        const int m = a.plen[pid];
-        pat = a.flat + a.offs[pid];
-        if (m <= 0) {  // empty pattern: every row (server.c:782-808)
-          f = 0; l = im.total_length - 1; i = 0;
-        } else {
-          const int c = pat[m - 1];
-          if (c >= kAlphaDev) { f = im.total_length; l = f - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
-          else { f = __ldg(im.C + c); l = __ldg(im.C + c + 1) - 1; }
-          i = m - 1;
-        }
-        have = true;
-      } else {
-        exhausted = true;
-      }
-    }
-    if (!__any_sync(kFull, have)) break;
+    retire_and_fetch(s, true, im, a, work, lane, gleader);
+    if (!__any_sync(kFull, s.have)) break;
 
-    const bool stepping = have && f <= l && i > 0;
+    const bool stepping = s.have && s.f <= s.l && s.i > 0;
     int c = 0;
     int64_t row = 0;
     bool q = false, badc = false;
     if (stepping) {
-      c = pat[i - 1];
+      c = s.pat[s.i - 1];
       badc = c >= kAlphaDev;
-      row = which ? l : f - 1;
+      row = which ? s.l : s.f - 1;
       q = !badc && row >= 0;  // first == 0: Occ(c,-1) = 0 without touching the index (server.c:847-851)
     }
-    int64_t r = occ_descend<LPQ, STATS>(im, q, c, row, sub, &n_reads, &n_distinct);
+    int64_t r = occ_descend<LPQ, BW, STATS>(im, q, c, row, sub, &n_reads, &n_distinct);
     if (STATS && sub == 0) {
       n_occ += q ? 1 : 0;
       n_steps += (stepping && which == 0) ? 1 : 0;
@@ -223,35 +284,150 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const DevImage im, cons
     const int64_t other = __shfl_xor_sync(kFull, r, LPQ);
     if (stepping) {
       if (badc) {
-        f = im.total_length; l = f - 1;
+        s.f = im.total_length; s.l = s.f - 1;
       } else {
-        f = which ? other : r;
-        l = (which ? r : other) - 1;
+        s.f = which ? other : r;
+        s.l = (which ? r : other) - 1;
       }
-      i--;
+      s.i--;
     }
   }
-  if (STATS) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      n_reads += __shfl_xor_sync(kFull, n_reads, o);
-      n_distinct += __shfl_xor_sync(kFull, n_distinct, o);
-      n_occ += __shfl_xor_sync(kFull, n_occ, o);
-      n_steps += __shfl_xor_sync(kFull, n_steps, o);
-    }
-    if (lane == 0) {
-      atomicAdd(stats + 0, n_reads);
-      atomicAdd(stats + 1, n_distinct);
-      atomicAdd(stats + 2, n_occ);
-      atomicAdd(stats + 3, n_steps);
-    }
-  }
+  if (STATS) flush_stats(stats, lane, n_reads, n_distinct, n_occ, n_steps);
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, int MODE>
+// count, "sync" schedule: one group of LPQ lanes per pattern advances both ranks of a step.
+template <int LPQ, int BW, int MINB, bool STATS>
+__global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
+                                                                     unsigned long long* __restrict__ work,
+                                                                     unsigned long long* __restrict__ stats) {
+  constexpr int WPL = BW / LPQ;
+  constexpr uint32_t BITS = (BW - 1) * 32;
+  unsigned long long n_ranks = 0, n_blocks = 0, n_occ = 0, n_steps = 0;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPQ - 1);
+  const int gleader = lane & ~(LPQ - 1);
+  PatternState s;
+  bool cross_pending = false;  // row `last` lies in another bucket than `first-1`: its descent is the next round
+  int c = 0;
+  int64_t obA = 0, obB = 0;    // Occ bases; become C[c]+Occ(c,first-1) and C[c]+Occ(c,last)
+
+  for (;;) {
+    retire_and_fetch(s, !cross_pending, im, a, work, lane, gleader);
+    if (!__any_sync(kFull, s.have)) break;
+
+    // ---- set-up of one round (normally a whole backward-search step), all groups together
+    bool stepping = s.have && (cross_pending || (s.f <= s.l && s.i > 0));
+    bool actA = false, actB = false;
+    uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0;
+    int L = 0;
+    if (stepping) {
+      int64_t g;
+      uint32_t rb;
+      split_row(im, s.l, g, rb);
+      if (!cross_pending) {
+        c = s.pat[s.i - 1];
+        if (STATS && sub == 0) n_steps++;
+        if (c >= kAlphaDev) {  // symbol outside the alphabet: empty range
+          s.f = im.total_length; s.l = s.f - 1; s.i--;
+          stepping = false;
+        } else {
+          const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+          obB = rec_occ_base(rv);
+          leaf = static_cast<uint32_t>(rv.z);
+          idxB = rb + 1;
+          if (STATS && sub == 0) n_occ++;
+          if (s.f == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
+            obA = __ldg(im.C + c);
+            actB = true;
+          } else {
+            int64_t gA;
+            uint32_t rbA;
+            split_row(im, s.f - 1, gA, rbA);
+            idxA = rbA + 1;
+            actA = true;
+            if (STATS && sub == 0) n_occ++;
+            if (gA == g) {
+              obA = obB;
+              actB = true;
+            } else {  // first-1 sits in another bucket: this round does A, the next one B
+              const int4 ra = __ldg(reinterpret_cast<const int4*>(im.occ + gA * kAlphaStride + c));
+              obA = rec_occ_base(ra);
+              leaf = static_cast<uint32_t>(ra.z);
+              g = gA;
+              cross_pending = true;
+            }
+          }
+        }
+      } else {  // second round of a cross-bucket step: row `last`
+        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+        obB = rec_occ_base(rv);
+        leaf = static_cast<uint32_t>(rv.z);
+        idxB = rb + 1;
+        actB = true;
+        cross_pending = false;
+      }
+      if (stepping) {
+        if (leaf == 0) {  // symbol absent from the bucket: Occ is the bucket base (index.c:2080-2089)
+          actA = actB = false;
+        } else {
+          const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+          base = br.x;
+          node = br.y;
+          L = 31 - __clz(leaf);
+        }
+      }
+    }
+    const bool jobA = actA, jobB = actB;
+    const bool finish = stepping && !cross_pending;
+
+    // ---- descend: one level per iteration for every group
+    int lvl = 0;
+    while (__any_sync(kFull, actA || actB)) {
+      const bool any = actA || actB;
+      const uint32_t pA = actA ? idxA - 1 : 0u;
+      const uint32_t pB = actB ? idxB - 1 : 0u;
+      const uint32_t kA = pA / BITS, kB = pB / BITS;
+      const uint32_t offA = pA - kA * BITS, offB = pB - kB * BITS;
+      const bool two = actA && actB && kA != kB;  // the two positions need different blocks
+      BlockWords<LPQ, BW> p, q;
+      p.clear();
+      if (any) p.load(im.blocks, base + (actA ? kA : kB), sub);
+      if (two) q.load(im.blocks, base + kB, sub);
+      uint4 nr = make_uint4(0, 0, 0, 0);
+      if (any && lvl + 1 < L) nr = __ldg(reinterpret_cast<const uint4*>(im.nodes + node));
+      if (!two) {
+#pragma unroll
+        for (int t = 0; t < WPL; t++) q.w[t] = p.w[t];
+      }
+      const uint32_t packed = group_sum<LPQ>(p.count_upto(offA, sub) | (q.count_upto(offB, sub) << 16));
+      const uint32_t onesA = group_lane0<LPQ>(p.w[0]) + (packed & 0xffffu);
+      const uint32_t onesB = group_lane0<LPQ>(q.w[0]) + (packed >> 16);
+      if (STATS && any && sub == 0) {
+        n_blocks += two ? 2 : 1;
+        n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
+      }
+      lvl++;
+      if (any) {
+        const uint32_t b = (leaf >> (L - lvl)) & 1u;
+        if (actA) { idxA = b ? onesA : idxA - onesA; actA = idxA != 0 && lvl < L; }  // wtree.c:1109-1110
+        if (actB) { idxB = b ? onesB : idxB - onesB; actB = idxB != 0 && lvl < L; }
+        base = b ? nr.y : nr.x;
+        node = b ? nr.w : nr.z;
+      }
+    }
+    if (jobA) obA += idxA;
+    if (jobB) obB += idxB;
+    if (finish) { s.f = obA; s.l = obB - 1; s.i--; }
+  }
+  if (STATS) flush_stats(stats, lane, n_ranks, n_blocks, n_occ, n_steps);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int LPQ, int BW, int MODE>
 __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const WalkArgs a,
                                                          unsigned long long* __restrict__ work) {
+  constexpr uint32_t BITS = (BW - 1) * 32;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPQ - 1);
   const int gleader = lane & ~(LPQ - 1);
@@ -306,12 +482,12 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
     bool desc = act;
     while (__any_sync(kFull, desc)) {
       const uint32_t p = desc ? idx1 - 1 : 0u;
-      const uint32_t k = p / kBitsPerBlock;
-      const uint32_t off = p - k * kBitsPerBlock;
+      const uint32_t k = p / BITS;
+      const uint32_t off = p - k * BITS;
       uint4 nr = make_uint4(0, 0, 0, 0);
       if (desc) nr = __ldg(reinterpret_cast<const uint4*>(im.nodes + node));
       uint32_t ones, bit;
-      block_rank<LPQ, true>(im.blocks, base + k, off, desc, sub, ones, bit);
+      block_rank<LPQ, BW, true>(im.blocks, base + k, off, desc, sub, ones, bit);
       if (desc) {
         idx1 = bit ? ones : (idx1 - ones);
         const uint32_t info = bit ? nr.w : nr.z;
@@ -335,14 +511,13 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
       const uint2 mr = __ldg(reinterpret_cast<const uint2*>(im.mark + rec));
       mark_base = mr.x;
       markval_off = mr.y;
-      const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + rec));
-      occ_base = static_cast<int64_t>(static_cast<uint32_t>(rv.x)) | (static_cast<int64_t>(rv.y) << 32);
+      occ_base = rec_occ_base(__ldg(reinterpret_cast<const int4*>(im.occ + rec)));
     }
     const uint32_t mp = ok ? count - 1 : 0u;
-    const uint32_t mk = mp / kBitsPerBlock;
-    const uint32_t moff = mp - mk * kBitsPerBlock;
+    const uint32_t mk = mp / BITS;
+    const uint32_t moff = mp - mk * BITS;
     uint32_t mones, mbit;
-    block_rank<LPQ, true>(im.blocks, mark_base + mk, moff, ok, sub, mones, mbit);
+    block_rank<LPQ, BW, true>(im.blocks, mark_base + mk, moff, ok, sub, mones, mbit);
     int64_t offset = -1;
     if (ok && mbit) offset = __ldg(im.markvals + markval_base + markval_off + (mones - 1));
     // LF: row' = C[ch] + occs before the bucket + count - 1; stop at a document boundary
@@ -360,7 +535,7 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
         if (offset >= 0) {
           if (lane == gleader) a.out_offset[rid] = offset + steps;
           have = false;
-        } else if (next < 0) {  // unmarked document start: the index violates should_mark()
+        } else if (next < 0 || steps > im.total_length) {  // unmarked document start: index violates should_mark()
           if (lane == gleader) { atomicExch(a.status, 3); a.out_offset[rid] = -1; }
           have = false;
         } else {
@@ -391,7 +566,7 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ>
+template <int LPQ, int BW>
 __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const OccArgs a) {
   constexpr int QPW = 32 / LPQ;
   const int lane = threadIdx.x & 31;
@@ -409,7 +584,7 @@ __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const 
       row = a.rows[item];
       q = c < kAlphaDev && row >= im.first_row && row < im.end_row;
     }
-    const int64_t r = occ_descend<LPQ>(im, q, c, row, sub);
+    const int64_t r = occ_descend<LPQ, BW>(im, q, c, row, sub);
     if (item < a.n && sub == 0) a.out[item] = q ? r : -1;
   }
 }
@@ -430,60 +605,68 @@ inline int grid_for(int64_t groups_needed, int groups_per_block, int sm_count, i
 }
 
 }  // namespace
-}  // namespace fmb
 
-#include "fm_count_merged.cuh"
-
-namespace fmb {
-
-cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long long* d_work, int lpq, int sm_count,
+// sched: pair schedule = lanes per Occ query (4 or 8); sync schedule = 1000 + 10*lanes + MINB.
+cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long long* d_work, int sched, int sm_count,
                          cudaStream_t stream, int64_t* launch_counter, unsigned long long* d_stats) {
   if (a.npats <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  // lpq encodes the schedule: 4/8 = "pair" (two sub-groups per pattern), 100+{2,4,8} = "merged pair"
-  // (fm_count_merged.cuh).  d_stats selects the instrumented twin (never the timed path).
-#define FM_LAUNCH_COUNT(KERNEL, LANES_PER_PATTERN)                                                      \
-  do {                                                                                                  \
-    static const int bps = blocks_per_sm(KERNEL);                                                       \
-    KERNEL<<<grid_for(a.npats, kThreads / (LANES_PER_PATTERN), sm_count, bps), kThreads, 0, stream>>>(   \
-        im, a, d_work, d_stats);                                                                        \
+  const int code = im.block_words * 10000 + sched;
+#define FM_LAUNCH(KERNEL, LANES_PER_PATTERN)                                                             \
+  do {                                                                                                   \
+    static const int bps = blocks_per_sm(KERNEL);                                                        \
+    KERNEL<<<grid_for(a.npats, kThreads / (LANES_PER_PATTERN), sm_count, bps), kThreads, 0, stream>>>(    \
+        im, a, d_work, d_stats);                                                                         \
   } while (0)
-  // merged schedule codes: 1000 + 10*lanes + min resident blocks per SM (register budget)
-#define FM_MERGED_CASE(LANES, MINB)                                                                      \
-    case 1000 + 10 * (LANES) + (MINB):                                                                   \
-      if (d_stats) FM_LAUNCH_COUNT((count_merged_kernel<LANES, MINB, true>), LANES);                     \
-      else FM_LAUNCH_COUNT((count_merged_kernel<LANES, MINB, false>), LANES);                            \
-      break;
-  switch (lpq) {
-    FM_MERGED_CASE(2, 3) FM_MERGED_CASE(2, 4)
-    FM_MERGED_CASE(4, 4) FM_MERGED_CASE(4, 5) FM_MERGED_CASE(4, 6)
-    FM_MERGED_CASE(8, 5) FM_MERGED_CASE(8, 6)
-    case 8: if (d_stats) FM_LAUNCH_COUNT((count_kernel<8, true>), 16); else FM_LAUNCH_COUNT((count_kernel<8, false>), 16); break;
-    case 4: if (d_stats) FM_LAUNCH_COUNT((count_kernel<4, true>), 8); else FM_LAUNCH_COUNT((count_kernel<4, false>), 8); break;
+#define FM_SYNC(BW, LANES, MINB)                                                                         \
+  case (BW) * 10000 + 1000 + 10 * (LANES) + (MINB):                                                      \
+    if (d_stats) FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, true>), LANES);                           \
+    else FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, false>), LANES);                                  \
+    break;
+#define FM_PAIR(BW, LANES)                                                                               \
+  case (BW) * 10000 + (LANES):                                                                           \
+    if (d_stats) FM_LAUNCH((count_pair_kernel<LANES, BW, true>), 2 * (LANES));                           \
+    else FM_LAUNCH((count_pair_kernel<LANES, BW, false>), 2 * (LANES));                                  \
+    break;
+  switch (code) {
+    FM_PAIR(32, 4) FM_PAIR(32, 8) FM_PAIR(16, 4) FM_PAIR(16, 2) FM_PAIR(8, 2)
+    FM_SYNC(32, 8, 5) FM_SYNC(32, 4, 4) FM_SYNC(32, 4, 5) FM_SYNC(32, 2, 3) FM_SYNC(32, 2, 4)
+    FM_SYNC(16, 4, 5) FM_SYNC(16, 4, 6) FM_SYNC(16, 2, 4) FM_SYNC(16, 2, 5) FM_SYNC(16, 1, 3) FM_SYNC(16, 1, 4)
+    FM_SYNC(8, 2, 5) FM_SYNC(8, 2, 6) FM_SYNC(8, 1, 4) FM_SYNC(8, 1, 5) FM_SYNC(8, 1, 6)
     default: return cudaErrorInvalidValue;
   }
-#undef FM_MERGED_CASE
-#undef FM_LAUNCH_COUNT
+#undef FM_SYNC
+#undef FM_PAIR
+#undef FM_LAUNCH
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();
 }
 
-template <int LPQ>
-static cudaError_t launch_walk_lpq(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work,
+template <int LPQ, int BW>
+static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work,
                                    int sm_count, cudaStream_t stream) {
   const int gpb = kThreads / LPQ;
   if (mode == kWalkLocate) {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, kWalkLocate>);
-    walk_kernel<LPQ, kWalkLocate><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate>);
+    walk_kernel<LPQ, BW, kWalkLocate><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else if (mode == kWalkStep) {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, kWalkStep>);
-    walk_kernel<LPQ, kWalkStep><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkStep>);
+    walk_kernel<LPQ, BW, kWalkStep><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, kWalkExtract>);
-    walk_kernel<LPQ, kWalkExtract><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkExtract>);
+    walk_kernel<LPQ, BW, kWalkExtract><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   }
   return cudaGetLastError();
+}
+
+// lanes per query for the walk / occ kernels: 4 or 8 at 128-byte blocks, 2 or 4 at 64, 1 or 2 at 32
+static int walk_lanes(const DevImage& im, int lpq) {
+  const int max_lanes = im.block_words / 4;  // at least one 128-bit load per lane
+  int lanes = lpq;
+  while (lanes > max_lanes) lanes >>= 1;
+  if (lanes < max_lanes / 2) lanes = max_lanes / 2;
+  return lanes < 1 ? 1 : lanes;
 }
 
 cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work, int lpq,
@@ -491,8 +674,15 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
   if (a.nrows <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  e = (lpq == 8) ? launch_walk_lpq<8>(im, a, mode, d_work, sm_count, stream)
-                 : launch_walk_lpq<4>(im, a, mode, d_work, sm_count, stream);
+  switch (im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 3208: e = launch_walk_cfg<8, 32>(im, a, mode, d_work, sm_count, stream); break;
+    case 3204: e = launch_walk_cfg<4, 32>(im, a, mode, d_work, sm_count, stream); break;
+    case 1604: e = launch_walk_cfg<4, 16>(im, a, mode, d_work, sm_count, stream); break;
+    case 1602: e = launch_walk_cfg<2, 16>(im, a, mode, d_work, sm_count, stream); break;
+    case 802: e = launch_walk_cfg<2, 8>(im, a, mode, d_work, sm_count, stream); break;
+    case 801: e = launch_walk_cfg<1, 8>(im, a, mode, d_work, sm_count, stream); break;
+    default: return cudaErrorInvalidValue;
+  }
   if (launch_counter) ++*launch_counter;
   return e;
 }
@@ -500,13 +690,21 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
 cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* /*d_work*/, int lpq, int sm_count,
                        cudaStream_t stream, int64_t* launch_counter) {
   if (a.n <= 0) return cudaSuccess;
-  if (lpq == 8) {
-    static const int bps = blocks_per_sm(occ_kernel<8>);
-    occ_kernel<8><<<grid_for(a.n, kThreads / 8, sm_count, bps), kThreads, 0, stream>>>(im, a);
-  } else {
-    static const int bps = blocks_per_sm(occ_kernel<4>);
-    occ_kernel<4><<<grid_for(a.n, kThreads / 4, sm_count, bps), kThreads, 0, stream>>>(im, a);
+#define FM_OCC(LANES, BW)                                                                                 \
+  do {                                                                                                    \
+    static const int bps = blocks_per_sm(occ_kernel<LANES, BW>);                                          \
+    occ_kernel<LANES, BW><<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a); \
+  } while (0)
+  switch (im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 3208: FM_OCC(8, 32); break;
+    case 3204: FM_OCC(4, 32); break;
+    case 1604: FM_OCC(4, 16); break;
+    case 1602: FM_OCC(2, 16); break;
+    case 802: FM_OCC(2, 8); break;
+    case 801: FM_OCC(1, 8); break;
+    default: return cudaErrorInvalidValue;
   }
+#undef FM_OCC
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();
 }

@@ -32,9 +32,15 @@ struct BucketPlan {
   int64_t n_markvals = 0;  // total ones over the bucket's mark tables
 };
 
-inline int64_t blocks_for_bits(int64_t nbits) { return std::max<int64_t>(1, (nbits + kBitsPerBlock - 1) / kBitsPerBlock); }
+// rank block geometry chosen at load time: bw 32-bit words per block, (bw-1)*32 payload bits
+thread_local int t_block_words = kDefaultBlockWords;
+inline int64_t bits_per_block() { return int64_t(t_block_words - 1) * 32; }
+inline int64_t blocks_for_bits(int64_t nbits) {
+  return std::max<int64_t>(1, (nbits + bits_per_block() - 1) / bits_per_block());
+}
 
-void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p) {
+void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p, int bw) {
+  t_block_words = bw;
   parse_bucket_tables(blk, bh, bpb, bucket, &p->tab);
   const BucketTables& t = p->tab;
   // wavelet tree directory
@@ -93,12 +99,13 @@ void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, Bu
 int64_t fill_blocks(const uint32_t* bits, int64_t nbits, uint32_t* dst_blocks) {
   const int64_t nb = blocks_for_bits(nbits);
   const int64_t nwords = (nbits + 31) / 32;
+  const int bw = t_block_words, pw = bw - 1;
   uint32_t ones = 0;
   for (int64_t k = 0; k < nb; k++) {
-    uint32_t* w = dst_blocks + k * kBlockWords;
+    uint32_t* w = dst_blocks + k * bw;
     w[0] = ones;
-    const int64_t w0 = k * 31;
-    for (int j = 0; j < 31; j++) {
+    const int64_t w0 = k * pw;
+    for (int j = 0; j < pw; j++) {
       const uint32_t v = (w0 + j < nwords) ? bits[w0 + j] : 0u;
       w[1 + j] = v;
       ones += uint32_t(__builtin_popcount(v));
@@ -120,6 +127,8 @@ struct Scratch {
 void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh, int64_t blk_num, int bucket,
                  const BucketPlan& p, HostImage* im, int64_t local_bucket, Scratch* scratch,
                  std::atomic<int64_t>* markval_used) {
+  const int kBlockWords = im->block_words;
+  t_block_words = kBlockWords;
   const BucketTables& t = p.tab;
   const int bpb = files.buckets_per_block();
   const uint8_t* wt = blk.at(t.off_wtree, 4);
@@ -260,10 +269,34 @@ void parallel_for(int64_t n, int nthreads, F&& fn) {
 
 }  // namespace
 
-HostRank host_rank(const uint32_t* rank_words, uint32_t base_block, uint32_t index1) {
+namespace {
+std::atomic<int> g_default_block_words{0};
+}
+
+int default_block_words() {
+  int v = g_default_block_words.load();
+  if (v == 0) {
+    v = kDefaultBlockWords;
+    if (const char* e = std::getenv("FEMTO_B200_BLOCK_BYTES")) {
+      const int b = std::atoi(e);
+      if (b == 32 || b == 64 || b == 128) v = b / 4;
+    }
+    g_default_block_words.store(v);
+  }
+  return v;
+}
+
+bool set_default_block_words(int words) {
+  if (words != 8 && words != 16 && words != 32) return false;
+  g_default_block_words.store(words);
+  return true;
+}
+
+HostRank host_rank(const uint32_t* rank_words, int block_words, uint32_t base_block, uint32_t index1) {
   const uint32_t p = index1 - 1;
-  const uint32_t k = p / kBitsPerBlock, off = p % kBitsPerBlock;
-  const uint32_t* w = rank_words + (size_t(base_block) + k) * kBlockWords;
+  const uint32_t bits = uint32_t(block_words - 1) * 32;
+  const uint32_t k = p / bits, off = p % bits;
+  const uint32_t* w = rank_words + (size_t(base_block) + k) * size_t(block_words);
   uint32_t ones = w[0];
   const uint32_t full = off / 32, rem = off % 32;
   for (uint32_t j = 0; j < full; j++) ones += uint32_t(__builtin_popcount(w[1 + j]));
@@ -272,14 +305,19 @@ HostRank host_rank(const uint32_t* rank_words, uint32_t base_block, uint32_t ind
   return HostRank{ones, (last >> (31 - rem)) & 1u};
 }
 
-std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads) {
+std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
+                                            int block_words) {
   if (nshards < 1 || shard < 0 || shard >= nshards) throw Error(FM_ERR_PARAM, "bad shard");
+  if (block_words == 0) block_words = default_block_words();
+  if (block_words != 8 && block_words != 16 && block_words != 32) throw Error(FM_ERR_PARAM, "rank block must be 32, 64 or 128 bytes");
   if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
   auto files = IndexFiles::open(path);
   const BlockHeader& h = files->header();
   const int bpb = files->buckets_per_block();
   std::unique_ptr<HostImage> im(new HostImage());
   im->hdr = h;
+  im->block_words = block_words;
+  const int kBlockWords = block_words;
 
   // data blocks of this shard: b with b*nshards/nblocks == shard
   int64_t b0 = h.nblocks, b1 = 0;
@@ -333,7 +371,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
     for (int k = 0; k < bhs[lb].num_buckets; k++) where[size_t(bucket0[lb] + k)] = {int32_t(lb), int32_t(k)};
   parallel_for(nb, nthreads, [&](int64_t g, int) {
     const auto [lb, k] = where[size_t(g)];
-    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)]);
+    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)], block_words);
   });
 
   int64_t nodes = 0, blocks = 0, vals = 0, wt_blocks = 0;

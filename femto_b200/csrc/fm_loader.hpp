@@ -19,7 +19,8 @@ struct HostImage {
   int64_t first_row = 0, end_row = 0;
   int max_code_len = 0;
   // tables
-  uint32_t* rank_words = nullptr;   // n_rank_blocks * 32 words (calloc'ed)
+  int block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
+  uint32_t* rank_words = nullptr;   // n_rank_blocks * block_words words (calloc'ed)
   int64_t n_rank_blocks = 0;
   int64_t n_wtree_blocks = 0;       // of which wavelet-tree payload (the rest are mark bit-vectors)
   std::vector<NodeRec> nodes;
@@ -36,11 +37,16 @@ struct HostImage {
 };
 
 // shard/nshards select data blocks b with b*nshards/nblocks == shard (all blocks when nshards==1).
-std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads);
+// block_words: 32, 16 or 8 (128/64/32-byte rank blocks); 0 = the process default (env
+// FEMTO_B200_BLOCK_BYTES or set_default_block_words, else 128-byte blocks).
+std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
+                                            int block_words = 0);
+int default_block_words();
+bool set_default_block_words(int words);
 
 // Host-side rank over the image (used by the loader's self-check and by unit tests of the
 // image layout; NOT a query fallback -- the C ABI never calls it).
 struct HostRank { uint32_t ones; uint32_t bit; };
-HostRank host_rank(const uint32_t* rank_words, uint32_t base_block, uint32_t index1);
+HostRank host_rank(const uint32_t* rank_words, int block_words, uint32_t base_block, uint32_t index1);
 
 }  // namespace fmb

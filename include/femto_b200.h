@@ -65,6 +65,8 @@ typedef struct {
   int64_t rank_block_bytes;  /* of which wavelet-tree rank blocks */
   int32_t device;            /* CUDA device ordinal */
   int32_t max_code_len;      /* deepest wavelet-tree leaf over all resident buckets */
+  int32_t rank_block_size;   /* bytes per rank block of the HBM image: 128, 64 or 32 */
+  int32_t reserved;
 } fm_info_t;
 
 /* --------------------------------------------------------------------------
@@ -168,10 +170,15 @@ int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
  * default 4). */
 int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
 
-/* Tuning knob of the count kernel.  merged != 0 (default, lanes 4): one group of `lanes` (2, 4 or
- * 8) lanes per pattern advances both Occ of a step together and reads a shared rank block once;
- * merged == 0: two sub-groups of `lanes` (4 or 8) lanes per pattern, one per Occ. */
+/* Tuning knob of the count kernel.  merged != 0 (default): one group of `lanes` lanes per pattern
+ * advances both Occ of a step together and reads a shared rank block once; merged == 0: two
+ * sub-groups of `lanes` lanes per pattern, one per Occ.  Lane counts available: 128-byte rank
+ * blocks 2/4/8 (merged) 4/8 (pair); 64-byte 1/2/4 and 2/4; 32-byte 1/2 and 2. */
 int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes);
+
+/* Rank block size (bytes: 128, 64 or 32) of the HBM image built by subsequent fm_open calls.
+ * Initial value: environment FEMTO_B200_BLOCK_BYTES, else 128. */
+int fm_set_default_block_bytes(int bytes);
 
 /* --------------------------------------------------------------------------
  * Index construction (host side; "next" row f-1 of the scope table).  Emits an

@@ -34,6 +34,59 @@ def edge_patterns():
             np.array([5], dtype=np.uint16), np.array([5, 5, 5], dtype=np.uint16)]
 
 
+@pytest.fixture(scope="module")
+def gpu_indexes_small_blocks(built_indexes):
+    """The same indexes loaded with 64- and 32-byte rank blocks."""
+    from femto_b200 import _lib
+    lib = _lib.load()
+    opened = {}
+    for bb in (64, 32):
+        assert lib.fm_set_default_block_bytes(bb) == 0
+        try:
+            for name, path in built_indexes.items():
+                opened[(name, bb)] = fb.Index(path, device=0)
+                assert opened[(name, bb)].info.rank_block_size == bb
+        finally:
+            lib.fm_set_default_block_bytes(128)
+    yield opened
+    for ix in opened.values():
+        ix.close()
+
+
+@pytest.mark.parametrize("cfg", [(64, 1, 1), (64, 1, 2), (64, 1, 4), (64, 0, 2), (64, 0, 4),
+                                 (32, 1, 1), (32, 1, 2), (32, 0, 2)])
+@pytest.mark.parametrize("name", ALL)
+def test_count_small_rank_blocks(name, cfg, gpu_indexes_small_blocks, built_indexes, corpora):
+    bb, merged, lanes = cfg
+    docs, _ = corpora[name]
+    ix = gpu_indexes_small_blocks[(name, bb)]
+    ix.set_count_schedule(merged, lanes)
+    pats = corpus.sample_patterns(docs, 1200, [1, 2, 3, 4, 5, 6, 8, 12, 16, 24, 32, 64], seed=33) + edge_patterns()
+    with Oracle(built_indexes[name]) as o:
+        of, ol = o.count(pats)
+    f, l = ix.count(pats)
+    assert (f == of).all() and (l == ol).all()
+
+
+@pytest.mark.parametrize("bb", [64, 32])
+@pytest.mark.parametrize("name", ["multi_doc_mixed", "skewed_deep", "english_100k", "gen400_small_blocks"])
+def test_locate_extract_small_rank_blocks(name, bb, gpu_indexes_small_blocks, built_indexes, corpora):
+    docs, _ = corpora[name]
+    ix = gpu_indexes_small_blocks[(name, bb)]
+    pats = corpus.sample_patterns(docs, 200, [1, 2, 3, 4, 6, 8, 16], seed=43)
+    with Oracle(built_indexes[name]) as o:
+        want = o.locate(pats, 50)
+        n = o.header_info()["total_length"]
+        rows = np.arange(n) if n <= 3000 else np.random.default_rng(1).integers(0, n, 2000)
+        ch, nxt, off = ix.back_step(rows)
+        for i, r in enumerate(rows):
+            assert (int(ch[i]), int(nxt[i]), int(off[i])) == o.back_step(int(r))
+    got = ix.locate(pats, 50)
+    assert all((a == b).all() for a, b in zip(got, want))
+    for d in range(len(docs)):
+        assert bytes((ix.extract(d) - fb.CHARACTER_OFFSET).astype(np.uint8)) == docs[d]
+
+
 @pytest.mark.parametrize("sched", [(1, 4), (1, 2), (1, 8), (0, 4), (0, 8)])
 @pytest.mark.parametrize("name", ALL)
 def test_count_matches_oracle(name, sched, gpu_indexes, built_indexes, corpora):

@@ -17,10 +17,14 @@ from oracle.bindings import Oracle
 
 
 class Image:
-    def __init__(self, path, shard=0, nshards=1):
+    def __init__(self, path, shard=0, nshards=1, block_bytes=128):
         self.lib = _lib.load()
         err = C.c_int()
-        self.h = self.lib.fm_debug_image_open(os.fsencode(path), shard, nshards, 4, C.byref(err))
+        assert self.lib.fm_set_default_block_bytes(block_bytes) == 0
+        try:
+            self.h = self.lib.fm_debug_image_open(os.fsencode(path), shard, nshards, 4, C.byref(err))
+        finally:
+            self.lib.fm_set_default_block_bytes(128)
         assert self.h, f"image open failed err={err.value}"
 
     def stats(self):
@@ -58,10 +62,26 @@ def test_image_matches_oracle_exhaustive(name, built_indexes):
     im.close()
 
 
-@pytest.mark.parametrize("name", ["acgt_64k", "bytes_200k", "skewed_deep", "english_100k"])
-def test_image_matches_oracle_sampled(name, built_indexes):
+@pytest.mark.parametrize("block_bytes", [64, 32])
+@pytest.mark.parametrize("name", ["two_docs", "gen400_small_blocks", "multi_doc_mixed"])
+def test_image_small_rank_blocks_exhaustive(name, block_bytes, built_indexes):
+    """The 64- and 32-byte rank block layouts decode to the same Occ / LF / marks."""
     path = built_indexes[name]
-    im = Image(path)
+    im = Image(path, block_bytes=block_bytes)
+    with Oracle(path) as o:
+        n = o.header_info()["total_length"]
+        for row in range(0, n, 1 if n <= 500 else 3):
+            assert im.back_step(row) == o.back_step(row), row
+            for ch in range(0, 261, 2):
+                assert im.occ(ch, row) == o.occ(ch, row)[0], (ch, row)
+    im.close()
+
+
+@pytest.mark.parametrize("block_bytes", [128, 64, 32])
+@pytest.mark.parametrize("name", ["acgt_64k", "bytes_200k", "skewed_deep", "english_100k"])
+def test_image_matches_oracle_sampled(name, block_bytes, built_indexes):
+    path = built_indexes[name]
+    im = Image(path, block_bytes=block_bytes)
     rng = np.random.default_rng(9)
     with Oracle(path) as o:
         n = o.header_info()["total_length"]
