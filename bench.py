@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--sched", choices=["merged", "pair"], default="merged", help="count kernel schedule")
     ap.add_argument("--block-bytes", type=int, default=0, help="rank block size of the HBM image (128/64/32)")
     ap.add_argument("--cache-dir", default=os.environ.get("FEMTO_B200_CACHE", "/tmp/femto_b200_cache"))
+    ap.add_argument("--locate-npats", type=int, default=100000, help="patterns of the locate leg (configs[2])")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -341,6 +342,20 @@ def main():
     h2d = npats * 4 + npats * m * 2 + npats * 8
     d2h = npats * 16
 
+    # ---- locate (BASELINE configs[2]): text-sampled patterns, count + SA-sample walk, host buffers ----
+    nloc = min(args.locate_npats, npats)
+    loc_flat = h_flat[0].numpy()[:nloc].reshape(-1).view(np.uint16)
+    loc_plen, loc_offs = h_plen.numpy()[:nloc], h_offs.numpy()[:nloc]
+    loc_cap = nloc * 8
+    noccs, lstart, lout = ix.locate_flat(loc_plen, loc_flat, loc_offs, 2**31 - 1, loc_cap)   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        noccs, lstart, lout = ix.locate_flat(loc_plen, loc_flat, loc_offs, 2**31 - 1, loc_cap)
+    barrier()
+    locate_s = (time.perf_counter() - t0) / 3
+    locate_results = int(noccs.sum())
+
     # ---- max over ranks ---------------------------------------------------------------------
     times = torch.tensor([kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
     if world > 1:
@@ -383,6 +398,7 @@ def main():
     # ---- cpu_baseline + in-run parity: the unmodified reference on a bounded sample ----------
     cpu = None
     parity = None
+    locate_cpu = None
     if not args.no_cpu_baseline:
         from oracle.bindings import have_reference
         pats_host = last_batch.cpu().numpy()
@@ -399,6 +415,21 @@ def main():
                              f"(1 server thread as shipped, src/main/server.c:3597), {secs:.1f}s"}
             if not ok:
                 raise SystemExit("PARITY FAILURE: GPU first/last differ from the reference on the bench batch")
+            # locate: the reference on a bounded sample of the locate batch (in-process, 1 server thread)
+            from oracle.bindings import Reference
+            lsample = int(max(64, min(nloc, rate * 0.5 * min(args.cpu_sample_seconds, 10.0))))
+            lp2d = h_flat[0].numpy()[:lsample].view(np.uint16)
+            with Reference(index_path) as r:
+                t0 = time.perf_counter()
+                rloc = r.locate([lp2d[i] for i in range(lsample)], 2**31 - 1)
+                lsecs = time.perf_counter() - t0
+            lok = all((lout[lstart[i]:lstart[i] + noccs[i]] == rloc[i]).all() and len(rloc[i]) == noccs[i]
+                      for i in range(lsample))
+            locate_cpu = {"value": round(lsample / lsecs, 1), "unit": "patterns/s", "cores": 1, "kind": "reference",
+                          "sample": f"first {lsample} patterns of the locate batch, parallel_locate via oracle/_ref, "
+                                    f"{lsecs:.1f}s", "bit_exact_vs_reference": bool(lok)}
+            if not lok:
+                raise SystemExit("PARITY FAILURE: GPU locate offsets differ from the reference")
         else:
             from oracle.bindings import Oracle
             sample = 2000
@@ -434,6 +465,10 @@ def main():
                 "api": "fm_count_flat (pinned host buffers in/out)"},
         "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "parity": parity,
+        "locate": {"metric": "patterns/sec (locate, count + SA-sample walk, host buffers in/out)",
+                   "value": round(nloc / locate_s, 1), "unit": "patterns/s", "patterns": nloc,
+                   "occurrences": locate_results, "ms_per_batch": round(locate_s * 1e3, 3),
+                   "api": "fm_locate_flat", "cpu_baseline": locate_cpu},
     }
     print(json.dumps(out), flush=True)
     ix.close()

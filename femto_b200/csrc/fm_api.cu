@@ -108,7 +108,7 @@ struct fm_index {
   std::vector<int64_t> doc_ends, doc_eof_rows;
   // per-call scratch, serialised by mu
   std::mutex mu;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
   DevBuf d_in[4], d_out[4];
   HostBuf h_stage[2];
   int64_t launches = 0;
@@ -120,9 +120,10 @@ namespace {
 // count schedule codes understood by launch_count: pair = lanes per Occ query;
 // sync = 1000 + 10*lanes + resident blocks per SM the variant is compiled for.
 int sync_sched(int block_words, int lanes) {
-  const int minb = block_words == 32 ? (lanes == 8 ? 5 : lanes == 4 ? 5 : 4)
-                 : block_words == 16 ? (lanes == 4 ? 6 : lanes == 2 ? 5 : 4)
-                                     : (lanes == 2 ? 6 : 5);
+  // register budgets picked from the sweep in profiles/r01_count_schedule_sweep.md
+  const int minb = block_words == 32 ? (lanes == 8 ? 5 : lanes == 4 ? 4 : 3)
+                 : block_words == 16 ? (lanes == 4 ? 6 : 4)
+                                     : (lanes == 2 ? 6 : 4);
   return 1000 + 10 * lanes + minb;
 }
 
@@ -164,6 +165,7 @@ void destroy(fm_index* ix) {
   for (auto& b : ix->d_out) b.release();
   for (auto& b : ix->h_stage) b.release();
   if (ix->stream) cudaStreamDestroy(ix->stream);
+  if (ix->stream2) cudaStreamDestroy(ix->stream2);
   delete ix;
 }
 
@@ -192,6 +194,7 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     CK(cudaGetDeviceProperties(&prop, device));
     ix->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
     int64_t total = 0;
     upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * size_t(host->block_words), &total);
     upload(&ix->d_nodes, host->nodes.data(), host->nodes.size(), &total);
@@ -200,7 +203,8 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     upload(&ix->d_buckets, host->buckets.data(), host->buckets.size(), &total);
     upload(&ix->d_markvals, host->markvals.data(), host->markvals.size(), &total);
     upload(&ix->d_C, host->C.data(), host->C.size(), &total);
-    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 64));
+    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 16 * sizeof(unsigned long long)));  // queue slots:
+    // 0 host-buffer calls, 1..7 caller-stream launches, 8..11 chunks of a pipelined host-buffer call
     CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_status), 64));
     CK(cudaMemset(ix->d_status, 0, 64));
 
@@ -291,6 +295,32 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   int64_t* d_offs = static_cast<int64_t*>(ix->d_in[2].get(size_t(npats) * 8));
   int64_t* d_first = static_cast<int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
   int64_t* d_last = last ? static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8)) : nullptr;
+
+  // Large batches whose patterns lie in the flat buffer in order are cut into chunks that
+  // alternate between two streams, so the H2D copy of chunk k+1 and the D2H copy of chunk k-1
+  // overlap the kernel of chunk k (copy engines and SMs run concurrently).
+  constexpr int64_t kChunkMin = 1 << 16;
+  const int nchunks = int(std::min<int64_t>(4, npats / kChunkMin));
+  bool ordered = nchunks >= 2 && ix->stream2 != nullptr;
+  for (int64_t i = 1; ordered && i < npats; i++) ordered = offs[i] >= offs[i - 1] + plen[i - 1];
+  if (ordered) {
+    cudaStream_t st[2] = {ix->stream, ix->stream2};
+    for (int k = 0; k < nchunks; k++) {
+      cudaStream_t cs = st[k & 1];
+      const int64_t lo = npats * k / nchunks, hi = npats * (k + 1) / nchunks, n = hi - lo;
+      const int64_t flo = offs[lo], fhi = (k + 1 < nchunks) ? offs[hi] : flat_len;
+      CK(cudaMemcpyAsync(d_plen + lo, plen + lo, size_t(n) * 4, cudaMemcpyHostToDevice, cs));
+      CK(cudaMemcpyAsync(d_offs + lo, offs + lo, size_t(n) * 8, cudaMemcpyHostToDevice, cs));
+      if (fhi > flo) CK(cudaMemcpyAsync(d_flat + flo, flat + flo, size_t(fhi - flo) * 2, cudaMemcpyHostToDevice, cs));
+      CountArgs a{n, d_plen + lo, d_flat, d_offs + lo, d_first + lo, d_last ? d_last + lo : nullptr};
+      CK(launch_count(ix->im, a, ix->d_work + 8 + k, ix->count_sched, ix->sm_count, cs, &ix->launches));
+      CK(cudaMemcpyAsync(first + lo, d_first + lo, size_t(n) * 8, cudaMemcpyDeviceToHost, cs));
+      if (last) CK(cudaMemcpyAsync(last + lo, d_last + lo, size_t(n) * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    CK(cudaStreamSynchronize(st[0]));
+    CK(cudaStreamSynchronize(st[1]));
+    return FM_OK;
+  }
   CK(cudaMemcpyAsync(d_plen, plen, size_t(npats) * 4, cudaMemcpyHostToDevice, s));
   if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * 2, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
