@@ -33,9 +33,14 @@ constexpr int kThreads = 256;
 constexpr int kEscSeofDev = 2;  // ESCAPE_CODE_SEOF, src/main/index_types.h:42-48
 constexpr int kAlphaDev = 261;
 
-__device__ __forceinline__ uint32_t top_mask(int n) {
-  // the n (>= 0) most significant bits set; n >= 32 gives all ones (the funnel shift clamps at 32)
-  return __funnelshift_rc(0u, 0xFFFFFFFFu, static_cast<uint32_t>(n));
+__device__ __forceinline__ uint32_t popc_top(uint32_t w, int keep) {
+  // ones among the `keep` most significant bits of w: keep >= 32 counts the whole word, keep <= 0
+  // nothing.  shr.b32 clamps shift amounts above 31 to 32 (result 0), so only the lower bound of
+  // the shift needs an explicit max.
+  uint32_t shifted;
+  const uint32_t sh = static_cast<uint32_t>(max(32 - keep, 0));
+  asm("shr.b32 %0, %1, %2;" : "=r"(shifted) : "r"(w), "r"(sh));
+  return __popc(shifted);
 }
 
 // The WPL words of rank block `blk` that belong to lane `sub` of its group.
@@ -67,7 +72,7 @@ struct BlockWords {
 #pragma unroll
     for (int t = 0; t < WPL; t++) {
       const uint32_t word = (t == 0 && sub == 0) ? 0u : w[t];
-      c += __popc(word & top_mask(max(nb - 32 * t, 0)));
+      c += popc_top(word, nb - 32 * t);
     }
     return c;
   }
@@ -301,7 +306,6 @@ template <int LPQ, int BW, int MINB, bool STATS>
 __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
                                                                      unsigned long long* __restrict__ work,
                                                                      unsigned long long* __restrict__ stats) {
-  constexpr int WPL = BW / LPQ;
   constexpr uint32_t BITS = (BW - 1) * 32;
   unsigned long long n_ranks = 0, n_blocks = 0, n_occ = 0, n_steps = 0;
   const int lane = threadIdx.x & 31;
@@ -390,16 +394,17 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
       const uint32_t kA = pA / BITS, kB = pB / BITS;
       const uint32_t offA = pA - kA * BITS, offB = pB - kB * BITS;
       const bool two = actA && actB && kA != kB;  // the two positions need different blocks
+      // p serves position A, q position B.  When both positions share a block (the common case) or
+      // only one is active, q re-reads p's line: an L1 hit, no second HBM access.
       BlockWords<LPQ, BW> p, q;
       p.clear();
-      if (any) p.load(im.blocks, base + (actA ? kA : kB), sub);
-      if (two) q.load(im.blocks, base + kB, sub);
+      q.clear();
+      if (any) {
+        p.load(im.blocks, base + (actA ? kA : kB), sub);
+        q.load(im.blocks, base + (actB ? kB : kA), sub);
+      }
       uint4 nr = make_uint4(0, 0, 0, 0);
       if (any && lvl + 1 < L) nr = __ldg(reinterpret_cast<const uint4*>(im.nodes + node));
-      if (!two) {
-#pragma unroll
-        for (int t = 0; t < WPL; t++) q.w[t] = p.w[t];
-      }
       const uint32_t packed = group_sum<LPQ>(p.count_upto(offA, sub) | (q.count_upto(offB, sub) << 16));
       const uint32_t onesA = group_lane0<LPQ>(p.w[0]) + (packed & 0xffffu);
       const uint32_t onesB = group_lane0<LPQ>(q.w[0]) + (packed >> 16);
