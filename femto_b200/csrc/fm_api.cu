@@ -503,6 +503,26 @@ int fm_count_device(fm_index_t* ix, int64_t npats, const int32_t* d_plen, const 
   });
 }
 
+int fm_count_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, const int32_t* d_plen,
+                        const uint16_t* d_flat, const int64_t* d_offs, int32_t* d_dest, int nshards, void* stream) {
+  return guarded(ix, "fm_count_shard_step", [&]() -> int {
+    if (nstates < 0 || nshards < 1) return fail(FM_ERR_PARAM, "fm_count_shard_step: bad argument");
+    ShardArgs a{};
+    a.n = nstates;
+    a.state = d_state;
+    a.plen = d_plen;
+    a.flat = d_flat;
+    a.offs = d_offs;
+    a.dest = d_dest;
+    a.nshards = nshards;
+    a.block_size = ix->info.block_size;
+    a.nblocks = ix->info.num_blocks;
+    CK(launch_count_shard(ix->im, a, ix->lanes_per_query, ix->sm_count, static_cast<cudaStream_t>(stream),
+                          &ix->launches));
+    return FM_OK;
+  });
+}
+
 int fm_locate_rows(fm_index_t* ix, int64_t nrows, const int64_t* rows, int64_t* offsets) {
   return guarded(ix, "fm_locate_rows", [&]() -> int {
     if (nrows < 0 || (nrows && (!rows || !offsets))) return fail(FM_ERR_PARAM, "fm_locate_rows: bad argument");

@@ -594,6 +594,82 @@ __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range-sharded count: advance pattern states while the BWT rows they need are resident here.
+template <int LPQ, int BW>
+__global__ void __launch_bounds__(kThreads) count_shard_kernel(const DevImage im, const ShardArgs a) {
+  constexpr int QPW = 32 / LPQ;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPQ - 1);
+  const int qi = lane / LPQ;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t base = warp * QPW; base < a.n; base += nwarps * QPW) {
+    const int64_t item = base + qi;
+    bool running = item < a.n;
+    int64_t pid = 0, f = 0, l = -1, obA = 0;
+    int i = 0, phase = 2, home = 0, dest = -1;
+    const uint16_t* pat = nullptr;
+    if (running) {
+      const int64_t* s = a.state + item * kShardStateWords;
+      pid = s[0]; f = s[1]; l = s[2]; i = static_cast<int>(s[3]); obA = s[4];
+      phase = static_cast<int>(s[5] & 15);
+      home = static_cast<int>(s[5] >> 4);
+      pat = a.flat + a.offs[pid];
+      if (phase == 3) {  // new pattern: [C[c], C[c+1]-1] for its last symbol (server.c:781-801)
+        const int m = a.plen[pid];
+        if (m <= 0) { f = 0; l = im.total_length - 1; i = 0; }
+        else {
+          const int c = pat[m - 1];
+          if (c >= kAlphaDev) { f = im.total_length; l = f - 1; }
+          else { f = __ldg(im.C + c); l = __ldg(im.C + c + 1) - 1; }
+          i = m - 1;
+        }
+        phase = 0;
+      }
+    }
+    for (;;) {
+      bool q = false;
+      int c = 0;
+      int64_t row = 0;
+      if (running) {
+        if (phase == 2) {
+          dest = home; running = false;
+        } else if (phase == 0 && (f > l || i == 0)) {
+          phase = 2; dest = home; running = false;
+        } else {
+          c = pat[i - 1];
+          if (phase == 0 && c >= kAlphaDev) {
+            f = im.total_length; l = f - 1; i--;
+          } else if (phase == 0 && f == 0) {
+            obA = __ldg(im.C + c); phase = 1;  // Occ(c,-1) = 0 (server.c:847-851)
+          } else {
+            row = phase == 0 ? f - 1 : l;
+            if (row >= im.first_row && row < im.end_row) {
+              q = true;
+            } else {
+              dest = static_cast<int>(((row / a.block_size) * a.nshards) / a.nblocks);
+              running = false;
+            }
+          }
+        }
+      }
+      if (!__any_sync(kFull, running)) break;
+      const int64_t r = occ_descend<LPQ, BW>(im, q, c, row, sub);
+      if (q) {
+        if (phase == 0) { obA = r; phase = 1; }
+        else { f = obA; l = r - 1; i--; phase = 0; }
+      }
+    }
+    if (item < a.n && sub == 0) {
+      int64_t* s = a.state + item * kShardStateWords;
+      s[1] = f; s[2] = l; s[3] = i; s[4] = obA;
+      s[5] = static_cast<int64_t>(phase) | (static_cast<int64_t>(home) << 4);
+      a.dest[item] = dest;
+    }
+  }
+}
+
 template <typename K>
 int blocks_per_sm(K kernel) {
   int n = 0;
@@ -690,6 +766,28 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
   }
   if (launch_counter) ++*launch_counter;
   return e;
+}
+
+cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lpq, int sm_count, cudaStream_t stream,
+                               int64_t* launch_counter) {
+  if (a.n <= 0) return cudaSuccess;
+#define FM_SHARD(LANES, BW)                                                                               \
+  do {                                                                                                    \
+    static const int bps = blocks_per_sm(count_shard_kernel<LANES, BW>);                                  \
+    count_shard_kernel<LANES, BW><<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a); \
+  } while (0)
+  switch (im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 3208: FM_SHARD(8, 32); break;
+    case 3204: FM_SHARD(4, 32); break;
+    case 1604: FM_SHARD(4, 16); break;
+    case 1602: FM_SHARD(2, 16); break;
+    case 802: FM_SHARD(2, 8); break;
+    case 801: FM_SHARD(1, 8); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef FM_SHARD
+  if (launch_counter) ++*launch_counter;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* /*d_work*/, int lpq, int sm_count,

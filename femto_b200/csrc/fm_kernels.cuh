@@ -44,6 +44,24 @@ struct OccArgs {
   int64_t* out;  // C[ch] + Occ(ch,row)
 };
 
+// Range-sharded count: pattern states travel between the GPUs that own the
+// BWT rows they need.  One state = 6 int64: pid, first, last, i, obA (C[c]+Occ(c,first-1) once
+// known), meta = phase | home_rank << 4.  phase: 3 new (initialise from the pattern), 0 needs
+// Occ(c,first-1), 1 needs Occ(c,last), 2 finished (travel home).  The kernel advances every state
+// while the rows it needs are resident and writes the rank that must see it next into dest[].
+constexpr int kShardStateWords = 6;
+struct ShardArgs {
+  int64_t n;
+  int64_t* state;        // [n][kShardStateWords]
+  const int32_t* plen;   // all patterns of the batch are replicated on every rank
+  const uint16_t* flat;
+  const int64_t* offs;
+  int32_t* dest;         // out: rank owning the next row needed (or the home rank when finished)
+  int32_t nshards;
+  int32_t block_size;    // rows per data block; shard(row) = (row / block_size) * nshards / nblocks
+  int64_t nblocks;
+};
+
 // lanes_per_query: 4 or 8.  Each launch bumps *launch_counter (host) by the number of kernels launched.
 // d_stats (optional, 4 x uint64 zeroed by the caller) selects the instrumented kernel variant:
 // [0] rank blocks requested, [1] distinct rank blocks per step and level, [2] Occ evaluations,
@@ -55,5 +73,7 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
                         int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
 cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* d_work_counter,
                        int lanes_per_query, int sm_count, cudaStream_t stream, int64_t* launch_counter);
+cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lanes_per_query, int sm_count,
+                               cudaStream_t stream, int64_t* launch_counter);
 
 }  // namespace fmb

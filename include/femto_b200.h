@@ -105,6 +105,19 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
 int fm_count_device(fm_index_t* ix, int64_t npats, const int32_t* d_plen, const uint16_t* d_flat,
                     const int64_t* d_offs, int64_t* d_first, int64_t* d_last, void* stream);
 
+/* Range-sharded count (index opened with fm_open_shard).  A batch is a set
+ * of pattern STATES that travel between the GPUs owning the BWT rows they need next; this call
+ * advances every state while its rows are resident on ix's device.  d_state holds nstates rows of
+ * 6 int64 {pattern id, first, last, i, C[c]+Occ(c,first-1) when known, phase | home_rank<<4};
+ * phase 3 = new (initialised here from the pattern), 0 = needs Occ(c,first-1), 1 = needs
+ * Occ(c,last), 2 = finished.  d_dest[k] receives the rank that must see state k next (its home
+ * rank once finished).  The whole pattern batch (d_plen/d_flat/d_offs, indexed by pattern id) is
+ * replicated on every rank.  All pointers are device pointers; asynchronous on `stream`.
+ * femto_b200/sharded.py drives the exchange between ranks with NCCL all-to-all. */
+int fm_count_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, const int32_t* d_plen,
+                        const uint16_t* d_flat, const int64_t* d_offs, int32_t* d_dest, int nshards,
+                        void* stream);
+
 /* --------------------------------------------------------------------------
  * locate.  Mirrors parallel_locate (src/main/femto.c:331-399): for pattern i,
  * noccs[i] offsets are returned in BWT row order first..; offsets[i] is malloc()ed
