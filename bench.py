@@ -406,7 +406,7 @@ def main():
     cpu = None
     parity = None
     locate_cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reference CPU leg: rank 0 at N=1 only
         from oracle.bindings import have_reference
         pats_host = last_batch.cpu().numpy()
         if have_reference():
@@ -456,7 +456,7 @@ def main():
     out = {
         "metric": "patterns/sec (count)", "value": round(value, 1), "unit": "patterns/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u32 popcount",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic", "impl": "b200",
         "config": {"workload": workload, "patterns_per_gpu_per_step": npats, "pattern_length": m,
                    "index": index_name(args), "index_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
@@ -537,7 +537,7 @@ def run_sharded(args, index_path, text, workload, rank, world, local, device):
         out = {
             "metric": "patterns/sec (count)", "value": round(total / (ms_per_step / 1e3), 1), "unit": "patterns/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u32 popcount",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic", "impl": "b200",
             "config": {"workload": workload, "patterns_per_gpu_per_step": npats, "pattern_length": m,
                        "index": index_name(args), "index_load_s": round(load_s, 1),
