@@ -237,6 +237,37 @@ def test_device_pointer_api_with_torch(built_indexes, corpora):
         assert (d_first.cpu().numpy() == of).all() and (d_last.cpu().numpy() == ol).all()
 
 
+def test_mixed_length_zipf_batch(tmp_path):
+    """BASELINE configs[3] in miniature: lengths Zipf-distributed over [8,256] on an English-like
+    multi-document corpus (deep Huffman trees, patterns dying at different steps, groups of a warp
+    finishing at different times)."""
+    docs = [corpus.english_like(200000, 200 + d) for d in range(5)]
+    path = str(tmp_path / "english_1m")
+    fb.build_index_host(docs, path, block_size=1 << 18, bucket_size=1 << 14, chunk_size=2048)
+    rng = np.random.default_rng(17)
+    ranks = np.arange(8, 257)
+    p = (1.0 / (ranks - 7)) / (1.0 / (ranks - 7)).sum()
+    lengths = rng.choice(ranks, 20000, p=p).tolist()
+    pats = corpus.sample_patterns(docs, 20000, lengths, seed=18, random_fraction=0.2)
+    # mutate a symbol in a quarter of the patterns so that they die somewhere in the middle
+    for k in range(0, len(pats), 4):
+        q = pats[k].copy()
+        q[int(rng.integers(0, len(q)))] = 5 + int(rng.integers(97, 123))
+        pats[k] = q
+    with fb.Index(path) as ix, Oracle(path) as o:
+        for sched in ((1, 4), (0, 4)):
+            ix.set_count_schedule(*sched)
+            f, l = ix.count(pats)
+            sub = list(range(0, len(pats), 7))
+            of, ol = o.count([pats[i] for i in sub])
+            assert (f[sub] == of).all() and (l[sub] == ol).all()
+        cnt = np.maximum(l - f + 1, 0)
+        assert (cnt[1::4] >= 1).sum() > 3000                 # text-sampled ones are found
+        loc = ix.locate(pats[:2000], 30)
+        oloc = o.locate(pats[:2000:5], 30)
+        assert all((a == b).all() for a, b in zip(loc[::5], oloc))
+
+
 def test_properties_at_scale(tmp_path):
     """Size-independent properties on a corpus too large for the scalar oracle to sweep:
     count == occurrences found by locate, every located offset matches the text, LF is a
