@@ -212,6 +212,19 @@ class Index:
                "fm_occ")
         return out[:len(rows)]
 
+    def backward_step(self, first: np.ndarray, last: np.ndarray, ch: np.ndarray):
+        """One backward-search step per (range, symbol): backward_search_query (server.c:948)."""
+        first = np.ascontiguousarray(first, dtype=np.int64)
+        last = np.ascontiguousarray(last, dtype=np.int64)
+        ch = np.ascontiguousarray(ch, dtype=np.uint16)
+        n = len(first)
+        nf = np.zeros(max(n, 1), dtype=np.int64)
+        nl = np.zeros(max(n, 1), dtype=np.int64)
+        _check(self.lib.fm_backward_step(self.h, n, _ptr(first, C.c_int64), _ptr(last, C.c_int64),
+                                         _ptr(ch, C.c_uint16), _ptr(nf, C.c_int64), _ptr(nl, C.c_int64)),
+               "fm_backward_step")
+        return nf[:n], nl[:n]
+
     # -- documents -------------------------------------------------------------------------
     def doc_info(self, doc: int) -> Tuple[int, int]:
         a, b = C.c_int64(), C.c_int64()

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "fm_locate_rows_device": (C.c_int, [vp, i64, vp, vp, vp]),
     "fm_back_step": (C.c_int, [vp, i64, P(i64), P(i32), P(i64), P(i64)]),
     "fm_occ": (C.c_int, [vp, i64, P(u16), P(i64), P(i64)]),
+    "fm_backward_step": (C.c_int, [vp, i64, P(i64), P(i64), P(u16), P(i64), P(i64)]),
     "fm_doc_info": (C.c_int, [vp, i64, P(i64), P(i64)]),
     "fm_resolve": (C.c_int, [vp, i64, P(i64), P(i64), P(i64)]),
     "fm_extract": (C.c_int, [vp, i64, P(u16), i64, P(i64)]),

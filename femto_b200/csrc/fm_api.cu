@@ -105,7 +105,7 @@ struct fm_index {
   unsigned long long* d_work = nullptr;  // work-queue counters (one per concurrent launch slot)
   int32_t* d_status = nullptr;
   // host-side header tables
-  std::vector<int64_t> doc_ends, doc_eof_rows;
+  std::vector<int64_t> doc_ends, doc_eof_rows, C_host;
   // per-call scratch, serialised by mu
   std::mutex mu;
   cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -239,6 +239,7 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->info.device = device;
     ix->info.max_code_len = host->max_code_len;
     ix->info.rank_block_size = host->block_words * 4;
+    ix->C_host = host->C;
     ix->doc_ends = std::move(host->doc_ends);
     ix->doc_eof_rows = std::move(host->doc_eof_rows);
   } catch (const CudaFail& e) {
@@ -267,13 +268,19 @@ int guarded(fm_index* ix, const char* what, F&& body) {
 }
 
 // Validate a flat pattern batch on the host and return the number of symbols referenced.
-int check_patterns(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t* flat_len) {
+// `ordered` (optional) reports whether the patterns lie in the flat buffer in batch order without
+// overlap -- the layout that allows chunked, pipelined transfers.
+int check_patterns(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t* flat_len,
+                   bool* ordered = nullptr) {
   int64_t end = 0;
+  bool ord = true;
   for (int64_t i = 0; i < npats; i++) {
     if (plen[i] < 0 || offs[i] < 0) return FM_ERR_PARAM;
+    ord = ord && offs[i] >= end;
     end = std::max(end, offs[i] + plen[i]);
   }
   *flat_len = end;
+  if (ordered) *ordered = ord;
   return FM_OK;
 }
 
@@ -287,7 +294,7 @@ int walk_status(fm_index* ix) {
 
 // count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
 int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, int64_t flat_len,
-               const int64_t* offs, int64_t* first, int64_t* last) {
+               const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false) {
   if (npats == 0) return FM_OK;
   cudaStream_t s = ix->stream;
   int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
@@ -301,8 +308,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   // overlap the kernel of chunk k (copy engines and SMs run concurrently).
   constexpr int64_t kChunkMin = 1 << 16;
   const int nchunks = int(std::min<int64_t>(4, npats / kChunkMin));
-  bool ordered = nchunks >= 2 && ix->stream2 != nullptr;
-  for (int64_t i = 1; ordered && i < npats; i++) ordered = offs[i] >= offs[i - 1] + plen[i - 1];
+  const bool ordered = in_order && nchunks >= 2 && ix->stream2 != nullptr;
   if (ordered) {
     cudaStream_t st[2] = {ix->stream, ix->stream2};
     for (int k = 0; k < nchunks; k++) {
@@ -440,11 +446,12 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
   return guarded(ix, "fm_count_flat", [&]() -> int {
     if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
     int64_t flat_len = 0;
-    if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
+    bool ordered = false;
+    if (check_patterns(npats, plen, offs, &flat_len, &ordered)) return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
     if (flat_len && !flat) return fail(FM_ERR_PARAM, "fm_count_flat: null pattern buffer");
     if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
       return fail(FM_ERR_MISSING, "fm_count_flat: index is a shard; use the sharded driver");
-    return count_host(ix, npats, plen, flat, flat_len, offs, first, last);
+    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered);
   });
 }
 
@@ -485,7 +492,8 @@ int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* 
     uint16_t* flat = nullptr;
     int64_t flat_len = 0;
     gather_patterns(ix, npats, plen, pats, &offs, &flat, &flat_len);
-    return count_host(ix, npats, reinterpret_cast<const int32_t*>(plen), flat, flat_len, offs.data(), first, last);
+    return count_host(ix, npats, reinterpret_cast<const int32_t*>(plen), flat, flat_len, offs.data(), first, last,
+                      /*in_order=*/true);
   });
 }
 
@@ -673,6 +681,41 @@ int fm_occ(fm_index_t* ix, int64_t n, const uint16_t* ch, const int64_t* rows, i
     CK(cudaStreamSynchronize(s));
     for (int64_t i = 0; i < n; i++)
       if (c_plus_occ[i] < 0) return fail(FM_ERR_PARAM, "fm_occ: symbol or row out of range");
+    return FM_OK;
+  });
+}
+
+int fm_backward_step(fm_index_t* ix, int64_t n, const int64_t* first, const int64_t* last, const uint16_t* ch,
+                     int64_t* new_first, int64_t* new_last) {
+  return guarded(ix, "fm_backward_step", [&]() -> int {
+    if (n < 0 || (n && (!first || !last || !ch || !new_first || !new_last)))
+      return fail(FM_ERR_PARAM, "fm_backward_step: bad argument");
+    if (n == 0) return FM_OK;
+    // two Occ evaluations per range: rows first-1 and last (do_backward_search_query, server.c:980-1112)
+    std::vector<uint16_t> qc(size_t(2 * n));
+    std::vector<int64_t> qr(size_t(2 * n)), res(size_t(2 * n));
+    for (int64_t i = 0; i < n; i++) {
+      if (ch[i] >= kAlpha || last[i] < 0 || last[i] >= ix->info.total_length || first[i] < 0 || first[i] > last[i] + 1)
+        return fail(FM_ERR_PARAM, "fm_backward_step: symbol or range out of bounds");
+      qc[size_t(2 * i)] = qc[size_t(2 * i + 1)] = ch[i];
+      qr[size_t(2 * i)] = first[i] > 0 ? first[i] - 1 : last[i];  // first == 0: Occ(c,-1) = 0, slot unused
+      qr[size_t(2 * i + 1)] = last[i];
+    }
+    cudaStream_t s = ix->stream;
+    uint16_t* d_ch = static_cast<uint16_t*>(ix->d_in[1].get(size_t(2 * n) * 2));
+    int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(2 * n) * 8));
+    int64_t* d_out = static_cast<int64_t*>(ix->d_out[2].get(size_t(2 * n) * 8));
+    CK(cudaMemcpyAsync(d_ch, qc.data(), size_t(2 * n) * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_rows, qr.data(), size_t(2 * n) * 8, cudaMemcpyHostToDevice, s));
+    OccArgs a{2 * n, d_ch, d_rows, d_out};
+    CK(launch_occ(ix->im, a, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(res.data(), d_out, size_t(2 * n) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; i++) {
+      if (res[size_t(2 * i + 1)] < 0) return fail(FM_ERR_MISSING, "fm_backward_step: row not resident (sharded index)");
+      new_first[i] = first[i] > 0 ? res[size_t(2 * i)] : ix->C_host[ch[i]];
+      new_last[i] = res[size_t(2 * i + 1)] - 1;
+    }
     return FM_OK;
   });
 }

@@ -154,6 +154,15 @@ int fm_back_step(fm_index_t* ix, int64_t nrows, const int64_t* rows, int32_t* ch
  * (src/main/index.c:1698-1765, 1973-2100).  Host buffers. */
 int fm_occ(fm_index_t* ix, int64_t n, const uint16_t* ch, const int64_t* rows, int64_t* c_plus_occ);
 
+/* One backward-search step for a batch of (range, symbol) triples -- the reference's
+ * backward_search_query (src/main/server.c:948-1122), the primitive its regexp / approximate-match
+ * NFA simulation issues per frontier edge (server.h:518-564):
+ *   new_first[i] = C[ch] + Occ(ch, first[i]-1)   (C[ch] when first[i]==0)
+ *   new_last[i]  = C[ch] + Occ(ch, last[i]) - 1
+ * Host buffers; ranges must satisfy 0 <= first <= last+1, last < total_length. */
+int fm_backward_step(fm_index_t* ix, int64_t n, const int64_t* first, const int64_t* last,
+                     const uint16_t* ch, int64_t* new_first, int64_t* new_last);
+
 /* --------------------------------------------------------------------------
  * Documents.  fm_doc_info: length (incl. its SEOF) and EOF row (header tables,
  * src/main/index.c:1668-1696).  fm_resolve: text offset -> (document, offset in

@@ -171,6 +171,29 @@ def test_extract_and_doc_tables(name, gpu_indexes, built_indexes, corpora):
             assert (int(doc[i]), int(doff[i])) == o.resolve(int(off))
 
 
+@pytest.mark.parametrize("name", ["multi_doc_mixed", "english_100k", "bytes_200k"])
+def test_backward_step_api_reproduces_count(name, gpu_indexes, built_indexes, corpora):
+    """fm_backward_step (the reference's backward_search_query, one step per call) iterated over a
+    pattern must walk through exactly the ranges of the oracle's backward search."""
+    docs, _ = corpora[name]
+    ix = gpu_indexes[name]
+    pats = [p for p in corpus.sample_patterns(docs, 400, [6], seed=61) if len(p) == 6]
+    with Oracle(built_indexes[name]) as o:
+        first = np.array([o.C(int(p[-1])) for p in pats], dtype=np.int64)
+        last = np.array([o.C(int(p[-1]) + 1) - 1 for p in pats], dtype=np.int64)
+        alive = np.ones(len(pats), dtype=bool)
+        for k in range(4, -1, -1):
+            alive &= first <= last
+            idx = np.nonzero(alive)[0]
+            if len(idx) == 0:
+                break
+            ch = np.array([pats[i][k] for i in idx], dtype=np.uint16)
+            nf, nl = ix.backward_step(first[idx], last[idx], ch)
+            first[idx], last[idx] = nf, nl
+        of, ol = o.count(pats)
+    assert (first == of).all() and (last == ol).all()
+
+
 def test_golden_reference_outputs():
     """Committed answers of the unmodified reference on indexes built by the reference."""
     for case in sorted(os.listdir(GOLDEN_DIR)):
