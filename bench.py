@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per pattern group (2, 4 or 8); 0 = engine default")
     ap.add_argument("--sched", choices=["merged", "pair"], default="merged", help="count kernel schedule")
     ap.add_argument("--block-bytes", type=int, default=0, help="rank block size of the HBM image (128/64/32)")
+    ap.add_argument("--paired-levels", type=int, default=-1,
+                    help="1: two wavelet-tree levels per rank block, 0: one; default: the library's")
     ap.add_argument("--parallelism", choices=["replica", "sharded"], default="replica",
                     help="N>1: replicate the index and split patterns (default), or shard the index by BWT "
                          "row range and route pattern states with NCCL all-to-all")
@@ -268,11 +270,16 @@ def main():
 
     if args.block_bytes:
         assert lib.fm_set_default_block_bytes(args.block_bytes) == 0
+    if args.paired_levels >= 0:
+        assert lib.fm_set_default_paired_levels(args.paired_levels) == 0
     t0 = time.time()
     ix = fb.Index(index_path, device=local)
     load_s = time.time() - t0
     block_bytes = int(ix.info.rank_block_size)
-    if args.lanes or args.sched != "merged":
+    paired = bool(ix.info.paired_levels)
+    if paired and args.lanes:
+        ix.set_count_schedule(True, args.lanes)
+    elif args.lanes or args.sched != "merged":
         ix.set_count_schedule(args.sched == "merged", args.lanes or {128: 4, 64: 2, 32: 1}[block_bytes])
     log(f"index resident: {ix.info.hbm_bytes / 2**30:.2f} GiB HBM, loaded in {load_s:.1f}s, "
         f"max code length {ix.info.max_code_len}")
@@ -386,7 +393,9 @@ def main():
     st = ix.count_stats(h_plen.numpy(), hb, h_offs.numpy())
     # per distinct rank block: 128 B payload line + 16 B node record; per Occ evaluation:
     # 16 B OccRec + 16 B BucketRec; per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
-    alg_bytes = (st["distinct_block_reads"] * (block_bytes + 16) + st["occ_evals"] * 32 + npats * (m * 2 + 28))
+    # (paired-level blocks: one block answers two levels and comes with an 8 B grandchild record)
+    alg_bytes = (st["distinct_block_reads"] * (block_bytes + (8 if paired else 16)) + st["occ_evals"] * 32 +
+                 npats * (m * 2 + 28))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
@@ -462,7 +471,7 @@ def main():
                    "index": index_name(args), "index_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
                    "index_load_s": round(load_s, 1), "index_build": build_info,
                    "parallelism": f"replica x{world} (patterns split, no collective)",
-                   "rank_block_bytes": block_bytes,
+                   "rank_block_bytes": block_bytes, "paired_levels": paired,
                    "count_schedule": os.environ.get("FEMTO_B200_COUNT_SCHED") or
                                      f"{args.sched}/{args.lanes or 'default'} lanes per pattern group",
                    "l2_policy": "inputs larger than L2: each step reads ~%.1f GB of a %.1f GiB image; %d distinct batches cycled"

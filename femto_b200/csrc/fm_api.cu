@@ -127,8 +127,14 @@ int sync_sched(int block_words, int lanes) {
   return 1000 + 10 * lanes + minb;
 }
 
-int default_count_sched(int block_words) {
-  int sched = sync_sched(block_words, block_words == 32 ? 4 : block_words == 16 ? 2 : 1);
+int paired_sched(int block_words, int lanes) {
+  const int minb = block_words == 32 ? (lanes == 4 ? 5 : lanes == 2 ? 4 : 3) : (lanes == 2 ? 5 : 4);
+  return 1000 + 10 * lanes + minb;
+}
+
+int default_count_sched(int block_words, bool paired) {
+  int sched = paired ? paired_sched(block_words, block_words == 32 ? 4 : 2)
+                     : sync_sched(block_words, block_words == 32 ? 4 : block_words == 16 ? 2 : 1);
   if (const char* e = std::getenv("FEMTO_B200_COUNT_SCHED")) {  // tuning experiments only
     const int v = std::atoi(e);
     if (v > 0) sched = v;
@@ -197,7 +203,8 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
     int64_t total = 0;
     upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * size_t(host->block_words), &total);
-    upload(&ix->d_nodes, host->nodes.data(), host->nodes.size(), &total);
+    if (host->paired) upload(&ix->d_nodes, host->supers.data(), host->supers.size(), &total);
+    else upload(&ix->d_nodes, host->nodes.data(), host->nodes.size(), &total);
     upload(&ix->d_occ, host->occ.data(), host->occ.size(), &total);
     upload(&ix->d_mark, host->mark.data(), host->mark.size(), &total);
     upload(&ix->d_buckets, host->buckets.data(), host->buckets.size(), &total);
@@ -210,7 +217,10 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
 
     const BlockHeader& h = host->hdr;
     ix->im.blocks = static_cast<const uint4*>(ix->d_blocks);
-    ix->im.nodes = static_cast<const NodeRec*>(ix->d_nodes);
+    if (host->paired) ix->im.supers = static_cast<const SuperRec*>(ix->d_nodes);
+    else ix->im.nodes = static_cast<const NodeRec*>(ix->d_nodes);
+    ix->im.paired = host->paired ? 1 : 0;
+    ix->info.paired_levels = ix->im.paired;
     ix->im.occ = static_cast<const OccRec*>(ix->d_occ);
     ix->im.mark = static_cast<const MarkRec*>(ix->d_mark);
     ix->im.buckets = static_cast<const BucketRec*>(ix->d_buckets);
@@ -235,7 +245,7 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->info.hbm_bytes = total;
     ix->info.rank_block_bytes = host->n_rank_blocks * int64_t(host->block_words) * 4;
     ix->im.block_words = host->block_words;
-    ix->count_sched = default_count_sched(host->block_words);
+    ix->count_sched = default_count_sched(host->block_words, host->paired);
     ix->info.device = device;
     ix->info.max_code_len = host->max_code_len;
     ix->info.rank_block_size = host->block_words * 4;
@@ -407,7 +417,8 @@ int fm_info(const fm_index_t* ix, fm_info_t* out) {
 int64_t fm_kernel_launches(const fm_index_t* ix) { return ix ? ix->launches : 0; }
 
 int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
-  if (!ix || (lanes != 4 && lanes != 8)) return fail(FM_ERR_PARAM, "fm_set_lanes_per_query: lanes must be 4 or 8");
+  if (!ix || (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8))
+    return fail(FM_ERR_PARAM, "fm_set_lanes_per_query: lanes must be 1, 2, 4 or 8");
   ix->lanes_per_query = lanes;
   return FM_OK;
 }
@@ -415,6 +426,12 @@ int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
 int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
   if (!ix) return fail(FM_ERR_PARAM, "fm_set_count_schedule: null index");
   const int bw = ix->im.block_words;
+  if (ix->im.paired) {  // paired-level blocks: merged schedule only, a lane owns whole 32-byte slices
+    if (!((bw == 32 && (lanes == 1 || lanes == 2 || lanes == 4)) || (bw == 16 && (lanes == 1 || lanes == 2))))
+      return fail(FM_ERR_PARAM, "fm_set_count_schedule: lane count not available for paired-level blocks");
+    ix->count_sched = paired_sched(bw, lanes);
+    return FM_OK;
+  }
   // each lane must own at least 2 words of the block (sync) / 4 words (pair)
   const bool ok = merged ? ((bw == 32 && (lanes == 2 || lanes == 4 || lanes == 8)) ||
                             (bw == 16 && (lanes == 1 || lanes == 2 || lanes == 4)) ||
@@ -428,6 +445,11 @@ int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
 
 int fm_set_default_block_bytes(int bytes) {
   if (!set_default_block_words(bytes / 4) || bytes % 4) return fail(FM_ERR_PARAM, "fm_set_default_block_bytes: 32, 64 or 128");
+  return FM_OK;
+}
+
+int fm_set_default_paired_levels(int on) {
+  set_default_paired_levels(on != 0);
   return FM_OK;
 }
 

@@ -46,7 +46,7 @@ void fm_debug_image_stats(void* h, int64_t* out) {
   const HostImage& im = *static_cast<DebugImage*>(h)->im;
   out[0] = im.n_rank_blocks;
   out[1] = im.n_wtree_blocks;
-  out[2] = int64_t(im.nodes.size());
+  out[2] = int64_t(im.paired ? im.supers.size() : im.nodes.size());
   out[3] = im.nbuckets;
   out[4] = int64_t(im.markvals.size());
   out[5] = im.first_row;
@@ -65,6 +65,32 @@ int64_t fm_debug_image_occ(void* h, int ch, int64_t row) {
   const BucketRec& br = im.buckets[size_t(g)];
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1;
   const int L = 31 - __builtin_clz(o.leaf);
+  if (im.paired) {
+    for (int lvl = 0; lvl < L; lvl += 2) {
+      const uint32_t b1 = (o.leaf >> (L - lvl - 1)) & 1u;
+      const HostPairedRank r = host_paired_rank(im.rank_words, im.block_words, base, idx1, int(b1));
+      const SuperRec& sr = im.supers[node];
+      idx1 = r.index1;
+      if (lvl + 1 == L) {
+        if (!(sr.child_info[b1] & kChildLeaf)) return -2;
+        break;
+      }
+      if (sr.child_info[b1] & kChildLeaf) return -2;
+      if (idx1 == 0) break;
+      const uint32_t b2 = (o.leaf >> (L - lvl - 2)) & 1u;
+      idx1 = b2 ? r.ones2 : idx1 - r.ones2;
+      if (idx1 == 0) break;
+      const uint32_t* gc = sr.gc[2 * b1 + b2];
+      if (lvl + 2 == L) {
+        if (!(gc[1] & kChildLeaf)) return -2;
+        break;
+      }
+      if (gc[1] & kChildLeaf) return -2;
+      base = gc[0];
+      node = gc[1];
+    }
+    return o.occ_base + idx1;
+  }
   for (int lvl = 1; lvl <= L; lvl++) {
     const HostRank r = host_rank(im.rank_words, im.block_words, base, idx1);
     const uint32_t b = (o.leaf >> (L - lvl)) & 1u;
@@ -88,7 +114,18 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
   if (!split(im, row, &g, &rb)) return -1;
   const BucketRec& br = im.buckets[size_t(g)];
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1, ch = 0;
-  for (int guard = 0; guard < 64; guard++) {
+  for (int guard = 0; guard < 64 && im.paired; guard++) {
+    const HostPairedRank r = host_paired_rank(im.rank_words, im.block_words, base, idx1, -1);
+    const SuperRec& sr = im.supers[node];
+    idx1 = r.index1;
+    if (sr.child_info[r.bit1] & kChildLeaf) { ch = sr.child_info[r.bit1] & 0xffffu; break; }
+    idx1 = r.bit2 ? r.ones2 : idx1 - r.ones2;
+    const uint32_t* gc = sr.gc[2 * r.bit1 + r.bit2];
+    if (gc[1] & kChildLeaf) { ch = gc[1] & 0xffffu; break; }
+    base = gc[0];
+    node = gc[1];
+  }
+  for (int guard = 0; guard < 64 && !im.paired; guard++) {
     const HostRank r = host_rank(im.rank_words, im.block_words, base, idx1);
     idx1 = r.bit ? r.ones : idx1 - r.ones;
     const NodeRec& nr = im.nodes[node];

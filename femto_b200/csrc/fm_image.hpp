@@ -40,6 +40,34 @@ struct alignas(16) NodeRec {
   uint32_t child_info[2];  // kChildLeaf | symbol   or   node index of the internal child
 };
 
+// ---- paired-level layout (optional, chosen at load time) -------------------------------------
+// Backward search is bound by the NUMBER of dependent random HBM reads (one per wavelet-tree
+// level), not by their size.  The paired layout answers TWO levels from one block: a block of an
+// even-depth node X ("super node") carries kPairedSlicePos positions of X per 32-byte slice and,
+// for the same positions, the bits those positions contribute to X's two children:
+//
+//   slice s (8 words):  h0 = ones of X before the block
+//                       h1 = s even: ones of child 0's sequence before the bits stored here
+//                            s odd : ones of child 1's sequence before the bits stored here
+//                                    + all ones of the block's children region
+//                       X0..X2  bits [96 s, 96 s + 96) of the block's stretch of X, MSB-first
+//                       R0..R2  bits [96 s, 96 s + 96) of the block's children region
+//   children region (96 * slices bits): child 0's bits for the zeros of the stretch, in order,
+//   from the front; child 1's bits for the ones of the stretch, REVERSED, from the back.  So the
+//   first j bits of either child stored here are a prefix (child 0) or a suffix (child 1) of
+//   the region, and both ranks are single-ended popcounts:
+//       rank1(child 0, j) = h1(even) + ones(region[0, j))
+//       rank1(child 1, j) = h1(odd)  - ones(region[0, RB - j))
+//   A leaf child contributes no bits.  Mark bit-vectors keep the plain one-level blocks.
+constexpr int kPairedSliceWords = 8;
+constexpr int kPairedSlicePos = 96;
+
+struct alignas(16) SuperRec {
+  uint32_t gc[4][2];       // grandchild 2*b1+b2: {first block, kChildLeaf | symbol  or  SuperRec index}
+  uint32_t child_info[2];  // child b1: kChildLeaf | symbol, or 0 when it is an internal node
+  uint32_t pad[2];
+};
+
 struct alignas(16) OccRec {
   int64_t occ_base;  // C[ch] + occurrences of ch before this bucket
   uint32_t leaf;     // wavelet-tree leaf id (1<<len | code) of ch in this bucket, 0 = absent
@@ -60,8 +88,9 @@ struct alignas(16) BucketRec {
 // Device view handed to kernels by value.
 struct DevImage {
   const uint4* blocks = nullptr;        // rank blocks, 8 x uint4 each
-  const NodeRec* nodes = nullptr;
-  const OccRec* occ = nullptr;          // [nbuckets][kAlphaStride]
+  const NodeRec* nodes = nullptr;       // plain layout
+  const SuperRec* supers = nullptr;     // paired-level layout (then nodes == nullptr)
+  const OccRec* occ = nullptr;         // [nbuckets][kAlphaStride]
   const MarkRec* mark = nullptr;        // [nbuckets][kAlphaStride]
   const BucketRec* buckets = nullptr;   // [nbuckets]
   const int64_t* markvals = nullptr;    // sampled SA values
@@ -72,6 +101,7 @@ struct DevImage {
   int32_t bucket_size = 0;
   int32_t bucket_shift = -1;            // log2(bucket_size) when it is a power of two, else -1
   int32_t block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
+  int32_t paired = 0;                        // 1: wavelet blocks use the paired-level layout
 };
 
 }  // namespace fmb

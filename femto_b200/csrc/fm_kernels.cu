@@ -192,6 +192,121 @@ __device__ __forceinline__ int64_t occ_descend(const DevImage& im, bool active, 
   return occ_base + static_cast<int64_t>(leaf ? idx1 : 0u);
 }
 
+// ---- paired-level blocks (fm_image.hpp): a lane owns SPL = BW/8/LPQ whole 32-byte slices ----------
+constexpr int kPairedX = 2;  // first X word of a slice
+constexpr int kPairedR = 5;  // first children-region word of a slice
+
+template <int BW>
+__device__ __forceinline__ void paired_split(uint32_t p, uint32_t& k, uint32_t& off) {
+  constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
+  k = p / B;
+  off = p - k * B;
+}
+
+// ones among the first n bits of the block's X stretch (FIRST = kPairedX) or children region
+// (FIRST = kPairedR) that this lane holds
+template <int LPQ, int BW, int FIRST>
+__device__ __forceinline__ uint32_t paired_count(const BlockWords<LPQ, BW>& b, int n, int sub) {
+  constexpr int SPL = BW / kPairedSliceWords / LPQ;
+  int keep = n - kPairedSlicePos * SPL * sub;
+  uint32_t c = 0;
+#pragma unroll
+  for (int sl = 0; sl < SPL; sl++) {
+#pragma unroll
+    for (int t = 0; t < 3; t++) c += popc_top(b.w[sl * kPairedSliceWords + FIRST + t], keep - 32 * t);
+    keep -= kPairedSlicePos;
+  }
+  return c;
+}
+
+// bit q of the X stretch / children region, fetched from the lane that holds it
+template <int LPQ, int BW, int FIRST>
+__device__ __forceinline__ uint32_t paired_bit(const BlockWords<LPQ, BW>& b, uint32_t q) {
+  constexpr int SPL = BW / kPairedSliceWords / LPQ;
+  const uint32_t gs = q / kPairedSlicePos, r = q - gs * kPairedSlicePos;
+  const int t_sel = static_cast<int>(gs % SPL) * kPairedSliceWords + FIRST + static_cast<int>(r >> 5);
+  uint32_t mine = 0;
+#pragma unroll
+  for (int sl = 0; sl < SPL; sl++)
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int wi = sl * kPairedSliceWords + FIRST + t;
+      mine = (wi == t_sel) ? b.w[wi] : mine;
+    }
+  const uint32_t word = LPQ == 1 ? mine : __shfl_sync(kFull, mine, gs / SPL, LPQ);
+  return (word >> (31 - (r & 31))) & 1u;
+}
+
+// header word h1 of child b1: slice b1's second word
+template <int LPQ, int BW>
+__device__ __forceinline__ uint32_t paired_h1(const BlockWords<LPQ, BW>& b, uint32_t b1) {
+  constexpr int SPL = BW / kPairedSliceWords / LPQ;
+  if (SPL >= 2) return group_lane0<LPQ>(b1 ? b.w[kPairedSliceWords + 1] : b.w[1]);
+  return __shfl_sync(kFull, b.w[1], b1, LPQ);
+}
+
+// occ_descend over paired-level blocks: two wavelet-tree levels per block read.
+template <int LPQ, int BW>
+__device__ __forceinline__ int64_t occ_descend_paired(const DevImage& im, bool active, int c, int64_t row, int sub) {
+  constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
+  int64_t occ_base = 0;
+  uint32_t leaf = 0, base = 0, node = 0, idx1 = 0;
+  int L = 0;
+  if (active) {
+    int64_t g;
+    uint32_t rb;
+    split_row(im, row, g, rb);
+    const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+    occ_base = rec_occ_base(rv);
+    leaf = static_cast<uint32_t>(rv.z);
+    if (leaf) {
+      const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+      base = br.x;
+      node = br.y;
+      L = 31 - __clz(leaf);
+      idx1 = rb + 1;
+    }
+  }
+  bool desc = active && leaf != 0;
+  int lvl = 0;
+  while (__any_sync(kFull, desc)) {
+    uint32_t k, off;
+    paired_split<BW>(desc ? idx1 - 1 : 0u, k, off);
+    const bool has2 = lvl + 2 <= L;
+    const uint32_t b1 = desc ? (leaf >> (L - lvl - 1)) & 1u : 0u;
+    const uint32_t b2 = (desc && has2) ? (leaf >> (L - lvl - 2)) & 1u : 0u;
+    BlockWords<LPQ, BW> w;
+    w.clear();
+    if (desc) w.load(im.blocks, base + k, sub);
+    uint2 gc = make_uint2(0, 0);
+    if (desc && lvl + 2 < L) gc = __ldg(reinterpret_cast<const uint2*>(im.supers[node].gc[2 * b1 + b2]));
+    const uint32_t cx = group_sum<LPQ>(paired_count<LPQ, BW, kPairedX>(w, static_cast<int>(off) + 1, sub));
+    const uint32_t ones1 = w.w[0] + cx;
+    const uint32_t i1 = b1 ? ones1 : idx1 - ones1;        // index -= occs[!bit]  (wtree.c:1109)
+    const uint32_t j = b1 ? cx : off + 1 - cx;            // of the child's first i1 bits, those stored here
+    const uint32_t hi = b1 ? B - j : j;
+    const uint32_t cr = group_sum<LPQ>(paired_count<LPQ, BW, kPairedR>(w, static_cast<int>(hi), sub));
+    const uint32_t h1 = paired_h1<LPQ, BW>(w, b1);
+    const uint32_t ones2 = b1 ? h1 - cr : h1 + cr;
+    const uint32_t i2 = b2 ? ones2 : i1 - ones2;
+    lvl += 2;
+    if (desc) {
+      idx1 = has2 ? i2 : i1;
+      if (i1 == 0) idx1 = 0;
+      desc = idx1 != 0 && lvl < L;
+      base = gc.x;
+      node = gc.y;
+    }
+  }
+  return occ_base + static_cast<int64_t>(leaf ? idx1 : 0u);
+}
+
+template <int LPQ, int BW, bool PAIRED>
+__device__ __forceinline__ int64_t occ_any(const DevImage& im, bool active, int c, int64_t row, int sub) {
+  if constexpr (PAIRED) return occ_descend_paired<LPQ, BW>(im, active, c, row, sub);
+  else return occ_descend<LPQ, BW, false>(im, active, c, row, sub);
+}
+
 // Shared by both count schedules: retire a finished pattern, pull the next one from the queue.
 // "first > last || i == 0" ends the reference's while loop (server.c:832-841).
 struct PatternState {
@@ -302,7 +417,7 @@ __global__ void __launch_bounds__(kThreads) count_pair_kernel(const DevImage im,
 
 // ---------------------------------------------------------------------------------------------
 // count, "sync" schedule: one group of LPQ lanes per pattern advances both ranks of a step.
-template <int LPQ, int BW, int MINB, bool STATS>
+template <int LPQ, int BW, int MINB, bool STATS, bool PAIRED = false>
 __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
                                                                      unsigned long long* __restrict__ work,
                                                                      unsigned long long* __restrict__ stats) {
@@ -385,8 +500,62 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
     const bool jobA = actA, jobB = actB;
     const bool finish = stepping && !cross_pending;
 
-    // ---- descend: one level per iteration for every group
+    // ---- descend: one level (two with paired-level blocks) per iteration for every group
     int lvl = 0;
+    if constexpr (PAIRED) {
+      constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
+      while (__any_sync(kFull, actA || actB)) {
+        const bool any = actA || actB;
+        uint32_t kA, kB, offA, offB;
+        paired_split<BW>(actA ? idxA - 1 : 0u, kA, offA);
+        paired_split<BW>(actB ? idxB - 1 : 0u, kB, offB);
+        const bool two = actA && actB && kA != kB;
+        const bool has2 = lvl + 2 <= L;
+        const uint32_t b1 = any ? (leaf >> (L - lvl - 1)) & 1u : 0u;
+        const uint32_t b2 = (any && has2) ? (leaf >> (L - lvl - 2)) & 1u : 0u;
+        BlockWords<LPQ, BW> p, q;
+        p.clear();
+        q.clear();
+        if (any) {
+          p.load(im.blocks, base + (actA ? kA : kB), sub);
+          q.load(im.blocks, base + (actB ? kB : kA), sub);
+        }
+        uint2 gc = make_uint2(0, 0);
+        if (any && lvl + 2 < L) gc = __ldg(reinterpret_cast<const uint2*>(im.supers[node].gc[2 * b1 + b2]));
+        // level one: ranks in the super node
+        const uint32_t px = group_sum<LPQ>(paired_count<LPQ, BW, kPairedX>(p, static_cast<int>(offA) + 1, sub) |
+                                           (paired_count<LPQ, BW, kPairedX>(q, static_cast<int>(offB) + 1, sub) << 16));
+        const uint32_t cxA = px & 0xffffu, cxB = px >> 16;
+        const uint32_t onesA = p.w[0] + cxA, onesB = q.w[0] + cxB;
+        const uint32_t i1A = b1 ? onesA : idxA - onesA;  // wtree.c:1109-1110
+        const uint32_t i1B = b1 ? onesB : idxB - onesB;
+        // level two: ranks in child b1 over the bits stored in the same block
+        const uint32_t jA = b1 ? cxA : offA + 1 - cxA, jB = b1 ? cxB : offB + 1 - cxB;
+        const uint32_t hiA = b1 ? B - jA : jA, hiB = b1 ? B - jB : jB;
+        const uint32_t pr = group_sum<LPQ>(paired_count<LPQ, BW, kPairedR>(p, static_cast<int>(hiA), sub) |
+                                           (paired_count<LPQ, BW, kPairedR>(q, static_cast<int>(hiB), sub) << 16));
+        const uint32_t h1A = paired_h1<LPQ, BW>(p, b1), h1B = paired_h1<LPQ, BW>(q, b1);
+        const uint32_t o2A = b1 ? h1A - (pr & 0xffffu) : h1A + (pr & 0xffffu);
+        const uint32_t o2B = b1 ? h1B - (pr >> 16) : h1B + (pr >> 16);
+        if (STATS && any && sub == 0) {
+          n_blocks += two ? 2 : 1;
+          n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
+        }
+        lvl += 2;
+        if (any) {
+          if (actA) {
+            idxA = (i1A == 0) ? 0u : (!has2 ? i1A : (b2 ? o2A : i1A - o2A));
+            actA = idxA != 0 && lvl < L;
+          }
+          if (actB) {
+            idxB = (i1B == 0) ? 0u : (!has2 ? i1B : (b2 ? o2B : i1B - o2B));
+            actB = idxB != 0 && lvl < L;
+          }
+          base = gc.x;
+          node = gc.y;
+        }
+      }
+    } else
     while (__any_sync(kFull, actA || actB)) {
       const bool any = actA || actB;
       const uint32_t pA = actA ? idxA - 1 : 0u;
@@ -429,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, int BW, int MODE>
+template <int LPQ, int BW, int MODE, bool PAIRED = false>
 __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const WalkArgs a,
                                                          unsigned long long* __restrict__ work) {
   constexpr uint32_t BITS = (BW - 1) * 32;
@@ -485,6 +654,53 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
       idx1 = rb + 1;
     }
     bool desc = act;
+    if constexpr (PAIRED) {
+      constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
+      while (__any_sync(kFull, desc)) {
+        uint32_t k, off;
+        paired_split<BW>(desc ? idx1 - 1 : 0u, k, off);
+        BlockWords<LPQ, BW> w;
+        w.clear();
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        uint2 ci = make_uint2(0, 0);
+        if (desc) {
+          w.load(im.blocks, base + k, sub);
+          const uint4* rec = reinterpret_cast<const uint4*>(im.supers + node);
+          r0 = __ldg(rec);                                          // grandchildren 0, 1
+          r1 = __ldg(rec + 1);                                      // grandchildren 2, 3
+          ci = __ldg(reinterpret_cast<const uint2*>(rec + 2));      // child_info
+        }
+        const uint32_t cx = group_sum<LPQ>(paired_count<LPQ, BW, kPairedX>(w, static_cast<int>(off) + 1, sub));
+        const uint32_t bit1 = paired_bit<LPQ, BW, kPairedX>(w, off);
+        const uint32_t ones1 = w.w[0] + cx;
+        const uint32_t i1 = bit1 ? ones1 : idx1 - ones1;
+        const uint32_t j = max(bit1 ? cx : off + 1 - cx, 1u);  // >= 1: the position itself is one of them
+        const uint32_t rp = bit1 ? B - j : j - 1;              // region bit of the child at index i1-1
+        const uint32_t cr = group_sum<LPQ>(paired_count<LPQ, BW, kPairedR>(w, static_cast<int>(bit1 ? B - j : j), sub));
+        const uint32_t bit2 = paired_bit<LPQ, BW, kPairedR>(w, rp);
+        const uint32_t h1 = paired_h1<LPQ, BW>(w, bit1);
+        const uint32_t ones2 = bit1 ? h1 - cr : h1 + cr;
+        if (desc) {
+          const uint32_t info1 = bit1 ? ci.y : ci.x;
+          if (info1 & kChildLeaf) {
+            idx1 = i1;
+            ch = info1 & 0xffffu;
+            desc = false;
+          } else {
+            idx1 = bit2 ? ones2 : i1 - ones2;
+            const uint4 rr = bit1 ? r1 : r0;
+            const uint32_t gbase = bit2 ? rr.z : rr.x, ginfo = bit2 ? rr.w : rr.y;
+            if (ginfo & kChildLeaf) {
+              ch = ginfo & 0xffffu;
+              desc = false;
+            } else {
+              base = gbase;
+              node = ginfo;
+            }
+          }
+        }
+      }
+    } else
     while (__any_sync(kFull, desc)) {
       const uint32_t p = desc ? idx1 - 1 : 0u;
       const uint32_t k = p / BITS;
@@ -571,7 +787,7 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, int BW>
+template <int LPQ, int BW, bool PAIRED = false>
 __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const OccArgs a) {
   constexpr int QPW = 32 / LPQ;
   const int lane = threadIdx.x & 31;
@@ -589,14 +805,14 @@ __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const 
       row = a.rows[item];
       q = c < kAlphaDev && row >= im.first_row && row < im.end_row;
     }
-    const int64_t r = occ_descend<LPQ, BW>(im, q, c, row, sub);
+    const int64_t r = occ_any<LPQ, BW, PAIRED>(im, q, c, row, sub);
     if (item < a.n && sub == 0) a.out[item] = q ? r : -1;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Range-sharded count: advance pattern states while the BWT rows they need are resident here.
-template <int LPQ, int BW>
+template <int LPQ, int BW, bool PAIRED = false>
 __global__ void __launch_bounds__(kThreads) count_shard_kernel(const DevImage im, const ShardArgs a) {
   constexpr int QPW = 32 / LPQ;
   const int lane = threadIdx.x & 31;
@@ -655,7 +871,7 @@ __global__ void __launch_bounds__(kThreads) count_shard_kernel(const DevImage im
         }
       }
       if (!__any_sync(kFull, running)) break;
-      const int64_t r = occ_descend<LPQ, BW>(im, q, c, row, sub);
+      const int64_t r = occ_any<LPQ, BW, PAIRED>(im, q, c, row, sub);
       if (q) {
         if (phase == 0) { obA = r; phase = 1; }
         else { f = obA; l = r - 1; i--; phase = 0; }
@@ -693,7 +909,7 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
   if (a.npats <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  const int code = im.block_words * 10000 + sched;
+  const int code = (im.paired ? 1000000 : 0) + im.block_words * 10000 + sched;
 #define FM_LAUNCH(KERNEL, LANES_PER_PATTERN)                                                             \
   do {                                                                                                   \
     static const int bps = blocks_per_sm(KERNEL);                                                        \
@@ -705,6 +921,11 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     if (d_stats) FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, true>), LANES);                           \
     else FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, false>), LANES);                                  \
     break;
+#define FM_SYNC2(BW, LANES, MINB)                                                                        \
+  case 1000000 + (BW) * 10000 + 1000 + 10 * (LANES) + (MINB):                                            \
+    if (d_stats) FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, true, true>), LANES);                     \
+    else FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, false, true>), LANES);                            \
+    break;
 #define FM_PAIR(BW, LANES)                                                                               \
   case (BW) * 10000 + (LANES):                                                                           \
     if (d_stats) FM_LAUNCH((count_pair_kernel<LANES, BW, true>), 2 * (LANES));                           \
@@ -715,35 +936,40 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     FM_SYNC(32, 8, 5) FM_SYNC(32, 4, 4) FM_SYNC(32, 4, 5) FM_SYNC(32, 2, 3) FM_SYNC(32, 2, 4)
     FM_SYNC(16, 4, 5) FM_SYNC(16, 4, 6) FM_SYNC(16, 2, 4) FM_SYNC(16, 2, 5) FM_SYNC(16, 1, 3) FM_SYNC(16, 1, 4)
     FM_SYNC(8, 2, 5) FM_SYNC(8, 2, 6) FM_SYNC(8, 1, 4) FM_SYNC(8, 1, 5) FM_SYNC(8, 1, 6)
+    FM_SYNC2(32, 4, 4) FM_SYNC2(32, 4, 5) FM_SYNC2(32, 4, 6) FM_SYNC2(32, 2, 3) FM_SYNC2(32, 2, 4) FM_SYNC2(32, 2, 5)
+    FM_SYNC2(32, 1, 2) FM_SYNC2(32, 1, 3) FM_SYNC2(16, 2, 4) FM_SYNC2(16, 2, 5) FM_SYNC2(16, 2, 6)
+    FM_SYNC2(16, 1, 3) FM_SYNC2(16, 1, 4) FM_SYNC2(16, 1, 5)
     default: return cudaErrorInvalidValue;
   }
 #undef FM_SYNC
+#undef FM_SYNC2
 #undef FM_PAIR
 #undef FM_LAUNCH
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();
 }
 
-template <int LPQ, int BW>
+template <int LPQ, int BW, bool PAIRED = false>
 static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work,
                                    int sm_count, cudaStream_t stream) {
   const int gpb = kThreads / LPQ;
   if (mode == kWalkLocate) {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate>);
-    walk_kernel<LPQ, BW, kWalkLocate><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, PAIRED>);
+    walk_kernel<LPQ, BW, kWalkLocate, PAIRED><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else if (mode == kWalkStep) {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkStep>);
-    walk_kernel<LPQ, BW, kWalkStep><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkStep, PAIRED>);
+    walk_kernel<LPQ, BW, kWalkStep, PAIRED><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkExtract>);
-    walk_kernel<LPQ, BW, kWalkExtract><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkExtract, PAIRED>);
+    walk_kernel<LPQ, BW, kWalkExtract, PAIRED><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   }
   return cudaGetLastError();
 }
 
 // lanes per query for the walk / occ kernels: 4 or 8 at 128-byte blocks, 2 or 4 at 64, 1 or 2 at 32
 static int walk_lanes(const DevImage& im, int lpq) {
-  const int max_lanes = im.block_words / 4;  // at least one 128-bit load per lane
+  // at least one 128-bit load per lane; paired-level blocks: whole 32-byte slices per lane
+  const int max_lanes = im.paired ? im.block_words / 8 : im.block_words / 4;
   int lanes = lpq;
   while (lanes > max_lanes) lanes >>= 1;
   if (lanes < max_lanes / 2) lanes = max_lanes / 2;
@@ -755,7 +981,11 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
   if (a.nrows <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  switch (im.block_words * 100 + walk_lanes(im, lpq)) {
+  switch ((im.paired ? 10000 : 0) + im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 13204: e = launch_walk_cfg<4, 32, true>(im, a, mode, d_work, sm_count, stream); break;
+    case 13202: e = launch_walk_cfg<2, 32, true>(im, a, mode, d_work, sm_count, stream); break;
+    case 11602: e = launch_walk_cfg<2, 16, true>(im, a, mode, d_work, sm_count, stream); break;
+    case 11601: e = launch_walk_cfg<1, 16, true>(im, a, mode, d_work, sm_count, stream); break;
     case 3208: e = launch_walk_cfg<8, 32>(im, a, mode, d_work, sm_count, stream); break;
     case 3204: e = launch_walk_cfg<4, 32>(im, a, mode, d_work, sm_count, stream); break;
     case 1604: e = launch_walk_cfg<4, 16>(im, a, mode, d_work, sm_count, stream); break;
@@ -771,12 +1001,17 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
 cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lpq, int sm_count, cudaStream_t stream,
                                int64_t* launch_counter) {
   if (a.n <= 0) return cudaSuccess;
-#define FM_SHARD(LANES, BW)                                                                               \
+#define FM_SHARD(LANES, BW, ...)                                                                          \
   do {                                                                                                    \
-    static const int bps = blocks_per_sm(count_shard_kernel<LANES, BW>);                                  \
-    count_shard_kernel<LANES, BW><<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a); \
+    static const int bps = blocks_per_sm(count_shard_kernel<LANES, BW, ##__VA_ARGS__>);                   \
+    count_shard_kernel<LANES, BW, ##__VA_ARGS__>                                                          \
+        <<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a);               \
   } while (0)
-  switch (im.block_words * 100 + walk_lanes(im, lpq)) {
+  switch ((im.paired ? 10000 : 0) + im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 13204: FM_SHARD(4, 32, true); break;
+    case 13202: FM_SHARD(2, 32, true); break;
+    case 11602: FM_SHARD(2, 16, true); break;
+    case 11601: FM_SHARD(1, 16, true); break;
     case 3208: FM_SHARD(8, 32); break;
     case 3204: FM_SHARD(4, 32); break;
     case 1604: FM_SHARD(4, 16); break;
@@ -793,12 +1028,17 @@ cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lpq, 
 cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* /*d_work*/, int lpq, int sm_count,
                        cudaStream_t stream, int64_t* launch_counter) {
   if (a.n <= 0) return cudaSuccess;
-#define FM_OCC(LANES, BW)                                                                                 \
+#define FM_OCC(LANES, BW, ...)                                                                            \
   do {                                                                                                    \
-    static const int bps = blocks_per_sm(occ_kernel<LANES, BW>);                                          \
-    occ_kernel<LANES, BW><<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a); \
+    static const int bps = blocks_per_sm(occ_kernel<LANES, BW, ##__VA_ARGS__>);                           \
+    occ_kernel<LANES, BW, ##__VA_ARGS__>                                                                  \
+        <<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a);               \
   } while (0)
-  switch (im.block_words * 100 + walk_lanes(im, lpq)) {
+  switch ((im.paired ? 10000 : 0) + im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 13204: FM_OCC(4, 32, true); break;
+    case 13202: FM_OCC(2, 32, true); break;
+    case 11602: FM_OCC(2, 16, true); break;
+    case 11601: FM_OCC(1, 16, true); break;
     case 3208: FM_OCC(8, 32); break;
     case 3204: FM_OCC(4, 32); break;
     case 1604: FM_OCC(4, 16); break;

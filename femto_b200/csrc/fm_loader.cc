@@ -27,10 +27,15 @@ struct BucketPlan {
   std::vector<int64_t> mark_bits;
   std::vector<uint32_t> markarr_offs;
   int64_t n_blocks = 0, n_wtree_blocks = 0;
+  // paired-level layout: internal nodes at even depth own the blocks ("super nodes")
+  std::vector<int32_t> super_of;    // per internal node: its index among the bucket's super nodes, or -1
+  int64_t n_records = 0;            // NodeRec (plain) or SuperRec (paired) entries of this bucket
   // assigned bases
   int64_t node_base = 0, block_base = 0, markval_base = 0;
   int64_t n_markvals = 0;  // total ones over the bucket's mark tables
 };
+
+inline int node_depth(uint32_t heap_id) { return 31 - __builtin_clz(heap_id); }
 
 // rank block geometry chosen at load time: bw 32-bit words per block, (bw-1)*32 payload bits
 thread_local int t_block_words = kDefaultBlockWords;
@@ -39,7 +44,14 @@ inline int64_t blocks_for_bits(int64_t nbits) {
   return std::max<int64_t>(1, (nbits + bits_per_block() - 1) / bits_per_block());
 }
 
-void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p, int bw) {
+// paired-level layout: a block of a super node X holds 96 positions of X per 32-byte slice and the
+// same positions' bits of X's two children (see fm_image.hpp)
+inline int64_t paired_positions(int bw) { return int64_t(kPairedSlicePos) * (bw / kPairedSliceWords); }
+inline int64_t paired_blocks_for_bits(int64_t nbits, int bw) {
+  return std::max<int64_t>(1, (nbits + paired_positions(bw) - 1) / paired_positions(bw));
+}
+
+void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p, int bw, bool paired) {
   t_block_words = bw;
   parse_bucket_tables(blk, bh, bpb, bucket, &p->tab);
   const BucketTables& t = p->tab;
@@ -63,9 +75,21 @@ void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, Bu
       nbits = bseq_length(open_bseq(wt + p->node_offs[k], wt_avail - p->node_offs[k]));
     }
     p->node_bits[k] = nbits;
-    p->n_blocks += blocks_for_bits(nbits);
+    if (!paired) p->n_blocks += blocks_for_bits(nbits);
   }
   if (p->node_ids[0] != 1) throw Error(FM_ERR_FORMAT, "wavelet tree has no root");
+  p->n_records = int64_t(n_int);
+  if (paired) {
+    p->super_of.assign(n_int, -1);
+    int32_t ns = 0;
+    for (uint32_t k = 0; k < n_int; k++) {
+      if (node_depth(p->node_ids[k]) % 2 == 0) {
+        p->super_of[k] = ns++;
+        p->n_blocks += paired_blocks_for_bits(p->node_bits[k], bw);
+      }
+    }
+    p->n_records = ns;
+  }
   p->n_wtree_blocks = p->n_blocks;
   // mark tables / arrays: u32 offsets per in-use symbol, relative to the section start
   const int n = t.n_in_use;
@@ -124,6 +148,149 @@ struct Scratch {
   }
 };
 
+// ---- paired-level layout ------------------------------------------------------------------
+// copy `len` bits from src (MSB-first words) starting at bit src_off to dst starting at dst_off;
+// dst bits must be zero beforehand
+void copy_bits(uint32_t* dst, int64_t dst_off, const uint32_t* src, int64_t src_off, int64_t len) {
+  while (len > 0) {
+    const int so = int(src_off & 31), dof = int(dst_off & 31);
+    const int take = int(std::min<int64_t>(len, std::min(32 - so, 32 - dof)));
+    const uint32_t chunk = (src[src_off >> 5] << so) >> (32 - take);  // top-aligned -> low `take` bits
+    dst[dst_off >> 5] |= chunk << (32 - dof - take);
+    src_off += take;
+    dst_off += take;
+    len -= take;
+  }
+}
+
+int64_t count_ones(const uint32_t* bits, int64_t from, int64_t to) {  // ones in [from, to)
+  int64_t c = 0;
+  while (from < to) {
+    const int o = int(from & 31);
+    const int take = int(std::min<int64_t>(to - from, 32 - o));
+    const uint32_t chunk = (bits[from >> 5] << o) >> (32 - take);
+    c += __builtin_popcount(chunk);
+    from += take;
+  }
+  return c;
+}
+
+// Builds the blocks and SuperRecs of one bucket's wavelet tree; returns the block cursor after them.
+int64_t fill_wavelet_paired(const Blob& blk, const BucketPlan& p, HostImage* im, int64_t local_bucket,
+                            const std::unordered_map<uint32_t, uint32_t>& leaf_sym) {
+  const BucketTables& t = p.tab;
+  const int bw = im->block_words;
+  const int64_t B = paired_positions(bw);
+  const int slices = bw / kPairedSliceWords;
+  const int stretch_words = 3 * slices;  // words of X payload per block; the children region has as many
+  uint32_t xs[12], rs[12];
+  const uint8_t* wt = blk.at(t.off_wtree, 4);
+  const size_t wt_avail = size_t(t.off_marktab) - size_t(t.off_wtree);
+  const size_t n_int = p.node_ids.size();
+  auto index_of = [&](uint32_t id) -> int {
+    auto it = std::lower_bound(p.node_ids.begin(), p.node_ids.end(), id);
+    return (it != p.node_ids.end() && *it == id) ? int(it - p.node_ids.begin()) : -1;
+  };
+  auto expand = [&](int k, std::vector<uint32_t>& out) {
+    const int64_t nbits = p.node_bits[size_t(k)];
+    out.assign(size_t((nbits + 31) / 32) + 2, 0u);
+    if (nbits > 0) {
+      const int64_t got = bseq_expand(open_bseq(wt + p.node_offs[size_t(k)], wt_avail - p.node_offs[size_t(k)]), out.data(), nbits);
+      if (got != nbits) throw Error(FM_ERR_FORMAT, "bseq expansion length mismatch");
+    }
+  };
+  // block base of every super node
+  std::vector<int64_t> base(n_int, 0);
+  int64_t cursor = p.block_base;
+  for (size_t k = 0; k < n_int; k++) {
+    if (p.super_of[k] < 0) continue;
+    base[k] = cursor;
+    cursor += paired_blocks_for_bits(p.node_bits[k], bw);
+  }
+  std::vector<uint32_t> X, C0, C1;
+  for (size_t k = 0; k < n_int; k++) {
+    if (p.super_of[k] < 0) continue;
+    const uint32_t id = p.node_ids[k];
+    const int c0 = index_of(2 * id), c1 = index_of(2 * id + 1);
+    const int64_t n = p.node_bits[k];
+    expand(int(k), X);
+    const int64_t onesX = count_ones(X.data(), 0, n);
+    if (c0 >= 0) { expand(c0, C0); if (p.node_bits[size_t(c0)] != n - onesX) throw Error(FM_ERR_FORMAT, "wavelet child 0 length mismatch"); }
+    if (c1 >= 0) { expand(c1, C1); if (p.node_bits[size_t(c1)] != onesX) throw Error(FM_ERR_FORMAT, "wavelet child 1 length mismatch"); }
+    // blocks
+    const int64_t nb = paired_blocks_for_bits(n, bw);
+    int64_t ones_before = 0, c0_ones_before = 0, c1_ones_before = 0;
+    for (int64_t j = 0; j < nb; j++) {
+      uint32_t* w = im->rank_words + (base[k] + j) * bw;
+      const int64_t p0 = j * B, p1 = std::min<int64_t>(n, p0 + B), len = p1 - p0;
+      const int64_t ones = count_ones(X.data(), p0, p1), z = len - ones;
+      const int64_t zeros_before = p0 - ones_before;
+      std::fill(xs, xs + stretch_words, 0u);
+      std::fill(rs, rs + stretch_words, 0u);
+      copy_bits(xs, 0, X.data(), p0, len);
+      int64_t c0_ones = 0, c1_ones = 0;
+      if (c0 >= 0) {  // child 0: the stretch's zeros, in order, from the front of the region
+        copy_bits(rs, 0, C0.data(), zeros_before, z);
+        c0_ones = count_ones(C0.data(), zeros_before, zeros_before + z);
+      }
+      if (c1 >= 0) {  // child 1: the stretch's ones, reversed, from the back
+        for (int64_t i = 0; i < ones; i++) {
+          const int64_t src = ones_before + i;
+          if ((C1[size_t(src >> 5)] >> (31 - (src & 31))) & 1u) {
+            const int64_t dst = B - 1 - i;
+            rs[dst >> 5] |= 1u << (31 - (dst & 31));
+            c1_ones++;
+          }
+        }
+      }
+      for (int s = 0; s < slices; s++) {
+        uint32_t* sw = w + s * kPairedSliceWords;
+        sw[0] = uint32_t(ones_before);
+        sw[1] = (s & 1) ? uint32_t(c1_ones_before + c0_ones + c1_ones) : uint32_t(c0_ones_before);
+        for (int t = 0; t < 3; t++) {
+          sw[2 + t] = xs[3 * s + t];
+          sw[5 + t] = rs[3 * s + t];
+        }
+      }
+      c0_ones_before += c0_ones;
+      c1_ones_before += c1_ones;
+      ones_before += ones;
+    }
+    // record: children and grandchildren
+    SuperRec& sr = im->supers[size_t(p.node_base) + size_t(p.super_of[k])];
+    for (uint32_t b1 = 0; b1 < 2; b1++) {
+      const uint32_t child = 2 * id + b1;
+      const int ci = b1 ? c1 : c0;
+      if (ci < 0) {
+        auto ls = leaf_sym.find(child);
+        sr.child_info[b1] = kChildLeaf | (ls == leaf_sym.end() ? kEndOfBucketSym : ls->second);
+      } else {
+        sr.child_info[b1] = 0;
+      }
+      for (uint32_t b2 = 0; b2 < 2; b2++) {
+        const uint32_t gc = 2 * child + b2;
+        const uint32_t slot = b1 * 2 + b2;
+        sr.gc[slot][0] = 0;
+        sr.gc[slot][1] = kChildLeaf | kEndOfBucketSym;
+        if (ci < 0) continue;  // the child is a leaf: no grandchildren
+        const int gi = index_of(gc);
+        if (gi >= 0) {
+          sr.gc[slot][0] = uint32_t(base[size_t(gi)]);
+          sr.gc[slot][1] = uint32_t(p.node_base + p.super_of[size_t(gi)]);
+        } else {
+          auto ls = leaf_sym.find(gc);
+          sr.gc[slot][1] = kChildLeaf | (ls == leaf_sym.end() ? kEndOfBucketSym : ls->second);
+        }
+      }
+    }
+    sr.pad[0] = sr.pad[1] = 0;
+  }
+  BucketRec& br = im->buckets[size_t(local_bucket)];
+  br.root_base = uint32_t(base[0]);
+  br.root_node = uint32_t(p.node_base + p.super_of[0]);
+  return cursor;
+}
+
 void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh, int64_t blk_num, int bucket,
                  const BucketPlan& p, HostImage* im, int64_t local_bucket, Scratch* scratch,
                  std::atomic<int64_t>* markval_used) {
@@ -143,7 +310,8 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   // rank blocks of every internal node, in directory order
   std::vector<int64_t> node_block(n_int);
   int64_t cursor = p.block_base;
-  for (size_t k = 0; k < n_int; k++) {
+  if (im->paired) cursor = fill_wavelet_paired(blk, p, im, local_bucket, leaf_sym);
+  for (size_t k = 0; k < n_int && !im->paired; k++) {
     node_block[k] = cursor;
     const int64_t nbits = p.node_bits[k];
     if (nbits > 0) {
@@ -156,7 +324,7 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   }
 
   // node records
-  for (size_t k = 0; k < n_int; k++) {
+  for (size_t k = 0; k < n_int && !im->paired; k++) {
     NodeRec& nr = im->nodes[size_t(p.node_base) + k];
     for (uint32_t b = 0; b < 2; b++) {
       const uint32_t child = p.node_ids[k] * 2 + b;
@@ -174,8 +342,10 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   }
 
   BucketRec& br = im->buckets[size_t(local_bucket)];
-  br.root_base = uint32_t(node_block[0]);
-  br.root_node = uint32_t(p.node_base);
+  if (!im->paired) {
+    br.root_base = uint32_t(node_block[0]);
+    br.root_node = uint32_t(p.node_base);
+  }
   br.markval_base = uint64_t(p.markval_base);
 
   // per-symbol records
@@ -286,6 +456,22 @@ int default_block_words() {
   return v;
 }
 
+namespace {
+std::atomic<int> g_default_paired{-1};
+}
+
+bool default_paired_levels() {
+  int v = g_default_paired.load();
+  if (v < 0) {
+    const char* e = std::getenv("FEMTO_B200_PAIRED_LEVELS");
+    v = (e && std::atoi(e) != 0) ? 1 : 0;
+    g_default_paired.store(v);
+  }
+  return v != 0;
+}
+
+void set_default_paired_levels(bool on) { g_default_paired.store(on ? 1 : 0); }
+
 bool set_default_block_words(int words) {
   if (words != 8 && words != 16 && words != 32) return false;
   g_default_block_words.store(words);
@@ -305,11 +491,37 @@ HostRank host_rank(const uint32_t* rank_words, int block_words, uint32_t base_bl
   return HostRank{ones, (last >> (31 - rem)) & 1u};
 }
 
+HostPairedRank host_paired_rank(const uint32_t* rank_words, int block_words, uint32_t base_block, uint32_t index1,
+                                int follow) {
+  const uint32_t B = uint32_t(paired_positions(block_words));
+  const uint32_t p = index1 - 1, k = p / B, off = p % B;
+  const uint32_t* w = rank_words + (size_t(base_block) + k) * size_t(block_words);
+  auto xbit = [&](uint32_t q) { return (w[8 * (q / 96) + 2 + (q % 96) / 32] >> (31 - (q & 31))) & 1u; };
+  auto rbit = [&](uint32_t q) { return (w[8 * (q / 96) + 5 + (q % 96) / 32] >> (31 - (q & 31))) & 1u; };
+  HostPairedRank r{};
+  uint32_t cnt = 0;
+  for (uint32_t q = 0; q <= off; q++) cnt += xbit(q);
+  r.bit1 = xbit(off);
+  const uint32_t b1 = follow < 0 ? r.bit1 : uint32_t(follow);
+  const uint32_t ones1 = w[0] + cnt;
+  r.index1 = b1 ? ones1 : index1 - ones1;
+  const uint32_t j = b1 ? cnt : off + 1 - cnt;  // of the child's first index1 bits, those stored in this block
+  const uint32_t hi = b1 ? B - j : j;
+  uint32_t rc = 0;
+  for (uint32_t q = 0; q < hi; q++) rc += rbit(q);
+  const uint32_t h1 = w[8 * b1 + 1];
+  r.ones2 = b1 ? h1 - rc : h1 + rc;
+  r.bit2 = j == 0 ? 0u : rbit(b1 ? B - j : j - 1);
+  return r;
+}
+
 std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
-                                            int block_words) {
+                                            int block_words, int paired_levels) {
   if (nshards < 1 || shard < 0 || shard >= nshards) throw Error(FM_ERR_PARAM, "bad shard");
   if (block_words == 0) block_words = default_block_words();
   if (block_words != 8 && block_words != 16 && block_words != 32) throw Error(FM_ERR_PARAM, "rank block must be 32, 64 or 128 bytes");
+  const bool paired = paired_levels < 0 ? default_paired_levels() : paired_levels != 0;
+  if (paired && block_words < 16) throw Error(FM_ERR_PARAM, "the paired-level layout needs 64- or 128-byte blocks");
   if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
   auto files = IndexFiles::open(path);
   const BlockHeader& h = files->header();
@@ -317,6 +529,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
   std::unique_ptr<HostImage> im(new HostImage());
   im->hdr = h;
   im->block_words = block_words;
+  im->paired = paired;
   const int kBlockWords = block_words;
 
   // data blocks of this shard: b with b*nshards/nblocks == shard
@@ -371,7 +584,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
     for (int k = 0; k < bhs[lb].num_buckets; k++) where[size_t(bucket0[lb] + k)] = {int32_t(lb), int32_t(k)};
   parallel_for(nb, nthreads, [&](int64_t g, int) {
     const auto [lb, k] = where[size_t(g)];
-    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)], block_words);
+    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)], block_words, paired);
   });
 
   int64_t nodes = 0, blocks = 0, vals = 0, wt_blocks = 0;
@@ -380,7 +593,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
     p.node_base = nodes;
     p.block_base = blocks;
     p.markval_base = vals;
-    nodes += int64_t(p.node_ids.size());
+    nodes += p.n_records;
     blocks += p.n_blocks;
     wt_blocks += p.n_wtree_blocks;
     vals += p.n_markvals;
@@ -393,7 +606,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
   im->n_wtree_blocks = wt_blocks;
   im->rank_words = static_cast<uint32_t*>(std::calloc(size_t(std::max<int64_t>(blocks, 1)) * kBlockWords, 4));
   if (!im->rank_words) throw Error(FM_ERR_MEM, "out of host memory for the rank image");
-  im->nodes.resize(size_t(nodes));
+  if (paired) im->supers.resize(size_t(nodes)); else im->nodes.resize(size_t(nodes));
   im->occ.resize(size_t(nb) * kAlphaStride);
   im->mark.resize(size_t(nb) * kAlphaStride);
   im->buckets.resize(size_t(nb));

@@ -20,10 +20,12 @@ struct HostImage {
   int max_code_len = 0;
   // tables
   int block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
+  bool paired = false;                   // paired-level wavelet blocks (fm_image.hpp)
   uint32_t* rank_words = nullptr;   // n_rank_blocks * block_words words (calloc'ed)
   int64_t n_rank_blocks = 0;
   int64_t n_wtree_blocks = 0;       // of which wavelet-tree payload (the rest are mark bit-vectors)
-  std::vector<NodeRec> nodes;
+  std::vector<NodeRec> nodes;       // plain layout
+  std::vector<SuperRec> supers;     // paired-level layout
   std::vector<OccRec> occ;
   std::vector<MarkRec> mark;
   std::vector<BucketRec> buckets;
@@ -39,14 +41,30 @@ struct HostImage {
 // shard/nshards select data blocks b with b*nshards/nblocks == shard (all blocks when nshards==1).
 // block_words: 32, 16 or 8 (128/64/32-byte rank blocks); 0 = the process default (env
 // FEMTO_B200_BLOCK_BYTES or set_default_block_words, else 128-byte blocks).
+// paired_levels: 1 = paired-level wavelet blocks, 0 = one level per block, -1 = process default
+// (env FEMTO_B200_PAIRED_LEVELS or set_default_paired_levels).
 std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
-                                            int block_words = 0);
+                                            int block_words = 0, int paired_levels = -1);
 int default_block_words();
 bool set_default_block_words(int words);
+bool default_paired_levels();
+void set_default_paired_levels(bool on);
 
 // Host-side rank over the image (used by the loader's self-check and by unit tests of the
 // image layout; NOT a query fallback -- the C ABI never calls it).
 struct HostRank { uint32_t ones; uint32_t bit; };
 HostRank host_rank(const uint32_t* rank_words, int block_words, uint32_t base_block, uint32_t index1);
+
+// Two levels of a paired-level block (fm_image.hpp): level one as host_rank, taking child `follow`
+// (0/1) or the child named by the bit at the position (follow < 0); then the rank of that child over
+// its first `index1` bits.
+struct HostPairedRank {
+  uint32_t bit1;    // bit of the super node at the position
+  uint32_t index1;  // 1-based index in the chosen child (0: none of its bits precede)
+  uint32_t ones2;   // ones among the child's first index1 bits (internal child only)
+  uint32_t bit2;    // the child's bit at index1-1 (internal child, index1 > 0)
+};
+HostPairedRank host_paired_rank(const uint32_t* rank_words, int block_words, uint32_t base_block, uint32_t index1,
+                                int follow);
 
 }  // namespace fmb

@@ -66,7 +66,7 @@ typedef struct {
   int32_t device;            /* CUDA device ordinal */
   int32_t max_code_len;      /* deepest wavelet-tree leaf over all resident buckets */
   int32_t rank_block_size;   /* bytes per rank block of the HBM image: 128, 64 or 32 */
-  int32_t reserved;
+  int32_t paired_levels;     /* 1: wavelet-tree blocks answer two levels per read (fm_set_default_paired_levels) */
 } fm_info_t;
 
 /* --------------------------------------------------------------------------
@@ -188,8 +188,9 @@ int64_t fm_kernel_launches(const fm_index_t* ix);
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
                    const int64_t* offs, uint64_t* stats4);
 
-/* Tuning knob: lanes cooperating on one rank query in the locate/extract/occ kernels (4 or 8;
- * default 4). */
+/* Tuning knob: lanes cooperating on one rank query in the locate/extract/occ kernels (1, 2, 4 or
+ * 8; default 4).  The value is clamped to what the image's block layout offers: 4 or 8 lanes on
+ * 128-byte blocks, 2 or 4 on 64-byte, 1 or 2 on 32-byte; paired-level blocks half of that. */
 int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
 
 /* Tuning knob of the count kernel.  merged != 0 (default): one group of `lanes` lanes per pattern
@@ -201,6 +202,14 @@ int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes);
 /* Rank block size (bytes: 128, 64 or 32) of the HBM image built by subsequent fm_open calls.
  * Initial value: environment FEMTO_B200_BLOCK_BYTES, else 128. */
 int fm_set_default_block_bytes(int bytes);
+
+/* Wavelet-tree block layout of the HBM image built by subsequent fm_open calls.  on != 0: a block
+ * holds a stretch of an even-depth node together with the matching bits of both children, so one
+ * 128- or 64-byte read answers two wavelet-tree levels (half the dependent HBM reads of the
+ * one-level layout, about 1.3x its size; needs 128- or 64-byte blocks).  on == 0: one level per
+ * block.  With the paired layout the count kernel always uses the merged schedule.
+ * Initial value: environment FEMTO_B200_PAIRED_LEVELS, else 0. */
+int fm_set_default_paired_levels(int on);
 
 /* --------------------------------------------------------------------------
  * Index construction (host side; "next" row f-1 of the scope table).  Emits an

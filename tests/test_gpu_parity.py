@@ -320,3 +320,75 @@ def test_properties_at_scale(tmp_path):
         for d in range(2):
             got = bytes((ix.extract(d) - 5).astype(np.uint8))
             assert got == docs[d]
+
+
+# ---- paired-level wavelet blocks (two levels per HBM read; fm_image.hpp) ----------------------------
+@pytest.fixture(scope="module")
+def gpu_indexes_paired(built_indexes):
+    from femto_b200 import _lib
+    lib = _lib.load()
+    opened = {}
+    for bb in (128, 64):
+        assert lib.fm_set_default_block_bytes(bb) == 0
+        assert lib.fm_set_default_paired_levels(1) == 0
+        try:
+            for name, path in built_indexes.items():
+                opened[(name, bb)] = fb.Index(path, device=0)
+                assert opened[(name, bb)].info.rank_block_size == bb
+                assert opened[(name, bb)].info.paired_levels == 1
+        finally:
+            lib.fm_set_default_block_bytes(128)
+            lib.fm_set_default_paired_levels(0)
+    yield opened
+    for ix in opened.values():
+        ix.close()
+
+
+@pytest.mark.parametrize("cfg", [(128, 4), (128, 2), (128, 1), (64, 2), (64, 1)])
+@pytest.mark.parametrize("name", ALL)
+def test_count_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpora):
+    bb, lanes = cfg
+    docs, _ = corpora[name]
+    ix = gpu_indexes_paired[(name, bb)]
+    ix.set_count_schedule(1, lanes)
+    pats = corpus.sample_patterns(docs, 1500, [1, 2, 3, 4, 5, 6, 8, 12, 16, 24, 32, 64], seed=35) + edge_patterns()
+    with Oracle(built_indexes[name]) as o:
+        of, ol = o.count(pats)
+    f, l = ix.count(pats)
+    assert (f == of).all() and (l == ol).all()
+    plen, flat, offs = fb.flatten_patterns(pats)
+    f2, l2 = ix.count_flat(plen, flat, offs)
+    assert (f2 == of).all() and (l2 == ol).all()
+
+
+@pytest.mark.parametrize("cfg", [(128, 4), (128, 2), (64, 2), (64, 1)])
+@pytest.mark.parametrize("name", ALL)
+def test_walks_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpora):
+    """occ / back_step / locate / extract over paired-level blocks, every lane configuration."""
+    bb, lanes = cfg
+    docs, _ = corpora[name]
+    ix = gpu_indexes_paired[(name, bb)]
+    ix.set_lanes_per_query(lanes)
+    pats = corpus.sample_patterns(docs, 200, [1, 2, 3, 4, 6, 8, 16], seed=45) + edge_patterns()[1:]
+    with Oracle(built_indexes[name]) as o:
+        n = o.header_info()["total_length"]
+        rng = np.random.default_rng(6)
+        if n <= 500:
+            rows = np.repeat(np.arange(n), 261)
+            chs = np.tile(np.arange(261), n)
+        else:
+            rows = rng.integers(0, n, 5000)
+            chs = rng.integers(0, 261, 5000)
+        got = ix.occ(chs, rows)
+        want = np.array([o.occ(int(c), int(r))[0] for c, r in zip(chs, rows)], dtype=np.int64)
+        assert (got == want).all()
+        srows = np.arange(n) if n <= 3000 else np.concatenate([rng.integers(0, n, 2000), [0, n - 1]])
+        ch, nxt, off = ix.back_step(srows)
+        for i, r in enumerate(srows):
+            assert (int(ch[i]), int(nxt[i]), int(off[i])) == o.back_step(int(r)), r
+        want_loc = o.locate(pats, 50)
+    got_loc = ix.locate(pats, 50)
+    assert all((a == b).all() for a, b in zip(got_loc, want_loc))
+    for d in range(len(docs)):
+        assert bytes((ix.extract(d) - fb.CHARACTER_OFFSET).astype(np.uint8)) == docs[d]
+    ix.set_lanes_per_query(4)
