@@ -404,12 +404,27 @@ def main():
                 "kernel_ms": round(ms_per_step, 4),
                 "rank_blocks_requested": st["block_reads"], "rank_blocks_distinct": st["distinct_block_reads"],
                 "occ_evals": st["occ_evals"], "backward_steps": st["steps"]}
+    layout_key = f"{'paired' if paired else 'plain'}{block_bytes}"
+    roofline["layout"] = layout_key
     traffic_file = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file):  # dram bytes of one launch from the committed ncu --set full capture
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(traffic_file)).get(layout_key, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
+    # The count kernel is a chain of dependent random reads; the rate at which this GPU serves such
+    # reads (measured right here by fm_probe_random_reads with the same access size) is the
+    # ceiling that binds before HBM bandwidth does.
+    try:
+        probe = ix.probe_random_reads(block_bytes, steps=300)
+        ach = st["distinct_block_reads"] / (ms_per_step / 1e3)
+        roofline["random_access"] = {
+            "bytes_per_access": block_bytes, "achieved_gaccess_s": round(ach / 1e9, 2),
+            "peak_gaccess_s": round(probe["accesses_per_s"] / 1e9, 2),
+            "frac": round(ach / probe["accesses_per_s"], 4), "peak_gb_s": round(probe["gb_per_s"], 1),
+            "peak_source": "fm_probe_random_reads: dependent uniform random reads over the same image, all SMs"}
+    except Exception as e:  # noqa: BLE001
+        roofline["random_access"] = {"error": str(e)}
 
     # ---- cpu_baseline + in-run parity: the unmodified reference on a bounded sample ----------
     cpu = None

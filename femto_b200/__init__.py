@@ -142,6 +142,16 @@ class Index:
         return {"block_reads": int(st[0]), "distinct_block_reads": int(st[1]), "occ_evals": int(st[2]),
                 "steps": int(st[3])}
 
+    def probe_random_reads(self, bytes_per_access: int, steps: int = 400) -> dict:
+        """Dependent random reads over the resident rank blocks (fm_probe_random_reads): the
+        access-rate ceiling of this GPU's memory system for the count kernel's access shape."""
+        acc, ms = C.c_int64(), C.c_double()
+        _check(self.lib.fm_probe_random_reads(self.h, bytes_per_access, steps, C.byref(acc), C.byref(ms)),
+               "fm_probe_random_reads")
+        return {"accesses": int(acc.value), "ms": float(ms.value),
+                "accesses_per_s": acc.value / (ms.value / 1e3) if ms.value > 0 else 0.0,
+                "gb_per_s": acc.value * bytes_per_access / (ms.value / 1e3) / 1e9 if ms.value > 0 else 0.0}
+
     def count_device(self, npats: int, d_plen: int, d_flat: int, d_offs: int, d_first: int, d_last: int,
                      stream: int = 0) -> None:
         """Device-pointer form (integers are raw device addresses, e.g. ``tensor.data_ptr()``)."""

@@ -128,12 +128,13 @@ int sync_sched(int block_words, int lanes) {
 }
 
 int paired_sched(int block_words, int lanes) {
-  const int minb = block_words == 32 ? (lanes == 4 ? 5 : lanes == 2 ? 4 : 3) : (lanes == 2 ? 5 : 4);
+  // profiles/r01_paired_level_sweep.md
+  const int minb = block_words == 32 ? (lanes == 4 ? 6 : lanes == 2 ? 4 : 3) : 4;
   return 1000 + 10 * lanes + minb;
 }
 
 int default_count_sched(int block_words, bool paired) {
-  int sched = paired ? paired_sched(block_words, block_words == 32 ? 4 : 2)
+  int sched = paired ? paired_sched(block_words, 2)
                      : sync_sched(block_words, block_words == 32 ? 4 : block_words == 16 ? 2 : 1);
   if (const char* e = std::getenv("FEMTO_B200_COUNT_SCHED")) {  // tuning experiments only
     const int v = std::atoi(e);
@@ -444,12 +445,13 @@ int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
 }
 
 int fm_set_default_block_bytes(int bytes) {
-  if (!set_default_block_words(bytes / 4) || bytes % 4) return fail(FM_ERR_PARAM, "fm_set_default_block_bytes: 32, 64 or 128");
+  if (bytes < 0 || bytes % 4 || !set_default_block_words(bytes / 4))
+    return fail(FM_ERR_PARAM, "fm_set_default_block_bytes: 32, 64, 128 or 0");
   return FM_OK;
 }
 
 int fm_set_default_paired_levels(int on) {
-  set_default_paired_levels(on != 0);
+  set_default_paired_levels(on);
   return FM_OK;
 }
 
@@ -500,6 +502,39 @@ int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
     CK(launch_count(ix->im, a, ix->d_work, ix->count_sched, ix->sm_count, s, &ix->launches, d_stats));
     CK(cudaMemcpyAsync(stats4, d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return FM_OK;
+  });
+}
+
+int fm_probe_random_reads(fm_index_t* ix, int bytes_per_access, int steps, int64_t* accesses, double* ms) {
+  return guarded(ix, "fm_probe_random_reads", [&]() -> int {
+    if (!accesses || !ms || steps <= 0) return fail(FM_ERR_PARAM, "fm_probe_random_reads: bad argument");
+    const uint64_t units = uint64_t(ix->info.rank_block_bytes) / uint64_t(std::max(bytes_per_access, 1));
+    if (units == 0) return fail(FM_ERR_PARAM, "fm_probe_random_reads: image smaller than one access");
+    cudaStream_t s = ix->stream;
+    unsigned long long* d_sink = static_cast<unsigned long long*>(ix->d_out[3].get(64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    cudaError_t le = launch_probe(ix->im.blocks, units, bytes_per_access, std::min(steps, 64), ix->sm_count, s,
+                                  d_sink, accesses);  // warm-up
+    if (le == cudaSuccess) {
+      CK(cudaEventRecord(e0, s));
+      le = launch_probe(ix->im.blocks, units, bytes_per_access, steps, ix->sm_count, s, d_sink, accesses);
+      CK(cudaEventRecord(e1, s));
+    }
+    if (le != cudaSuccess) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      return fail(FM_ERR_PARAM, "fm_probe_random_reads: bytes_per_access must be 32, 64 or 128");
+    }
+    ix->launches += 2;
+    CK(cudaStreamSynchronize(s));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms = double(t);
     return FM_OK;
   });
 }

@@ -1025,6 +1025,59 @@ cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lpq, 
   return cudaGetLastError();
 }
 
+namespace {
+
+// Dependent random reads with the access shape of the query kernels: LPA lanes x 16 bytes per
+// access, the next address of a chain derived from the data just read.
+template <int LPA>
+__global__ void __launch_bounds__(kThreads) probe_kernel(const uint4* __restrict__ base, uint64_t n_units, int steps,
+                                                         unsigned long long* __restrict__ sink) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPA - 1);
+  const uint64_t group = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPA;
+  uint32_t xa = static_cast<uint32_t>(group * 2654435761u + 12345u);
+  uint32_t xb = static_cast<uint32_t>(group * 2246822519u + 977u);
+  for (int s = 0; s < steps; s++) {
+    const uint64_t ua = (static_cast<uint64_t>(xa) * n_units) >> 32;  // uniform in [0, n_units)
+    const uint64_t ub = (static_cast<uint64_t>(xb) * n_units) >> 32;
+    const uint4 va = __ldg(base + ua * LPA + sub);
+    const uint4 vb = __ldg(base + ub * LPA + sub);
+    uint32_t fa = va.x ^ va.y ^ va.z ^ va.w, fb = vb.x ^ vb.y ^ vb.z ^ vb.w;
+#pragma unroll
+    for (int o = LPA / 2; o > 0; o >>= 1) {
+      fa ^= __shfl_xor_sync(kFull, fa, o);
+      fb ^= __shfl_xor_sync(kFull, fb, o);
+    }
+    xa = (xa ^ fa) * 2654435761u + 0x9e3779b9u + static_cast<uint32_t>(s);
+    xb = (xb ^ fb) * 2246822519u + 0x85ebca6bu + static_cast<uint32_t>(s);
+  }
+  if ((xa ^ xb) == 0x12345678u && sub == 0) atomicAdd(sink, 1ull);  // keeps the chains alive
+}
+
+}  // namespace
+
+cudaError_t launch_probe(const uint4* base, uint64_t n_units, int bytes_per_access, int steps, int sm_count,
+                         cudaStream_t stream, unsigned long long* d_sink, int64_t* accesses) {
+  if (n_units == 0 || steps <= 0) return cudaErrorInvalidValue;
+  int bps = 1;
+  int64_t groups = 0;
+#define FM_PROBE(LPA)                                                                    \
+  do {                                                                                   \
+    bps = blocks_per_sm(probe_kernel<LPA>);                                              \
+    groups = static_cast<int64_t>(sm_count) * bps * kThreads / (LPA);                    \
+    probe_kernel<LPA><<<sm_count * bps, kThreads, 0, stream>>>(base, n_units, steps, d_sink); \
+  } while (0)
+  switch (bytes_per_access) {
+    case 128: FM_PROBE(8); break;
+    case 64: FM_PROBE(4); break;
+    case 32: FM_PROBE(2); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef FM_PROBE
+  if (accesses) *accesses = groups * 2 * steps;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long* /*d_work*/, int lpq, int sm_count,
                        cudaStream_t stream, int64_t* launch_counter) {
   if (a.n <= 0) return cudaSuccess;

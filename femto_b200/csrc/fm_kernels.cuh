@@ -76,4 +76,11 @@ cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long*
 cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lanes_per_query, int sm_count,
                                cudaStream_t stream, int64_t* launch_counter);
 
+// Measurement aid (the ceiling bench.py quotes for the count kernel): `steps` rounds of dependent
+// uniformly random reads of `bytes_per_access` (32, 64 or 128, naturally aligned) over `n_units`
+// such units starting at `base`; one 128-bit load per lane, two independent chains per lane
+// group, every SM filled.  *accesses receives the number of reads the launch performs.
+cudaError_t launch_probe(const uint4* base, uint64_t n_units, int bytes_per_access, int steps, int sm_count,
+                         cudaStream_t stream, unsigned long long* d_sink, int64_t* accesses);
+
 }  // namespace fmb

@@ -443,37 +443,33 @@ namespace {
 std::atomic<int> g_default_block_words{0};
 }
 
-int default_block_words() {
-  int v = g_default_block_words.load();
-  if (v == 0) {
-    v = kDefaultBlockWords;
-    if (const char* e = std::getenv("FEMTO_B200_BLOCK_BYTES")) {
-      const int b = std::atoi(e);
-      if (b == 32 || b == 64 || b == 128) v = b / 4;
-    }
-    g_default_block_words.store(v);
-  }
-  return v;
-}
-
 namespace {
 std::atomic<int> g_default_paired{-1};
 }
 
-bool default_paired_levels() {
-  int v = g_default_paired.load();
-  if (v < 0) {
-    const char* e = std::getenv("FEMTO_B200_PAIRED_LEVELS");
-    v = (e && std::atoi(e) != 0) ? 1 : 0;
-    g_default_paired.store(v);
+// The fastest layout measured on B200 (profiles/r01_paired_level_sweep.md) is the default:
+// paired-level wavelet blocks of 64 bytes; one-level images default to 128-byte blocks.
+int default_block_words(bool paired) {
+  const int v = g_default_block_words.load();
+  if (v != 0) return v;
+  if (const char* e = std::getenv("FEMTO_B200_BLOCK_BYTES")) {
+    const int b = std::atoi(e);
+    if (b == 32 || b == 64 || b == 128) return b / 4;
   }
-  return v != 0;
+  return paired ? 16 : kDefaultBlockWords;
 }
 
-void set_default_paired_levels(bool on) { g_default_paired.store(on ? 1 : 0); }
+bool default_paired_levels() {
+  const int v = g_default_paired.load();
+  if (v >= 0) return v != 0;
+  if (const char* e = std::getenv("FEMTO_B200_PAIRED_LEVELS")) return std::atoi(e) != 0;
+  return true;
+}
+
+void set_default_paired_levels(int on) { g_default_paired.store(on < 0 ? -1 : (on ? 1 : 0)); }
 
 bool set_default_block_words(int words) {
-  if (words != 8 && words != 16 && words != 32) return false;
+  if (words != 0 && words != 8 && words != 16 && words != 32) return false;
   g_default_block_words.store(words);
   return true;
 }
@@ -518,9 +514,9 @@ HostPairedRank host_paired_rank(const uint32_t* rank_words, int block_words, uin
 std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
                                             int block_words, int paired_levels) {
   if (nshards < 1 || shard < 0 || shard >= nshards) throw Error(FM_ERR_PARAM, "bad shard");
-  if (block_words == 0) block_words = default_block_words();
-  if (block_words != 8 && block_words != 16 && block_words != 32) throw Error(FM_ERR_PARAM, "rank block must be 32, 64 or 128 bytes");
   const bool paired = paired_levels < 0 ? default_paired_levels() : paired_levels != 0;
+  if (block_words == 0) block_words = default_block_words(paired);
+  if (block_words != 8 && block_words != 16 && block_words != 32) throw Error(FM_ERR_PARAM, "rank block must be 32, 64 or 128 bytes");
   if (paired && block_words < 16) throw Error(FM_ERR_PARAM, "the paired-level layout needs 64- or 128-byte blocks");
   if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
   auto files = IndexFiles::open(path);

@@ -39,16 +39,17 @@ struct HostImage {
 };
 
 // shard/nshards select data blocks b with b*nshards/nblocks == shard (all blocks when nshards==1).
-// block_words: 32, 16 or 8 (128/64/32-byte rank blocks); 0 = the process default (env
-// FEMTO_B200_BLOCK_BYTES or set_default_block_words, else 128-byte blocks).
 // paired_levels: 1 = paired-level wavelet blocks, 0 = one level per block, -1 = process default
-// (env FEMTO_B200_PAIRED_LEVELS or set_default_paired_levels).
+// (set_default_paired_levels, else env FEMTO_B200_PAIRED_LEVELS, else paired).
+// block_words: 32, 16 or 8 (128/64/32-byte rank blocks); 0 = the process default
+// (set_default_block_words, else env FEMTO_B200_BLOCK_BYTES, else 64-byte blocks for the paired
+// layout and 128-byte blocks for the one-level layout).
 std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
                                             int block_words = 0, int paired_levels = -1);
-int default_block_words();
-bool set_default_block_words(int words);
+int default_block_words(bool paired);
+bool set_default_block_words(int words);     // 0 = back to the built-in default
 bool default_paired_levels();
-void set_default_paired_levels(bool on);
+void set_default_paired_levels(int on);      // negative = back to the built-in default
 
 // Host-side rank over the image (used by the loader's self-check and by unit tests of the
 // image layout; NOT a query fallback -- the C ABI never calls it).

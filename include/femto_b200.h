@@ -188,6 +188,12 @@ int64_t fm_kernel_launches(const fm_index_t* ix);
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
                    const int64_t* offs, uint64_t* stats4);
 
+/* Measurement aid: the ceiling the count kernel is compared with in bench.py.  Runs `steps`
+ * rounds of dependent, uniformly random, naturally aligned reads of bytes_per_access (32, 64 or
+ * 128) bytes over the resident rank blocks with every SM filled, and reports how many reads were
+ * made and the CUDA-event time of the launch.  Touches no query state. */
+int fm_probe_random_reads(fm_index_t* ix, int bytes_per_access, int steps, int64_t* accesses, double* ms);
+
 /* Tuning knob: lanes cooperating on one rank query in the locate/extract/occ kernels (1, 2, 4 or
  * 8; default 4).  The value is clamped to what the image's block layout offers: 4 or 8 lanes on
  * 128-byte blocks, 2 or 4 on 64-byte, 1 or 2 on 32-byte; paired-level blocks half of that. */
@@ -196,20 +202,23 @@ int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
 /* Tuning knob of the count kernel.  merged != 0 (default): one group of `lanes` lanes per pattern
  * advances both Occ of a step together and reads a shared rank block once; merged == 0: two
  * sub-groups of `lanes` lanes per pattern, one per Occ.  Lane counts available: 128-byte rank
- * blocks 2/4/8 (merged) 4/8 (pair); 64-byte 1/2/4 and 2/4; 32-byte 1/2 and 2. */
+ * blocks 2/4/8 (merged) 4/8 (pair); 64-byte 1/2/4 and 2/4; 32-byte 1/2 and 2.  Paired-level images
+ * (below) always run the merged schedule, with 1/2/4 lanes on 128-byte and 1/2 on 64-byte blocks. */
 int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes);
 
-/* Rank block size (bytes: 128, 64 or 32) of the HBM image built by subsequent fm_open calls.
- * Initial value: environment FEMTO_B200_BLOCK_BYTES, else 128. */
-int fm_set_default_block_bytes(int bytes);
-
-/* Wavelet-tree block layout of the HBM image built by subsequent fm_open calls.  on != 0: a block
- * holds a stretch of an even-depth node together with the matching bits of both children, so one
- * 128- or 64-byte read answers two wavelet-tree levels (half the dependent HBM reads of the
- * one-level layout, about 1.3x its size; needs 128- or 64-byte blocks).  on == 0: one level per
- * block.  With the paired layout the count kernel always uses the merged schedule.
- * Initial value: environment FEMTO_B200_PAIRED_LEVELS, else 0. */
+/* Wavelet-tree block layout of the HBM image built by subsequent fm_open calls.
+ *   on > 0  (the default): paired levels.  A block holds a stretch of an even-depth node together
+ *           with the matching bits of both children, so one 64- or 128-byte read answers two
+ *           wavelet-tree levels: half the dependent HBM reads of the one-level layout, at about
+ *           1.3x its size.
+ *   on == 0: one level per block.
+ *   on < 0 : back to the default (environment FEMTO_B200_PAIRED_LEVELS, else paired). */
 int fm_set_default_paired_levels(int on);
+
+/* Rank block size in bytes of the HBM image built by subsequent fm_open calls: 128 or 64 (paired
+ * levels), 128, 64 or 32 (one level per block); 0 = back to the default (environment
+ * FEMTO_B200_BLOCK_BYTES, else 64 for paired levels and 128 for one level per block). */
+int fm_set_default_block_bytes(int bytes);
 
 /* --------------------------------------------------------------------------
  * Index construction (host side; "next" row f-1 of the scope table).  Emits an

@@ -18,9 +18,25 @@ ALL = ["two_docs", "gen400_big_buckets", "gen400_small_buckets", "gen400_small_b
        "gen3", "single_symbol", "multi_doc_mixed", "acgt_64k", "bytes_200k", "skewed_deep", "english_100k"]
 
 
+def open_with_layout(built_indexes, block_bytes, paired):
+    from femto_b200 import _lib
+    lib = _lib.load()
+    assert lib.fm_set_default_block_bytes(block_bytes) == 0
+    assert lib.fm_set_default_paired_levels(int(paired)) == 0
+    try:
+        opened = {name: fb.Index(path, device=0) for name, path in built_indexes.items()}
+    finally:
+        lib.fm_set_default_block_bytes(0)
+        lib.fm_set_default_paired_levels(-1)
+    for ix in opened.values():
+        assert ix.info.rank_block_size == block_bytes and ix.info.paired_levels == int(paired)
+    return opened
+
+
 @pytest.fixture(scope="module")
 def gpu_indexes(built_indexes):
-    opened = {name: fb.Index(path, device=0) for name, path in built_indexes.items()}
+    """One wavelet-tree level per 128-byte rank block (the layout the schedule matrix below covers)."""
+    opened = open_with_layout(built_indexes, 128, False)
     yield opened
     for ix in opened.values():
         ix.close()
@@ -37,17 +53,10 @@ def edge_patterns():
 @pytest.fixture(scope="module")
 def gpu_indexes_small_blocks(built_indexes):
     """The same indexes loaded with 64- and 32-byte rank blocks."""
-    from femto_b200 import _lib
-    lib = _lib.load()
     opened = {}
     for bb in (64, 32):
-        assert lib.fm_set_default_block_bytes(bb) == 0
-        try:
-            for name, path in built_indexes.items():
-                opened[(name, bb)] = fb.Index(path, device=0)
-                assert opened[(name, bb)].info.rank_block_size == bb
-        finally:
-            lib.fm_set_default_block_bytes(128)
+        for name, ix in open_with_layout(built_indexes, bb, False).items():
+            opened[(name, bb)] = ix
     yield opened
     for ix in opened.values():
         ix.close()
@@ -278,7 +287,7 @@ def test_mixed_length_zipf_batch(tmp_path):
         q[int(rng.integers(0, len(q)))] = 5 + int(rng.integers(97, 123))
         pats[k] = q
     with fb.Index(path) as ix, Oracle(path) as o:
-        for sched in ((1, 4), (0, 4)):
+        for sched in ((1, 2), (1, 1)):                       # default image: paired levels, 64-byte blocks
             ix.set_count_schedule(*sched)
             f, l = ix.count(pats)
             sub = list(range(0, len(pats), 7))
@@ -325,20 +334,10 @@ def test_properties_at_scale(tmp_path):
 # ---- paired-level wavelet blocks (two levels per HBM read; fm_image.hpp) ----------------------------
 @pytest.fixture(scope="module")
 def gpu_indexes_paired(built_indexes):
-    from femto_b200 import _lib
-    lib = _lib.load()
     opened = {}
     for bb in (128, 64):
-        assert lib.fm_set_default_block_bytes(bb) == 0
-        assert lib.fm_set_default_paired_levels(1) == 0
-        try:
-            for name, path in built_indexes.items():
-                opened[(name, bb)] = fb.Index(path, device=0)
-                assert opened[(name, bb)].info.rank_block_size == bb
-                assert opened[(name, bb)].info.paired_levels == 1
-        finally:
-            lib.fm_set_default_block_bytes(128)
-            lib.fm_set_default_paired_levels(0)
+        for name, ix in open_with_layout(built_indexes, bb, True).items():
+            opened[(name, bb)] = ix
     yield opened
     for ix in opened.values():
         ix.close()
@@ -392,3 +391,15 @@ def test_walks_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpo
     for d in range(len(docs)):
         assert bytes((ix.extract(d) - fb.CHARACTER_OFFSET).astype(np.uint8)) == docs[d]
     ix.set_lanes_per_query(4)
+
+
+def test_default_layout_and_probe(built_indexes):
+    """fm_open without tuning calls builds the paired-level 64-byte image; the random-read probe runs."""
+    ix = fb.Index(built_indexes["bytes_200k"], device=0)
+    assert ix.info.paired_levels == 1 and ix.info.rank_block_size == 64
+    for b in (32, 64, 128):
+        r = ix.probe_random_reads(b, steps=50)
+        assert r["accesses"] > 0 and r["ms"] > 0
+    with pytest.raises(Exception):
+        ix.probe_random_reads(48, steps=10)
+    ix.close()

@@ -25,8 +25,8 @@ class Image:
         try:
             self.h = self.lib.fm_debug_image_open(os.fsencode(path), shard, nshards, 4, C.byref(err))
         finally:
-            self.lib.fm_set_default_block_bytes(128)
-            self.lib.fm_set_default_paired_levels(0)
+            self.lib.fm_set_default_block_bytes(0)
+            self.lib.fm_set_default_paired_levels(-1)
         assert self.h, f"image open failed err={err.value}"
 
     def stats(self):
@@ -105,8 +105,8 @@ def test_paired_level_layout_needs_wide_blocks(built_indexes):
         assert not lib.fm_debug_image_open(os.fsencode(built_indexes["two_docs"]), 0, 1, 1, C.byref(err))
         assert err.value != 0
     finally:
-        lib.fm_set_default_block_bytes(128)
-        lib.fm_set_default_paired_levels(0)
+        lib.fm_set_default_block_bytes(0)
+        lib.fm_set_default_paired_levels(-1)
 
 
 @pytest.mark.parametrize("layout", [(128, False), (64, False), (32, False), (128, True), (64, True)])
