@@ -58,8 +58,8 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per pattern group (2, 4 or 8); 0 = engine default")
     ap.add_argument("--sched", choices=["merged", "pair"], default="merged", help="count kernel schedule")
     ap.add_argument("--block-bytes", type=int, default=0, help="rank block size of the HBM image (128/64/32)")
-    ap.add_argument("--paired-levels", type=int, default=-1,
-                    help="1: two wavelet-tree levels per rank block, 0: one; default: the library's")
+    ap.add_argument("--levels", type=int, default=0,
+                    help="wavelet-tree levels per rank block read: 1, 2 (paired) or 4 (quad); default: the library's")
     ap.add_argument("--parallelism", choices=["replica", "sharded"], default="replica",
                     help="N>1: replicate the index and split patterns (default), or shard the index by BWT "
                          "row range and route pattern states with NCCL all-to-all")
@@ -270,14 +270,14 @@ def main():
 
     if args.block_bytes:
         assert lib.fm_set_default_block_bytes(args.block_bytes) == 0
-    if args.paired_levels >= 0:
-        assert lib.fm_set_default_paired_levels(args.paired_levels) == 0
+    if args.levels:
+        assert lib.fm_set_default_levels_per_block(args.levels) == 0
     t0 = time.time()
     ix = fb.Index(index_path, device=local)
     load_s = time.time() - t0
     block_bytes = int(ix.info.rank_block_size)
-    paired = bool(ix.info.paired_levels)
-    if paired and args.lanes:
+    levels = int(ix.info.levels_per_block)
+    if levels > 1 and args.lanes:
         ix.set_count_schedule(True, args.lanes)
     elif args.lanes or args.sched != "merged":
         ix.set_count_schedule(args.sched == "merged", args.lanes or {128: 4, 64: 2, 32: 1}[block_bytes])
@@ -393,8 +393,10 @@ def main():
     st = ix.count_stats(h_plen.numpy(), hb, h_offs.numpy())
     # per distinct rank block: 128 B payload line + 16 B node record; per Occ evaluation:
     # 16 B OccRec + 16 B BucketRec; per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
-    # (paired-level blocks: one block answers two levels and comes with an 8 B grandchild record)
-    alg_bytes = (st["distinct_block_reads"] * (block_bytes + (8 if paired else 16)) + st["occ_evals"] * 32 +
+    # (paired-/quad-level blocks answer 2 / 4 levels each and come with an 8 B record of the next
+    # node; of a quad-level block a query reads 64 B of bits and an 8 B header entry)
+    per_block = {1: block_bytes + 16, 2: block_bytes + 8, 4: 64 + 8 + 8}[levels]
+    alg_bytes = (st["distinct_block_reads"] * per_block + st["occ_evals"] * 32 +
                  npats * (m * 2 + 28))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
@@ -404,7 +406,7 @@ def main():
                 "kernel_ms": round(ms_per_step, 4),
                 "rank_blocks_requested": st["block_reads"], "rank_blocks_distinct": st["distinct_block_reads"],
                 "occ_evals": st["occ_evals"], "backward_steps": st["steps"]}
-    layout_key = f"{'paired' if paired else 'plain'}{block_bytes}"
+    layout_key = {1: "plain", 2: "paired", 4: "quad"}[levels] + str(block_bytes)
     roofline["layout"] = layout_key
     traffic_file = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
     if os.path.exists(traffic_file):  # dram bytes of one launch from the committed ncu --set full capture
@@ -486,7 +488,7 @@ def main():
                    "index": index_name(args), "index_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
                    "index_load_s": round(load_s, 1), "index_build": build_info,
                    "parallelism": f"replica x{world} (patterns split, no collective)",
-                   "rank_block_bytes": block_bytes, "paired_levels": paired,
+                   "rank_block_bytes": block_bytes, "levels_per_block": levels,
                    "count_schedule": os.environ.get("FEMTO_B200_COUNT_SCHED") or
                                      f"{args.sched}/{args.lanes or 'default'} lanes per pattern group",
                    "l2_policy": "inputs larger than L2: each step reads ~%.1f GB of a %.1f GiB image; %d distinct batches cycled"

@@ -21,7 +21,7 @@ class FmInfo(C.Structure):
         ("total_length", i64), ("num_documents", i64), ("num_blocks", i64),
         ("block_size", i32), ("bucket_size", i32), ("mark_period", i32), ("chunk_size", i32),
         ("first_row", i64), ("end_row", i64), ("hbm_bytes", i64), ("rank_block_bytes", i64),
-        ("device", i32), ("max_code_len", i32), ("rank_block_size", i32), ("paired_levels", i32),
+        ("device", i32), ("max_code_len", i32), ("rank_block_size", i32), ("levels_per_block", i32),
     ]
 
 
@@ -53,7 +53,7 @@ PROTOTYPES = {
     "fm_set_lanes_per_query": (C.c_int, [vp, C.c_int]),
     "fm_set_count_schedule": (C.c_int, [vp, C.c_int, C.c_int]),
     "fm_set_default_block_bytes": (C.c_int, [C.c_int]),
-    "fm_set_default_paired_levels": (C.c_int, [C.c_int]),
+    "fm_set_default_levels_per_block": (C.c_int, [C.c_int]),
     "fm_count_stats": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), P(C.c_uint64)]),
     "fm_probe_random_reads": (C.c_int, [vp, C.c_int, C.c_int, P(i64), P(C.c_double)]),
     "fm_builder_create": (C.c_int, [C.c_char_p, i64, i64, P(i64), i32, i32, i32, i32, C.c_int, P(vp)]),

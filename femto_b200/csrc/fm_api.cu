@@ -133,9 +133,12 @@ int paired_sched(int block_words, int lanes) {
   return 1000 + 10 * lanes + minb;
 }
 
-int default_count_sched(int block_words, bool paired) {
-  int sched = paired ? paired_sched(block_words, 2)
-                     : sync_sched(block_words, block_words == 32 ? 4 : block_words == 16 ? 2 : 1);
+constexpr int kQuadSched = 1000 + 10 * 2 + 4;  // quad-level blocks: 2 lanes per pattern
+
+int default_count_sched(int block_words, int levels) {
+  int sched = levels == 4 ? kQuadSched
+            : levels == 2 ? paired_sched(block_words, 2)
+                          : sync_sched(block_words, block_words == 32 ? 4 : block_words == 16 ? 2 : 1);
   if (const char* e = std::getenv("FEMTO_B200_COUNT_SCHED")) {  // tuning experiments only
     const int v = std::atoi(e);
     if (v > 0) sched = v;
@@ -204,7 +207,8 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
     int64_t total = 0;
     upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * size_t(host->block_words), &total);
-    if (host->paired) upload(&ix->d_nodes, host->supers.data(), host->supers.size(), &total);
+    if (host->levels == 4) upload(&ix->d_nodes, host->quads.data(), host->quads.size(), &total);
+    else if (host->levels == 2) upload(&ix->d_nodes, host->supers.data(), host->supers.size(), &total);
     else upload(&ix->d_nodes, host->nodes.data(), host->nodes.size(), &total);
     upload(&ix->d_occ, host->occ.data(), host->occ.size(), &total);
     upload(&ix->d_mark, host->mark.data(), host->mark.size(), &total);
@@ -218,10 +222,11 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
 
     const BlockHeader& h = host->hdr;
     ix->im.blocks = static_cast<const uint4*>(ix->d_blocks);
-    if (host->paired) ix->im.supers = static_cast<const SuperRec*>(ix->d_nodes);
+    if (host->levels == 4) ix->im.quads = static_cast<const QuadRec*>(ix->d_nodes);
+    else if (host->levels == 2) ix->im.supers = static_cast<const SuperRec*>(ix->d_nodes);
     else ix->im.nodes = static_cast<const NodeRec*>(ix->d_nodes);
-    ix->im.paired = host->paired ? 1 : 0;
-    ix->info.paired_levels = ix->im.paired;
+    ix->im.levels = host->levels;
+    ix->info.levels_per_block = host->levels;
     ix->im.occ = static_cast<const OccRec*>(ix->d_occ);
     ix->im.mark = static_cast<const MarkRec*>(ix->d_mark);
     ix->im.buckets = static_cast<const BucketRec*>(ix->d_buckets);
@@ -246,7 +251,7 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->info.hbm_bytes = total;
     ix->info.rank_block_bytes = host->n_rank_blocks * int64_t(host->block_words) * 4;
     ix->im.block_words = host->block_words;
-    ix->count_sched = default_count_sched(host->block_words, host->paired);
+    ix->count_sched = default_count_sched(host->block_words, host->levels);
     ix->info.device = device;
     ix->info.max_code_len = host->max_code_len;
     ix->info.rank_block_size = host->block_words * 4;
@@ -427,7 +432,12 @@ int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
 int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
   if (!ix) return fail(FM_ERR_PARAM, "fm_set_count_schedule: null index");
   const int bw = ix->im.block_words;
-  if (ix->im.paired) {  // paired-level blocks: merged schedule only, a lane owns whole 32-byte slices
+  if (ix->im.levels == 4) {
+    if (lanes != 2) return fail(FM_ERR_PARAM, "fm_set_count_schedule: quad-level blocks run with 2 lanes per pattern");
+    ix->count_sched = kQuadSched;
+    return FM_OK;
+  }
+  if (ix->im.levels == 2) {  // paired-level blocks: merged schedule only, a lane owns whole 32-byte slices
     if (!((bw == 32 && (lanes == 1 || lanes == 2 || lanes == 4)) || (bw == 16 && (lanes == 1 || lanes == 2))))
       return fail(FM_ERR_PARAM, "fm_set_count_schedule: lane count not available for paired-level blocks");
     ix->count_sched = paired_sched(bw, lanes);
@@ -450,8 +460,8 @@ int fm_set_default_block_bytes(int bytes) {
   return FM_OK;
 }
 
-int fm_set_default_paired_levels(int on) {
-  set_default_paired_levels(on);
+int fm_set_default_levels_per_block(int levels) {
+  if (!set_default_levels_per_block(levels)) return fail(FM_ERR_PARAM, "fm_set_default_levels_per_block: 1, 2, 4 or 0");
   return FM_OK;
 }
 

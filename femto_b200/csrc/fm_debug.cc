@@ -46,7 +46,7 @@ void fm_debug_image_stats(void* h, int64_t* out) {
   const HostImage& im = *static_cast<DebugImage*>(h)->im;
   out[0] = im.n_rank_blocks;
   out[1] = im.n_wtree_blocks;
-  out[2] = int64_t(im.paired ? im.supers.size() : im.nodes.size());
+  out[2] = int64_t(im.levels == 4 ? im.quads.size() : im.levels == 2 ? im.supers.size() : im.nodes.size());
   out[3] = im.nbuckets;
   out[4] = int64_t(im.markvals.size());
   out[5] = im.first_row;
@@ -65,7 +65,25 @@ int64_t fm_debug_image_occ(void* h, int ch, int64_t row) {
   const BucketRec& br = im.buckets[size_t(g)];
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1;
   const int L = 31 - __builtin_clz(o.leaf);
-  if (im.paired) {
+  if (im.levels == 4) {
+    for (int lvl = 0; lvl < L; lvl += 4) {
+      const int rem = L - lvl;  // code bits left; a code ending inside the block is extended with 0 bits
+      const uint32_t path = rem >= 4 ? (o.leaf >> (rem - 4)) & 15u : (o.leaf << (4 - rem)) & 15u;
+      const HostQuadRank r = host_quad_rank(im.rank_words, base, idx1, int(path));
+      idx1 = r.index1;
+      const uint32_t* ex = im.quads[node].exit[path];
+      if (rem <= 4) {
+        if (!(ex[1] & kChildLeaf) || (ex[1] & 0xffffu) != uint32_t(ch)) return -2;
+        break;
+      }
+      if (ex[1] & kChildLeaf) return -2;
+      if (idx1 == 0) break;
+      base = ex[0];
+      node = ex[1];
+    }
+    return o.occ_base + idx1;
+  }
+  if (im.levels == 2) {
     for (int lvl = 0; lvl < L; lvl += 2) {
       const uint32_t b1 = (o.leaf >> (L - lvl - 1)) & 1u;
       const HostPairedRank r = host_paired_rank(im.rank_words, im.block_words, base, idx1, int(b1));
@@ -114,7 +132,15 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
   if (!split(im, row, &g, &rb)) return -1;
   const BucketRec& br = im.buckets[size_t(g)];
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1, ch = 0;
-  for (int guard = 0; guard < 64 && im.paired; guard++) {
+  for (int guard = 0; guard < 64 && im.levels == 4; guard++) {
+    const HostQuadRank r = host_quad_rank(im.rank_words, base, idx1, -1);
+    const uint32_t* ex = im.quads[node].exit[r.exit];
+    idx1 = r.index1;
+    if (ex[1] & kChildLeaf) { ch = ex[1] & 0xffffu; break; }
+    base = ex[0];
+    node = ex[1];
+  }
+  for (int guard = 0; guard < 64 && im.levels == 2; guard++) {
     const HostPairedRank r = host_paired_rank(im.rank_words, im.block_words, base, idx1, -1);
     const SuperRec& sr = im.supers[node];
     idx1 = r.index1;
@@ -125,7 +151,7 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
     base = gc[0];
     node = gc[1];
   }
-  for (int guard = 0; guard < 64 && !im.paired; guard++) {
+  for (int guard = 0; guard < 64 && im.levels == 1; guard++) {
     const HostRank r = host_rank(im.rank_words, im.block_words, base, idx1);
     idx1 = r.bit ? r.ones : idx1 - r.ones;
     const NodeRec& nr = im.nodes[node];

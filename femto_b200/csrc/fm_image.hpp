@@ -68,6 +68,38 @@ struct alignas(16) SuperRec {
   uint32_t pad[2];
 };
 
+// ---- quad-level layout ------------------------------------------------------------------------
+// The memory system serves a fixed number of independent random reads per second whatever their
+// width up to a 128-byte line (profiles/r01_paired_level_sweep.md), so the quad layout spends the
+// whole line on FOUR levels: a block of a node X at depth 0, 4, 8, ... ("quad node") carries
+// kQuadPos positions of X and the bits those positions contribute to X's children,
+// grandchildren and great-grandchildren (block levels 1..3; block-local heap ids 1 = X,
+// 2..3, 4..7, 8..15).  Codes that end inside a block are extended with 0 bits, a leaf behaving
+// like a node whose bits are all 0, so every query leaves a block through one of 16 exits.
+//
+//   words 0..15   H[q], q = the 4 path bits b1 b2 b3 b4:
+//                   bits 0..23  E(q): positions routed to exit q by the node's earlier blocks
+//                   bits 24..31 q even: anchor of the level-2 node on the path (b1 b2)
+//                               q odd : anchor of the level-3 node on the path (b1 b2 b3)
+//   words 16..31  four regions of kQuadPos bits, one per block level, MSB-first;
+//                 word w of region l is block word 16 + 8 (w >> 1) + 2 l + (w & 1), so that a
+//                 lane of a 2-lane group loads words (2 sub, 2 sub + 1) of all four regions
+//                 with two 128-bit loads.
+//   Region l is partitioned among the level-l nodes.  Node v with parent u occupying [LO, HI):
+//   a 0-child stores its bits forward from LO, a 1-child stores them REVERSED, backward from
+//   HI; the anchor of a node is that LO resp. HI.  (Level 1: 0 and kQuadPos, not stored.)  The first
+//   j bits of a node are the range [anchor, anchor + j) resp. [anchor - j, anchor), their ones c
+//   give the next j' = b ? c : j - c, and the result after four levels is E(q) + j''''.
+//   Positions past the end of the node's sequence count as 0 bits.  Needs bucket_size < 2^24.
+constexpr int kQuadPos = 128;
+constexpr int kQuadBlockWords = 32;
+
+struct alignas(16) QuadRec {
+  // exit q: {first block, QuadRec index} of the quad node there, or {0, kChildLeaf | symbol} when
+  // the path b1..b4 is a leaf's code extended with 0 bits
+  uint32_t exit[16][2];
+};
+
 struct alignas(16) OccRec {
   int64_t occ_base;  // C[ch] + occurrences of ch before this bucket
   uint32_t leaf;     // wavelet-tree leaf id (1<<len | code) of ch in this bucket, 0 = absent
@@ -90,6 +122,7 @@ struct DevImage {
   const uint4* blocks = nullptr;        // rank blocks, 8 x uint4 each
   const NodeRec* nodes = nullptr;       // plain layout
   const SuperRec* supers = nullptr;     // paired-level layout (then nodes == nullptr)
+  const QuadRec* quads = nullptr;       // quad-level layout
   const OccRec* occ = nullptr;         // [nbuckets][kAlphaStride]
   const MarkRec* mark = nullptr;        // [nbuckets][kAlphaStride]
   const BucketRec* buckets = nullptr;   // [nbuckets]
@@ -101,7 +134,7 @@ struct DevImage {
   int32_t bucket_size = 0;
   int32_t bucket_shift = -1;            // log2(bucket_size) when it is a power of two, else -1
   int32_t block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
-  int32_t paired = 0;                        // 1: wavelet blocks use the paired-level layout
+  int32_t levels = 1;                        // wavelet-tree levels answered per block read: 1, 2 (paired) or 4 (quad)
 };
 
 }  // namespace fmb

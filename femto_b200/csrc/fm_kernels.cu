@@ -301,9 +301,129 @@ __device__ __forceinline__ int64_t occ_descend_paired(const DevImage& im, bool a
   return occ_base + static_cast<int64_t>(leaf ? idx1 : 0u);
 }
 
-template <int LPQ, int BW, bool PAIRED>
+// ---- quad-level blocks (fm_image.hpp): 2 lanes per group; lane `sub` holds words 2 sub and
+// 2 sub + 1 (bits [64 sub, 64 sub + 64)) of each of the four regions --------------------------------
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, int s) {  // v >> s, 0 when s >= 32 (s >= 0)
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+  return r;
+}
+
+struct QuadWords {
+  uint32_t d[8];  // d[2 l], d[2 l + 1]: this lane's two words of region l
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int t = 0; t < 8; t++) d[t] = 0;
+  }
+  __device__ __forceinline__ void load(const uint4* __restrict__ blocks, uint32_t blk, int sub) {
+    const uint4* b = blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4) + 4 + 2 * sub;
+    const uint4 x = __ldg(b), y = __ldg(b + 1);
+    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    d[4] = y.x; d[5] = y.y; d[6] = y.z; d[7] = y.w;
+  }
+  // ones of region L within [a, b), a and b given relative to this lane's first bit
+  template <int L>
+  __device__ __forceinline__ uint32_t range(int a, int b) const {
+    const uint32_t m0 = shr_clamp(kFull, max(a, 0)) & ~shr_clamp(kFull, max(b, 0));
+    const uint32_t m1 = shr_clamp(kFull, max(a - 32, 0)) & ~shr_clamp(kFull, max(b - 32, 0));
+    return __popc(d[2 * L] & m0) + __popc(d[2 * L + 1] & m1);
+  }
+  // bit `pos` of region L, fetched from the lane that holds it
+  template <int L>
+  __device__ __forceinline__ uint32_t bit(uint32_t pos) const {
+    const uint32_t wi = pos >> 5;
+    const uint32_t mine = (wi & 1u) ? d[2 * L + 1] : d[2 * L];
+    const uint32_t word = __shfl_sync(kFull, mine, wi >> 1, 2);
+    return (word >> (31 - (pos & 31))) & 1u;
+  }
+};
+
+// H[2 path3], H[2 path3 + 1]: both exits below the level-3 node and, in their top bytes, the
+// anchors of the level-2 and level-3 nodes on the path
+__device__ __forceinline__ uint2 quad_header(const uint4* __restrict__ blocks, uint32_t blk, uint32_t path3) {
+  return __ldg(reinterpret_cast<const uint2*>(blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4)) + path3);
+}
+
+// the four path bits of one block for a code of L bits of which lvl are consumed; a code that
+// ends inside the block is extended with 0 bits
+__device__ __forceinline__ uint32_t quad_path(uint32_t leaf, int L, int lvl) {
+  const int rem = L - lvl;
+  return rem >= 4 ? (leaf >> (rem - 4)) & 15u : (leaf << (4 - rem)) & 15u;
+}
+
+// One block for one position: j = positions of the block's stretch up to and including ours.
+// Returns the 1-based index in the node at exit `nib`.
+__device__ __forceinline__ uint32_t quad_levels(const QuadWords& w, const uint2 h, uint32_t nib, int j, int sub) {
+  const int lb = 64 * sub;
+  uint32_t c = group_sum<2>(popc_top(w.d[0], j - lb) + popc_top(w.d[1], j - lb - 32));
+  uint32_t b = (nib >> 3) & 1u;
+  j = b ? c : j - c;
+  int a = b ? kQuadPos - j : 0;
+  c = group_sum<2>(w.range<1>(a - lb, a + j - lb));
+  b = (nib >> 2) & 1u;
+  j = b ? c : j - c;
+  a = static_cast<int>(h.x >> 24) - (b ? j : 0);
+  c = group_sum<2>(w.range<2>(a - lb, a + j - lb));
+  b = (nib >> 1) & 1u;
+  j = b ? c : j - c;
+  a = static_cast<int>(h.y >> 24) - (b ? j : 0);
+  c = group_sum<2>(w.range<3>(a - lb, a + j - lb));
+  b = nib & 1u;
+  j = b ? c : j - c;
+  return ((b ? h.y : h.x) & 0xffffffu) + static_cast<uint32_t>(j);
+}
+
+// occ_descend over quad-level blocks: four wavelet-tree levels per block read.
+__device__ __forceinline__ int64_t occ_descend_quad(const DevImage& im, bool active, int c, int64_t row, int sub) {
+  int64_t occ_base = 0;
+  uint32_t leaf = 0, base = 0, node = 0, idx1 = 0;
+  int L = 0;
+  if (active) {
+    int64_t g;
+    uint32_t rb;
+    split_row(im, row, g, rb);
+    const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+    occ_base = rec_occ_base(rv);
+    leaf = static_cast<uint32_t>(rv.z);
+    if (leaf) {
+      const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+      base = br.x;
+      node = br.y;
+      L = 31 - __clz(leaf);
+      idx1 = rb + 1;
+    }
+  }
+  bool desc = active && leaf != 0;
+  int lvl = 0;
+  while (__any_sync(kFull, desc)) {
+    const uint32_t p = desc ? idx1 - 1 : 0u;
+    const uint32_t blk = base + (p >> 7);
+    const uint32_t nib = desc ? quad_path(leaf, L, lvl) : 0u;
+    QuadWords w;
+    w.clear();
+    uint2 h = make_uint2(0, 0), ex = make_uint2(0, 0);
+    if (desc) {
+      w.load(im.blocks, blk, sub);
+      h = quad_header(im.blocks, blk, nib >> 1);
+      if (lvl + 4 < L) ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
+    }
+    const uint32_t r = quad_levels(w, h, nib, static_cast<int>(p & 127u) + 1, sub);
+    lvl += 4;
+    if (desc) {
+      idx1 = r;
+      desc = idx1 != 0 && lvl < L;
+      base = ex.x;
+      node = ex.y;
+    }
+  }
+  return occ_base + static_cast<int64_t>(leaf ? idx1 : 0u);
+}
+
+// LV = wavelet-tree levels per block of the image: 1, 2 (paired) or 4 (quad)
+template <int LPQ, int BW, int LV>
 __device__ __forceinline__ int64_t occ_any(const DevImage& im, bool active, int c, int64_t row, int sub) {
-  if constexpr (PAIRED) return occ_descend_paired<LPQ, BW>(im, active, c, row, sub);
+  if constexpr (LV == 4) return occ_descend_quad(im, active, c, row, sub);
+  else if constexpr (LV == 2) return occ_descend_paired<LPQ, BW>(im, active, c, row, sub);
   else return occ_descend<LPQ, BW, false>(im, active, c, row, sub);
 }
 
@@ -417,7 +537,7 @@ __global__ void __launch_bounds__(kThreads) count_pair_kernel(const DevImage im,
 
 // ---------------------------------------------------------------------------------------------
 // count, "sync" schedule: one group of LPQ lanes per pattern advances both ranks of a step.
-template <int LPQ, int BW, int MINB, bool STATS, bool PAIRED = false>
+template <int LPQ, int BW, int MINB, bool STATS, int LV = 1>
 __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
                                                                      unsigned long long* __restrict__ work,
                                                                      unsigned long long* __restrict__ stats) {
@@ -502,7 +622,74 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
 
     // ---- descend: one level (two with paired-level blocks) per iteration for every group
     int lvl = 0;
-    if constexpr (PAIRED) {
+    if constexpr (LV == 4) {
+      static_assert(LV != 4 || (LPQ == 2 && BW == kQuadBlockWords), "quad-level blocks: 2 lanes, 128 bytes");
+      while (__any_sync(kFull, actA || actB)) {
+        const bool any = actA || actB;
+        const uint32_t pA = actA ? idxA - 1 : 0u, pB = actB ? idxB - 1 : 0u;
+        const uint32_t kA = pA >> 7, kB = pB >> 7;
+        const bool two = actA && actB && kA != kB;
+        const uint32_t blkA = base + (actA ? kA : kB), blkB = base + (actB ? kB : kA);
+        const uint32_t nib = any ? quad_path(leaf, L, lvl) : 0u;
+        // p serves position A, q position B; a shared block is re-read from L1
+        QuadWords p, q;
+        p.clear();
+        q.clear();
+        uint2 hp = make_uint2(0, 0), hq = hp, ex = hp;
+        if (any) {
+          p.load(im.blocks, blkA, sub);
+          q.load(im.blocks, blkB, sub);
+          hp = quad_header(im.blocks, blkA, nib >> 1);
+          hq = quad_header(im.blocks, blkB, nib >> 1);
+          if (lvl + 4 < L) ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
+        }
+        const int lb = 64 * sub;
+        int jA = static_cast<int>(pA & 127u) + 1, jB = static_cast<int>(pB & 127u) + 1;
+        // level 0: the node's own stretch, prefix [0, j)
+        uint32_t c = group_sum<2>((popc_top(p.d[0], jA - lb) + popc_top(p.d[1], jA - lb - 32)) |
+                                  ((popc_top(q.d[0], jB - lb) + popc_top(q.d[1], jB - lb - 32)) << 16));
+        uint32_t b = (nib >> 3) & 1u;
+        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+        jB = b ? (c >> 16) : jB - (c >> 16);
+        // level 1: child b, forward from 0 or backward from the end of the region
+        int aA = b ? kQuadPos - jA : 0, aB = b ? kQuadPos - jB : 0;
+        c = group_sum<2>(p.range<1>(aA - lb, aA + jA - lb) | (q.range<1>(aB - lb, aB + jB - lb) << 16));
+        b = (nib >> 2) & 1u;
+        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+        jB = b ? (c >> 16) : jB - (c >> 16);
+        // level 2: anchored at the header's level-2 anchor
+        aA = static_cast<int>(hp.x >> 24) - (b ? jA : 0);
+        aB = static_cast<int>(hq.x >> 24) - (b ? jB : 0);
+        c = group_sum<2>(p.range<2>(aA - lb, aA + jA - lb) | (q.range<2>(aB - lb, aB + jB - lb) << 16));
+        b = (nib >> 1) & 1u;
+        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+        jB = b ? (c >> 16) : jB - (c >> 16);
+        // level 3
+        aA = static_cast<int>(hp.y >> 24) - (b ? jA : 0);
+        aB = static_cast<int>(hq.y >> 24) - (b ? jB : 0);
+        c = group_sum<2>(p.range<3>(aA - lb, aA + jA - lb) | (q.range<3>(aB - lb, aB + jB - lb) << 16));
+        b = nib & 1u;
+        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+        jB = b ? (c >> 16) : jB - (c >> 16);
+        if (STATS && any && sub == 0) {
+          n_blocks += two ? 2 : 1;
+          n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
+        }
+        lvl += 4;
+        if (any) {
+          if (actA) {
+            idxA = ((b ? hp.y : hp.x) & 0xffffffu) + static_cast<uint32_t>(jA);
+            actA = idxA != 0 && lvl < L;
+          }
+          if (actB) {
+            idxB = ((b ? hq.y : hq.x) & 0xffffffu) + static_cast<uint32_t>(jB);
+            actB = idxB != 0 && lvl < L;
+          }
+          base = ex.x;
+          node = ex.y;
+        }
+      }
+    } else if constexpr (LV == 2) {
       constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
       while (__any_sync(kFull, actA || actB)) {
         const bool any = actA || actB;
@@ -598,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, int BW, int MODE, bool PAIRED = false>
+template <int LPQ, int BW, int MODE, int LV = 1>
 __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const WalkArgs a,
                                                          unsigned long long* __restrict__ work) {
   constexpr uint32_t BITS = (BW - 1) * 32;
@@ -654,7 +841,57 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
       idx1 = rb + 1;
     }
     bool desc = act;
-    if constexpr (PAIRED) {
+    if constexpr (LV == 4) {
+      static_assert(LV != 4 || (LPQ == 2 && BW == kQuadBlockWords), "quad-level blocks: 2 lanes, 128 bytes");
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(im.blocks);
+      while (__any_sync(kFull, desc)) {
+        const uint32_t p = desc ? idx1 - 1 : 0u;
+        const uint32_t blk = base + (p >> 7);
+        const uint32_t* hw = words + static_cast<size_t>(blk) * kQuadBlockWords;
+        QuadWords w;
+        w.clear();
+        if (desc) w.load(im.blocks, blk, sub);
+        const int lb = 64 * sub;
+        int j = static_cast<int>(p & 127u) + 1;
+        // level 0: follow the bit at our position; j stays >= 1 all the way down
+        uint32_t c = group_sum<2>(popc_top(w.d[0], j - lb) + popc_top(w.d[1], j - lb - 32));
+        uint32_t b = w.bit<0>(static_cast<uint32_t>(j - 1));
+        uint32_t path = b;
+        j = b ? c : j - c;
+        // level 1
+        int a = b ? kQuadPos - j : 0;
+        c = group_sum<2>(w.range<1>(a - lb, a + j - lb));
+        uint32_t nb = w.bit<1>(static_cast<uint32_t>(b ? a : a + j - 1));
+        j = nb ? c : j - c;
+        b = nb;
+        path = (path << 1) | b;
+        // level 2: anchor in the top byte of H[4 * (b1 b2)] (an L1 hit: the line was just read)
+        a = static_cast<int>((desc ? __ldg(hw + (path << 2)) : 0u) >> 24) - (b ? j : 0);
+        c = group_sum<2>(w.range<2>(a - lb, a + j - lb));
+        nb = w.bit<2>(static_cast<uint32_t>(b ? a : a + j - 1));
+        j = nb ? c : j - c;
+        b = nb;
+        path = (path << 1) | b;
+        // level 3: anchor in the top byte of H[2 * (b1 b2 b3) + 1]; the exits' counts below it
+        const uint2 h = desc ? __ldg(reinterpret_cast<const uint2*>(hw) + path) : make_uint2(0, 0);
+        a = static_cast<int>(h.y >> 24) - (b ? j : 0);
+        c = group_sum<2>(w.range<3>(a - lb, a + j - lb));
+        nb = w.bit<3>(static_cast<uint32_t>(b ? a : a + j - 1));
+        j = nb ? c : j - c;
+        path = (path << 1) | nb;
+        if (desc) {
+          const uint2 ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[path]));
+          idx1 = ((nb ? h.y : h.x) & 0xffffffu) + static_cast<uint32_t>(j);
+          if (ex.y & kChildLeaf) {
+            ch = ex.y & 0xffffu;
+            desc = false;
+          } else {
+            base = ex.x;
+            node = ex.y;
+          }
+        }
+      }
+    } else if constexpr (LV == 2) {
       constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
       while (__any_sync(kFull, desc)) {
         uint32_t k, off;
@@ -787,7 +1024,7 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, int BW, bool PAIRED = false>
+template <int LPQ, int BW, int LV = 1>
 __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const OccArgs a) {
   constexpr int QPW = 32 / LPQ;
   const int lane = threadIdx.x & 31;
@@ -805,14 +1042,14 @@ __global__ void __launch_bounds__(kThreads) occ_kernel(const DevImage im, const 
       row = a.rows[item];
       q = c < kAlphaDev && row >= im.first_row && row < im.end_row;
     }
-    const int64_t r = occ_any<LPQ, BW, PAIRED>(im, q, c, row, sub);
+    const int64_t r = occ_any<LPQ, BW, LV>(im, q, c, row, sub);
     if (item < a.n && sub == 0) a.out[item] = q ? r : -1;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Range-sharded count: advance pattern states while the BWT rows they need are resident here.
-template <int LPQ, int BW, bool PAIRED = false>
+template <int LPQ, int BW, int LV = 1>
 __global__ void __launch_bounds__(kThreads) count_shard_kernel(const DevImage im, const ShardArgs a) {
   constexpr int QPW = 32 / LPQ;
   const int lane = threadIdx.x & 31;
@@ -871,7 +1108,7 @@ __global__ void __launch_bounds__(kThreads) count_shard_kernel(const DevImage im
         }
       }
       if (!__any_sync(kFull, running)) break;
-      const int64_t r = occ_any<LPQ, BW, PAIRED>(im, q, c, row, sub);
+      const int64_t r = occ_any<LPQ, BW, LV>(im, q, c, row, sub);
       if (q) {
         if (phase == 0) { obA = r; phase = 1; }
         else { f = obA; l = r - 1; i--; phase = 0; }
@@ -909,7 +1146,7 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
   if (a.npats <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  const int code = (im.paired ? 1000000 : 0) + im.block_words * 10000 + sched;
+  const int code = (im.levels - 1) * 1000000 + im.block_words * 10000 + sched;
 #define FM_LAUNCH(KERNEL, LANES_PER_PATTERN)                                                             \
   do {                                                                                                   \
     static const int bps = blocks_per_sm(KERNEL);                                                        \
@@ -923,8 +1160,13 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     break;
 #define FM_SYNC2(BW, LANES, MINB)                                                                        \
   case 1000000 + (BW) * 10000 + 1000 + 10 * (LANES) + (MINB):                                            \
-    if (d_stats) FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, true, true>), LANES);                     \
-    else FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, false, true>), LANES);                            \
+    if (d_stats) FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, true, 2>), LANES);                        \
+    else FM_LAUNCH((count_sync_kernel<LANES, BW, MINB, false, 2>), LANES);                               \
+    break;
+#define FM_SYNC4(MINB)                                                                                   \
+  case 3000000 + 32 * 10000 + 1000 + 10 * 2 + (MINB):                                                    \
+    if (d_stats) FM_LAUNCH((count_sync_kernel<2, 32, MINB, true, 4>), 2);                                \
+    else FM_LAUNCH((count_sync_kernel<2, 32, MINB, false, 4>), 2);                                       \
     break;
 #define FM_PAIR(BW, LANES)                                                                               \
   case (BW) * 10000 + (LANES):                                                                           \
@@ -939,29 +1181,31 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     FM_SYNC2(32, 4, 4) FM_SYNC2(32, 4, 5) FM_SYNC2(32, 4, 6) FM_SYNC2(32, 2, 3) FM_SYNC2(32, 2, 4) FM_SYNC2(32, 2, 5)
     FM_SYNC2(32, 1, 2) FM_SYNC2(32, 1, 3) FM_SYNC2(16, 2, 4) FM_SYNC2(16, 2, 5) FM_SYNC2(16, 2, 6)
     FM_SYNC2(16, 1, 3) FM_SYNC2(16, 1, 4) FM_SYNC2(16, 1, 5)
+    FM_SYNC4(3) FM_SYNC4(4) FM_SYNC4(5) FM_SYNC4(6) FM_SYNC4(8)
     default: return cudaErrorInvalidValue;
   }
 #undef FM_SYNC
 #undef FM_SYNC2
+#undef FM_SYNC4
 #undef FM_PAIR
 #undef FM_LAUNCH
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();
 }
 
-template <int LPQ, int BW, bool PAIRED = false>
+template <int LPQ, int BW, int LV = 1>
 static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work,
                                    int sm_count, cudaStream_t stream) {
   const int gpb = kThreads / LPQ;
   if (mode == kWalkLocate) {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, PAIRED>);
-    walk_kernel<LPQ, BW, kWalkLocate, PAIRED><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV>);
+    walk_kernel<LPQ, BW, kWalkLocate, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else if (mode == kWalkStep) {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkStep, PAIRED>);
-    walk_kernel<LPQ, BW, kWalkStep, PAIRED><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkStep, LV>);
+    walk_kernel<LPQ, BW, kWalkStep, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else {
-    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkExtract, PAIRED>);
-    walk_kernel<LPQ, BW, kWalkExtract, PAIRED><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkExtract, LV>);
+    walk_kernel<LPQ, BW, kWalkExtract, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   }
   return cudaGetLastError();
 }
@@ -969,7 +1213,7 @@ static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMo
 // lanes per query for the walk / occ kernels: 4 or 8 at 128-byte blocks, 2 or 4 at 64, 1 or 2 at 32
 static int walk_lanes(const DevImage& im, int lpq) {
   // at least one 128-bit load per lane; paired-level blocks: whole 32-byte slices per lane
-  const int max_lanes = im.paired ? im.block_words / 8 : im.block_words / 4;
+  const int max_lanes = im.levels == 4 ? 2 : im.levels == 2 ? im.block_words / 8 : im.block_words / 4;
   int lanes = lpq;
   while (lanes > max_lanes) lanes >>= 1;
   if (lanes < max_lanes / 2) lanes = max_lanes / 2;
@@ -981,11 +1225,12 @@ cudaError_t launch_walk(const DevImage& im, const WalkArgs& a, WalkMode mode, un
   if (a.nrows <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  switch ((im.paired ? 10000 : 0) + im.block_words * 100 + walk_lanes(im, lpq)) {
-    case 13204: e = launch_walk_cfg<4, 32, true>(im, a, mode, d_work, sm_count, stream); break;
-    case 13202: e = launch_walk_cfg<2, 32, true>(im, a, mode, d_work, sm_count, stream); break;
-    case 11602: e = launch_walk_cfg<2, 16, true>(im, a, mode, d_work, sm_count, stream); break;
-    case 11601: e = launch_walk_cfg<1, 16, true>(im, a, mode, d_work, sm_count, stream); break;
+  switch ((im.levels - 1) * 10000 + im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 33202: e = launch_walk_cfg<2, 32, 4>(im, a, mode, d_work, sm_count, stream); break;
+    case 13204: e = launch_walk_cfg<4, 32, 2>(im, a, mode, d_work, sm_count, stream); break;
+    case 13202: e = launch_walk_cfg<2, 32, 2>(im, a, mode, d_work, sm_count, stream); break;
+    case 11602: e = launch_walk_cfg<2, 16, 2>(im, a, mode, d_work, sm_count, stream); break;
+    case 11601: e = launch_walk_cfg<1, 16, 2>(im, a, mode, d_work, sm_count, stream); break;
     case 3208: e = launch_walk_cfg<8, 32>(im, a, mode, d_work, sm_count, stream); break;
     case 3204: e = launch_walk_cfg<4, 32>(im, a, mode, d_work, sm_count, stream); break;
     case 1604: e = launch_walk_cfg<4, 16>(im, a, mode, d_work, sm_count, stream); break;
@@ -1007,11 +1252,12 @@ cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lpq, 
     count_shard_kernel<LANES, BW, ##__VA_ARGS__>                                                          \
         <<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a);               \
   } while (0)
-  switch ((im.paired ? 10000 : 0) + im.block_words * 100 + walk_lanes(im, lpq)) {
-    case 13204: FM_SHARD(4, 32, true); break;
-    case 13202: FM_SHARD(2, 32, true); break;
-    case 11602: FM_SHARD(2, 16, true); break;
-    case 11601: FM_SHARD(1, 16, true); break;
+  switch ((im.levels - 1) * 10000 + im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 33202: FM_SHARD(2, 32, 4); break;
+    case 13204: FM_SHARD(4, 32, 2); break;
+    case 13202: FM_SHARD(2, 32, 2); break;
+    case 11602: FM_SHARD(2, 16, 2); break;
+    case 11601: FM_SHARD(1, 16, 2); break;
     case 3208: FM_SHARD(8, 32); break;
     case 3204: FM_SHARD(4, 32); break;
     case 1604: FM_SHARD(4, 16); break;
@@ -1087,11 +1333,12 @@ cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long*
     occ_kernel<LANES, BW, ##__VA_ARGS__>                                                                  \
         <<<grid_for(a.n, kThreads / (LANES), sm_count, bps), kThreads, 0, stream>>>(im, a);               \
   } while (0)
-  switch ((im.paired ? 10000 : 0) + im.block_words * 100 + walk_lanes(im, lpq)) {
-    case 13204: FM_OCC(4, 32, true); break;
-    case 13202: FM_OCC(2, 32, true); break;
-    case 11602: FM_OCC(2, 16, true); break;
-    case 11601: FM_OCC(1, 16, true); break;
+  switch ((im.levels - 1) * 10000 + im.block_words * 100 + walk_lanes(im, lpq)) {
+    case 33202: FM_OCC(2, 32, 4); break;
+    case 13204: FM_OCC(4, 32, 2); break;
+    case 13202: FM_OCC(2, 32, 2); break;
+    case 11602: FM_OCC(2, 16, 2); break;
+    case 11601: FM_OCC(1, 16, 2); break;
     case 3208: FM_OCC(8, 32); break;
     case 3204: FM_OCC(4, 32); break;
     case 1604: FM_OCC(4, 16); break;

@@ -51,7 +51,7 @@ inline int64_t paired_blocks_for_bits(int64_t nbits, int bw) {
   return std::max<int64_t>(1, (nbits + paired_positions(bw) - 1) / paired_positions(bw));
 }
 
-void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p, int bw, bool paired) {
+void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, BucketPlan* p, int bw, int levels) {
   t_block_words = bw;
   parse_bucket_tables(blk, bh, bpb, bucket, &p->tab);
   const BucketTables& t = p->tab;
@@ -75,17 +75,18 @@ void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, Bu
       nbits = bseq_length(open_bseq(wt + p->node_offs[k], wt_avail - p->node_offs[k]));
     }
     p->node_bits[k] = nbits;
-    if (!paired) p->n_blocks += blocks_for_bits(nbits);
+    if (levels == 1) p->n_blocks += blocks_for_bits(nbits);
   }
   if (p->node_ids[0] != 1) throw Error(FM_ERR_FORMAT, "wavelet tree has no root");
   p->n_records = int64_t(n_int);
-  if (paired) {
+  if (levels > 1) {  // nodes at depth 0, levels, 2*levels, ... own the blocks
     p->super_of.assign(n_int, -1);
     int32_t ns = 0;
     for (uint32_t k = 0; k < n_int; k++) {
-      if (node_depth(p->node_ids[k]) % 2 == 0) {
+      if (node_depth(p->node_ids[k]) % levels == 0) {
         p->super_of[k] = ns++;
-        p->n_blocks += paired_blocks_for_bits(p->node_bits[k], bw);
+        p->n_blocks += levels == 2 ? paired_blocks_for_bits(p->node_bits[k], bw)
+                                   : std::max<int64_t>(1, (p->node_bits[k] + kQuadPos - 1) / kQuadPos);
       }
     }
     p->n_records = ns;
@@ -291,6 +292,131 @@ int64_t fill_wavelet_paired(const Blob& blk, const BucketPlan& p, HostImage* im,
   return cursor;
 }
 
+// ---- quad-level layout (fm_image.hpp) ---------------------------------------------------------
+// Builds the blocks and QuadRecs of one bucket's wavelet tree; returns the block cursor after them.
+int64_t fill_wavelet_quad(const Blob& blk, const BucketPlan& p, HostImage* im, int64_t local_bucket,
+                          const std::unordered_map<uint32_t, uint32_t>& leaf_sym) {
+  const BucketTables& t = p.tab;
+  constexpr int P = kQuadPos, BW = kQuadBlockWords;
+  const uint8_t* wt = blk.at(t.off_wtree, 4);
+  const size_t wt_avail = size_t(t.off_marktab) - size_t(t.off_wtree);
+  const size_t n_int = p.node_ids.size();
+  auto index_of = [&](uint64_t id) -> int {
+    if (id > 0xffffffffull) return -1;
+    auto it = std::lower_bound(p.node_ids.begin(), p.node_ids.end(), uint32_t(id));
+    return (it != p.node_ids.end() && *it == uint32_t(id)) ? int(it - p.node_ids.begin()) : -1;
+  };
+  auto expand = [&](int k, std::vector<uint32_t>& out) {
+    const int64_t nbits = p.node_bits[size_t(k)];
+    out.assign(size_t((nbits + 31) / 32) + 2, 0u);
+    if (nbits > 0) {
+      const int64_t got = bseq_expand(open_bseq(wt + p.node_offs[size_t(k)], wt_avail - p.node_offs[size_t(k)]), out.data(), nbits);
+      if (got != nbits) throw Error(FM_ERR_FORMAT, "bseq expansion length mismatch");
+    }
+  };
+  std::vector<int64_t> base(n_int, 0);
+  int64_t cursor = p.block_base;
+  for (size_t k = 0; k < n_int; k++) {
+    if (p.super_of[k] < 0) continue;
+    base[k] = cursor;
+    cursor += std::max<int64_t>(1, (p.node_bits[k] + P - 1) / P);
+  }
+  std::vector<uint32_t> seq[16];
+  for (size_t k = 0; k < n_int; k++) {
+    if (p.super_of[k] < 0) continue;
+    const uint64_t id = p.node_ids[k];
+    const int64_t n = p.node_bits[k];
+    // block-local members: v = 2^l + r  <->  tree node id * 2^l + r
+    bool internal[16] = {false};
+    int64_t len[16] = {0};
+    for (int v = 1; v < 16; v++) {
+      const int l = 31 - __builtin_clz(unsigned(v));
+      const int mi = (v == 1) ? int(k) : (internal[v >> 1] ? index_of((id << l) + uint64_t(v - (1 << l))) : -1);
+      internal[v] = mi >= 0;
+      if (internal[v]) {
+        expand(mi, seq[v]);
+        len[v] = p.node_bits[size_t(mi)];
+      }
+    }
+    int64_t pos_before[32] = {0};  // positions routed to member / exit v by earlier blocks
+    const int64_t nb = std::max<int64_t>(1, (n + P - 1) / P);
+    for (int64_t j = 0; j < nb; j++) {
+      uint32_t* w = im->rank_words + (base[k] + j) * BW;
+      uint32_t region[4][4] = {{0}};
+      int cnt[32] = {0}, real[32] = {0}, lo[32] = {0}, hi[32] = {0};
+      cnt[1] = P;
+      real[1] = int(std::max<int64_t>(0, std::min<int64_t>(P, n - j * P)));
+      lo[1] = 0;
+      hi[1] = P;
+      for (int v = 1; v < 16; v++) {
+        const int l = 31 - __builtin_clz(unsigned(v));
+        const bool forward = v == 1 || (v & 1) == 0;
+        int ones = 0;
+        if (internal[v]) {
+          if (pos_before[v] + real[v] > len[v]) throw Error(FM_ERR_FORMAT, "wavelet tree child shorter than its parent says");
+          const uint32_t* s = seq[v].data();
+          for (int i = 0; i < real[v]; i++) {
+            const int64_t idx = pos_before[v] + i;
+            if ((s[idx >> 5] >> (31 - (idx & 31))) & 1u) {
+              const int pos = forward ? lo[v] + i : hi[v] - 1 - i;
+              region[l][pos >> 5] |= 1u << (31 - (pos & 31));
+              ones++;
+            }
+          }
+        }
+        const int c0 = 2 * v, c1 = 2 * v + 1;
+        cnt[c1] = real[c1] = ones;
+        cnt[c0] = cnt[v] - ones;   // positions past the end of the sequence travel down the 0 side
+        real[c0] = real[v] - ones;
+        lo[c0] = lo[v];
+        hi[c0] = lo[v] + cnt[c0];
+        hi[c1] = hi[v];
+        lo[c1] = hi[v] - cnt[c1];
+      }
+      for (int q = 0; q < 16; q++) {
+        const int64_t e = pos_before[16 + q];
+        if (e >= (int64_t(1) << 24)) throw Error(FM_ERR_FULL, "bucket too large for the quad-level layout");
+        const int path3 = q >> 1, v2 = 4 + (path3 >> 1), v3 = 8 + path3;
+        const int anchor = (q & 1) ? ((v3 & 1) ? hi[v3] : lo[v3]) : ((v2 & 1) ? hi[v2] : lo[v2]);
+        w[q] = uint32_t(e) | (uint32_t(anchor) << 24);
+      }
+      for (int l = 0; l < 4; l++)
+        for (int wi = 0; wi < 4; wi++) w[16 + 8 * (wi >> 1) + 2 * l + (wi & 1)] = region[l][wi];
+      for (int v = 1; v < 32; v++) pos_before[v] += real[v];
+    }
+    for (int v = 1; v < 16; v++)
+      if (internal[v] && pos_before[v] != len[v]) throw Error(FM_ERR_FORMAT, "wavelet tree child length mismatch");
+    // record: the 16 exits
+    QuadRec& qr = im->quads[size_t(p.node_base) + size_t(p.super_of[k])];
+    for (int q = 0; q < 16; q++) {
+      uint64_t cur = id;
+      qr.exit[q][0] = 0;
+      qr.exit[q][1] = kChildLeaf | kEndOfBucketSym;
+      bool done = false;
+      for (int d = 0; d < 4 && !done; d++) {
+        const uint64_t child = 2 * cur + uint64_t((q >> (3 - d)) & 1);
+        if (index_of(child) >= 0) {
+          cur = child;
+          continue;
+        }
+        done = true;  // a leaf: its exit is its code extended with 0 bits
+        auto ls = child <= 0xffffffffull ? leaf_sym.find(uint32_t(child)) : leaf_sym.end();
+        const bool zero_tail = (q & ((1 << (3 - d)) - 1)) == 0;
+        if (ls != leaf_sym.end() && zero_tail) qr.exit[q][1] = kChildLeaf | ls->second;
+      }
+      if (!done) {
+        const int gi = index_of(cur);
+        qr.exit[q][0] = uint32_t(base[size_t(gi)]);
+        qr.exit[q][1] = uint32_t(p.node_base + p.super_of[size_t(gi)]);
+      }
+    }
+  }
+  BucketRec& br = im->buckets[size_t(local_bucket)];
+  br.root_base = uint32_t(base[0]);
+  br.root_node = uint32_t(p.node_base + p.super_of[0]);
+  return cursor;
+}
+
 void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh, int64_t blk_num, int bucket,
                  const BucketPlan& p, HostImage* im, int64_t local_bucket, Scratch* scratch,
                  std::atomic<int64_t>* markval_used) {
@@ -310,8 +436,9 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   // rank blocks of every internal node, in directory order
   std::vector<int64_t> node_block(n_int);
   int64_t cursor = p.block_base;
-  if (im->paired) cursor = fill_wavelet_paired(blk, p, im, local_bucket, leaf_sym);
-  for (size_t k = 0; k < n_int && !im->paired; k++) {
+  if (im->levels == 2) cursor = fill_wavelet_paired(blk, p, im, local_bucket, leaf_sym);
+  if (im->levels == 4) cursor = fill_wavelet_quad(blk, p, im, local_bucket, leaf_sym);
+  for (size_t k = 0; k < n_int && im->levels == 1; k++) {
     node_block[k] = cursor;
     const int64_t nbits = p.node_bits[k];
     if (nbits > 0) {
@@ -324,7 +451,7 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   }
 
   // node records
-  for (size_t k = 0; k < n_int && !im->paired; k++) {
+  for (size_t k = 0; k < n_int && im->levels == 1; k++) {
     NodeRec& nr = im->nodes[size_t(p.node_base) + k];
     for (uint32_t b = 0; b < 2; b++) {
       const uint32_t child = p.node_ids[k] * 2 + b;
@@ -342,7 +469,7 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   }
 
   BucketRec& br = im->buckets[size_t(local_bucket)];
-  if (!im->paired) {
+  if (im->levels == 1) {
     br.root_base = uint32_t(node_block[0]);
     br.root_node = uint32_t(p.node_base);
   }
@@ -444,29 +571,37 @@ std::atomic<int> g_default_block_words{0};
 }
 
 namespace {
-std::atomic<int> g_default_paired{-1};
+std::atomic<int> g_default_paired{-1};  // levels per block chosen by set_default_levels_per_block, -1 = none
+constexpr int kDefaultLevelsPerBlock = 2;
 }
 
-// The fastest layout measured on B200 (profiles/r01_paired_level_sweep.md) is the default:
-// paired-level wavelet blocks of 64 bytes; one-level images default to 128-byte blocks.
-int default_block_words(bool paired) {
+// Block size when none was chosen: 64 bytes for the paired layout, 128 bytes for one level per
+// block (profiles/r01_paired_level_sweep.md).
+int default_block_words(int levels) {
+  if (levels == 4) return kQuadBlockWords;  // the quad layout is defined for 128-byte blocks only
   const int v = g_default_block_words.load();
   if (v != 0) return v;
   if (const char* e = std::getenv("FEMTO_B200_BLOCK_BYTES")) {
     const int b = std::atoi(e);
     if (b == 32 || b == 64 || b == 128) return b / 4;
   }
-  return paired ? 16 : kDefaultBlockWords;
+  return levels == 2 ? 16 : kDefaultBlockWords;
 }
 
-bool default_paired_levels() {
-  const int v = g_default_paired.load();
-  if (v >= 0) return v != 0;
-  if (const char* e = std::getenv("FEMTO_B200_PAIRED_LEVELS")) return std::atoi(e) != 0;
+int default_levels_per_block() {
+  int v = g_default_paired.load();
+  if (v <= 0) {
+    v = kDefaultLevelsPerBlock;
+    if (const char* e = std::getenv("FEMTO_B200_LEVELS_PER_BLOCK")) v = std::atoi(e);
+  }
+  return (v == 1 || v == 2 || v == 4) ? v : kDefaultLevelsPerBlock;
+}
+
+bool set_default_levels_per_block(int levels) {
+  if (levels != 0 && levels != 1 && levels != 2 && levels != 4) return false;
+  g_default_paired.store(levels == 0 ? -1 : levels);
   return true;
 }
-
-void set_default_paired_levels(int on) { g_default_paired.store(on < 0 ? -1 : (on ? 1 : 0)); }
 
 bool set_default_block_words(int words) {
   if (words != 0 && words != 8 && words != 16 && words != 32) return false;
@@ -511,13 +646,40 @@ HostPairedRank host_paired_rank(const uint32_t* rank_words, int block_words, uin
   return r;
 }
 
+HostQuadRank host_quad_rank(const uint32_t* rank_words, uint32_t base_block, uint32_t index1, int path) {
+  const uint32_t p = index1 - 1, k = p / kQuadPos;
+  uint32_t j = p % kQuadPos + 1;
+  const uint32_t* w = rank_words + (size_t(base_block) + k) * size_t(kQuadBlockWords);
+  auto rbit = [&](int l, uint32_t pos) {
+    const uint32_t wi = pos >> 5;
+    return (w[16 + 8 * (wi >> 1) + 2 * uint32_t(l) + (wi & 1)] >> (31 - (pos & 31))) & 1u;
+  };
+  uint32_t q = 0;
+  for (int l = 0; l < 4; l++) {
+    const bool back = l > 0 && (q & 1u);
+    uint32_t anchor = 0;
+    if (l == 1) anchor = back ? kQuadPos : 0;
+    if (l == 2) anchor = w[q << 2] >> 24;
+    if (l == 3) anchor = w[(q << 1) | 1u] >> 24;
+    const uint32_t a = back ? anchor - j : anchor;
+    uint32_t cnt = 0;
+    for (uint32_t x = a; x < a + j; x++) cnt += rbit(l, x);
+    const uint32_t bit = path >= 0 ? (uint32_t(path) >> (3 - l)) & 1u : (j ? rbit(l, back ? anchor - j : anchor + j - 1) : 0u);
+    j = bit ? cnt : j - cnt;
+    q = (q << 1) | bit;
+  }
+  return HostQuadRank{q, (w[q] & 0xffffffu) + j};
+}
+
 std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
-                                            int block_words, int paired_levels) {
+                                            int block_words, int levels) {
   if (nshards < 1 || shard < 0 || shard >= nshards) throw Error(FM_ERR_PARAM, "bad shard");
-  const bool paired = paired_levels < 0 ? default_paired_levels() : paired_levels != 0;
-  if (block_words == 0) block_words = default_block_words(paired);
+  if (levels == 0) levels = default_levels_per_block();
+  if (levels != 1 && levels != 2 && levels != 4) throw Error(FM_ERR_PARAM, "levels per block must be 1, 2 or 4");
+  if (block_words == 0) block_words = default_block_words(levels);
   if (block_words != 8 && block_words != 16 && block_words != 32) throw Error(FM_ERR_PARAM, "rank block must be 32, 64 or 128 bytes");
-  if (paired && block_words < 16) throw Error(FM_ERR_PARAM, "the paired-level layout needs 64- or 128-byte blocks");
+  if (levels == 2 && block_words < 16) throw Error(FM_ERR_PARAM, "the paired-level layout needs 64- or 128-byte blocks");
+  if (levels == 4 && block_words != kQuadBlockWords) throw Error(FM_ERR_PARAM, "the quad-level layout needs 128-byte blocks");
   if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
   auto files = IndexFiles::open(path);
   const BlockHeader& h = files->header();
@@ -525,7 +687,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
   std::unique_ptr<HostImage> im(new HostImage());
   im->hdr = h;
   im->block_words = block_words;
-  im->paired = paired;
+  im->levels = levels;
   const int kBlockWords = block_words;
 
   // data blocks of this shard: b with b*nshards/nblocks == shard
@@ -580,7 +742,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
     for (int k = 0; k < bhs[lb].num_buckets; k++) where[size_t(bucket0[lb] + k)] = {int32_t(lb), int32_t(k)};
   parallel_for(nb, nthreads, [&](int64_t g, int) {
     const auto [lb, k] = where[size_t(g)];
-    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)], block_words, paired);
+    plan_bucket(blobs[size_t(lb)], bhs[size_t(lb)], bpb, k, &plans[size_t(g)], block_words, levels);
   });
 
   int64_t nodes = 0, blocks = 0, vals = 0, wt_blocks = 0;
@@ -602,7 +764,9 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
   im->n_wtree_blocks = wt_blocks;
   im->rank_words = static_cast<uint32_t*>(std::calloc(size_t(std::max<int64_t>(blocks, 1)) * kBlockWords, 4));
   if (!im->rank_words) throw Error(FM_ERR_MEM, "out of host memory for the rank image");
-  if (paired) im->supers.resize(size_t(nodes)); else im->nodes.resize(size_t(nodes));
+  if (levels == 4) im->quads.resize(size_t(nodes));
+  else if (levels == 2) im->supers.resize(size_t(nodes));
+  else im->nodes.resize(size_t(nodes));
   im->occ.resize(size_t(nb) * kAlphaStride);
   im->mark.resize(size_t(nb) * kAlphaStride);
   im->buckets.resize(size_t(nb));

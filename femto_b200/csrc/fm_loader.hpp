@@ -20,12 +20,13 @@ struct HostImage {
   int max_code_len = 0;
   // tables
   int block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
-  bool paired = false;                   // paired-level wavelet blocks (fm_image.hpp)
+  int levels = 1;                        // wavelet-tree levels per block: 1, 2 (paired) or 4 (quad); fm_image.hpp
   uint32_t* rank_words = nullptr;   // n_rank_blocks * block_words words (calloc'ed)
   int64_t n_rank_blocks = 0;
   int64_t n_wtree_blocks = 0;       // of which wavelet-tree payload (the rest are mark bit-vectors)
   std::vector<NodeRec> nodes;       // plain layout
   std::vector<SuperRec> supers;     // paired-level layout
+  std::vector<QuadRec> quads;       // quad-level layout
   std::vector<OccRec> occ;
   std::vector<MarkRec> mark;
   std::vector<BucketRec> buckets;
@@ -39,17 +40,18 @@ struct HostImage {
 };
 
 // shard/nshards select data blocks b with b*nshards/nblocks == shard (all blocks when nshards==1).
-// paired_levels: 1 = paired-level wavelet blocks, 0 = one level per block, -1 = process default
-// (set_default_paired_levels, else env FEMTO_B200_PAIRED_LEVELS, else paired).
+// levels: wavelet-tree levels answered per block read (fm_image.hpp): 1, 2 (paired) or 4 (quad);
+// 0 = the process default (set_default_levels_per_block, else env FEMTO_B200_LEVELS_PER_BLOCK,
+// else paired).
 // block_words: 32, 16 or 8 (128/64/32-byte rank blocks); 0 = the process default
 // (set_default_block_words, else env FEMTO_B200_BLOCK_BYTES, else 64-byte blocks for the paired
-// layout and 128-byte blocks for the one-level layout).
+// layout and 128-byte blocks otherwise).  Paired needs >= 64 bytes, quad exactly 128.
 std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, int nshards, int nthreads,
-                                            int block_words = 0, int paired_levels = -1);
-int default_block_words(bool paired);
-bool set_default_block_words(int words);     // 0 = back to the built-in default
-bool default_paired_levels();
-void set_default_paired_levels(int on);      // negative = back to the built-in default
+                                            int block_words = 0, int levels = 0);
+int default_block_words(int levels);
+bool set_default_block_words(int words);          // 0 = back to the built-in default
+int default_levels_per_block();
+bool set_default_levels_per_block(int levels);    // 0 = back to the built-in default
 
 // Host-side rank over the image (used by the loader's self-check and by unit tests of the
 // image layout; NOT a query fallback -- the C ABI never calls it).
@@ -67,5 +69,13 @@ struct HostPairedRank {
 };
 HostPairedRank host_paired_rank(const uint32_t* rank_words, int block_words, uint32_t base_block, uint32_t index1,
                                 int follow);
+
+// All four levels of a quad-level block: follows `path` (b1 b2 b3 b4 as a number) or, when
+// path < 0, the bits found at the position.
+struct HostQuadRank {
+  uint32_t exit;    // the 4 path bits taken
+  uint32_t index1;  // 1-based index in the node at that exit
+};
+HostQuadRank host_quad_rank(const uint32_t* rank_words, uint32_t base_block, uint32_t index1, int path);
 
 }  // namespace fmb

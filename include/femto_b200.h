@@ -66,7 +66,7 @@ typedef struct {
   int32_t device;            /* CUDA device ordinal */
   int32_t max_code_len;      /* deepest wavelet-tree leaf over all resident buckets */
   int32_t rank_block_size;   /* bytes per rank block of the HBM image: 128, 64 or 32 */
-  int32_t paired_levels;     /* 1: wavelet-tree blocks answer two levels per read (fm_set_default_paired_levels) */
+  int32_t levels_per_block;  /* wavelet-tree levels one rank block read answers: 1, 2 or 4 */
 } fm_info_t;
 
 /* --------------------------------------------------------------------------
@@ -203,21 +203,27 @@ int fm_set_lanes_per_query(fm_index_t* ix, int lanes);
  * advances both Occ of a step together and reads a shared rank block once; merged == 0: two
  * sub-groups of `lanes` lanes per pattern, one per Occ.  Lane counts available: 128-byte rank
  * blocks 2/4/8 (merged) 4/8 (pair); 64-byte 1/2/4 and 2/4; 32-byte 1/2 and 2.  Paired-level images
- * (below) always run the merged schedule, with 1/2/4 lanes on 128-byte and 1/2 on 64-byte blocks. */
+ * (below) always run the merged schedule, with 1/2/4 lanes on 128-byte and 1/2 on 64-byte blocks;
+ * quad-level images with 2 lanes. */
 int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes);
 
-/* Wavelet-tree block layout of the HBM image built by subsequent fm_open calls.
- *   on > 0  (the default): paired levels.  A block holds a stretch of an even-depth node together
- *           with the matching bits of both children, so one 64- or 128-byte read answers two
- *           wavelet-tree levels: half the dependent HBM reads of the one-level layout, at about
- *           1.3x its size.
- *   on == 0: one level per block.
- *   on < 0 : back to the default (environment FEMTO_B200_PAIRED_LEVELS, else paired). */
-int fm_set_default_paired_levels(int on);
+/* Wavelet-tree block layout of the HBM image built by subsequent fm_open calls: how many tree
+ * levels one rank block read answers.  Backward search is a chain of dependent random HBM reads
+ * and a B200 serves a fixed number of those per second whatever their width up to 128 bytes, so
+ * levels per read is what sets the speed.
+ *   1: one level per block (blocks of 128, 64 or 32 bytes).
+ *   2: paired levels.  A block holds a stretch of an even-depth node together with the matching
+ *      bits of both children (blocks of 64 or 128 bytes).
+ *   4: quad levels.  A 128-byte block holds 128 positions of a node at depth 0, 4, 8, ... and the
+ *      matching bits of its children, grandchildren and great-grandchildren
+ *      (needs bucket_size < 2^24 rows).
+ *   0: back to the default (environment FEMTO_B200_LEVELS_PER_BLOCK, else the built-in choice). */
+int fm_set_default_levels_per_block(int levels);
 
-/* Rank block size in bytes of the HBM image built by subsequent fm_open calls: 128 or 64 (paired
- * levels), 128, 64 or 32 (one level per block); 0 = back to the default (environment
- * FEMTO_B200_BLOCK_BYTES, else 64 for paired levels and 128 for one level per block). */
+/* Rank block size in bytes of the HBM image built by subsequent fm_open calls: 128, 64 or 32
+ * with one level per block, 128 or 64 with paired levels (quad levels always use 128);
+ * 0 = back to the default (environment FEMTO_B200_BLOCK_BYTES, else 64 for paired levels and
+ * 128 otherwise). */
 int fm_set_default_block_bytes(int bytes);
 
 /* --------------------------------------------------------------------------

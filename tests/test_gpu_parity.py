@@ -18,25 +18,26 @@ ALL = ["two_docs", "gen400_big_buckets", "gen400_small_buckets", "gen400_small_b
        "gen3", "single_symbol", "multi_doc_mixed", "acgt_64k", "bytes_200k", "skewed_deep", "english_100k"]
 
 
-def open_with_layout(built_indexes, block_bytes, paired):
+def open_with_layout(built_indexes, block_bytes, levels):
+    """Open every test index with `levels` wavelet-tree levels per rank block of block_bytes."""
     from femto_b200 import _lib
     lib = _lib.load()
     assert lib.fm_set_default_block_bytes(block_bytes) == 0
-    assert lib.fm_set_default_paired_levels(int(paired)) == 0
+    assert lib.fm_set_default_levels_per_block(levels) == 0
     try:
         opened = {name: fb.Index(path, device=0) for name, path in built_indexes.items()}
     finally:
         lib.fm_set_default_block_bytes(0)
-        lib.fm_set_default_paired_levels(-1)
+        lib.fm_set_default_levels_per_block(0)
     for ix in opened.values():
-        assert ix.info.rank_block_size == block_bytes and ix.info.paired_levels == int(paired)
+        assert ix.info.rank_block_size == block_bytes and ix.info.levels_per_block == levels
     return opened
 
 
 @pytest.fixture(scope="module")
 def gpu_indexes(built_indexes):
     """One wavelet-tree level per 128-byte rank block (the layout the schedule matrix below covers)."""
-    opened = open_with_layout(built_indexes, 128, False)
+    opened = open_with_layout(built_indexes, 128, 1)
     yield opened
     for ix in opened.values():
         ix.close()
@@ -55,7 +56,7 @@ def gpu_indexes_small_blocks(built_indexes):
     """The same indexes loaded with 64- and 32-byte rank blocks."""
     opened = {}
     for bb in (64, 32):
-        for name, ix in open_with_layout(built_indexes, bb, False).items():
+        for name, ix in open_with_layout(built_indexes, bb, 1).items():
             opened[(name, bb)] = ix
     yield opened
     for ix in opened.values():
@@ -287,8 +288,8 @@ def test_mixed_length_zipf_batch(tmp_path):
         q[int(rng.integers(0, len(q)))] = 5 + int(rng.integers(97, 123))
         pats[k] = q
     with fb.Index(path) as ix, Oracle(path) as o:
-        for sched in ((1, 2), (1, 1)):                       # default image: paired levels, 64-byte blocks
-            ix.set_count_schedule(*sched)
+        for _ in range(2):                                   # the default image and schedule, twice
+            ix.set_count_schedule(1, 2)
             f, l = ix.count(pats)
             sub = list(range(0, len(pats), 7))
             of, ol = o.count([pats[i] for i in sub])
@@ -331,24 +332,24 @@ def test_properties_at_scale(tmp_path):
             assert got == docs[d]
 
 
-# ---- paired-level wavelet blocks (two levels per HBM read; fm_image.hpp) ----------------------------
+# ---- paired- and quad-level wavelet blocks (2 / 4 tree levels per HBM read; fm_image.hpp) ------------
 @pytest.fixture(scope="module")
-def gpu_indexes_paired(built_indexes):
+def gpu_indexes_multilevel(built_indexes):
     opened = {}
-    for bb in (128, 64):
-        for name, ix in open_with_layout(built_indexes, bb, True).items():
-            opened[(name, bb)] = ix
+    for bb, levels in ((128, 2), (64, 2), (128, 4)):
+        for name, ix in open_with_layout(built_indexes, bb, levels).items():
+            opened[(name, bb, levels)] = ix
     yield opened
     for ix in opened.values():
         ix.close()
 
 
-@pytest.mark.parametrize("cfg", [(128, 4), (128, 2), (128, 1), (64, 2), (64, 1)])
+@pytest.mark.parametrize("cfg", [(128, 2, 4), (128, 2, 2), (128, 2, 1), (64, 2, 2), (64, 2, 1), (128, 4, 2)])
 @pytest.mark.parametrize("name", ALL)
-def test_count_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpora):
-    bb, lanes = cfg
+def test_count_multilevel_blocks(name, cfg, gpu_indexes_multilevel, built_indexes, corpora):
+    bb, levels, lanes = cfg
     docs, _ = corpora[name]
-    ix = gpu_indexes_paired[(name, bb)]
+    ix = gpu_indexes_multilevel[(name, bb, levels)]
     ix.set_count_schedule(1, lanes)
     pats = corpus.sample_patterns(docs, 1500, [1, 2, 3, 4, 5, 6, 8, 12, 16, 24, 32, 64], seed=35) + edge_patterns()
     with Oracle(built_indexes[name]) as o:
@@ -360,13 +361,13 @@ def test_count_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpo
     assert (f2 == of).all() and (l2 == ol).all()
 
 
-@pytest.mark.parametrize("cfg", [(128, 4), (128, 2), (64, 2), (64, 1)])
+@pytest.mark.parametrize("cfg", [(128, 2, 4), (128, 2, 2), (64, 2, 2), (64, 2, 1), (128, 4, 2)])
 @pytest.mark.parametrize("name", ALL)
-def test_walks_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpora):
-    """occ / back_step / locate / extract over paired-level blocks, every lane configuration."""
-    bb, lanes = cfg
+def test_walks_multilevel_blocks(name, cfg, gpu_indexes_multilevel, built_indexes, corpora):
+    """occ / back_step / locate / extract over paired- and quad-level blocks, every lane configuration."""
+    bb, levels, lanes = cfg
     docs, _ = corpora[name]
-    ix = gpu_indexes_paired[(name, bb)]
+    ix = gpu_indexes_multilevel[(name, bb, levels)]
     ix.set_lanes_per_query(lanes)
     pats = corpus.sample_patterns(docs, 200, [1, 2, 3, 4, 6, 8, 16], seed=45) + edge_patterns()[1:]
     with Oracle(built_indexes[name]) as o:
@@ -394,9 +395,9 @@ def test_walks_paired_levels(name, cfg, gpu_indexes_paired, built_indexes, corpo
 
 
 def test_default_layout_and_probe(built_indexes):
-    """fm_open without tuning calls builds the paired-level 64-byte image; the random-read probe runs."""
+    """fm_open without tuning calls builds a multi-level image; the random-read probe runs."""
     ix = fb.Index(built_indexes["bytes_200k"], device=0)
-    assert ix.info.paired_levels == 1 and ix.info.rank_block_size == 64
+    assert (ix.info.levels_per_block, ix.info.rank_block_size) in ((2, 64), (4, 128))
     for b in (32, 64, 128):
         r = ix.probe_random_reads(b, steps=50)
         assert r["accesses"] > 0 and r["ms"] > 0

@@ -17,16 +17,16 @@ from oracle.bindings import Oracle
 
 
 class Image:
-    def __init__(self, path, shard=0, nshards=1, block_bytes=128, paired=False):
+    def __init__(self, path, shard=0, nshards=1, block_bytes=128, levels=1):
         self.lib = _lib.load()
         err = C.c_int()
         assert self.lib.fm_set_default_block_bytes(block_bytes) == 0
-        assert self.lib.fm_set_default_paired_levels(int(paired)) == 0
+        assert self.lib.fm_set_default_levels_per_block(levels) == 0
         try:
             self.h = self.lib.fm_debug_image_open(os.fsencode(path), shard, nshards, 4, C.byref(err))
         finally:
             self.lib.fm_set_default_block_bytes(0)
-            self.lib.fm_set_default_paired_levels(-1)
+            self.lib.fm_set_default_levels_per_block(0)
         assert self.h, f"image open failed err={err.value}"
 
     def stats(self):
@@ -86,7 +86,23 @@ def test_paired_level_image_exhaustive(name, block_bytes, built_indexes):
     """The paired-level layout (two wavelet-tree levels per block, fm_image.hpp) decodes to the same
     Occ / LF / marks as the reference for every row and symbol."""
     path = built_indexes[name]
-    im = Image(path, block_bytes=block_bytes, paired=True)
+    im = Image(path, block_bytes=block_bytes, levels=2)
+    with Oracle(path) as o:
+        n = o.header_info()["total_length"]
+        for row in range(0, n, 1 if n <= 500 else 3):
+            assert im.back_step(row) == o.back_step(row), row
+            for ch in range(261):
+                assert im.occ(ch, row) == o.occ(ch, row)[0], (ch, row)
+    im.close()
+
+
+@pytest.mark.parametrize("name", ["two_docs", "gen400_small_blocks", "gen400_big_buckets", "gen400_small_buckets",
+                                  "gen13_small_blocks", "gen3", "single_symbol", "multi_doc_mixed"])
+def test_quad_level_image_exhaustive(name, built_indexes):
+    """The quad-level layout (four wavelet-tree levels per 128-byte block, fm_image.hpp) decodes to
+    the same Occ / LF / marks as the reference for every row and symbol."""
+    path = built_indexes[name]
+    im = Image(path, block_bytes=128, levels=4)
     with Oracle(path) as o:
         n = o.header_info()["total_length"]
         for row in range(0, n, 1 if n <= 500 else 3):
@@ -100,20 +116,20 @@ def test_paired_level_layout_needs_wide_blocks(built_indexes):
     lib = _lib.load()
     err = C.c_int()
     lib.fm_set_default_block_bytes(32)
-    lib.fm_set_default_paired_levels(1)
+    lib.fm_set_default_levels_per_block(2)
     try:
         assert not lib.fm_debug_image_open(os.fsencode(built_indexes["two_docs"]), 0, 1, 1, C.byref(err))
         assert err.value != 0
     finally:
         lib.fm_set_default_block_bytes(0)
-        lib.fm_set_default_paired_levels(-1)
+        lib.fm_set_default_levels_per_block(0)
 
 
-@pytest.mark.parametrize("layout", [(128, False), (64, False), (32, False), (128, True), (64, True)])
+@pytest.mark.parametrize("layout", [(128, 1), (64, 1), (32, 1), (128, 2), (64, 2), (128, 4)])
 @pytest.mark.parametrize("name", ["acgt_64k", "bytes_200k", "skewed_deep", "english_100k"])
 def test_image_matches_oracle_sampled(name, layout, built_indexes):
     path = built_indexes[name]
-    im = Image(path, block_bytes=layout[0], paired=layout[1])
+    im = Image(path, block_bytes=layout[0], levels=layout[1])
     rng = np.random.default_rng(9)
     with Oracle(path) as o:
         n = o.header_info()["total_length"]
