@@ -133,7 +133,7 @@ int paired_sched(int block_words, int lanes) {
   return 1000 + 10 * lanes + minb;
 }
 
-constexpr int kQuadSched = 1000 + 10 * 2 + 4;  // quad-level blocks: 2 lanes per pattern
+constexpr int kQuadSched = 1000 + 10 * 2 + 5;  // quad-level blocks: 2 lanes per pattern, 5 CTAs per SM
 
 int default_count_sched(int block_words, int levels) {
   int sched = levels == 4 ? kQuadSched

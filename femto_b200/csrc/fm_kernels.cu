@@ -564,53 +564,56 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
       int64_t g;
       uint32_t rb;
       split_row(im, s.l, g, rb);
+      bool hasA = false, cross = false;
+      uint32_t rbA = 0;
       if (!cross_pending) {
         c = s.pat[s.i - 1];
         if (STATS && sub == 0) n_steps++;
         if (c >= kAlphaDev) {  // symbol outside the alphabet: empty range
           s.f = im.total_length; s.l = s.f - 1; s.i--;
           stepping = false;
-        } else {
-          const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-          obB = rec_occ_base(rv);
-          leaf = static_cast<uint32_t>(rv.z);
-          idxB = rb + 1;
-          if (STATS && sub == 0) n_occ++;
-          if (s.f == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
-            obA = __ldg(im.C + c);
-            actB = true;
-          } else {
-            int64_t gA;
-            uint32_t rbA;
-            split_row(im, s.f - 1, gA, rbA);
-            idxA = rbA + 1;
-            actA = true;
-            if (STATS && sub == 0) n_occ++;
-            if (gA == g) {
-              obA = obB;
-              actB = true;
-            } else {  // first-1 sits in another bucket: this round does A, the next one B
-              const int4 ra = __ldg(reinterpret_cast<const int4*>(im.occ + gA * kAlphaStride + c));
-              obA = rec_occ_base(ra);
-              leaf = static_cast<uint32_t>(ra.z);
-              g = gA;
-              cross_pending = true;
-            }
-          }
+        } else if (s.f != 0) {
+          int64_t gA;
+          split_row(im, s.f - 1, gA, rbA);
+          hasA = true;
+          cross = gA != g;  // first-1 sits in another bucket: this round does A, the next one B
+          if (cross) g = gA;
         }
-      } else {  // second round of a cross-bucket step: row `last`
-        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-        obB = rec_occ_base(rv);
-        leaf = static_cast<uint32_t>(rv.z);
-        idxB = rb + 1;
-        actB = true;
-        cross_pending = false;
       }
       if (stepping) {
+        // the symbol's record and the bucket's root: two independent reads, issued together
+        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+        const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+        const int64_t ob = rec_occ_base(rv);
+        leaf = static_cast<uint32_t>(rv.z);
+        if (cross_pending) {  // second round of a cross-bucket step: row `last`
+          obB = ob;
+          idxB = rb + 1;
+          actB = true;
+          cross_pending = false;
+          if (STATS && sub == 0) n_occ++;
+        } else if (!hasA) {   // Occ(c,-1) = 0 without touching the index (server.c:847-851)
+          obA = __ldg(im.C + c);
+          obB = ob;
+          idxB = rb + 1;
+          actB = true;
+          if (STATS && sub == 0) n_occ++;
+        } else {
+          obA = ob;
+          idxA = rbA + 1;
+          actA = true;
+          if (STATS && sub == 0) n_occ += cross ? 1 : 2;
+          if (cross) {
+            cross_pending = true;
+          } else {
+            obB = ob;
+            idxB = rb + 1;
+            actB = true;
+          }
+        }
         if (leaf == 0) {  // symbol absent from the bucket: Occ is the bucket base (index.c:2080-2089)
           actA = actB = false;
         } else {
-          const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
           base = br.x;
           node = br.y;
           L = 31 - __clz(leaf);

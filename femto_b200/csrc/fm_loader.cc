@@ -164,6 +164,13 @@ void copy_bits(uint32_t* dst, int64_t dst_off, const uint32_t* src, int64_t src_
   }
 }
 
+inline uint32_t bit_reverse32(uint32_t v) {
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  return __builtin_bswap32(v);
+}
+
 int64_t count_ones(const uint32_t* bits, int64_t from, int64_t to) {  // ones in [from, to)
   int64_t c = 0;
   while (from < to) {
@@ -352,16 +359,17 @@ int64_t fill_wavelet_quad(const Blob& blk, const BucketPlan& p, HostImage* im, i
         const int l = 31 - __builtin_clz(unsigned(v));
         const bool forward = v == 1 || (v & 1) == 0;
         int ones = 0;
-        if (internal[v]) {
+        if (internal[v] && real[v] > 0) {
           if (pos_before[v] + real[v] > len[v]) throw Error(FM_ERR_FORMAT, "wavelet tree child shorter than its parent says");
-          const uint32_t* s = seq[v].data();
-          for (int i = 0; i < real[v]; i++) {
-            const int64_t idx = pos_before[v] + i;
-            if ((s[idx >> 5] >> (31 - (idx & 31))) & 1u) {
-              const int pos = forward ? lo[v] + i : hi[v] - 1 - i;
-              region[l][pos >> 5] |= 1u << (31 - (pos & 31));
-              ones++;
-            }
+          uint32_t y[5] = {0, 0, 0, 0, 0};  // the node's bits for this block's positions, in order
+          copy_bits(y, 0, seq[v].data(), pos_before[v], real[v]);
+          for (int t = 0; t < 4; t++) ones += __builtin_popcount(y[t]);
+          if (forward) {
+            copy_bits(region[l], lo[v], y, 0, real[v]);
+          } else {  // entry i goes to bit hi-1-i: place the reversed string so that it ends at hi
+            uint32_t r[5] = {0, 0, 0, 0, 0};
+            for (int t = 0; t < 4; t++) r[t] = bit_reverse32(y[3 - t]);
+            copy_bits(region[l], hi[v] - real[v], r, kQuadPos - real[v], real[v]);
           }
         }
         const int c0 = 2 * v, c1 = 2 * v + 1;
@@ -572,7 +580,8 @@ std::atomic<int> g_default_block_words{0};
 
 namespace {
 std::atomic<int> g_default_paired{-1};  // levels per block chosen by set_default_levels_per_block, -1 = none
-constexpr int kDefaultLevelsPerBlock = 2;
+// quad-level blocks are the fastest layout measured on B200 (profiles/r01_levels_per_block.md)
+constexpr int kDefaultLevelsPerBlock = 4;
 }
 
 // Block size when none was chosen: 64 bytes for the paired layout, 128 bytes for one level per
