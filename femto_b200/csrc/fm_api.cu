@@ -133,7 +133,11 @@ int paired_sched(int block_words, int lanes) {
   return 1000 + 10 * lanes + minb;
 }
 
-constexpr int kQuadSched = 1000 + 10 * 2 + 5;  // quad-level blocks: 2 lanes per pattern, 5 CTAs per SM
+// quad-level blocks: 1000 + 10 * k + CTAs per SM; k = 4: two lanes per pattern, short dependency
+// chain (default); k = 1: one lane per pattern; k = 2: the first two-lane kernel (kept for comparison,
+// reachable through FEMTO_B200_COUNT_SCHED only)
+constexpr int kQuadSchedLane = 1000 + 10 * 1 + 4;
+constexpr int kQuadSched = 1000 + 10 * 4 + 5;
 
 int default_count_sched(int block_words, int levels) {
   int sched = levels == 4 ? kQuadSched
@@ -226,6 +230,7 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     else if (host->levels == 2) ix->im.supers = static_cast<const SuperRec*>(ix->d_nodes);
     else ix->im.nodes = static_cast<const NodeRec*>(ix->d_nodes);
     ix->im.levels = host->levels;
+    ix->im.root_stride = host->root_stride;
     ix->info.levels_per_block = host->levels;
     ix->im.occ = static_cast<const OccRec*>(ix->d_occ);
     ix->im.mark = static_cast<const MarkRec*>(ix->d_mark);
@@ -433,8 +438,9 @@ int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
   if (!ix) return fail(FM_ERR_PARAM, "fm_set_count_schedule: null index");
   const int bw = ix->im.block_words;
   if (ix->im.levels == 4) {
-    if (lanes != 2) return fail(FM_ERR_PARAM, "fm_set_count_schedule: quad-level blocks run with 2 lanes per pattern");
-    ix->count_sched = kQuadSched;
+    if (lanes != 1 && lanes != 2)
+      return fail(FM_ERR_PARAM, "fm_set_count_schedule: quad-level blocks run with 1 or 2 lanes per pattern");
+    ix->count_sched = lanes == 1 ? kQuadSchedLane : kQuadSched;
     return FM_OK;
   }
   if (ix->im.levels == 2) {  // paired-level blocks: merged schedule only, a lane owns whole 32-byte slices
@@ -615,6 +621,27 @@ int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, 
     w.status = ix->d_status;
     ix->dev_slot = ix->dev_slot % 7 + 1;
     CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
+                   static_cast<cudaStream_t>(stream), &ix->launches));
+    return FM_OK;
+  });
+}
+
+int fm_locate_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, int32_t* d_dest, int nshards,
+                         void* stream) {
+  return guarded(ix, "fm_locate_shard_step", [&]() -> int {
+    if (nstates < 0 || nshards < 1 || (nstates && (!d_state || !d_dest)))
+      return fail(FM_ERR_PARAM, "fm_locate_shard_step: bad argument");
+    if (nstates == 0) return FM_OK;
+    WalkArgs w{};
+    w.nrows = nstates;
+    w.status = ix->d_status;
+    w.state = d_state;
+    w.dest = d_dest;
+    w.nshards = nshards;
+    w.block_size = ix->info.block_size;
+    w.nblocks = ix->info.num_blocks;
+    ix->dev_slot = ix->dev_slot % 7 + 1;
+    CK(launch_walk(ix->im, w, kWalkShard, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
                    static_cast<cudaStream_t>(stream), &ix->launches));
     return FM_OK;
   });

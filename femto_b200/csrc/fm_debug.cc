@@ -66,12 +66,15 @@ int64_t fm_debug_image_occ(void* h, int ch, int64_t row) {
   uint32_t base = br.root_base, node = br.root_node, idx1 = rb + 1;
   const int L = 31 - __builtin_clz(o.leaf);
   if (im.levels == 4) {
+    // the root area and OccRec::root_exit must name the same block / exit entry as the bucket record
+    if (int64_t(base) != g * im.root_stride) return -3;
     for (int lvl = 0; lvl < L; lvl += 4) {
       const int rem = L - lvl;  // code bits left; a code ending inside the block is extended with 0 bits
       const uint32_t path = rem >= 4 ? (o.leaf >> (rem - 4)) & 15u : (o.leaf << (4 - rem)) & 15u;
       const HostQuadRank r = host_quad_rank(im.rank_words, base, idx1, int(path));
       idx1 = r.index1;
       const uint32_t* ex = im.quads[node].exit[path];
+      if (lvl == 0 && ex != &im.quads[0].exit[0][0] + 2 * size_t(o.root_exit)) return -3;
       if (rem <= 4) {
         if (!(ex[1] & kChildLeaf) || (ex[1] & 0xffffu) != uint32_t(ch)) return -2;
         break;

@@ -91,6 +91,12 @@ struct alignas(16) SuperRec {
 //   j bits of a node are the range [anchor, anchor + j) resp. [anchor - j, anchor), their ones c
 //   give the next j' = b ? c : j - c, and the result after four levels is E(q) + j''''.
 //   Positions past the end of the node's sequence count as 0 bits.  Needs bucket_size < 2^24.
+//
+//   Root area.  The blocks of the ROOT quad nodes are not allocated with the rest of their bucket:
+//   they fill the front of the block array, bucket g (local) at [g * root_stride, (g + 1) *
+//   root_stride) with root_stride = ceil(bucket_size / kQuadPos).  The first block a backward-search
+//   step reads is therefore a function of the row alone -- g * root_stride + (row in bucket) /
+//   kQuadPos -- and its read is issued together with the (bucket, symbol) record instead of after it.
 constexpr int kQuadPos = 128;
 constexpr int kQuadBlockWords = 32;
 
@@ -103,7 +109,8 @@ struct alignas(16) QuadRec {
 struct alignas(16) OccRec {
   int64_t occ_base;  // C[ch] + occurrences of ch before this bucket
   uint32_t leaf;     // wavelet-tree leaf id (1<<len | code) of ch in this bucket, 0 = absent
-  uint32_t pad;
+  uint32_t root_exit;  // quad layout: 16 * (root QuadRec index) + first four path bits of ch, i.e. the
+                       // index of the exit entry {first block, QuadRec} the second block read needs
 };
 
 struct alignas(8) MarkRec {
@@ -135,6 +142,7 @@ struct DevImage {
   int32_t bucket_shift = -1;            // log2(bucket_size) when it is a power of two, else -1
   int32_t block_words = kDefaultBlockWords;  // 32-bit words per rank block (32, 16 or 8)
   int32_t levels = 1;                        // wavelet-tree levels answered per block read: 1, 2 (paired) or 4 (quad)
+  int64_t root_stride = 0;                   // quad layout: blocks per bucket in the root area
 };
 
 }  // namespace fmb

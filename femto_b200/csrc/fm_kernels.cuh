@@ -22,7 +22,8 @@ struct CountArgs {
 enum WalkMode : int {
   kWalkLocate = 0,  // follow LF until a marked row; out_offset[i] = SA[rows[i]]
   kWalkStep = 1,    // one LF step: out_ch, out_next, out_offset (mark of the row itself or -1)
-  kWalkExtract = 2  // nsteps[i] LF steps writing L right-to-left into out_sym[sym_off[i] + nsteps[i]-1-t]
+  kWalkExtract = 2, // nsteps[i] LF steps writing L right-to-left into out_sym[sym_off[i] + nsteps[i]-1-t]
+  kWalkShard = 3    // range-sharded locate: walk state[i] while its row is resident (see WalkArgs::state)
 };
 
 struct WalkArgs {
@@ -35,7 +36,18 @@ struct WalkArgs {
   const int64_t* sym_off;
   uint16_t* out_sym;
   int32_t* status;       // device int: set non-zero on malformed walk (unmarked document start, bad row)
+  // kWalkShard (index opened as a BWT row range): nrows states of kWalkStateWords int64
+  //   {slot at the home rank, row -- or the text offset once finished --, LF steps so far,
+  //    phase | home_rank << 4}, phase 0 = walking, 2 = finished.
+  // The kernel follows LF while the row is resident; dest[i] = the rank that must see state i
+  // next: the owner of its row, or its home rank once finished.
+  int64_t* state;
+  int32_t* dest;
+  int32_t nshards;
+  int32_t block_size;    // rows per data block; owner(row) = (row / block_size) * nshards / nblocks
+  int64_t nblocks;
 };
+constexpr int kWalkStateWords = 4;
 
 struct OccArgs {
   int64_t n;

@@ -27,6 +27,7 @@ struct BucketPlan {
   std::vector<int64_t> mark_bits;
   std::vector<uint32_t> markarr_offs;
   int64_t n_blocks = 0, n_wtree_blocks = 0;
+  int64_t n_root_blocks = 0;  // quad layout: blocks of the root node, placed outside [block_base, +n_blocks)
   // paired-level layout: internal nodes at even depth own the blocks ("super nodes")
   std::vector<int32_t> super_of;    // per internal node: its index among the bucket's super nodes, or -1
   int64_t n_records = 0;            // NodeRec (plain) or SuperRec (paired) entries of this bucket
@@ -85,8 +86,11 @@ void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, Bu
     for (uint32_t k = 0; k < n_int; k++) {
       if (node_depth(p->node_ids[k]) % levels == 0) {
         p->super_of[k] = ns++;
-        p->n_blocks += levels == 2 ? paired_blocks_for_bits(p->node_bits[k], bw)
-                                   : std::max<int64_t>(1, (p->node_bits[k] + kQuadPos - 1) / kQuadPos);
+        const int64_t nblk = levels == 2 ? paired_blocks_for_bits(p->node_bits[k], bw)
+                                         : std::max<int64_t>(1, (p->node_bits[k] + kQuadPos - 1) / kQuadPos);
+        // quad layout: the root's blocks live in the directly addressed root area (fm_image.hpp)
+        if (levels == 4 && k == 0) p->n_root_blocks = nblk;
+        else p->n_blocks += nblk;
       }
     }
     p->n_records = ns;
@@ -325,6 +329,10 @@ int64_t fill_wavelet_quad(const Blob& blk, const BucketPlan& p, HostImage* im, i
   int64_t cursor = p.block_base;
   for (size_t k = 0; k < n_int; k++) {
     if (p.super_of[k] < 0) continue;
+    if (k == 0) {  // root: block (row in bucket) / kQuadPos of the bucket's slot in the root area
+      base[k] = local_bucket * im->root_stride;
+      continue;
+    }
     base[k] = cursor;
     cursor += std::max<int64_t>(1, (p.node_bits[k] + P - 1) / P);
   }
@@ -489,7 +497,12 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
     OccRec& o = im->occ[rec0 + size_t(ch)];
     o.occ_base = files.C(ch) + files.block_occs(ch, blk_num) + int64_t(bucket_occs(blk, bh, bpb, ch, bucket));
     o.leaf = t.in_use[ch] ? t.leaf[t.ch_to_seq[ch]] : 0u;
-    o.pad = 0;
+    o.root_exit = 0;
+    if (im->levels == 4 && o.leaf) {  // index of the root QuadRec's exit entry on this symbol's path
+      const int len = 31 - __builtin_clz(o.leaf);
+      const uint32_t nib = len >= 4 ? (o.leaf >> (len - 4)) & 15u : (o.leaf << (4 - len)) & 15u;
+      o.root_exit = uint32_t(p.node_base + p.super_of[0]) * 16u + nib;
+    }
     MarkRec& m = im->mark[rec0 + size_t(ch)];
     m.mark_base = 0;
     m.markval_off = 0;
@@ -756,7 +769,13 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
 
   int64_t nodes = 0, blocks = 0, vals = 0, wt_blocks = 0;
   int max_len = 0;
+  if (levels == 4) {  // root area: bucket g's root blocks start at g * root_stride
+    im->root_stride = (int64_t(h.bucket_size) + kQuadPos - 1) / kQuadPos;
+    blocks = nb * im->root_stride;
+    wt_blocks = blocks;
+  }
   for (auto& p : plans) {
+    if (p.n_root_blocks > im->root_stride) throw Error(FM_ERR_FORMAT, "bucket longer than bucket_size");
     p.node_base = nodes;
     p.block_base = blocks;
     p.markval_base = vals;
@@ -766,7 +785,7 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
     vals += p.n_markvals;
     max_len = std::max(max_len, p.tab.max_len);
   }
-  if (blocks >= (int64_t(1) << 32) || nodes >= (int64_t(1) << 31))
+  if (blocks >= (int64_t(1) << 32) || nodes >= (int64_t(1) << (levels == 4 ? 27 : 31)))
     throw Error(FM_ERR_FULL, "shard too large for 32-bit rank block indices; use more shards");
   im->max_code_len = max_len;
   im->n_rank_blocks = blocks;

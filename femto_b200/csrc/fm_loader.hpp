@@ -23,6 +23,7 @@ struct HostImage {
   int levels = 1;                        // wavelet-tree levels per block: 1, 2 (paired) or 4 (quad); fm_image.hpp
   uint32_t* rank_words = nullptr;   // n_rank_blocks * block_words words (calloc'ed)
   int64_t n_rank_blocks = 0;
+  int64_t root_stride = 0;          // quad layout: blocks per bucket in the root area at the front (fm_image.hpp)
   int64_t n_wtree_blocks = 0;       // of which wavelet-tree payload (the rest are mark bit-vectors)
   std::vector<NodeRec> nodes;       // plain layout
   std::vector<SuperRec> supers;     // paired-level layout

@@ -1,4 +1,4 @@
-"""Range-sharded count across the GPUs of one box (second case).
+"""Range-sharded count and locate across the GPUs of one box (second case).
 
 When an index exceeds one GPU's HBM it is partitioned by BWT row range at data-block granularity
 (``fm_open_shard``: block b lives on rank b*G/nblocks; the header tables are replicated).  A
@@ -15,6 +15,13 @@ One all-to-all round per dependent remote row: at most 2 per backward-search ste
 is NCCL ``all_to_all_single`` over NVLink/NVSwitch (gloo on CPU for the host-logic tests); state
 volume is 48 B x patterns per round, far below link bandwidth -- the cost is the ~2(m-1) rounds,
 which is why batches should be large.
+
+Locate works the same way (``sharded_locate_rows``): the state of a sampled-SA walk is {result slot,
+row, LF steps so far, home}; every rank follows LF from its states while their rows are resident
+and a mark has not been reached (``walk_kernel`` in shard mode), then the states are exchanged by
+the rank owning their next row; a walk takes fewer than ``mark_period`` steps, so at most that
+many rounds.  ``sharded_locate`` chains the two: count, expand the ranges into rows with the
+reference's clipping rule, walk.
 
 The per-rank step function is pluggable so that the routing logic can be tested on CPU with an
 oracle-backed step (tests/test_sharded_routing.py) and run on GPUs with the CUDA kernel.
@@ -49,8 +56,9 @@ def exchange(states: torch.Tensor, dest: torch.Tensor, world: int, group=None) -
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     sc, rc = send_counts.tolist(), recv_counts.tolist()
-    recv = torch.empty((sum(rc), STATE_WORDS), dtype=torch.int64, device=states.device)
-    dist.all_to_all_single(recv.view(-1), send.view(-1), [c * STATE_WORDS for c in rc], [c * STATE_WORDS for c in sc],
+    words = states.shape[1]
+    recv = torch.empty((sum(rc), words), dtype=torch.int64, device=states.device)
+    dist.all_to_all_single(recv.view(-1), send.view(-1), [c * words for c in rc], [c * words for c in sc],
                            group=group)
     return recv
 
@@ -101,3 +109,79 @@ def cuda_step_fn(ix, d_plen: torch.Tensor, d_flat: torch.Tensor, d_offs: torch.T
                "fm_count_shard_step")
 
     return step
+
+
+# ---- locate ---------------------------------------------------------------------------------------
+WALK_WORDS = 4           # result slot, row (text offset once finished), LF steps so far, phase | home << 4
+
+# walk_fn(state[n,4] int64, dest[n] int32) -> None
+WalkFn = Callable[[torch.Tensor, torch.Tensor], None]
+
+
+def sharded_locate_rows(walk_fn: WalkFn, rows: torch.Tensor, rank: int, world: int, device,
+                        group=None, max_rounds: int = 100000) -> Tuple[torch.Tensor, int]:
+    """SA[row] for this rank's ``rows`` (global BWT rows, any shard).  Collective: every rank calls it
+    with its own rows (possibly none).  Returns (offsets aligned with rows, exchange rounds)."""
+    n = int(rows.shape[0])
+    out = torch.full((n,), -1, dtype=torch.int64, device=device)
+    states = torch.zeros((n, WALK_WORDS), dtype=torch.int64, device=device)
+    states[:, 0] = torch.arange(n, dtype=torch.int64, device=device)
+    states[:, 1] = rows.to(device=device, dtype=torch.int64)
+    states[:, 3] = rank << 4
+    rounds = 0
+    while True:
+        dest = torch.full((states.shape[0],), rank, dtype=torch.int32, device=device)
+        if states.shape[0]:
+            walk_fn(states, dest)
+        home_done = ((states[:, 3] & 15) == PHASE_DONE) & (dest == rank)
+        if bool(home_done.any()):
+            done = states[home_done]
+            out[done[:, 0]] = done[:, 1]
+            keep = ~home_done
+            states, dest = states[keep], dest[keep]
+        remaining = torch.tensor([states.shape[0]], dtype=torch.int64, device=device)
+        dist.all_reduce(remaining, group=group)
+        if int(remaining.item()) == 0:
+            break
+        states = exchange(states, dest, world, group)
+        rounds += 1
+        if rounds > max_rounds:
+            raise RuntimeError("sharded_locate_rows did not terminate")
+    return out, rounds
+
+
+def expand_ranges(first: torch.Tensor, last: torch.Tensor, max_occs: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Rows first..last of every non-empty range, clipped the way parallel_locate clips them
+    (src/main/server.c:4411-4415: ``last - first > max_occs`` cuts to max_occs rows, so a range
+    exactly one over keeps max_occs + 1).  Returns (rows, number of rows per range)."""
+    cnt = torch.clamp(last - first + 1, min=0)
+    over = (last - first) > max_occs
+    cnt = torch.where(over, torch.full_like(cnt, max_occs), cnt)
+    starts = torch.cumsum(cnt, 0) - cnt
+    total = int(cnt.sum().item())
+    owner = torch.repeat_interleave(torch.arange(cnt.shape[0], device=cnt.device), cnt)
+    rows = first[owner] + (torch.arange(total, device=cnt.device) - starts[owner])
+    return rows, cnt
+
+
+def sharded_locate(step_fn: StepFn, walk_fn: WalkFn, pid_lo: int, pid_hi: int, max_occs: int, rank: int,
+                   world: int, device, group=None):
+    """parallel_locate over a range-sharded index for patterns [pid_lo, pid_hi) of a batch replicated
+    on every rank.  Returns (noccs[n], offsets concatenated in pattern order, rounds_count, rounds_walk)."""
+    first, last, r1 = sharded_count(step_fn, pid_lo, pid_hi, rank, world, device, group)
+    rows, cnt = expand_ranges(first, last, max_occs)
+    offs, r2 = sharded_locate_rows(walk_fn, rows, rank, world, device, group)
+    return cnt, offs, r1, r2
+
+
+def cuda_walk_fn(ix, nshards: int) -> WalkFn:
+    """Walk function backed by walk_kernel in shard mode (fm_locate_shard_step)."""
+    from . import _check
+
+    def walk(states: torch.Tensor, dest: torch.Tensor) -> None:
+        assert states.is_cuda and states.is_contiguous() and dest.is_contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        _check(ix.lib.fm_locate_shard_step(ix.h, states.shape[0], states.data_ptr(), dest.data_ptr(), nshards, stream),
+               "fm_locate_shard_step")
+
+    return walk

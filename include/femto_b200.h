@@ -118,6 +118,18 @@ int fm_count_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, const
                         const uint16_t* d_flat, const int64_t* d_offs, int32_t* d_dest, int nshards,
                         void* stream);
 
+/* Range-sharded locate: the sampled-SA walk of do_back_query / do_context_query
+ * (src/main/server.c:2228-2359, 2627-2795) over an index opened with fm_open_shard.  The LF
+ * mapping sends a row to an arbitrary shard, so -- as for count -- the walk's STATE travels:
+ * d_state holds nstates rows of 4 int64 {result slot at the home rank, BWT row (the text offset
+ * once finished, -1 on a malformed index), LF steps taken so far, phase | home_rank<<4}; phase
+ * 0 = walking, 2 = finished.  This call follows LF from every state while its row is resident on
+ * ix's device and a mark has not been reached; d_dest[k] receives the rank that must see state k
+ * next (the owner of its row, or its home rank once finished).  Device pointers; asynchronous on
+ * `stream`.  femto_b200/sharded.py (sharded_locate_rows / sharded_locate) drives the exchange. */
+int fm_locate_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, int32_t* d_dest, int nshards,
+                         void* stream);
+
 /* --------------------------------------------------------------------------
  * locate.  Mirrors parallel_locate (src/main/femto.c:331-399): for pattern i,
  * noccs[i] offsets are returned in BWT row order first..; offsets[i] is malloc()ed

@@ -288,8 +288,8 @@ def test_mixed_length_zipf_batch(tmp_path):
         q[int(rng.integers(0, len(q)))] = 5 + int(rng.integers(97, 123))
         pats[k] = q
     with fb.Index(path) as ix, Oracle(path) as o:
-        for _ in range(2):                                   # the default image and schedule, twice
-            ix.set_count_schedule(1, 2)
+        for lanes in (1, 2, 1):                              # the default image, both quad schedules
+            ix.set_count_schedule(1, lanes)
             f, l = ix.count(pats)
             sub = list(range(0, len(pats), 7))
             of, ol = o.count([pats[i] for i in sub])
@@ -344,7 +344,7 @@ def gpu_indexes_multilevel(built_indexes):
         ix.close()
 
 
-@pytest.mark.parametrize("cfg", [(128, 2, 4), (128, 2, 2), (128, 2, 1), (64, 2, 2), (64, 2, 1), (128, 4, 2)])
+@pytest.mark.parametrize("cfg", [(128, 2, 4), (128, 2, 2), (128, 2, 1), (64, 2, 2), (64, 2, 1), (128, 4, 2), (128, 4, 1)])
 @pytest.mark.parametrize("name", ALL)
 def test_count_multilevel_blocks(name, cfg, gpu_indexes_multilevel, built_indexes, corpora):
     bb, levels, lanes = cfg

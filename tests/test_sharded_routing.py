@@ -85,6 +85,54 @@ def _worker(rank, world, port, index_path, pats, out_dir):
     dist.destroy_process_group()
 
 
+def oracle_walk_fn(index_path, rank, world):
+    """walk_kernel's shard mode (fm_kernels.cuh WalkArgs::state) restated with the oracle."""
+    from oracle.bindings import Oracle
+    o = Oracle(index_path)
+    info = o.header_info()
+    n, bs, nb = info["total_length"], info["block_size"], info["nblocks"]
+    blocks = [b for b in range(nb) if b * world // nb == rank]
+    lo_row = blocks[0] * bs if blocks else 0
+    hi_row = min(n, (blocks[-1] + 1) * bs) if blocks else 0
+
+    def walk(states, dest):
+        st = states.numpy()
+        for k in range(st.shape[0]):
+            slot, row, steps, meta = (int(x) for x in st[k])
+            home = meta >> 4
+            if meta & 15 == 2:
+                dest[k] = home
+                continue
+            while True:
+                if not (lo_row <= row < hi_row):
+                    st[k] = (slot, row, steps, home << 4)
+                    dest[k] = (row // bs) * world // nb
+                    break
+                ch, nxt, off = o.back_step(row)
+                if off >= 0:
+                    st[k] = (slot, off + steps, steps, 2 | (home << 4))
+                    dest[k] = home
+                    break
+                assert nxt >= 0
+                row, steps = nxt, steps + 1
+
+    return walk
+
+
+def _locate_worker(rank, world, port, index_path, pats, max_occs, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plen, flat, offs = fb.flatten_patterns(pats)
+    npat = len(pats)
+    lo, hi = npat * rank // world, npat * (rank + 1) // world
+    step = oracle_step_fn(index_path, rank, world, plen, flat, offs)
+    walk = oracle_walk_fn(index_path, rank, world)
+    cnt, offsets, r1, r2 = sharded.sharded_locate(step, walk, lo, hi, max_occs, rank, world, "cpu")
+    np.savez(os.path.join(out_dir, f"l{rank}.npz"), cnt=cnt.numpy(), offsets=offsets.numpy(), r1=r1, r2=r2)
+    dist.destroy_process_group()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -128,3 +176,35 @@ def test_exchange_routes_rows_by_destination(tmp_path):
         assert torch.equal(out, st)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,max_occs", [("acgt_64k", 7), ("english_100k", 40)])
+def test_sharded_locate_two_ranks_matches_oracle(name, max_occs, built_indexes, corpora, tmp_path):
+    """count -> clipped row ranges -> sampled-SA walks hopping between the two shards."""
+    from oracle.bindings import Oracle
+    docs, _ = corpora[name]
+    path = built_indexes[name]
+    pats = corpus.sample_patterns(docs, 90, [2, 3, 4, 6, 9, 14], seed=97)
+    pats += [np.zeros(0, dtype=np.uint16), np.array([300, 70], dtype=np.uint16)]
+    world = 2
+    mp.spawn(_locate_worker, args=(world, _free_port(), path, pats, max_occs, str(tmp_path)), nprocs=world, join=True)
+    with Oracle(path) as o:
+        want = o.locate(pats[:-1], max_occs)
+    parts = [np.load(tmp_path / f"l{r}.npz") for r in range(world)]
+    cnt = np.concatenate([p["cnt"] for p in parts])
+    offsets = np.concatenate([p["offsets"] for p in parts])
+    ends = np.cumsum(cnt)
+    for k, w in enumerate(want):
+        got = offsets[ends[k] - cnt[k]:ends[k]]
+        assert len(got) == len(w) and (got == w).all(), k
+    assert cnt[-1] == 0                                      # symbol outside the alphabet
+    assert int(parts[0]["r2"]) == int(parts[1]["r2"]) >= 1   # walks really changed shard
+
+
+def test_expand_ranges_clip_rule():
+    first = torch.tensor([5, 10, 20, 30, 7], dtype=torch.int64)
+    last = torch.tensor([4, 12, 24, 35, 7], dtype=torch.int64)   # empty, 3 rows, 5 rows, 6 rows, 1 row
+    rows, cnt = sharded.expand_ranges(first, last, 4)
+    # last - first > max_occs cuts to max_occs rows: 5 rows (one over) are kept, 6 rows become 4
+    assert cnt.tolist() == [0, 3, 5, 4, 1]
+    assert rows.tolist() == [10, 11, 12, 20, 21, 22, 23, 24, 30, 31, 32, 33, 7]
