@@ -133,11 +133,11 @@ int paired_sched(int block_words, int lanes) {
   return 1000 + 10 * lanes + minb;
 }
 
-// quad-level blocks: 1000 + 10 * k + CTAs per SM; k = 4: two lanes per pattern, short dependency
-// chain (default); k = 1: one lane per pattern; k = 2: the first two-lane kernel (kept for comparison,
-// reachable through FEMTO_B200_COUNT_SCHED only)
-constexpr int kQuadSchedLane = 1000 + 10 * 1 + 4;
-constexpr int kQuadSched = 1000 + 10 * 4 + 5;
+// quad-level blocks: 1000 + 10 * k + CTAs per SM; k = 2: two lanes per pattern evaluate both positions
+// of a step together (default; k = 3 adds the one-step-ahead symbol fetch); 60 + v: one lane per
+// Occ ("split" schedule, selectable with fm_set_count_schedule(.., 1))
+constexpr int kQuadSched = 1000 + 10 * 2 + 5;
+constexpr int kQuadSchedSplit = 1000 + 67;
 
 int default_count_sched(int block_words, int levels) {
   int sched = levels == 4 ? kQuadSched
@@ -440,7 +440,7 @@ int fm_set_count_schedule(fm_index_t* ix, int merged, int lanes) {
   if (ix->im.levels == 4) {
     if (lanes != 1 && lanes != 2)
       return fail(FM_ERR_PARAM, "fm_set_count_schedule: quad-level blocks run with 1 or 2 lanes per pattern");
-    ix->count_sched = lanes == 1 ? kQuadSchedLane : kQuadSched;
+    ix->count_sched = lanes == 1 ? kQuadSchedSplit : kQuadSched;
     return FM_OK;
   }
   if (ix->im.levels == 2) {  // paired-level blocks: merged schedule only, a lane owns whole 32-byte slices

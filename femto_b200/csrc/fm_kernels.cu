@@ -309,6 +309,13 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, int s) {  // v >> s, 0
   return r;
 }
 
+// Loads the scheduler must not sink towards their first use: they are issued early on purpose, so
+// that their latency overlaps the block read (ptxas otherwise moves them behind the evaluation).
+__device__ __forceinline__ uint2 ldg_pinned(const uint2* ptr) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr) : "memory");
+  return v;
+}
 struct QuadWords {
   uint32_t d[8];  // d[2 l], d[2 l + 1]: this lane's two words of region l
   __device__ __forceinline__ void clear() {
@@ -536,21 +543,7 @@ __global__ void __launch_bounds__(kThreads) count_pair_kernel(const DevImage im,
 }
 
 // ---------------------------------------------------------------------------------------------
-// count over quad-level blocks, ONE lane per pattern ("lane" schedule).
-//
-// Why: the two-lane kernel below spends a third of its issue slots on per-warp overhead that serves
-// only 16 patterns, and every backward-search step is a chain of four dependent memory stages
-// (pattern symbol -> (bucket, symbol) record -> root block -> second block), 57 % of all stall
-// samples (profiles/r01_count_quad128_ncu_details.txt).  Here
-//   * a warp carries 32 patterns, so the set-up and loop overhead per pattern halves and twice as
-//     many block reads are in flight per resident warp;
-//   * the root block of a step is addressed from the row alone (root area, fm_image.hpp): its read
-//     is issued together with the (bucket, symbol) record, not after it;
-//   * the symbol of the next step is fetched one step ahead.
-// A lane holds the 64 region bytes of a block in 16 registers and evaluates position first-1 and
-// position last from the same registers; when the two positions need different blocks (wide
-// ranges, or a 128-position boundary between them) the lanes concerned read the second block in a
-// divergent tail of the round.
+// The 64 region bytes of one quad-level block held by ONE lane (split schedule below).
 struct QuadLine {
   uint32_t r[4][4];  // r[l][w]: word w of the block's level-l region
   __device__ __forceinline__ void load(const uint4* __restrict__ blocks, uint32_t blk) {
@@ -600,331 +593,119 @@ struct QuadLine {
   }
 };
 
-template <int MINB, bool STATS>
-__global__ void __launch_bounds__(kThreads, MINB) count_quad_lane_kernel(const DevImage im, const CountArgs a,
+// ---------------------------------------------------------------------------------------------
+// count over quad-level blocks, one lane per Occ ("split" schedule).
+//
+// A pattern owns two adjacent lanes: lane 0 evaluates C[c] + Occ(c, first-1), lane 1 evaluates
+// C[c] + Occ(c, last).  Each lane runs a complete, independent Occ: its own row, bucket, record
+// and blocks, all four levels of a block from the 16 registers it loaded itself.  Consequences:
+//   * no shuffle and no packed arithmetic inside the descent -- the lanes meet once per step, to
+//     exchange the two results;
+//   * one block evaluation per lane and iteration instead of two per lane pair;
+//   * rows in different buckets or different blocks need no special case;
+//   * when both rows lie in the same block (the common case once the range is narrow) the two
+//     lanes load the same addresses and the hardware merges them into one line request.
+// The root block of a step is addressed from the row alone (root area, fm_image.hpp) and requested
+// together with the (bucket, symbol) record; the next symbol is fetched one step ahead.
+//
+// Measured (profiles/r01_quad_schedules.md): 1.06 G warp instructions per 1 Mi-pattern launch
+// against 1.72 G of the two-lane schedule, but 237 M patterns/s against 360 M: the header entry
+// and the exit entry can only be requested once the record has arrived, so a step still pays
+// record -> header in series, and four 128-bit loads per lane and block keep the load/store unit's
+// queue full (MIO / LG throttle 17 % of the stall samples).  Kept selectable
+// (fm_set_count_schedule(ix, 1, 1)) as the simpler formulation; not the default.
+template <int MINB, bool STATS, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const DevImage im, const CountArgs a,
                                                                           unsigned long long* __restrict__ work,
                                                                           unsigned long long* __restrict__ stats) {
   unsigned long long n_ranks = 0, n_blocks = 0, n_occ = 0, n_steps = 0;
   const int lane = threadIdx.x & 31;
-  const uint2* __restrict__ exits = reinterpret_cast<const uint2*>(im.quads);
-  int64_t f = 0, l = -1, pid = -1;
-  int i = 0, c = 0, cn = 0;
-  const uint16_t* pat = nullptr;
-  bool have = false, exhausted = false, cross_pending = false;
-  int64_t obA = 0, obB = 0;
-
-  for (;;) {
-    // ---- retire finished patterns ("first > last || i == 0", server.c:832-841), pull new ones
-    if (have && !cross_pending && (f > l || i == 0)) {
-      if (a.last) { a.first[pid] = f; a.last[pid] = l; }
-      else a.first[pid] = l - f + 1;  // parallel_count with last==NULL (femto.c:313-318)
-      have = false;
-    }
-    const bool need = !have && !exhausted;
-    const unsigned want = __ballot_sync(kFull, need);
-    if (want) {  // one atomic per warp
-      const int leader = __ffs(want) - 1;
-      unsigned long long first_idx = 0;
-      if (lane == leader) first_idx = atomicAdd(work, static_cast<unsigned long long>(__popc(want)));
-      first_idx = __shfl_sync(kFull, first_idx, leader);
-      if (need) {
-        const int64_t idx = static_cast<int64_t>(first_idx) + __popc(want & ((1u << lane) - 1u));
-        if (idx < a.npats) {
-          pid = idx;
-          const int m = a.plen[pid];
-          pat = a.flat + a.offs[pid];
-          if (m <= 0) {  // empty pattern: every row (server.c:782-808)
-            f = 0; l = im.total_length - 1; i = 0;
-          } else {
-            const int c0 = pat[m - 1];
-            if (c0 >= kAlphaDev) { f = im.total_length; l = f - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
-            else { f = __ldg(im.C + c0); l = __ldg(im.C + c0 + 1) - 1; }
-            i = m - 1;
-            if (i > 0) cn = pat[i - 1];
-          }
-          have = true;
-        } else {
-          exhausted = true;
-        }
-      }
-    }
-    if (!__any_sync(kFull, have)) break;
-
-    // ---- set-up of one round (normally a whole backward-search step)
-    bool stepping = have && (cross_pending || (f <= l && i > 0));
-    bool actA = false, actB = false;
-    uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0;
-    int L = 0;
-    QuadLine line;
-    if (stepping) {
-      int64_t g;
-      uint32_t rb, rbA = 0;
-      split_row(im, l, g, rb);
-      bool hasA = false, cross = false;
-      if (!cross_pending) {
-        c = cn;
-        if (i >= 2) cn = pat[i - 2];  // the next step's symbol, one step ahead
-        if (STATS) n_steps++;
-        if (c >= kAlphaDev) {  // symbol outside the alphabet: empty range
-          f = im.total_length; l = f - 1; i--;
-          stepping = false;
-        } else if (f != 0) {
-          int64_t gA;
-          split_row(im, f - 1, gA, rbA);
-          hasA = true;
-          cross = gA != g;  // first-1 sits in another bucket: this round does A, the next one B
-          if (cross) g = gA;
-        }
-      }
-      if (stepping) {
-        // root block of the first position and the symbol's record: independent reads
-        base = static_cast<uint32_t>(g * im.root_stride);
-        line.load(im.blocks, base + ((hasA ? rbA : rb) >> 7));
-        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-        const int64_t ob = rec_occ_base(rv);
-        leaf = static_cast<uint32_t>(rv.z);
-        node = static_cast<uint32_t>(rv.w) >> 4;
-        if (cross_pending) {  // second round of a cross-bucket step: row `last`
-          obB = ob; idxB = rb + 1; actB = true;
-          cross_pending = false;
-          if (STATS) n_occ++;
-        } else if (!hasA) {   // Occ(c,-1) = 0 without touching the index (server.c:847-851)
-          obA = __ldg(im.C + c);
-          obB = ob; idxB = rb + 1; actB = true;
-          if (STATS) n_occ++;
-        } else {
-          obA = ob; idxA = rbA + 1; actA = true;
-          if (STATS) n_occ += cross ? 1 : 2;
-          if (cross) cross_pending = true;
-          else { obB = ob; idxB = rb + 1; actB = true; }
-        }
-        if (leaf == 0) actA = actB = false;  // symbol absent from the bucket (index.c:2080-2089)
-        else L = 31 - __clz(leaf);
-      }
-    }
-    const bool jobA = actA, jobB = actB;
-    const bool finish = stepping && !cross_pending;
-
-    // ---- descend: four wavelet-tree levels per iteration
-    int lvl = 0;
-    while (__any_sync(kFull, actA || actB)) {
-      const bool any = actA || actB;
-      const uint32_t pA = actA ? idxA - 1 : 0u, pB = actB ? idxB - 1 : 0u;
-      const uint32_t kA = pA >> 7, kB = pB >> 7;
-      const bool two = actA && actB && kA != kB;
-      const uint32_t blk = base + (actA ? kA : kB);
-      const uint32_t nib = any ? quad_path(leaf, L, lvl) : 0u;
-      uint2 h = make_uint2(0, 0), ex = h;
-      if (any) {
-        if (lvl > 0) line.load(im.blocks, blk);  // the root block was requested during set-up
-        h = quad_header(im.blocks, blk, nib >> 1);
-        if (lvl + 4 < L) ex = __ldg(exits + (static_cast<size_t>(node) * 16 + nib));
-      }
-      const int jA = static_cast<int>(pA & 127u) + 1, jB = static_cast<int>(pB & 127u) + 1;
-      uint32_t rA = 0, rB = 0;
-      if (any) {
-        rA = line.eval(h, nib, jA);
-        rB = line.eval(h, nib, jB);
-      }
-      if (__any_sync(kFull, two)) {
-        if (two) {  // position B lies in another block of the same node
-          line.load(im.blocks, base + kB);
-          h = quad_header(im.blocks, base + kB, nib >> 1);
-          rB = line.eval(h, nib, jB);
-        }
-      }
-      if (STATS && any) {
-        n_blocks += two ? 2 : 1;
-        n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
-      }
-      lvl += 4;
-      if (actA) { idxA = rA; actA = idxA != 0 && lvl < L; }
-      if (actB) { idxB = rB; actB = idxB != 0 && lvl < L; }
-      base = ex.x;
-      node = ex.y;
-    }
-    if (jobA) obA += idxA;
-    if (jobB) obB += idxB;
-    if (finish) { f = obA; l = obB - 1; i--; }
-  }
-  if (STATS) flush_stats(stats, lane, n_ranks, n_blocks, n_occ, n_steps);
-}
-
-// ---------------------------------------------------------------------------------------------
-// count over quad-level blocks, TWO lanes per pattern, short dependency chain ("chain" schedule).
-//
-// Same lane layout as count_sync_kernel<2, 32, ., ., 4> (lane `sub` holds words 2 sub, 2 sub + 1
-// of each region; both positions of a step evaluated together, counts packed into one shuffle),
-// but the memory stages of a step are no longer in series:
-//   * the root block is addressed from the row alone (root area, fm_image.hpp), so its read is
-//     issued in the set-up together with the (bucket, symbol) record instead of after it;
-//   * the symbol of the next step is fetched one step ahead;
-//   * the block of the next iteration is requested at the end of the current one;
-//   * position B re-reads a line only when it really lies in another block.
-// What stays in series per step: two block reads (tree depth 8) and the small reads that hang
-// off the record (header entry of the root block, exit entry) which overlap the root block read.
-template <int MINB, bool STATS, int THREADS = kThreads>
-__global__ void __launch_bounds__(THREADS, MINB) count_quad_chain_kernel(const DevImage im, const CountArgs a,
-                                                                           unsigned long long* __restrict__ work,
-                                                                           unsigned long long* __restrict__ stats) {
-  unsigned long long n_ranks = 0, n_blocks = 0, n_occ = 0, n_steps = 0;
-  const int lane = threadIdx.x & 31;
   const int sub = lane & 1;
   const int gleader = lane & ~1;
-  const int lb = 64 * sub;
   const uint2* __restrict__ exits = reinterpret_cast<const uint2*>(im.quads);
   PatternState s;
-  bool cross_pending = false;
   int c = 0, cn = 0;
-  int64_t obA = 0, obB = 0;
 
   for (;;) {
     {
       const int64_t pid0 = s.pid;
-      retire_and_fetch(s, !cross_pending, im, a, work, lane, gleader);
+      retire_and_fetch(s, true, im, a, work, lane, gleader);
       if (s.have && s.pid != pid0 && s.i > 0) cn = s.pat[s.i - 1];  // a new pattern: its first symbol to extend by
     }
     if (!__any_sync(kFull, s.have)) break;
 
-    // ---- set-up of one round (normally a whole backward-search step)
-    bool stepping = s.have && (cross_pending || (s.f <= s.l && s.i > 0));
-    bool actA = false, actB = false;
-    uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0, blkA = 0, blkB = 0;
+    // ---- set-up of one backward-search step: this lane's row, record and root block
+    bool stepping = s.have && s.f <= s.l && s.i > 0;
+    bool act = false;
+    uint32_t idx = 0, base = 0, node = 0, leaf = 0;
     int L = 0;
-    QuadWords p, q;
-    p.clear();
-    q.clear();
+    int64_t ob = 0;
+    QuadLine line;
     if (stepping) {
-      int64_t g;
-      uint32_t rb, rbA = 0;
-      split_row(im, s.l, g, rb);
-      bool hasA = false, cross = false;
-      if (!cross_pending) {
-        c = cn;
-        if (s.i >= 2) cn = s.pat[s.i - 2];  // the next step's symbol, one step ahead
-        if (STATS && sub == 0) n_steps++;
-        if (c >= kAlphaDev) {  // symbol outside the alphabet: empty range
-          s.f = im.total_length; s.l = s.f - 1; s.i--;
-          stepping = false;
-        } else if (s.f != 0) {
-          int64_t gA;
-          split_row(im, s.f - 1, gA, rbA);
-          hasA = true;
-          cross = gA != g;  // first-1 sits in another bucket: this round does A, the next one B
-          if (cross) g = gA;
-        }
-      }
-      if (stepping) {
-        base = static_cast<uint32_t>(g * im.root_stride);
-        const bool onlyB = cross_pending || !hasA;
-        const bool both = hasA && !cross;
-        idxA = onlyB ? 0u : rbA + 1;
-        idxB = (onlyB || both) ? rb + 1 : 0u;
-        // root blocks and the symbol's record: independent reads, issued together
-        blkA = base + ((onlyB ? rb : rbA) >> 7);
-        blkB = base + ((both ? rb : (onlyB ? rb : rbA)) >> 7);
-        p.load(im.blocks, blkA, sub);
-        if (blkB != blkA) q.load(im.blocks, blkB, sub);
-        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-        const int64_t ob = rec_occ_base(rv);
-        leaf = static_cast<uint32_t>(rv.z);
-        node = static_cast<uint32_t>(rv.w) >> 4;
-        if (cross_pending) {  // second round of a cross-bucket step: row `last`
-          obB = ob; actB = true;
-          cross_pending = false;
-          if (STATS && sub == 0) n_occ++;
-        } else if (!hasA) {   // Occ(c,-1) = 0 without touching the index (server.c:847-851)
-          obA = __ldg(im.C + c);
-          obB = ob; actB = true;
-          if (STATS && sub == 0) n_occ++;
+      c = cn;
+      if (s.i >= 2) cn = s.pat[s.i - 2];  // the next step's symbol, one step ahead
+      if (STATS && sub == 0) n_steps++;
+      if (c >= kAlphaDev) {  // symbol outside the alphabet: empty range
+        s.f = im.total_length; s.l = s.f - 1; s.i--;
+        stepping = false;
+      } else {
+        const int64_t row = sub ? s.l : s.f - 1;
+        if (row < 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
+          ob = __ldg(im.C + c);
         } else {
-          obA = ob; actA = true;
-          if (STATS && sub == 0) n_occ += cross ? 1 : 2;
-          if (cross) cross_pending = true;
-          else { obB = ob; actB = true; }
-        }
-        if (leaf == 0) {  // symbol absent from the bucket: Occ is the bucket base (index.c:2080-2089)
-          actA = actB = false;
-          idxA = idxB = 0;
-        } else {
-          L = 31 - __clz(leaf);
+          int64_t g;
+          uint32_t rb;
+          split_row(im, row, g, rb);
+          base = static_cast<uint32_t>(g * im.root_stride);
+          line.load(im.blocks, base + (rb >> 7));  // independent of the record read below
+          const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+          ob = rec_occ_base(rv);
+          leaf = static_cast<uint32_t>(rv.z);
+          node = static_cast<uint32_t>(rv.w) >> 4;
+          if (STATS) n_occ++;
+          if (leaf) {  // else: symbol absent from the bucket, Occ is the bucket base (index.c:2080-2089)
+            L = 31 - __clz(leaf);
+            idx = rb + 1;
+            act = true;
+          }
         }
       }
     }
-    const bool jobA = actA, jobB = actB;
-    const bool finish = stepping && !cross_pending;
 
-    // ---- descend: four wavelet-tree levels per iteration; the blocks are already on their way
+    // ---- descend: four wavelet-tree levels per iteration
     int lvl = 0;
-    while (__any_sync(kFull, actA || actB)) {
-      const bool any = actA || actB;
-      const bool two = blkA != blkB;
-      const uint32_t nib = any ? quad_path(leaf, L, lvl) : 0u;
-      uint2 hp = make_uint2(0, 0), hq = hp, ex = hp;
-      if (any) {
-        hp = quad_header(im.blocks, blkA, nib >> 1);
-        if (two) hq = quad_header(im.blocks, blkB, nib >> 1);
-        if (lvl + 4 < L) ex = __ldg(exits + (static_cast<size_t>(node) * 16 + nib));
+    while (__any_sync(kFull, act)) {
+      const uint32_t p = act ? idx - 1 : 0u;
+      const uint32_t blk = base + (p >> 7);
+      if (STATS) {
+        const uint32_t oblk = __shfl_xor_sync(kFull, blk, 1);
+        const bool oact = __shfl_xor_sync(kFull, act ? 1 : 0, 1) != 0;
+        if (act) {
+          n_ranks++;
+          n_blocks += (sub == 1 && oact && oblk == blk) ? 0 : 1;
+        }
       }
-      if (!two) {  // both positions in one block: B is evaluated from the same line
-        hq = hp;
-#pragma unroll
-        for (int t = 0; t < 8; t++) q.d[t] = p.d[t];
-      }
-      const uint32_t pA = actA ? idxA - 1 : 0u, pB = actB ? idxB - 1 : 0u;
-      int jA = static_cast<int>(pA & 127u) + 1, jB = static_cast<int>(pB & 127u) + 1;
-      // level 0: the node's own stretch, prefix [0, j)
-      uint32_t cc = group_sum<2>((popc_top(p.d[0], jA - lb) + popc_top(p.d[1], jA - lb - 32)) |
-                                 ((popc_top(q.d[0], jB - lb) + popc_top(q.d[1], jB - lb - 32)) << 16));
-      uint32_t b = (nib >> 3) & 1u;
-      jA = b ? (cc & 0xffffu) : jA - (cc & 0xffffu);
-      jB = b ? (cc >> 16) : jB - (cc >> 16);
-      // level 1: child b, forward from 0 or backward from the end of the region
-      int aA = b ? kQuadPos - jA : 0, aB = b ? kQuadPos - jB : 0;
-      cc = group_sum<2>(p.range<1>(aA - lb, aA + jA - lb) | (q.range<1>(aB - lb, aB + jB - lb) << 16));
-      b = (nib >> 2) & 1u;
-      jA = b ? (cc & 0xffffu) : jA - (cc & 0xffffu);
-      jB = b ? (cc >> 16) : jB - (cc >> 16);
-      // level 2: anchored at the header's level-2 anchor
-      aA = static_cast<int>(hp.x >> 24) - (b ? jA : 0);
-      aB = static_cast<int>(hq.x >> 24) - (b ? jB : 0);
-      cc = group_sum<2>(p.range<2>(aA - lb, aA + jA - lb) | (q.range<2>(aB - lb, aB + jB - lb) << 16));
-      b = (nib >> 1) & 1u;
-      jA = b ? (cc & 0xffffu) : jA - (cc & 0xffffu);
-      jB = b ? (cc >> 16) : jB - (cc >> 16);
-      // level 3
-      aA = static_cast<int>(hp.y >> 24) - (b ? jA : 0);
-      aB = static_cast<int>(hq.y >> 24) - (b ? jB : 0);
-      cc = group_sum<2>(p.range<3>(aA - lb, aA + jA - lb) | (q.range<3>(aB - lb, aB + jB - lb) << 16));
-      b = nib & 1u;
-      jA = b ? (cc & 0xffffu) : jA - (cc & 0xffffu);
-      jB = b ? (cc >> 16) : jB - (cc >> 16);
-      if (STATS && any && sub == 0) {
-        n_blocks += (actA && actB && two) ? 2 : 1;
-        n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
+      if (act) {
+        const uint32_t nib = quad_path(leaf, L, lvl);
+        uint2 ex = make_uint2(0, 0);
+        if (lvl + 4 < L) ex = ldg_pinned(exits + (static_cast<size_t>(node) * 16 + nib));
+        const uint2 h = ldg_pinned(reinterpret_cast<const uint2*>(im.blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4)) + (nib >> 1));
+        if (lvl > 0) line.load(im.blocks, blk);  // the root block was requested during set-up
+        idx = line.eval(h, nib, static_cast<int>(p & 127u) + 1);
+        act = idx != 0 && lvl + 4 < L;
+        base = ex.x;
+        node = ex.y;
       }
       lvl += 4;
-      if (actA) {
-        idxA = ((b ? hp.y : hp.x) & 0xffffffu) + static_cast<uint32_t>(jA);
-        actA = idxA != 0 && lvl < L;
-      }
-      if (actB) {
-        idxB = ((b ? hq.y : hq.x) & 0xffffffu) + static_cast<uint32_t>(jB);
-        actB = idxB != 0 && lvl < L;
-      }
-      base = ex.x;
-      node = ex.y;
-      if (actA || actB) {  // request the blocks of the next iteration
-        const uint32_t kA = (idxA - 1) >> 7, kB = (idxB - 1) >> 7;
-        blkA = base + (actA ? kA : kB);
-        blkB = base + (actB ? kB : kA);
-        p.load(im.blocks, blkA, sub);
-        if (blkB != blkA) q.load(im.blocks, blkB, sub);
-      }
     }
-    if (jobA) obA += idxA;
-    if (jobB) obB += idxB;
-    if (finish) { s.f = obA; s.l = obB - 1; s.i--; }
+    // lane 0 now holds the new first, lane 1 the new last + 1
+    ob += idx;
+    const int64_t other = __shfl_xor_sync(kFull, ob, 1);
+    if (stepping) {
+      s.f = sub ? other : ob;
+      s.l = (sub ? ob : other) - 1;
+      s.i--;
+    }
   }
   if (STATS) flush_stats(stats, lane, n_ranks, n_blocks, n_occ, n_steps);
 }
@@ -1603,23 +1384,14 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     if (d_stats) FM_LAUNCH((count_sync_kernel<2, 32, MINB, true, 4>), 2);                                \
     else FM_LAUNCH((count_sync_kernel<2, 32, MINB, false, 4>), 2);                                       \
     break;
-#define FM_QUAD_LANE(MINB)                                                                               \
-  case 3000000 + 32 * 10000 + 1000 + 10 * 1 + (MINB):                                                    \
-    if (d_stats) FM_LAUNCH((count_quad_lane_kernel<MINB, true>), 1);                                     \
-    else FM_LAUNCH((count_quad_lane_kernel<MINB, false>), 1);                                            \
-    break;
-#define FM_QUAD_CHAIN(MINB)                                                                              \
-  case 3000000 + 32 * 10000 + 1000 + 10 * 4 + (MINB):                                                    \
-    if (d_stats) FM_LAUNCH((count_quad_chain_kernel<MINB, true>), 2);                                    \
-    else FM_LAUNCH((count_quad_chain_kernel<MINB, false>), 2);                                           \
-    break;
-#define FM_QUAD_CHAIN128(MINB)   /* 128-thread CTAs: finer register / occupancy steps */               \
-  case 3000000 + 32 * 10000 + 1000 + 10 * 5 + ((MINB) - 8):                                              \
+#define FM_QUAD_SPLIT(CODE, THREADS, MINB)                                                               \
+  case 3000000 + 32 * 10000 + 1000 + (CODE):                                                             \
     do {                                                                                                 \
-      auto kern = d_stats ? count_quad_chain_kernel<MINB, true, 128> : count_quad_chain_kernel<MINB, false, 128>; \
+      auto kern = d_stats ? count_quad_split_kernel<MINB, true, THREADS>                                 \
+                          : count_quad_split_kernel<MINB, false, THREADS>;                               \
       int bps = 0;                                                                                       \
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 128, 0) != cudaSuccess || bps < 1) bps = 1; \
-      kern<<<grid_for(a.npats, 128 / 2, sm_count, bps), 128, 0, stream>>>(im, a, d_work, d_stats);         \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, THREADS, 0) != cudaSuccess || bps < 1) bps = 1; \
+      kern<<<grid_for(a.npats, (THREADS) / 2, sm_count, bps), THREADS, 0, stream>>>(im, a, d_work, d_stats); \
     } while (0);                                                                                         \
     break;
 #define FM_PAIR(BW, LANES)                                                                               \
@@ -1636,17 +1408,14 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     FM_SYNC2(32, 1, 2) FM_SYNC2(32, 1, 3) FM_SYNC2(16, 2, 4) FM_SYNC2(16, 2, 5) FM_SYNC2(16, 2, 6)
     FM_SYNC2(16, 1, 3) FM_SYNC2(16, 1, 4) FM_SYNC2(16, 1, 5)
     FM_SYNC4(3) FM_SYNC4(4) FM_SYNC4(5) FM_SYNC4(6) FM_SYNC4(8)
-    FM_QUAD_LANE(2) FM_QUAD_LANE(3) FM_QUAD_LANE(4) FM_QUAD_LANE(5) FM_QUAD_LANE(6)
-    FM_QUAD_CHAIN(3) FM_QUAD_CHAIN(4) FM_QUAD_CHAIN(5) FM_QUAD_CHAIN(6) FM_QUAD_CHAIN(8)
-    FM_QUAD_CHAIN128(9) FM_QUAD_CHAIN128(10) FM_QUAD_CHAIN128(11)
+    /* split schedule: 60 + k */
+    FM_QUAD_SPLIT(65, 256, 5) FM_QUAD_SPLIT(67, 128, 9)
     default: return cudaErrorInvalidValue;
   }
 #undef FM_SYNC
 #undef FM_SYNC2
 #undef FM_SYNC4
-#undef FM_QUAD_LANE
-#undef FM_QUAD_CHAIN
-#undef FM_QUAD_CHAIN128
+#undef FM_QUAD_SPLIT
 #undef FM_PAIR
 #undef FM_LAUNCH
   if (launch_counter) ++*launch_counter;
