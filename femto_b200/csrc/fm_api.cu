@@ -108,10 +108,13 @@ struct fm_index {
   std::vector<int64_t> doc_ends, doc_eof_rows, C_host;
   // per-call scratch, serialised by mu
   std::mutex mu;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   DevBuf d_in[4], d_out[4];
-  HostBuf h_stage[2];
+  HostBuf h_stage[2], h_marks;
   int64_t launches = 0;
+  int64_t last_h2d = 0, last_d2h = 0;  // bytes copied by the most recent host-buffer count call
+  bool stream_ok = true;               // cleared when a streamed batch stalled (e.g. under a serialising profiler)
   int dev_slot = 0;
 };
 
@@ -178,8 +181,11 @@ void destroy(fm_index* ix) {
   for (auto& b : ix->d_in) b.release();
   for (auto& b : ix->d_out) b.release();
   for (auto& b : ix->h_stage) b.release();
+  ix->h_marks.release();
+  for (cudaEvent_t e : ix->ev) if (e) cudaEventDestroy(e);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   if (ix->stream2) cudaStreamDestroy(ix->stream2);
+  if (ix->stream3) cudaStreamDestroy(ix->stream3);
   delete ix;
 }
 
@@ -209,6 +215,8 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ix->stream3, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ix->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int64_t total = 0;
     upload(&ix->d_blocks, host->rank_words, size_t(host->n_rank_blocks) * size_t(host->block_words), &total);
     if (host->levels == 4) upload(&ix->d_nodes, host->quads.data(), host->quads.size(), &total);
@@ -220,7 +228,8 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     upload(&ix->d_markvals, host->markvals.data(), host->markvals.size(), &total);
     upload(&ix->d_C, host->C.data(), host->C.size(), &total);
     CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 16 * sizeof(unsigned long long)));  // queue slots:
-    // 0 host-buffer calls, 1..7 caller-stream launches, 8..11 chunks of a pipelined host-buffer call
+    // 0 host-buffer calls, 1..7 caller-stream launches, 8..9 the two kernels of a streamed
+    // host-buffer call, 12..13 their arrival counters (CountArgs::avail)
     CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_status), 64));
     CK(cudaMemset(ix->d_status, 0, 64));
 
@@ -305,6 +314,53 @@ int check_patterns(int64_t npats, const int32_t* plen, const int64_t* offs, int6
   return FM_OK;
 }
 
+// One pass over plen / offs of a large batch, split over a few host threads (the pass is on the
+// critical path of every host-buffer call: 12 bytes per pattern).  Reports
+//   bad      a negative length or offset,
+//   dense    pattern i starts where pattern i-1 ends (then the batch is in order and flat_len is the
+//            end of the last pattern),
+//   uniform  dense, starting at 0, all of one length m > 0: pattern i starts at i * m and neither plen
+//            nor offs has to travel to the device (CountArgs::uniform_len).
+struct BatchShape {
+  bool bad = false, dense = true;
+  int uniform = 0;
+  int64_t flat_len = 0;
+};
+
+BatchShape scan_batch(int64_t npats, const int32_t* plen, const int64_t* offs) {
+  BatchShape r;
+  if (npats == 0) return r;
+  const int nt = int(std::min<int64_t>(8, std::max<int64_t>(1, npats >> 17)));
+  std::vector<char> bad(size_t(nt), 0), dense(size_t(nt), 1), same(size_t(nt), 1);
+  const int32_t m0 = plen[0];
+  auto work = [&](int t) {
+    const int64_t lo = npats * t / nt, hi = npats * (t + 1) / nt;
+    bool b = false, d = true, sm = true;
+    for (int64_t i = lo; i < hi; i++) {
+      b |= (plen[i] < 0) | (offs[i] < 0);
+      sm &= plen[i] == m0;
+      if (i) d &= offs[i] == offs[i - 1] + plen[i - 1];
+    }
+    bad[size_t(t)] = b; dense[size_t(t)] = d; same[size_t(t)] = sm;
+  };
+  if (nt == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  }
+  bool sm = true;
+  for (int t = 0; t < nt; t++) { r.bad |= bad[size_t(t)] != 0; r.dense &= dense[size_t(t)] != 0; sm &= same[size_t(t)] != 0; }
+  if (r.bad) return r;
+  if (r.dense) {
+    r.flat_len = offs[npats - 1] + plen[npats - 1];
+    if (sm && m0 > 0 && offs[0] == 0) r.uniform = m0;
+  }
+  return r;
+}
+
 int walk_status(fm_index* ix) {
   int32_t st = 0;
   CK(cudaMemcpyAsync(&st, ix->d_status, sizeof(st), cudaMemcpyDeviceToHost, ix->stream));
@@ -315,7 +371,7 @@ int walk_status(fm_index* ix) {
 
 // count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
 int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, int64_t flat_len,
-               const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false) {
+               const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false, int uniform_len = 0) {
   if (npats == 0) return FM_OK;
   cudaStream_t s = ix->stream;
   int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
@@ -324,30 +380,100 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   int64_t* d_first = static_cast<int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
   int64_t* d_last = last ? static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8)) : nullptr;
 
-  // Large batches whose patterns lie in the flat buffer in order are cut into chunks that
-  // alternate between two streams, so the H2D copy of chunk k+1 and the D2H copy of chunk k-1
-  // overlap the kernel of chunk k (copy engines and SMs run concurrently).
-  constexpr int64_t kChunkMin = 1 << 16;
-  const int nchunks = int(std::min<int64_t>(4, npats / kChunkMin));
-  const bool ordered = in_order && nchunks >= 2 && ix->stream2 != nullptr;
-  if (ordered) {
-    cudaStream_t st[2] = {ix->stream, ix->stream2};
-    for (int k = 0; k < nchunks; k++) {
-      cudaStream_t cs = st[k & 1];
-      const int64_t lo = npats * k / nchunks, hi = npats * (k + 1) / nchunks, n = hi - lo;
-      const int64_t flo = offs[lo], fhi = (k + 1 < nchunks) ? offs[hi] : flat_len;
-      CK(cudaMemcpyAsync(d_plen + lo, plen + lo, size_t(n) * 4, cudaMemcpyHostToDevice, cs));
-      CK(cudaMemcpyAsync(d_offs + lo, offs + lo, size_t(n) * 8, cudaMemcpyHostToDevice, cs));
-      if (fhi > flo) CK(cudaMemcpyAsync(d_flat + flo, flat + flo, size_t(fhi - flo) * 2, cudaMemcpyHostToDevice, cs));
-      CountArgs a{n, d_plen + lo, d_flat, d_offs + lo, d_first + lo, d_last ? d_last + lo : nullptr};
-      CK(launch_count(ix->im, a, ix->d_work + 8 + k, ix->count_sched, ix->sm_count, cs, &ix->launches));
-      CK(cudaMemcpyAsync(first + lo, d_first + lo, size_t(n) * 8, cudaMemcpyDeviceToHost, cs));
-      if (last) CK(cudaMemcpyAsync(last + lo, d_last + lo, size_t(n) * 8, cudaMemcpyDeviceToHost, cs));
+  // Large batches whose patterns lie in the flat buffer in order are STREAMED: the count kernel is
+  // launched at once and pulls patterns from its queue as the copy stream delivers them (a device
+  // counter written after every chunk gates the queue, CountArgs::avail), so the host->device
+  // transfer overlaps the search instead of preceding it.  The batch runs as two kernels, one per
+  // half, so that the results of the first half travel back while the second half is searched.
+  constexpr int64_t kChunk = 1 << 16;  // patterns per copy chunk; a multiple of 32 keeps every 128-byte
+                                       // line of plen / offs inside one chunk
+  static const bool no_stream = std::getenv("FEMTO_B200_NO_STREAM") != nullptr;
+  if (in_order && npats >= 2 * kChunk && ix->stream2 && ix->stream3 && ix->stream_ok && !no_stream) {
+    const int m = uniform_len;
+    // the second kernel takes the last quarter: its results are the only transfer nothing overlaps
+    const int64_t mid = (npats - npats / 4) & ~int64_t(31);
+    const int64_t half_lo[2] = {0, mid}, half_hi[2] = {mid, npats};
+    // copy chunks grow from 8 Ki to 128 Ki patterns: the first patterns arrive after a few microseconds,
+    // the bulk travels in few, large transfers
+    auto chunk_at = [&](int64_t done) { return std::min<int64_t>(kChunk * 2, std::max<int64_t>(kChunk / 8, done)); };
+    int64_t nmarks = 0;
+    for (int h = 0; h < 2; h++)
+      for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo)) nmarks++;
+    unsigned long long* marks = static_cast<unsigned long long*>(ix->h_marks.get(size_t(nmarks) * 8));
+    unsigned long long* d_avail = ix->d_work + 12;
+    cudaStream_t sk = ix->stream, sc = ix->stream2, sr = ix->stream3;
+    // FEMTO_B200_TRACE=1: print when (ms after the start) the copies, each kernel and the results finish
+    static const bool trace = std::getenv("FEMTO_B200_TRACE") != nullptr;
+    cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (trace) for (cudaEvent_t& e : tev) CK(cudaEventCreate(&e));
+    CK(cudaMemsetAsync(d_avail, 0, 2 * sizeof(unsigned long long), sk));
+    if (trace) CK(cudaEventRecord(tev[0], sk));
+    CK(cudaEventRecord(ix->ev[0], sk));
+    CK(cudaStreamWaitEvent(sc, ix->ev[0], 0));
+    // kernels first: they spin on their arrival counters until the copies below land
+    for (int h = 0; h < 2; h++) {
+      const int64_t lo = half_lo[h], n = half_hi[h] - lo;
+      CountArgs a{n, d_plen + lo, m ? d_flat + lo * m : d_flat, d_offs + lo, d_first + lo,
+                  d_last ? d_last + lo : nullptr, d_avail + h, ix->d_status + 1, m};
+      CK(launch_count(ix->im, a, ix->d_work + 8 + h, ix->count_sched, ix->sm_count, sk, &ix->launches));
+      CK(cudaEventRecord(ix->ev[1 + h], sk));
+      if (trace) CK(cudaEventRecord(tev[1 + h], sk));
     }
-    CK(cudaStreamSynchronize(st[0]));
-    CK(cudaStreamSynchronize(st[1]));
-    return FM_OK;
+    // copies: chunk after chunk, each followed by its arrival mark.  Symbol ranges are cut at
+    // 128-byte boundaries of the device buffer so that no cache line is shared by two chunks (a
+    // line read for an early pattern must not hold not-yet-copied symbols of a later one).
+    int64_t k = 0, fdone = 0;
+    ix->last_h2d = (m ? 0 : npats * 12) + flat_len * 2 + nmarks * 8;
+    ix->last_d2h = npats * (last ? 16 : 8);
+    for (int h = 0; h < 2; h++) {
+      for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo), k++) {
+        const int64_t hi = std::min(half_hi[h], lo + chunk_at(lo));
+        if (!m) {
+          CK(cudaMemcpyAsync(d_plen + lo, plen + lo, size_t(hi - lo) * 4, cudaMemcpyHostToDevice, sc));
+          CK(cudaMemcpyAsync(d_offs + lo, offs + lo, size_t(hi - lo) * 8, cudaMemcpyHostToDevice, sc));
+        }
+        int64_t fend = hi < npats ? offs[hi] : flat_len;     // patterns [0, hi) end at or before this symbol
+        fend = std::min(flat_len, (fend + 63) & ~int64_t(63));
+        if (hi == npats) fend = flat_len;
+        if (fend > fdone) {
+          CK(cudaMemcpyAsync(d_flat + fdone, flat + fdone, size_t(fend - fdone) * 2, cudaMemcpyHostToDevice, sc));
+          fdone = fend;
+        }
+        marks[k] = static_cast<unsigned long long>(hi - half_lo[h]);
+        CK(cudaMemcpyAsync(d_avail + h, marks + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc));
+      }
+    }
+    if (trace) CK(cudaEventRecord(tev[3], sc));
+    // results: first half on its own stream as soon as its kernel is done, second half behind its kernel
+    CK(cudaStreamWaitEvent(sr, ix->ev[1], 0));
+    CK(cudaMemcpyAsync(first, d_first, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
+    if (last) CK(cudaMemcpyAsync(last, d_last, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
+    CK(cudaMemcpyAsync(first + mid, d_first + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
+    if (last) CK(cudaMemcpyAsync(last + mid, d_last + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
+    if (trace) {
+      CK(cudaEventRecord(tev[4], sr));
+      CK(cudaEventRecord(tev[5], sk));
+    }
+    int32_t stalled = 0;
+    CK(cudaMemcpyAsync(&stalled, ix->d_status + 1, sizeof(stalled), cudaMemcpyDeviceToHost, sk));
+    CK(cudaStreamSynchronize(sc));
+    CK(cudaStreamSynchronize(sr));
+    CK(cudaStreamSynchronize(sk));
+    if (trace) {
+      float t[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+      std::fprintf(stderr, "[femto_b200 trace] count %lld patterns: kernel A done %.3f ms, kernel B done %.3f, copies in done "
+                   "%.3f, results A out %.3f, results B out %.3f\n", (long long)npats, t[1], t[2], t[3], t[4], t[5]);
+      for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
+    if (!stalled) return FM_OK;
+    // The kernels did not see their patterns arrive (streams serialised by a profiler, or a copy
+    // stream that made no progress for 0.1 s): repeat the batch the plain way, and stay there.
+    CK(cudaMemsetAsync(ix->d_status + 1, 0, sizeof(int32_t), sk));
+    ix->stream_ok = false;
   }
+  ix->last_h2d = npats * 12 + flat_len * 2;
+  ix->last_d2h = npats * (last ? 16 : 8);
   CK(cudaMemcpyAsync(d_plen, plen, size_t(npats) * 4, cudaMemcpyHostToDevice, s));
   if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * 2, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
@@ -425,6 +551,13 @@ int fm_info(const fm_index_t* ix, fm_info_t* out) {
   return FM_OK;
 }
 
+int fm_last_transfer(const fm_index_t* ix, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!ix) return fail(FM_ERR_PARAM, "fm_last_transfer: null index");
+  if (h2d_bytes) *h2d_bytes = ix->last_h2d;
+  if (d2h_bytes) *d2h_bytes = ix->last_d2h;
+  return FM_OK;
+}
+
 int64_t fm_kernel_launches(const fm_index_t* ix) { return ix ? ix->launches : 0; }
 
 int fm_set_lanes_per_query(fm_index_t* ix, int lanes) {
@@ -487,11 +620,18 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
     if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
     int64_t flat_len = 0;
     bool ordered = false;
-    if (check_patterns(npats, plen, offs, &flat_len, &ordered)) return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
+    const BatchShape shape = scan_batch(npats, plen, offs);
+    if (shape.bad) return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
+    if (shape.dense) {
+      flat_len = shape.flat_len;
+      ordered = true;
+    } else if (check_patterns(npats, plen, offs, &flat_len, &ordered)) {
+      return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
+    }
     if (flat_len && !flat) return fail(FM_ERR_PARAM, "fm_count_flat: null pattern buffer");
     if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
       return fail(FM_ERR_MISSING, "fm_count_flat: index is a shard; use the sharded driver");
-    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered);
+    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered, shape.uniform);
   });
 }
 
@@ -565,8 +705,11 @@ int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* 
     uint16_t* flat = nullptr;
     int64_t flat_len = 0;
     gather_patterns(ix, npats, plen, pats, &offs, &flat, &flat_len);
+    int uniform = npats > 0 && plen[0] > 0 ? plen[0] : 0;  // gathered densely: equal lengths = uniform batch
+    for (int i = 0; i < npats && uniform; i++)
+      if (plen[i] != uniform) uniform = 0;
     return count_host(ix, npats, reinterpret_cast<const int32_t*>(plen), flat, flat_len, offs.data(), first, last,
-                      /*in_order=*/true);
+                      /*in_order=*/true, uniform);
   });
 }
 

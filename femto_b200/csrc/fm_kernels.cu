@@ -458,10 +458,25 @@ __device__ __forceinline__ void retire_and_fetch(PatternState& s, bool can_retir
   if (need && lane == gleader) idx = atomicAdd(work, 1ull);
   idx = __shfl_sync(kFull, idx, gleader);
   if (need) {
-    if (static_cast<int64_t>(idx) < a.npats) {
+    bool arrived = static_cast<int64_t>(idx) < a.npats;
+    if (arrived && a.avail) {  // streamed batch: wait until the copy stream has delivered this pattern
+      const volatile unsigned long long* av = a.avail;
+      for (unsigned spins = 0; *av <= idx; spins++) {
+        __nanosleep(400);
+        // Give up after ~0.1 s without touching the pattern (its bytes may not be there): the host
+        // then repeats the batch with the copies ahead of the kernel.  This is what happens under a
+        // profiler that serialises the streams, and it keeps a broken copy stream from hanging the GPU.
+        if (spins > (1u << 18) || *reinterpret_cast<volatile int32_t*>(a.stalled)) {
+          atomicExch(a.stalled, 1);
+          arrived = false;
+          break;
+        }
+      }
+    }
+    if (arrived) {
       s.pid = static_cast<int64_t>(idx);
-      const int m = a.plen[s.pid];
-      s.pat = a.flat + a.offs[s.pid];
+      const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.pid];
+      s.pat = a.flat + (a.uniform_len > 0 ? s.pid * m : a.offs[s.pid]);
       if (m <= 0) {  // empty pattern: every row (server.c:782-808)
         s.f = 0; s.l = im.total_length - 1; s.i = 0;
       } else {

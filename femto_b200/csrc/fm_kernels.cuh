@@ -17,6 +17,14 @@ struct CountArgs {
   const int64_t* offs;
   int64_t* first;
   int64_t* last;   // may be NULL: first[i] receives the count
+  // Streamed batches (host-buffer calls): the kernel is launched while the patterns are still being
+  // copied in; *avail (device memory, written by the copy stream after each chunk) = number of
+  // leading patterns whose plen / offs / symbols have arrived.  NULL = everything is there.
+  const unsigned long long* avail;
+  int32_t* stalled;  // set to 1 if a pattern did not arrive within ~10 s (the launch then ends; results invalid)
+  // > 0: every pattern has this length and pattern i starts at flat + i * uniform_len; plen and offs
+  // are not read (and need not be copied in).
+  int32_t uniform_len;
 };
 
 enum WalkMode : int {

@@ -192,6 +192,9 @@ void fm_host_free(void* p);
 
 /* Counters of the engine's own kernel launches since fm_open (all entry points). */
 int64_t fm_kernel_launches(const fm_index_t* ix);
+/* Bytes the most recent fm_count / fm_count_flat call copied host->device and device->host
+ * (a batch of equal-length, densely packed patterns travels without its length / offset arrays). */
+int fm_last_transfer(const fm_index_t* ix, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* Instrumented count (not a timed path): runs the same batch through a counter-carrying variant
  * of the count kernel and returns stats4 = { rank blocks requested, distinct rank blocks per

@@ -1,4 +1,5 @@
 # One GPU box visit: parity suite, default bench, ncu captures of the count kernel.
+# (ncu serialises streams, so the profiled runs take the plain host-buffer path: FEMTO_B200_NO_STREAM)
 # usage: bash scripts/gpu_round.sh <tag>   (files land in gpurun_out/<tag>_*)
 TAG=${1:-round}
 mkdir -p gpurun_out
@@ -13,7 +14,7 @@ print("cpu", json.dumps(d["cpu_baseline"])[:400])
 print("parity", json.dumps(d["parity"])[:300])
 print("locate", json.dumps(d["locate"])[:500])
 PY
-ncu --set full --clock-control none --import-source on -k regex:count_sync -s 2 -c 1 -f -o gpurun_out/${TAG}_count python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+FEMTO_B200_NO_STREAM=1 ncu --set full --clock-control none --import-source on -k regex:count_sync -s 2 -c 1 -f -o gpurun_out/${TAG}_count python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 ncu -i gpurun_out/${TAG}_count.ncu-rep --page details > gpurun_out/${TAG}_count_ncu_details.txt 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"count_|walk_|occ_|probe_" -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+FEMTO_B200_NO_STREAM=1 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"count_|walk_|occ_|probe_" -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 tail -4 gpurun_out/${TAG}_launches.csv

@@ -4,6 +4,8 @@ every L symbol, LF target and SA sample.  Run on the B200 box with `-m gpu`."""
 import json
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -404,3 +406,37 @@ def test_default_layout_and_probe(built_indexes):
     with pytest.raises(Exception):
         ix.probe_random_reads(48, steps=10)
     ix.close()
+
+
+# ---- streamed host-buffer batches (count kernel launched while the patterns are still arriving) ----
+@pytest.mark.parametrize("uniform", [True, False])
+def test_streamed_batch_equals_plain_batch(uniform, built_indexes, corpora):
+    """Batches of >= 128 Ki ordered patterns take the streamed path of fm_count_flat (two kernels gated
+    by arrival counters, uniform-length batches without plen / offs transfers).  Results must equal the
+    plain path (same patterns addressed out of order, which disables streaming) and the oracle."""
+    name = "english_100k"
+    docs, _ = corpora[name]
+    n = 300000 + 77                                           # several chunks per half, ragged tail
+    lengths = [12] if uniform else [1, 2, 3, 5, 8, 13, 21, 34]
+    base = corpus.sample_patterns(docs, 3000, lengths, seed=61, random_fraction=0.2)
+    rng = np.random.default_rng(62)
+    pick = rng.integers(0, len(base), n)
+    pats = [base[i] for i in pick]
+    plen, flat, offs = fb.flatten_patterns(pats)
+    with fb.Index(built_indexes[name], device=0) as ix, Oracle(built_indexes[name]) as o:
+        of, ol = o.count(base)
+        for _ in range(2):                                    # twice: device buffers are reused between calls
+            f, l = ix.count_flat(plen, flat, offs)
+            assert (f == of[pick]).all() and (l == ol[pick]).all()
+        # the same patterns, flat buffer reversed pattern by pattern: not "in order" -> plain path
+        order = np.arange(n)[::-1]
+        rflat = np.concatenate([pats[i] for i in order]).astype(np.uint16)
+        roffs = np.zeros(n, dtype=np.int64)
+        roffs[order] = np.concatenate([[0], np.cumsum(plen[order][:-1])])
+        f2, l2 = ix.count_flat(plen, rflat, roffs)
+        assert (f2 == f).all() and (l2 == l).all()
+        # last == NULL: counts in first (parallel_count, femto.c:313-318), streamed as well
+        cnt = np.empty(n, dtype=np.int64)
+        rc = ix.lib.fm_count_flat(ix.h, n, fb._ptr(plen, C.c_int32), fb._ptr(flat, C.c_uint16), fb._ptr(offs, C.c_int64),
+                                  fb._ptr(cnt, C.c_int64), None)
+        assert rc == 0 and (cnt == l - f + 1).all()
