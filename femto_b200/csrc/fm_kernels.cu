@@ -727,7 +727,10 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
 
 // ---------------------------------------------------------------------------------------------
 // count, "sync" schedule: one group of LPQ lanes per pattern advances both ranks of a step.
-template <int LPQ, int BW, int MINB, bool STATS, int LV = 1>
+// EXP (measurement variants of the quad branch, profiles/r01_quad_schedules.md; results unchanged):
+//   1 = position B re-reads its line only when it lies in another block (fewer L1 wavefronts),
+//   2 = 150 extra dependent ALU instructions per iteration (issue / ALU sensitivity).
+template <int LPQ, int BW, int MINB, bool STATS, int LV = 1, int EXP = 0>
 __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
                                                                      unsigned long long* __restrict__ work,
                                                                      unsigned long long* __restrict__ stats) {
@@ -831,10 +834,23 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
         uint2 hp = make_uint2(0, 0), hq = hp, ex = hp;
         if (any) {
           p.load(im.blocks, blkA, sub);
-          q.load(im.blocks, blkB, sub);
           hp = quad_header(im.blocks, blkA, nib >> 1);
-          hq = quad_header(im.blocks, blkB, nib >> 1);
+          if (EXP != 1 || two) {
+            q.load(im.blocks, blkB, sub);
+            hq = quad_header(im.blocks, blkB, nib >> 1);
+          }
           if (lvl + 4 < L) ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
+        }
+        if (EXP == 1 && !two) {
+          hq = hp;
+#pragma unroll
+          for (int t = 0; t < 8; t++) q.d[t] = p.d[t];
+        }
+        if (EXP == 2) {
+          uint32_t x = p.d[0] ^ nib;
+#pragma unroll
+          for (int t = 0; t < 50; t++) x = (x ^ (x >> 7)) + 0x9e3779b9u;
+          if (x == 0x12345u && lvl > 1000) actA = false;  // never true; keeps the chain alive
         }
         const int lb = 64 * sub;
         int jA = static_cast<int>(pA & 127u) + 1, jB = static_cast<int>(pB & 127u) + 1;
@@ -1399,6 +1415,11 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     if (d_stats) FM_LAUNCH((count_sync_kernel<2, 32, MINB, true, 4>), 2);                                \
     else FM_LAUNCH((count_sync_kernel<2, 32, MINB, false, 4>), 2);                                       \
     break;
+#define FM_SYNC4EXP(MINB, EXP)                                                                           \
+  case 3000000 + 32 * 10000 + 1000 + 70 + 10 * (EXP) + (MINB):                                           \
+    if (d_stats) FM_LAUNCH((count_sync_kernel<2, 32, MINB, true, 4, EXP>), 2);                           \
+    else FM_LAUNCH((count_sync_kernel<2, 32, MINB, false, 4, EXP>), 2);                                  \
+    break;
 #define FM_QUAD_SPLIT(CODE, THREADS, MINB)                                                               \
   case 3000000 + 32 * 10000 + 1000 + (CODE):                                                             \
     do {                                                                                                 \
@@ -1425,12 +1446,14 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     FM_SYNC4(3) FM_SYNC4(4) FM_SYNC4(5) FM_SYNC4(6) FM_SYNC4(8)
     /* split schedule: 60 + k */
     FM_QUAD_SPLIT(65, 256, 5) FM_QUAD_SPLIT(67, 128, 9)
+    FM_SYNC4EXP(4, 1) FM_SYNC4EXP(5, 1) FM_SYNC4EXP(5, 2)  /* codes 1084, 1085, 1095 */
     default: return cudaErrorInvalidValue;
   }
 #undef FM_SYNC
 #undef FM_SYNC2
 #undef FM_SYNC4
 #undef FM_QUAD_SPLIT
+#undef FM_SYNC4EXP
 #undef FM_PAIR
 #undef FM_LAUNCH
   if (launch_counter) ++*launch_counter;
