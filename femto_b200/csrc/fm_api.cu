@@ -139,7 +139,7 @@ int paired_sched(int block_words, int lanes) {
 // quad-level blocks: 1000 + 10 * k + CTAs per SM; k = 2: two lanes per pattern evaluate both positions
 // of a step together (default; k = 3 adds the one-step-ahead symbol fetch); 60 + v: one lane per
 // Occ ("split" schedule, selectable with fm_set_count_schedule(.., 1))
-constexpr int kQuadSched = 1000 + 10 * 2 + 5;
+constexpr int kQuadSched = 1000 + 10 * 2 + 4;  // 64 registers, no spills, 4 CTAs x 8 warps per SM
 constexpr int kQuadSchedSplit = 1000 + 67;
 
 int default_count_sched(int block_words, int levels) {

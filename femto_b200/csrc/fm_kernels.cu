@@ -323,10 +323,12 @@ struct QuadWords {
     for (int t = 0; t < 8; t++) d[t] = 0;
   }
   __device__ __forceinline__ void load(const uint4* __restrict__ blocks, uint32_t blk, int sub) {
+    // this lane's 32 bytes = one sector, fetched with ONE 256-bit load (sm_100: LDG.E.256): half the
+    // load instructions and L1 wavefronts of two 128-bit loads
     const uint4* b = blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4) + 4 + 2 * sub;
-    const uint4 x = __ldg(b), y = __ldg(b + 1);
-    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
-    d[4] = y.x; d[5] = y.y; d[6] = y.z; d[7] = y.w;
+    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+        : "l"(b));
   }
   // ones of region L within [a, b), a and b given relative to this lane's first bit
   template <int L>
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
 // ---------------------------------------------------------------------------------------------
 // count, "sync" schedule: one group of LPQ lanes per pattern advances both ranks of a step.
 // EXP (measurement variants of the quad branch, profiles/r01_quad_schedules.md; results unchanged):
-//   1 = position B re-reads its line only when it lies in another block (fewer L1 wavefronts),
+//   1 = position B always re-reads its line, also when it is A's (an L1 hit; the first version),
 //   2 = 150 extra dependent ALU instructions per iteration (issue / ALU sensitivity).
 template <int LPQ, int BW, int MINB, bool STATS, int LV = 1, int EXP = 0>
 __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
@@ -774,9 +776,11 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
         }
       }
       if (stepping) {
-        // the symbol's record and the bucket's root: two independent reads, issued together
+        // the symbol's record; the bucket's root comes with it (quad: root blocks are addressed by
+        // row, the root QuadRec is named by the record) or from the bucket record (other layouts)
         const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-        const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+        uint4 br = make_uint4(static_cast<uint32_t>(g * im.root_stride), static_cast<uint32_t>(rv.w) >> 4, 0, 0);
+        if (LV != 4) br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
         const int64_t ob = rec_occ_base(rv);
         leaf = static_cast<uint32_t>(rv.z);
         if (cross_pending) {  // second round of a cross-bucket step: row `last`
@@ -827,7 +831,8 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
         const bool two = actA && actB && kA != kB;
         const uint32_t blkA = base + (actA ? kA : kB), blkB = base + (actB ? kB : kA);
         const uint32_t nib = any ? quad_path(leaf, L, lvl) : 0u;
-        // p serves position A, q position B; a shared block is re-read from L1
+        // p serves position A, q position B; q is read only when B lies in another block -- the
+        // load / L1 path, not issue slots, is what this kernel saturates first
         QuadWords p, q;
         p.clear();
         q.clear();
@@ -835,13 +840,13 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
         if (any) {
           p.load(im.blocks, blkA, sub);
           hp = quad_header(im.blocks, blkA, nib >> 1);
-          if (EXP != 1 || two) {
+          if (EXP == 1 || two) {
             q.load(im.blocks, blkB, sub);
             hq = quad_header(im.blocks, blkB, nib >> 1);
           }
           if (lvl + 4 < L) ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
         }
-        if (EXP == 1 && !two) {
+        if (EXP != 1 && !two) {  // both positions in one block: evaluate B from A's registers
           hq = hp;
 #pragma unroll
           for (int t = 0; t < 8; t++) q.d[t] = p.d[t];
@@ -1446,7 +1451,7 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     FM_SYNC4(3) FM_SYNC4(4) FM_SYNC4(5) FM_SYNC4(6) FM_SYNC4(8)
     /* split schedule: 60 + k */
     FM_QUAD_SPLIT(65, 256, 5) FM_QUAD_SPLIT(67, 128, 9)
-    FM_SYNC4EXP(4, 1) FM_SYNC4EXP(5, 1) FM_SYNC4EXP(5, 2)  /* codes 1084, 1085, 1095 */
+    FM_SYNC4EXP(4, 1) FM_SYNC4EXP(5, 1) FM_SYNC4EXP(4, 2)  /* codes 1084, 1085, 1094 */
     default: return cudaErrorInvalidValue;
   }
 #undef FM_SYNC
