@@ -624,5 +624,15 @@ def run_reference_arm(args, index_path, text, workload):
     print(json.dumps(out), flush=True)
 
 
+def _stdout_only_for_the_result():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON
+    line on stdout.  Point fd 1 at stderr for the whole run and keep the real stdout for print()."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _stdout_only_for_the_result()
     main()
