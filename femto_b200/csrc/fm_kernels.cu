@@ -330,12 +330,27 @@ struct QuadWords {
         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
         : "l"(b));
   }
+  // Masks of this lane's 64 bits at positions >= x (x relative to the lane's first bit, any
+  // integer): .x for the first word, .y for the second.  ONE 64-bit shift of all-ones serves both
+  // words and needs no upper clamp (shr.b64 yields 0 for amounts >= 64); the lower clamp is the
+  // only other instruction.
+  static __device__ __forceinline__ uint2 mask_ge(int x) {
+    const uint32_t ux = static_cast<uint32_t>(max(x, 0));
+    unsigned long long m;
+    asm("shr.b64 %0, %1, %2;" : "=l"(m) : "l"(0xffffffffffffffffull), "r"(ux));
+    return make_uint2(static_cast<uint32_t>(m >> 32), static_cast<uint32_t>(m));
+  }
   // ones of region L within [a, b), a and b given relative to this lane's first bit
   template <int L>
   __device__ __forceinline__ uint32_t range(int a, int b) const {
-    const uint32_t m0 = shr_clamp(kFull, max(a, 0)) & ~shr_clamp(kFull, max(b, 0));
-    const uint32_t m1 = shr_clamp(kFull, max(a - 32, 0)) & ~shr_clamp(kFull, max(b - 32, 0));
-    return __popc(d[2 * L] & m0) + __popc(d[2 * L + 1] & m1);
+    const uint2 ma = mask_ge(a), mb = mask_ge(b);
+    return __popc(d[2 * L] & ma.x & ~mb.x) + __popc(d[2 * L + 1] & ma.y & ~mb.y);
+  }
+  // ones of region L at positions >= x (inv == 0) or < x (inv == ~0)
+  template <int L>
+  __device__ __forceinline__ uint32_t one_sided(int x, uint32_t inv) const {
+    const uint2 m = mask_ge(x);
+    return __popc(d[2 * L] & (m.x ^ inv)) + __popc(d[2 * L + 1] & (m.y ^ inv));
   }
   // bit `pos` of region L, fetched from the lane that holds it
   template <int L>
@@ -727,6 +742,41 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
   if (STATS) flush_stats(stats, lane, n_ranks, n_blocks, n_occ, n_steps);
 }
 
+// All four levels of one quad block for the two positions of a backward-search step: p / hp serve
+// position A, q / hq position B (the same objects when both positions lie in one block).  jA, jB:
+// positions of the block's stretch up to and including ours, replaced by the count at the exit;
+// returns the last path bit.  Warp-collective (one shuffle per level carries both counts).
+__device__ __forceinline__ uint32_t quad_eval_pair(const QuadWords& p, const QuadWords& q, const uint2 hp,
+                                                   const uint2 hq, uint32_t nib, int lb, int& jA, int& jB) {
+  // level 0: the node's own stretch, prefix [0, j)
+  uint32_t c = group_sum<2>(p.one_sided<0>(jA - lb, kFull) | (q.one_sided<0>(jB - lb, kFull) << 16));
+  uint32_t b = (nib >> 3) & 1u;
+  jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+  jB = b ? (c >> 16) : jB - (c >> 16);
+  // level 1: child 0 forward from 0, child 1 backward from the end of the region: one-sided too
+  uint32_t inv = b ? 0u : kFull;
+  c = group_sum<2>(p.one_sided<1>((b ? kQuadPos - jA : jA) - lb, inv) |
+                   (q.one_sided<1>((b ? kQuadPos - jB : jB) - lb, inv) << 16));
+  b = (nib >> 2) & 1u;
+  jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+  jB = b ? (c >> 16) : jB - (c >> 16);
+  // level 2: anchored at the header's level-2 anchor
+  int aA = static_cast<int>(hp.x >> 24) - (b ? jA : 0) - lb;
+  int aB = static_cast<int>(hq.x >> 24) - (b ? jB : 0) - lb;
+  c = group_sum<2>(p.range<2>(aA, aA + jA) | (q.range<2>(aB, aB + jB) << 16));
+  b = (nib >> 1) & 1u;
+  jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+  jB = b ? (c >> 16) : jB - (c >> 16);
+  // level 3
+  aA = static_cast<int>(hp.y >> 24) - (b ? jA : 0) - lb;
+  aB = static_cast<int>(hq.y >> 24) - (b ? jB : 0) - lb;
+  c = group_sum<2>(p.range<3>(aA, aA + jA) | (q.range<3>(aB, aB + jB) << 16));
+  b = nib & 1u;
+  jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
+  jB = b ? (c >> 16) : jB - (c >> 16);
+  return b;
+}
+
 // ---------------------------------------------------------------------------------------------
 // count, "sync" schedule: one group of LPQ lanes per pattern advances both ranks of a step.
 // EXP (measurement variants of the quad branch, profiles/r01_quad_schedules.md; results unchanged):
@@ -846,11 +896,6 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
           }
           if (lvl + 4 < L) ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
         }
-        if (EXP != 1 && !two) {  // both positions in one block: evaluate B from A's registers
-          hq = hp;
-#pragma unroll
-          for (int t = 0; t < 8; t++) q.d[t] = p.d[t];
-        }
         if (EXP == 2) {
           uint32_t x = p.d[0] ^ nib;
 #pragma unroll
@@ -859,32 +904,18 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
         }
         const int lb = 64 * sub;
         int jA = static_cast<int>(pA & 127u) + 1, jB = static_cast<int>(pB & 127u) + 1;
-        // level 0: the node's own stretch, prefix [0, j)
-        uint32_t c = group_sum<2>((popc_top(p.d[0], jA - lb) + popc_top(p.d[1], jA - lb - 32)) |
-                                  ((popc_top(q.d[0], jB - lb) + popc_top(q.d[1], jB - lb - 32)) << 16));
-        uint32_t b = (nib >> 3) & 1u;
-        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
-        jB = b ? (c >> 16) : jB - (c >> 16);
-        // level 1: child b, forward from 0 or backward from the end of the region
-        int aA = b ? kQuadPos - jA : 0, aB = b ? kQuadPos - jB : 0;
-        c = group_sum<2>(p.range<1>(aA - lb, aA + jA - lb) | (q.range<1>(aB - lb, aB + jB - lb) << 16));
-        b = (nib >> 2) & 1u;
-        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
-        jB = b ? (c >> 16) : jB - (c >> 16);
-        // level 2: anchored at the header's level-2 anchor
-        aA = static_cast<int>(hp.x >> 24) - (b ? jA : 0);
-        aB = static_cast<int>(hq.x >> 24) - (b ? jB : 0);
-        c = group_sum<2>(p.range<2>(aA - lb, aA + jA - lb) | (q.range<2>(aB - lb, aB + jB - lb) << 16));
-        b = (nib >> 1) & 1u;
-        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
-        jB = b ? (c >> 16) : jB - (c >> 16);
-        // level 3
-        aA = static_cast<int>(hp.y >> 24) - (b ? jA : 0);
-        aB = static_cast<int>(hq.y >> 24) - (b ? jB : 0);
-        c = group_sum<2>(p.range<3>(aA - lb, aA + jA - lb) | (q.range<3>(aB - lb, aB + jB - lb) << 16));
-        b = nib & 1u;
-        jA = b ? (c & 0xffffu) : jA - (c & 0xffffu);
-        jB = b ? (c >> 16) : jB - (c >> 16);
+        uint32_t b;
+        if (EXP == 1 || __any_sync(kFull, two)) {  // some pattern of the warp needs two blocks (rare once ranges are narrow)
+          if (EXP != 1 && !two) {
+            hq = hp;
+#pragma unroll
+            for (int t = 0; t < 8; t++) q.d[t] = p.d[t];
+          }
+          b = quad_eval_pair(p, q, hp, hq, nib, lb, jA, jB);
+        } else {                                   // every pattern evaluates both positions from one line
+          hq = hp;
+          b = quad_eval_pair(p, p, hp, hp, nib, lb, jA, jB);
+        }
         if (STATS && any && sub == 0) {
           n_blocks += two ? 2 : 1;
           n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
