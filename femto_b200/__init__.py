@@ -20,6 +20,7 @@ from . import _lib
 from ._lib import FmInfo
 
 CHARACTER_OFFSET = 5
+FM_ERR_FULL = 10          # include/femto_b200.h fm_err_t (ERR_FULL, utils/error.h)
 ALPHA_SIZE = 261
 ESCAPE_CODE_SEOF = 2
 
@@ -249,6 +250,25 @@ class Index:
         _check(self.lib.fm_resolve(self.h, n, _ptr(offsets, C.c_int64), _ptr(doc, C.c_int64), _ptr(off, C.c_int64)),
                "fm_resolve")
         return doc[:n], off[:n]
+
+    def doc_name(self, doc: int) -> bytes:
+        """The info bytes stored with the document at build time (document_info, index.c:1767-1784)."""
+        n = C.c_int64()
+        rc = self.lib.fm_doc_name(self.h, doc, None, 0, C.byref(n))
+        if rc not in (0, FM_ERR_FULL):
+            _check(rc, "fm_doc_name")
+        buf = C.create_string_buffer(max(n.value, 1))
+        _check(self.lib.fm_doc_name(self.h, doc, buf, n.value, C.byref(n)), "fm_doc_name")
+        return buf.raw[:n.value]
+
+    def range_documents(self, first: int, last: int) -> np.ndarray:
+        """Ascending document numbers holding the suffixes of rows first..last (range_to_results, documents)."""
+        cap = max(min(last - first + 1, int(self.info.num_documents)), 1)
+        docs = np.zeros(cap, dtype=np.int64)
+        n = C.c_int64()
+        _check(self.lib.fm_range_documents(self.h, first, last, _ptr(docs, C.c_int64), cap, C.byref(n)),
+               "fm_range_documents")
+        return docs[:n.value]
 
     def extract(self, doc: int) -> np.ndarray:
         ln, _ = self.doc_info(doc)

@@ -105,7 +105,8 @@ struct fm_index {
   unsigned long long* d_work = nullptr;  // work-queue counters (one per concurrent launch slot)
   int32_t* d_status = nullptr;
   // host-side header tables
-  std::vector<int64_t> doc_ends, doc_eof_rows, C_host;
+  std::vector<int64_t> doc_ends, doc_eof_rows, C_host, doc_info_off;
+  std::vector<uint8_t> doc_info_bytes;
   // per-call scratch, serialised by mu
   std::mutex mu;
   cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
@@ -272,6 +273,8 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->C_host = host->C;
     ix->doc_ends = std::move(host->doc_ends);
     ix->doc_eof_rows = std::move(host->doc_eof_rows);
+    ix->doc_info_off = std::move(host->doc_info_off);
+    ix->doc_info_bytes = std::move(host->doc_info_bytes);
   } catch (const CudaFail& e) {
     destroy(ix);
     return fail(FM_ERR_IO, std::string("fm_open: ") + e.what());
@@ -975,6 +978,46 @@ int fm_resolve(const fm_index_t* ix, int64_t n, const int64_t* offsets, int64_t*
     if (prev < 0) { doc[i] = 0; doc_off[i] = offsets[i]; }
     else { doc[i] = prev + 1; doc_off[i] = offsets[i] - ix->doc_ends[size_t(prev)]; }
   }
+  return FM_OK;
+}
+
+int fm_doc_name(const fm_index_t* ix, int64_t doc, void* out, int64_t out_cap, int64_t* out_len) {
+  if (!ix || !out_len) return fail(FM_ERR_PARAM, "fm_doc_name: null argument");
+  if (doc < 0 || doc >= ix->info.num_documents) return fail(FM_ERR_PARAM, "fm_doc_name: no such document");
+  const int64_t lo = ix->doc_info_off[size_t(doc)], len = ix->doc_info_off[size_t(doc) + 1] - lo;
+  *out_len = len;
+  if (len > out_cap) return fail(FM_ERR_FULL, "fm_doc_name: output buffer too small");
+  if (len > 0) {
+    if (!out) return fail(FM_ERR_PARAM, "fm_doc_name: null output");
+    std::memcpy(out, ix->doc_info_bytes.data() + lo, size_t(len));
+  }
+  return FM_OK;
+}
+
+int fm_range_documents(fm_index_t* ix, int64_t first, int64_t last, int64_t* docs, int64_t docs_cap, int64_t* ndocs) {
+  if (!ix || !ndocs) return fail(FM_ERR_PARAM, "fm_range_documents: null argument");
+  *ndocs = 0;
+  if (last < first) return FM_OK;
+  const int64_t n = last - first + 1;
+  std::vector<int64_t> offs;
+  try {
+    offs.resize(size_t(n));
+  } catch (const std::bad_alloc&) {
+    return fail(FM_ERR_MEM, "fm_range_documents: out of memory");
+  }
+  int rc = fm_locate_range(ix, first, last, offs.data());  // SA[first..last] on the GPU
+  if (rc) return rc;
+  // resolve_location (index.c:1587-1611) per offset, then the sorted set of documents
+  for (int64_t i = 0; i < n; i++) {
+    const auto it = std::upper_bound(ix->doc_ends.begin(), ix->doc_ends.end(), offs[size_t(i)]);
+    offs[size_t(i)] = int64_t(it - ix->doc_ends.begin());
+  }
+  std::sort(offs.begin(), offs.end());
+  offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+  *ndocs = int64_t(offs.size());
+  if (*ndocs > docs_cap) return fail(FM_ERR_FULL, "fm_range_documents: output buffer too small");
+  if (*ndocs && !docs) return fail(FM_ERR_PARAM, "fm_range_documents: null output");
+  std::copy(offs.begin(), offs.end(), docs);
   return FM_OK;
 }
 

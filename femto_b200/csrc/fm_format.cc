@@ -157,6 +157,17 @@ int64_t IndexFiles::doc_eof_row(int64_t doc) const {
   return int64_t(be64(header_.at(off, 8)));
 }
 
+std::pair<const uint8_t*, int64_t> IndexFiles::doc_info(int64_t doc) const {
+  if (doc < 0 || doc >= hdr_.ndocs) throw Error(FM_ERR_PARAM, "no such document");
+  // doc_info_off[ndocs+1] (absolute offsets in the header block) follows doc_eof_rows (index.c:882-898)
+  const size_t tab = size_t(kBlockHeaderBytes) + 8 * size_t(kAlpha) + 8 * size_t(kAlpha) * size_t(hdr_.nblocks) +
+                     16 * size_t(hdr_.ndocs) + 8 * size_t(doc);
+  const int64_t start = int64_t(be64(header_.at(tab, 8))), end = int64_t(be64(header_.at(tab + 8, 8)));
+  if (start < 0 || end < start) throw Error(FM_ERR_FORMAT, "bad document info offsets");
+  if (end == start) return {nullptr, 0};
+  return {header_.at(size_t(start), size_t(end - start)), end - start};
+}
+
 // ---------------------------------------------------------------- bucket tables
 namespace {
 struct MsbBitReader {

@@ -18,6 +18,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/femto_b200.h"
@@ -128,6 +129,8 @@ class IndexFiles {
   int64_t block_occs(int ch, int64_t blk) const;
   int64_t doc_end(int64_t doc) const;
   int64_t doc_eof_row(int64_t doc) const;
+  // document info bytes (name / URL given at build time): document_info, index.c:1767-1784
+  std::pair<const uint8_t*, int64_t> doc_info(int64_t doc) const;
 
  private:
   std::string path_;

@@ -729,9 +729,13 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
   for (int c = 0; c < 262; c++) im->C[size_t(c)] = files->C(c);
   im->doc_ends.resize(size_t(h.ndocs));
   im->doc_eof_rows.resize(size_t(h.ndocs));
+  im->doc_info_off.assign(size_t(h.ndocs) + 1, 0);
   for (int64_t d = 0; d < h.ndocs; d++) {
     im->doc_ends[size_t(d)] = files->doc_end(d);
     im->doc_eof_rows[size_t(d)] = files->doc_eof_row(d);
+    const auto info = files->doc_info(d);
+    if (info.second) im->doc_info_bytes.insert(im->doc_info_bytes.end(), info.first, info.first + info.second);
+    im->doc_info_off[size_t(d) + 1] = int64_t(im->doc_info_bytes.size());
   }
 
   // map blocks, validate headers

@@ -34,6 +34,8 @@ struct HostImage {
   std::vector<int64_t> markvals;
   std::vector<int64_t> C;           // 262 entries
   std::vector<int64_t> doc_ends, doc_eof_rows;
+  std::vector<int64_t> doc_info_off;  // ndocs + 1 offsets into doc_info_bytes
+  std::vector<uint8_t> doc_info_bytes;
   HostImage() = default;
   HostImage(const HostImage&) = delete;
   HostImage& operator=(const HostImage&) = delete;

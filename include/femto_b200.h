@@ -183,6 +183,16 @@ int fm_backward_step(fm_index_t* ix, int64_t n, const int64_t* first, const int6
  * (src/main/server.c:6364-6437). */
 int fm_doc_info(const fm_index_t* ix, int64_t doc, int64_t* doc_len, int64_t* eof_row);
 int fm_resolve(const fm_index_t* ix, int64_t n, const int64_t* offsets, int64_t* doc, int64_t* doc_off);
+/* The info bytes stored with a document at build time (its name / URL): document_info,
+ * src/main/index.c:1767-1784 (header_loc_request with HDR_LOC_REQUEST_DOC_INFO).  *out_len receives
+ * the length; FM_ERR_FULL when it exceeds out_cap. */
+int fm_doc_name(const fm_index_t* ix, int64_t doc, void* out, int64_t out_cap, int64_t* out_len);
+/* Documents that contain the suffixes of BWT rows first..last, ascending and unique: what the
+ * reference's range_to_results query delivers for RESULT_TYPE_DOCUMENTS (src/main/server.c:4549-4889;
+ * it unions the per-chunk document lists and locates the ragged ends, this call locates every row
+ * on the GPU and resolves the offsets with the header's document table -- same set).  *ndocs
+ * receives the number of documents; FM_ERR_FULL when it exceeds docs_cap. */
+int fm_range_documents(fm_index_t* ix, int64_t first, int64_t last, int64_t* docs, int64_t docs_cap, int64_t* ndocs);
 int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int64_t* out_len);
 
 /* --------------------------------------------------------------------------

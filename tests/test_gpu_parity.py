@@ -440,3 +440,31 @@ def test_streamed_batch_equals_plain_batch(uniform, built_indexes, corpora):
         rc = ix.lib.fm_count_flat(ix.h, n, fb._ptr(plen, C.c_int32), fb._ptr(flat, C.c_uint16), fb._ptr(offs, C.c_int64),
                                   fb._ptr(cnt, C.c_int64), None)
         assert rc == 0 and (cnt == l - f + 1).all()
+
+
+# ---- documents: info bytes and the documents of a row range ----------------
+def test_doc_names_and_range_documents(tmp_path):
+    """fm_doc_name returns the bytes stored at build time (document_info, index.c:1767-1784);
+    fm_range_documents = the ascending set of documents of SA[first..last] (range_to_results for
+    documents, server.c:4549-4889), checked against the oracle's locate + its document table."""
+    docs = [corpus.english_like(3000, 300 + d) for d in range(7)] + [b"", b"zzzz the end"]
+    names = [f"file://corpus/doc_{d:03d}.txt".encode() for d in range(len(docs))]
+    names[3] = b""                                           # a document without info bytes
+    path = str(tmp_path / "named")
+    fb.build_index_host(docs, path, doc_infos=names, block_size=4096, bucket_size=512, chunk_size=256)
+    with fb.Index(path) as ix, Oracle(path) as o:
+        assert [ix.doc_name(d) for d in range(len(docs))] == names
+        n = o.header_info()["total_length"]
+        sa = o.locate_range(0, n - 1)
+        doc_of = np.array([o.resolve(int(x))[0] for x in sa], dtype=np.int64)
+        for first, last in [(0, n - 1), (0, 0), (n - 1, n - 1), (17, 16), (100, 180), (2000, 2600), (n - 40, n - 1)]:
+            want = np.unique(doc_of[first:last + 1]) if last >= first else np.zeros(0, dtype=np.int64)
+            got = ix.range_documents(first, last)
+            assert (got == want).all() and len(got) == len(want), (first, last)
+        # a pattern's documents: count -> range -> documents
+        pats = corpus.sample_patterns(docs, 40, [2, 3, 5], seed=5)
+        f, l = ix.count(pats)
+        for p, a, b in zip(pats, f, l):
+            pb = bytes((p - 5).astype(np.uint8))
+            want = [d for d, text in enumerate(docs) if pb in text]
+            assert ix.range_documents(int(a), int(b)).tolist() == want
