@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--npats", type=int, default=1 << 20)
     ap.add_argument("--plen", type=int, default=PLEN_DEFAULT)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--patterns", choices=["text", "random"], default="text",
+                    help="text: sampled from the corpus (every pattern occurs, all plen-1 steps run; headline); "
+                         "random: uniform random symbols of the corpus alphabet (die after a few steps)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per pattern group (2, 4 or 8); 0 = engine default")
     ap.add_argument("--sched", choices=["merged", "pair"], default="merged", help="count kernel schedule")
     ap.add_argument("--block-bytes", type=int, default=0, help="rank block size of the HBM image (128/64/32)")
@@ -118,6 +121,11 @@ def sample_patterns(args, text, batch_id, rank):
     g = torch.Generator(device=text.device)
     g.manual_seed((args.seed + 1) * 1000003 + batch_id * 9176 + rank * 131)
     n = text.numel()
+    if args.patterns == "random":
+        sym = torch.randint(0, 256, (args.npats, args.plen), generator=g, device=text.device)
+        if args.kind == "acgt":
+            sym = torch.tensor(list(b"ACGT"), device=text.device)[sym & 3]
+        return (sym.to(torch.int16) + 5).contiguous()
     starts = torch.randint(0, n - args.plen + 1, (args.npats,), generator=g, device=text.device)
     idx = starts[:, None] + torch.arange(args.plen, device=text.device)[None, :]
     return (text[idx].to(torch.int16) + 5).contiguous()      # [npats, plen] alpha_t symbols
@@ -252,7 +260,8 @@ def main():
 
     index_path, build_info = ensure_index(args, device, rank, world if args.impl == "b200" else 1)
     text = corpus_tensor(args, device)
-    workload = (f"count() of {args.npats} text-sampled length-{args.plen} patterns on a {args.corpus_mib} MiB "
+    workload = (f"count() of {args.npats} {'text-sampled' if args.patterns == 'text' else 'uniform-random'} "
+                f"length-{args.plen} patterns on a {args.corpus_mib} MiB "
                 f"synthetic {'uniform byte' if args.kind == 'bytes' else 'ACGT'} corpus (1 document), "
                 f"default index params (block 128Mi rows, bucket 1Mi, mark_period 20, chunk 2048)")
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -112,7 +113,7 @@ struct fm_index {
   cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   DevBuf d_in[4], d_out[4];
-  HostBuf h_stage[2], h_marks;
+  HostBuf h_stage[2], h_marks, h_ranges;
   int64_t launches = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes copied by the most recent host-buffer count call
   bool stream_ok = true;               // cleared when a streamed batch stalled (e.g. under a serialising profiler)
@@ -183,6 +184,7 @@ void destroy(fm_index* ix) {
   for (auto& b : ix->d_out) b.release();
   for (auto& b : ix->h_stage) b.release();
   ix->h_marks.release();
+  ix->h_ranges.release();
   for (cudaEvent_t e : ix->ev) if (e) cudaEventDestroy(e);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   if (ix->stream2) cudaStreamDestroy(ix->stream2);
@@ -812,17 +814,22 @@ int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
       return fail(FM_ERR_PARAM, "fm_locate_flat: bad argument");
     int64_t flat_len = 0;
     if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_locate_flat: negative length/offset");
-    std::vector<int64_t> first(size_t(npats) + 1), last(size_t(npats) + 1);
-    int rc = count_host(ix, npats, plen, flat, flat_len, offs, first.data(), last.data());
+    // first/last land in pinned staging (a pageable destination would make the copy back synchronous and slow)
+    int64_t* first = static_cast<int64_t*>(ix->h_ranges.get(size_t(npats + 1) * 16));
+    int64_t* last = first + npats + 1;
+    static const bool trace = std::getenv("FEMTO_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = count_host(ix, npats, plen, flat, flat_len, offs, first, last);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     // clip as do_locate_query (server.c:4407-4415)
     int64_t total = 0;
     for (int64_t i = 0; i < npats; i++) {
-      int64_t f = first[size_t(i)], l = last[size_t(i)];
+      int64_t f = first[i], l = last[i];
       out_start[i] = total;
       if (f > l) { noccs[i] = 0; continue; }
       if (l - f > int64_t(max_occs_each)) l = f + int64_t(max_occs_each) - 1;
-      last[size_t(i)] = l;
+      last[i] = l;
       noccs[i] = int32_t(l - f + 1);
       total += l - f + 1;
     }
@@ -831,8 +838,16 @@ int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
     if (!out) return fail(FM_ERR_PARAM, "fm_locate_flat: null output");
     int64_t* rows = static_cast<int64_t*>(ix->h_stage[1].get(size_t(total) * 8));
     for (int64_t i = 0; i < npats; i++)
-      for (int32_t j = 0; j < noccs[i]; j++) rows[out_start[i] + j] = first[size_t(i)] + j;
-    return locate_rows_host(ix, total, rows, out);
+      for (int32_t j = 0; j < noccs[i]; j++) rows[out_start[i] + j] = first[i] + j;
+    const auto t2 = std::chrono::steady_clock::now();
+    rc = locate_rows_host(ix, total, rows, out);
+    if (trace) {
+      const auto t3 = std::chrono::steady_clock::now();
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      std::fprintf(stderr, "[femto_b200 trace] locate %lld patterns, %lld rows: count %.3f ms, ranges -> rows %.3f, walks %.3f\n",
+                   (long long)npats, (long long)total, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    }
+    return rc;
   });
 }
 
