@@ -373,13 +373,30 @@ def main():
     loc_flat = h_flat[0].numpy()[:nloc].reshape(-1).view(np.uint16)
     loc_plen, loc_offs = h_plen.numpy()[:nloc], h_offs.numpy()[:nloc]
     loc_cap = nloc * 8
-    noccs, lstart, lout = ix.locate_flat(loc_plen, loc_flat, loc_offs, 2**31 - 1, loc_cap)   # warm-up
+    # results land in pinned, preallocated host buffers, as for the count leg (the ctypes convenience
+    # wrapper Index.locate_flat allocates and zero-fills pageable arrays per call: not part of the path)
+    h_noccs = torch.zeros(nloc, dtype=torch.int32).pin_memory()
+    h_lstart = torch.zeros(nloc, dtype=torch.int64).pin_memory()
+    h_lout = torch.zeros(loc_cap, dtype=torch.int64).pin_memory()
+
+    def step_locate():
+        rc = lib.fm_locate_flat(ix.h, nloc, C.cast(h_plen.data_ptr(), C.POINTER(C.c_int32)),
+                                C.cast(h_flat[0].data_ptr(), C.POINTER(C.c_uint16)),
+                                C.cast(h_offs.data_ptr(), C.POINTER(C.c_int64)), 2**31 - 1,
+                                C.cast(h_noccs.data_ptr(), C.POINTER(C.c_int32)),
+                                C.cast(h_lstart.data_ptr(), C.POINTER(C.c_int64)),
+                                C.cast(h_lout.data_ptr(), C.POINTER(C.c_int64)), loc_cap)
+        if rc:
+            raise RuntimeError(f"fm_locate_flat rc={rc}: {lib.fm_last_error()}")
+
+    step_locate()                                                                             # warm-up
     barrier()
     t0 = time.perf_counter()
-    for _ in range(3):
-        noccs, lstart, lout = ix.locate_flat(loc_plen, loc_flat, loc_offs, 2**31 - 1, loc_cap)
+    for _ in range(5):
+        step_locate()
     barrier()
-    locate_s = (time.perf_counter() - t0) / 3
+    locate_s = (time.perf_counter() - t0) / 5
+    noccs, lstart, lout = h_noccs.numpy(), h_lstart.numpy(), h_lout.numpy()
     locate_results = int(noccs.sum())
 
     # ---- max over ranks ---------------------------------------------------------------------

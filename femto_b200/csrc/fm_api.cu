@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -290,14 +291,23 @@ template <typename F>
 int guarded(fm_index* ix, const char* what, F&& body) {
   if (!ix) return fail(FM_ERR_PARAM, std::string(what) + ": null index");
   std::lock_guard<std::mutex> lock(ix->mu);
+  // A failure may leave asynchronous copies from / to the caller's buffers in flight: drain the
+  // handle's streams before the error is reported, so that the caller may free them.
+  auto drain = [&]() {
+    for (cudaStream_t st : {ix->stream, ix->stream2, ix->stream3})
+      if (st) cudaStreamSynchronize(st);
+  };
   try {
     DeviceGuard guard(ix->device);
     return body();
   } catch (const CudaFail& e) {
+    drain();
     return fail(FM_ERR_IO, std::string(what) + ": " + e.what());
   } catch (const Error& e) {
+    drain();
     return fail(e.code, std::string(what) + ": " + e.what());
   } catch (const std::bad_alloc&) {
+    drain();
     return fail(FM_ERR_MEM, std::string(what) + ": out of memory");
   }
 }
@@ -376,14 +386,16 @@ int walk_status(fm_index* ix) {
 
 // count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
 int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, int64_t flat_len,
-               const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false, int uniform_len = 0) {
+               const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false, int uniform_len = 0,
+               bool to_host = true) {
+  // to_host == false: first/last stay in ix->d_out[0] / d_out[1] for a kernel that follows (locate)
   if (npats == 0) return FM_OK;
   cudaStream_t s = ix->stream;
   int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
   uint16_t* d_flat = static_cast<uint16_t*>(ix->d_in[1].get(size_t(std::max<int64_t>(flat_len, 1)) * 2));
   int64_t* d_offs = static_cast<int64_t*>(ix->d_in[2].get(size_t(npats) * 8));
   int64_t* d_first = static_cast<int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
-  int64_t* d_last = last ? static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8)) : nullptr;
+  int64_t* d_last = (last || !to_host) ? static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8)) : nullptr;
 
   // Large batches whose patterns lie in the flat buffer in order are STREAMED: the count kernel is
   // launched at once and pulls patterns from its queue as the copy stream delivers them (a device
@@ -429,7 +441,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     // line read for an early pattern must not hold not-yet-copied symbols of a later one).
     int64_t k = 0, fdone = 0;
     ix->last_h2d = (m ? 0 : npats * 12) + flat_len * 2 + nmarks * 8;
-    ix->last_d2h = npats * (last ? 16 : 8);
+    ix->last_d2h = to_host ? npats * (last ? 16 : 8) : 0;
     for (int h = 0; h < 2; h++) {
       for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo), k++) {
         const int64_t hi = std::min(half_hi[h], lo + chunk_at(lo));
@@ -451,10 +463,12 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     if (trace) CK(cudaEventRecord(tev[3], sc));
     // results: first half on its own stream as soon as its kernel is done, second half behind its kernel
     CK(cudaStreamWaitEvent(sr, ix->ev[1], 0));
-    CK(cudaMemcpyAsync(first, d_first, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
-    if (last) CK(cudaMemcpyAsync(last, d_last, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
-    CK(cudaMemcpyAsync(first + mid, d_first + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
-    if (last) CK(cudaMemcpyAsync(last + mid, d_last + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
+    if (to_host) {
+      CK(cudaMemcpyAsync(first, d_first, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
+      if (last) CK(cudaMemcpyAsync(last, d_last, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
+      CK(cudaMemcpyAsync(first + mid, d_first + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
+      if (last) CK(cudaMemcpyAsync(last + mid, d_last + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
+    }
     if (trace) {
       CK(cudaEventRecord(tev[4], sr));
       CK(cudaEventRecord(tev[5], sk));
@@ -484,6 +498,10 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
   CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
   CK(launch_count(ix->im, a, ix->d_work, ix->count_sched, ix->sm_count, s, &ix->launches));
+  if (!to_host) {  // results stay on the device; the caller's next kernel runs on the same stream
+    ix->last_d2h = 0;
+    return FM_OK;
+  }
   CK(cudaMemcpyAsync(first, d_first, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
   if (last) CK(cudaMemcpyAsync(last, d_last, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -814,40 +832,54 @@ int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
       return fail(FM_ERR_PARAM, "fm_locate_flat: bad argument");
     int64_t flat_len = 0;
     if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_locate_flat: negative length/offset");
-    // first/last land in pinned staging (a pageable destination would make the copy back synchronous and slow)
-    int64_t* first = static_cast<int64_t*>(ix->h_ranges.get(size_t(npats + 1) * 16));
-    int64_t* last = first + npats + 1;
+    if (npats == 0) return FM_OK;
+    if (npats > INT32_MAX) return fail(FM_ERR_PARAM, "fm_locate_flat: too many patterns in one call");
     static const bool trace = std::getenv("FEMTO_B200_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = count_host(ix, npats, plen, flat, flat_len, offs, first, last);
+    // count; the ranges stay in HBM
+    int rc = count_host(ix, npats, plen, flat, flat_len, offs, nullptr, nullptr, /*in_order=*/false, 0, /*to_host=*/false);
     if (rc) return rc;
+    cudaStream_t s = ix->stream;
+    const int64_t* d_first = static_cast<const int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
+    const int64_t* d_last = static_cast<const int64_t*>(ix->d_out[1].get(size_t(npats) * 8));
+    // ranges -> clipped sizes -> row starts, on the device (do_locate_query's clip, server.c:4407-4415)
+    int32_t* d_noccs = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));   // the pattern lengths are done with
+    int64_t* d_start = static_cast<int64_t*>(ix->d_in[2].get(size_t(npats) * 8));   // so are their offsets
+    const size_t scratch = expand_scratch_bytes(npats);
+    char* d_scr = static_cast<char*>(ix->d_out[3].get(scratch + 128));
+    int64_t* d_total = reinterpret_cast<int64_t*>(d_scr + ((scratch + 63) & ~size_t(63)));
+    CK(launch_clip_and_scan(npats, d_first, d_last, max_occs_each, d_noccs, d_start, d_total, d_scr, scratch, s,
+                            &ix->launches));
+    int64_t* h_total = static_cast<int64_t*>(ix->h_ranges.get(64));
+    CK(cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(noccs, d_noccs, size_t(npats) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out_start, d_start, size_t(npats) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int64_t total = *h_total;
     const auto t1 = std::chrono::steady_clock::now();
-    // clip as do_locate_query (server.c:4407-4415)
-    int64_t total = 0;
-    for (int64_t i = 0; i < npats; i++) {
-      int64_t f = first[i], l = last[i];
-      out_start[i] = total;
-      if (f > l) { noccs[i] = 0; continue; }
-      if (l - f > int64_t(max_occs_each)) l = f + int64_t(max_occs_each) - 1;
-      last[i] = l;
-      noccs[i] = int32_t(l - f + 1);
-      total += l - f + 1;
-    }
     if (total > out_cap) return fail(FM_ERR_FULL, "fm_locate_flat: output buffer too small");
     if (total == 0) return FM_OK;
     if (!out) return fail(FM_ERR_PARAM, "fm_locate_flat: null output");
-    int64_t* rows = static_cast<int64_t*>(ix->h_stage[1].get(size_t(total) * 8));
-    for (int64_t i = 0; i < npats; i++)
-      for (int32_t j = 0; j < noccs[i]; j++) rows[out_start[i] + j] = first[i] + j;
-    const auto t2 = std::chrono::steady_clock::now();
-    rc = locate_rows_host(ix, total, rows, out);
+    // rows first[i] .. first[i] + noccs[i] - 1 of every pattern, then the sampled-SA walks
+    int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(total) * 8));
+    int64_t* d_off = static_cast<int64_t*>(ix->d_out[2].get(size_t(total) * 8));
+    CK(launch_expand_rows(npats, total, d_first, d_start, d_rows, s, &ix->launches));
+    WalkArgs w{};
+    w.nrows = total;
+    w.rows = d_rows;
+    w.out_offset = d_off;
+    w.status = ix->d_status;
+    CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(out, d_off, size_t(total) * 8, cudaMemcpyDeviceToHost, s));
+    const int st = walk_status(ix);
     if (trace) {
-      const auto t3 = std::chrono::steady_clock::now();
+      const auto t2 = std::chrono::steady_clock::now();
       auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-      std::fprintf(stderr, "[femto_b200 trace] locate %lld patterns, %lld rows: count %.3f ms, ranges -> rows %.3f, walks %.3f\n",
-                   (long long)npats, (long long)total, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+      std::fprintf(stderr, "[femto_b200 trace] locate %lld patterns, %lld rows: count + ranges %.3f ms, rows + walks %.3f\n",
+                   (long long)npats, (long long)total, ms(t0, t1), ms(t1, t2));
     }
-    return rc;
+    if (st) return fail(st == 1 ? FM_ERR_PARAM : FM_ERR_INVALID, "locate: malformed walk (status " + std::to_string(st) + ")");
+    return FM_OK;
   });
 }
 

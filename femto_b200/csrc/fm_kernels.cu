@@ -25,6 +25,11 @@
 //          levels on the 4 GiB byte corpus) the block is read once and popcounted under two masks.
 #include "fm_kernels.cuh"
 
+#include <algorithm>
+#include <climits>
+
+#include <cub/device/device_scan.cuh>
+
 namespace fmb {
 namespace {
 
@@ -1573,6 +1578,84 @@ cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lpq, 
     default: return cudaErrorInvalidValue;
   }
 #undef FM_SHARD
+  if (launch_counter) ++*launch_counter;
+  return cudaGetLastError();
+}
+
+namespace {
+
+// noccs as 64-bit counts for the scan (a clipped range can still hold 2^31 rows)
+__global__ void __launch_bounds__(kThreads) clip_kernel(int64_t n, const int64_t* __restrict__ first,
+                                                         const int64_t* __restrict__ last, int64_t max_occs,
+                                                         int32_t* __restrict__ noccs, int64_t* __restrict__ cnt) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t f = first[i];
+  int64_t l = last[i];
+  int64_t c = 0;
+  if (f <= l) {
+    if (l - f > max_occs) l = f + max_occs - 1;  // do_locate_query's clip (server.c:4411-4415)
+    c = l - f + 1;
+  }
+  noccs[i] = static_cast<int32_t>(c);
+  cnt[i] = c;
+}
+
+__global__ void __launch_bounds__(kThreads) total_kernel(int64_t n, const int64_t* __restrict__ cnt,
+                                                          const int64_t* __restrict__ start, int64_t* __restrict__ total) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *total = n ? start[n - 1] + cnt[n - 1] : 0;
+}
+
+// one thread per output row: the pattern it belongs to is the last one starting at or before it
+__global__ void __launch_bounds__(kThreads) expand_rows_kernel(int64_t npats, int64_t total,
+                                                                const int64_t* __restrict__ first,
+                                                                const int64_t* __restrict__ start,
+                                                                int64_t* __restrict__ rows) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  int64_t lo = 0, hi = npats;  // upper_bound(start, k) - 1; patterns without rows share their successor's start
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(start + mid) <= k) lo = mid; else hi = mid;
+  }
+  rows[k] = __ldg(first + lo) + (k - __ldg(start + lo));
+}
+
+}  // namespace
+
+size_t expand_scratch_bytes(int64_t npats) {
+  size_t temp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, temp, static_cast<const int64_t*>(nullptr), static_cast<int64_t*>(nullptr),
+                                static_cast<int>(std::min<int64_t>(npats, INT32_MAX)));
+  // layout used by launch_clip_and_scan: [counts, 256-byte aligned][cub temporary storage]
+  const size_t cnt = (size_t(std::max<int64_t>(npats, 1)) * sizeof(int64_t) + 255) & ~size_t(255);
+  return cnt + ((temp + 255) & ~size_t(255)) + 256;
+}
+
+cudaError_t launch_clip_and_scan(int64_t npats, const int64_t* d_first, const int64_t* d_last, int max_occs,
+                                 int32_t* d_noccs, int64_t* d_out_start, int64_t* d_total, void* d_scratch,
+                                 size_t scratch_bytes, cudaStream_t stream, int64_t* launch_counter) {
+  if (npats <= 0 || npats > INT32_MAX) return cudaErrorInvalidValue;
+  const size_t cnt_bytes = size_t(npats) * sizeof(int64_t);
+  if (scratch_bytes < cnt_bytes) return cudaErrorInvalidValue;
+  int64_t* d_cnt = static_cast<int64_t*>(d_scratch);
+  void* d_temp = static_cast<char*>(d_scratch) + ((cnt_bytes + 255) & ~size_t(255));
+  size_t temp = scratch_bytes - ((cnt_bytes + 255) & ~size_t(255));
+  const int grid = static_cast<int>((npats + kThreads - 1) / kThreads);
+  clip_kernel<<<grid, kThreads, 0, stream>>>(npats, d_first, d_last, max_occs, d_noccs, d_cnt);
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp, d_cnt, d_out_start, static_cast<int>(npats), stream);
+  if (e != cudaSuccess) return e;
+  total_kernel<<<1, 32, 0, stream>>>(npats, d_cnt, d_out_start, d_total);
+  if (launch_counter) *launch_counter += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_expand_rows(int64_t npats, int64_t total, const int64_t* d_first, const int64_t* d_out_start,
+                               int64_t* d_rows, cudaStream_t stream, int64_t* launch_counter) {
+  if (total <= 0) return cudaSuccess;
+  const int64_t grid = (total + kThreads - 1) / kThreads;
+  if (grid > INT32_MAX) return cudaErrorInvalidValue;
+  expand_rows_kernel<<<static_cast<int>(grid), kThreads, 0, stream>>>(npats, total, d_first, d_out_start, d_rows);
   if (launch_counter) ++*launch_counter;
   return cudaGetLastError();
 }

@@ -96,6 +96,18 @@ cudaError_t launch_occ(const DevImage& im, const OccArgs& a, unsigned long long*
 cudaError_t launch_count_shard(const DevImage& im, const ShardArgs& a, int lanes_per_query, int sm_count,
                                cudaStream_t stream, int64_t* launch_counter);
 
+// Ranges -> rows on the device (parallel_locate between its count and its walks,
+// src/main/server.c:4407-4415): noccs[i] = rows of pattern i after the reference's clip
+// (`last - first > max_occs` cuts to max_occs rows), out_start = exclusive prefix sum of noccs,
+// *d_total = their sum.  scratch: device bytes for the scan, at least expand_scratch_bytes(npats).
+size_t expand_scratch_bytes(int64_t npats);
+cudaError_t launch_clip_and_scan(int64_t npats, const int64_t* d_first, const int64_t* d_last, int max_occs,
+                                 int32_t* d_noccs, int64_t* d_out_start, int64_t* d_total, void* d_scratch,
+                                 size_t scratch_bytes, cudaStream_t stream, int64_t* launch_counter);
+// rows[out_start[i] + j] = first[i] + j for j < noccs[i]; total = number of rows
+cudaError_t launch_expand_rows(int64_t npats, int64_t total, const int64_t* d_first, const int64_t* d_out_start,
+                               int64_t* d_rows, cudaStream_t stream, int64_t* launch_counter);
+
 // Measurement aid (the ceiling bench.py quotes for the count kernel): `steps` rounds of dependent
 // uniformly random reads of `bytes_per_access` (32, 64 or 128, naturally aligned) over `n_units`
 // such units starting at `base`; one 128-bit load per lane, two independent chains per lane
