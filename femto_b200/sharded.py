@@ -12,9 +12,10 @@ that owns the row it needs next:
         all ranks : all-to-all of the remaining states, keyed by the rank owning their next row
 
 One all-to-all round per dependent remote row: at most 2 per backward-search step.  The exchange
-is NCCL ``all_to_all_single`` over NVLink/NVSwitch (gloo on CPU for the host-logic tests); state
-volume is 48 B x patterns per round, far below link bandwidth -- the cost is the ~2(m-1) rounds,
-which is why batches should be large.
+is NCCL ``all_to_all_single`` over NVLink/NVSwitch (gloo on CPU for the host-logic tests), preceded
+by one ``all_gather`` of the per-destination counts that doubles as the termination test: one host
+synchronisation per round.  State volume is 48 B x patterns per round, far below link bandwidth --
+the cost is the ~2(m-1) rounds, which is why batches should be large.
 
 Locate works the same way (``sharded_locate_rows``): the state of a sampled-SA walk is {result slot,
 row, LF steps so far, home}; every rank follows LF from its states while their rows are resident
@@ -50,17 +51,32 @@ def new_states(pid_lo: int, pid_hi: int, home: int, device) -> torch.Tensor:
 
 def exchange(states: torch.Tensor, dest: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """All-to-all of state rows by destination rank (uneven splits)."""
-    order = torch.argsort(dest.long(), stable=True)
-    send = states[order].contiguous()
-    send_counts = torch.bincount(dest.long(), minlength=world).to(torch.int64)
-    recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts, group=group)
-    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    recv, _ = route(states, dest, world, group)
+    return recv
+
+
+def route(states: torch.Tensor, dest: torch.Tensor, world: int, group=None) -> Tuple[torch.Tensor, int]:
+    """One exchange round.  dest[k] in [0, world) = rank that must see state k next; dest[k] == world
+    drops the state (it has delivered its result).  ONE small collective carries every rank's send
+    counts to everybody -- which gives each rank its receive counts AND the number of states left in
+    the whole job -- then one all-to-all moves the states.  One host synchronisation per round.
+    Returns (received states, states left anywhere before this exchange)."""
     words = states.shape[1]
+    order = torch.argsort(dest)
+    counts = torch.bincount(dest, minlength=world + 1)[:world].to(torch.int64)
+    matrix = torch.empty((world, world), dtype=torch.int64, device=states.device)
+    dist.all_gather_into_tensor(matrix.view(-1), counts, group=group)
+    m = matrix.tolist()                                       # the round's only host synchronisation
+    left = sum(sum(r) for r in m)
+    rank = dist.get_rank(group)
+    sc, rc = m[rank], [m[r][rank] for r in range(world)]
+    if left == 0:
+        return states[:0], 0
+    send = states[order[:sum(sc)]].contiguous()
     recv = torch.empty((sum(rc), words), dtype=torch.int64, device=states.device)
     dist.all_to_all_single(recv.view(-1), send.view(-1), [c * words for c in rc], [c * words for c in sc],
                            group=group)
-    return recv
+    return recv, left
 
 
 def sharded_count(step_fn: StepFn, pid_lo: int, pid_hi: int, rank: int, world: int, device,
@@ -68,33 +84,29 @@ def sharded_count(step_fn: StepFn, pid_lo: int, pid_hi: int, rank: int, world: i
     """Count patterns [pid_lo, pid_hi) (this rank's share of a batch replicated on every rank).
     Returns (first, last, rounds) for this rank's patterns."""
     n_mine = pid_hi - pid_lo
-    first = torch.zeros(n_mine, dtype=torch.int64, device=device)
-    last = torch.zeros(n_mine, dtype=torch.int64, device=device)
+    # one spare slot at the end takes the writes of states that are not finished-and-home, so that
+    # delivering results needs no data-dependent indexing (no host synchronisation)
+    first = torch.zeros(n_mine + 1, dtype=torch.int64, device=device)
+    last = torch.zeros(n_mine + 1, dtype=torch.int64, device=device)
     states = new_states(pid_lo, pid_hi, rank, device)
     rounds = 0
     while True:
         dest = torch.full((states.shape[0],), rank, dtype=torch.int32, device=device)
         if states.shape[0]:
             step_fn(states, dest)
-        # finished states that are already home become results
-        phase = states[:, 5] & 15
-        home_done = (phase == PHASE_DONE) & (dest == rank)
-        if bool(home_done.any()):
-            done = states[home_done]
-            idx = done[:, 0] - pid_lo
-            first[idx] = done[:, 1]
-            last[idx] = done[:, 2]
-            keep = ~home_done
-            states, dest = states[keep], dest[keep]
-        remaining = torch.tensor([states.shape[0]], dtype=torch.int64, device=device)
-        dist.all_reduce(remaining, group=group)
-        if int(remaining.item()) == 0:
+        # finished states that are already home deliver their result and leave the job
+        home_done = ((states[:, 5] & 15) == PHASE_DONE) & (dest == rank)
+        slot = torch.where(home_done, states[:, 0] - pid_lo, torch.full_like(states[:, 0], n_mine))
+        first[slot] = states[:, 1]
+        last[slot] = states[:, 2]
+        dest = torch.where(home_done, torch.full_like(dest, world), dest)
+        states, left = route(states, dest.long(), world, group)
+        if left == 0:
             break
-        states = exchange(states, dest, world, group)
         rounds += 1
         if rounds > max_rounds:
             raise RuntimeError("sharded_count did not terminate")
-    return first, last, rounds
+    return first[:n_mine], last[:n_mine], rounds
 
 
 def cuda_step_fn(ix, d_plen: torch.Tensor, d_flat: torch.Tensor, d_offs: torch.Tensor, nshards: int) -> StepFn:
@@ -123,7 +135,7 @@ def sharded_locate_rows(walk_fn: WalkFn, rows: torch.Tensor, rank: int, world: i
     """SA[row] for this rank's ``rows`` (global BWT rows, any shard).  Collective: every rank calls it
     with its own rows (possibly none).  Returns (offsets aligned with rows, exchange rounds)."""
     n = int(rows.shape[0])
-    out = torch.full((n,), -1, dtype=torch.int64, device=device)
+    out = torch.full((n + 1,), -1, dtype=torch.int64, device=device)   # spare slot: see sharded_count
     states = torch.zeros((n, WALK_WORDS), dtype=torch.int64, device=device)
     states[:, 0] = torch.arange(n, dtype=torch.int64, device=device)
     states[:, 1] = rows.to(device=device, dtype=torch.int64)
@@ -134,20 +146,16 @@ def sharded_locate_rows(walk_fn: WalkFn, rows: torch.Tensor, rank: int, world: i
         if states.shape[0]:
             walk_fn(states, dest)
         home_done = ((states[:, 3] & 15) == PHASE_DONE) & (dest == rank)
-        if bool(home_done.any()):
-            done = states[home_done]
-            out[done[:, 0]] = done[:, 1]
-            keep = ~home_done
-            states, dest = states[keep], dest[keep]
-        remaining = torch.tensor([states.shape[0]], dtype=torch.int64, device=device)
-        dist.all_reduce(remaining, group=group)
-        if int(remaining.item()) == 0:
+        slot = torch.where(home_done, states[:, 0], torch.full_like(states[:, 0], n))
+        out[slot] = states[:, 1]
+        dest = torch.where(home_done, torch.full_like(dest, world), dest)
+        states, left = route(states, dest.long(), world, group)
+        if left == 0:
             break
-        states = exchange(states, dest, world, group)
         rounds += 1
         if rounds > max_rounds:
             raise RuntimeError("sharded_locate_rows did not terminate")
-    return out, rounds
+    return out[:n], rounds
 
 
 def expand_ranges(first: torch.Tensor, last: torch.Tensor, max_occs: int) -> Tuple[torch.Tensor, torch.Tensor]:
