@@ -17,7 +17,9 @@ Printed JSON (one line, rank 0):
   value      whole-job patterns/s with the pattern batch already resident in HBM (CUDA events
              around K launches of the count kernel through fm_count_device, max over ranks)
   e2e        the same through the host-buffer C-ABI call fm_count_flat: pinned host patterns in,
-             host first/last out, copies inside the timed region
+             host first/last out, copies inside the timed region (the call streams: kernel launched
+             ahead of the copies, gated by an arrival counter); h2d/d2h bytes = what the call copied
+  locate     BASELINE configs[2] through fm_locate_flat, pinned buffers in and out
   roofline   algorithmic HBM bytes per launch / kernel time, against MEASURED_PEAKS.json
   cpu_baseline  the unmodified reference (oracle/_ref) counting a bounded sample of the same
              batch on this box's host cores, 1 server thread as shipped; the sample doubles as

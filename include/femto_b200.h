@@ -95,7 +95,14 @@ int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* 
 
 /* Same operation with the patterns in one flat buffer: pattern i is
  * flat[offs[i] .. offs[i]+plen[i]).  This is the form the engine works on;
- * fm_count() gathers into it. */
+ * fm_count() gathers into it.
+ * Batches of >= 128 Ki patterns that lie in `flat` in batch order are STREAMED: the kernel is
+ * launched at once and takes patterns from its queue as the copy stream delivers them, the first
+ * results travel back while the last patterns are searched; a batch of equal-length, densely
+ * packed patterns travels without plen / offs.  Pinned buffers (fm_host_alloc) get the full
+ * PCIe rate.  Environment: FEMTO_B200_NO_STREAM=1 keeps copies and kernel in series (what a
+ * serialising profiler needs; the call also falls back to that by itself when the kernel sees no
+ * data arrive for ~0.1 s), FEMTO_B200_TRACE=1 prints the timeline of each call to stderr. */
 int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
                   const int64_t* offs, int64_t* first, int64_t* last);
 
