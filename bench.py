@@ -422,12 +422,14 @@ def main():
     # ---- roofline: algorithmic bytes of one launch (instrumented replay of the last batch) ----
     hb = h_flat[(args.warmup + args.steps - 1) % nbatch].numpy().reshape(-1).view(np.uint16)
     st = ix.count_stats(h_plen.numpy(), hb, h_offs.numpy())
-    # per distinct rank block: 128 B payload line + 16 B node record; per Occ evaluation:
-    # 16 B OccRec + 16 B BucketRec; per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
-    # (paired-/quad-level blocks answer 2 / 4 levels each and come with an 8 B record of the next
-    # node; of a quad-level block a query reads 64 B of bits and an 8 B header entry)
+    # per distinct rank block: 128 B payload line + 16 B node record (paired-/quad-level blocks answer
+    # 2 / 4 levels each and come with an 8 B record of the next node; of a quad-level block a query
+    # uses 64 B of bits and an 8 B header entry); per backward-search step: the symbol's 16 B OccRec,
+    # shared by the step's two Occ (+ the 16 B BucketRec in the layouts whose root is not addressed
+    # by row); per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
     per_block = {1: block_bytes + 16, 2: block_bytes + 8, 4: 64 + 8 + 8}[levels]
-    alg_bytes = (st["distinct_block_reads"] * per_block + st["occ_evals"] * 32 +
+    per_step = 16 if levels == 4 else 32
+    alg_bytes = (st["distinct_block_reads"] * per_block + st["steps"] * per_step +
                  npats * (m * 2 + 28))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
@@ -445,6 +447,13 @@ def main():
             roofline["traffic"] = json.load(open(traffic_file)).get(layout_key, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
+    if roofline["traffic"] and args.corpus_mib == 4096 and args.kind == "bytes" and args.patterns == "text" \
+            and npats == 1 << 20 and m == 32:
+        # what DRAM really moved (whole 128-byte lines; ncu capture of this workload) over the live kernel
+        # time: the figure north_star's "ncu-reported HBM GB/s vs peak" refers to, next to the stricter
+        # algorithmic one above
+        roofline["dram_gb_s"] = round(roofline["traffic"] / (ms_per_step / 1e3) / 1e9, 1)
+        roofline["dram_frac"] = round(roofline["traffic"] / (ms_per_step / 1e3) / 1e9 / peak, 4)
     # The count kernel is a chain of dependent random reads; the rate at which this GPU serves such
     # reads (measured right here by fm_probe_random_reads with the same access size) is the
     # ceiling that binds before HBM bandwidth does.
