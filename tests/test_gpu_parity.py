@@ -468,3 +468,50 @@ def test_doc_names_and_range_documents(tmp_path):
             pb = bytes((p - 5).astype(np.uint8))
             want = [d for d, text in enumerate(docs) if pb in text]
             assert ix.range_documents(int(a), int(b)).tolist() == want
+
+
+# ---- BASELINE configs[3] at a size the reference still opens quickly ------------------------------
+def test_mixed_length_zipf_on_64mib_english_like_corpus(tmp_path):
+    """Mixed-length batch (8-256 symbols, Zipf) on an English-like multi-document corpus of 64 MiB,
+    index built by the GPU pipeline with DEFAULT parameters (1 Mi-row buckets: Huffman trees of
+    depth 3-15, three quad rounds for the rare symbols).  A sample is checked against the oracle
+    (and the live reference where it travelled); the whole batch through count == locate sizes and
+    located offsets matching the text."""
+    import torch
+    from femto_b200 import build_gpu
+    ndocs, per = 16, 4 << 20
+    docs = [corpus.english_like(per, 900 + d) for d in range(ndocs)]
+    path = str(tmp_path / "english_64m")
+    dev = torch.device("cuda", 0)
+    t = build_gpu.build_index_gpu([torch.frombuffer(bytearray(d), dtype=torch.uint8).to(dev) for d in docs], path)
+    assert t["rows"] == ndocs * (per + 1)
+    rng = np.random.default_rng(23)
+    ranks = np.arange(8, 257)
+    p = (1.0 / (ranks - 7)) / (1.0 / (ranks - 7)).sum()
+    lengths = rng.choice(ranks, 200000, p=p).tolist()
+    pats = corpus.sample_patterns(docs, 200000, lengths, seed=24, random_fraction=0.1)
+    for k in range(0, len(pats), 5):                        # a fifth dies somewhere in the middle
+        q = pats[k].copy()
+        q[int(rng.integers(0, len(q)))] = 5 + int(rng.integers(65, 91))
+        pats[k] = q
+    plen, flat, offs = fb.flatten_patterns(pats)
+    with fb.Index(path) as ix:
+        f, l = ix.count_flat(plen, flat, offs)              # streamed path, ragged lengths
+        sub = list(range(0, len(pats), 997))
+        with Oracle(path) as o:
+            of, ol = o.count([pats[i] for i in sub])
+        assert (f[sub] == of).all() and (l[sub] == ol).all()
+        if have_reference():
+            with Reference(path) as r:
+                rf, rl = r.count([pats[i] for i in sub[:60]])
+            assert (f[sub[:60]] == rf).all() and (l[sub[:60]] == rl).all()
+        cnt = np.maximum(l - f + 1, 0)
+        assert (cnt[1::5] >= 1).mean() > 0.85               # unmutated and (90 %) text-sampled: found
+        text = b"".join(d + b"\x00" for d in docs)
+        k0 = [i for i in range(1, 4000, 5)]
+        loc = ix.locate([pats[i] for i in k0], 20)
+        for i, offs_ in zip(k0, loc):
+            assert len(offs_) == min(int(cnt[i]), 20) or (int(cnt[i]) == 21 and len(offs_) == 21)
+            pb = bytes((pats[i] - 5).astype(np.uint8))
+            for off in offs_:
+                assert text[off:off + len(pb)] == pb
