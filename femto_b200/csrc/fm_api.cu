@@ -384,12 +384,21 @@ int walk_status(fm_index* ix) {
   return st;
 }
 
+constexpr int kRetryValidated = -1000;  // count_host(lazy): the batch is not what its first / last pattern claimed
+
 // count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
 int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, int64_t flat_len,
                const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false, int uniform_len = 0,
-               bool to_host = true) {
+               bool to_host = true, bool lazy = false) {
   // to_host == false: first/last stay in ix->d_out[0] / d_out[1] for a kernel that follows (locate)
+  // lazy == true (streamed batches only): the caller has NOT validated plen / offs; in_order,
+  //   uniform_len and flat_len are its claims, derived from the first and last pattern.  Every chunk
+  //   is checked just before its copy is enqueued -- behind the kernel that is already running, so
+  //   the 12 bytes per pattern of validation leave the critical path.  A chunk that breaks the
+  //   claim aborts the kernels and the call returns kRetryValidated: nothing was read out of
+  //   bounds, the caller validates the whole batch and calls again.
   if (npats == 0) return FM_OK;
+  const auto t_call = std::chrono::steady_clock::now();
   cudaStream_t s = ix->stream;
   int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
   uint16_t* d_flat = static_cast<uint16_t*>(ix->d_in[1].get(size_t(std::max<int64_t>(flat_len, 1)) * 2));
@@ -405,7 +414,9 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   constexpr int64_t kChunk = 1 << 16;  // patterns per copy chunk; a multiple of 32 keeps every 128-byte
                                        // line of plen / offs inside one chunk
   static const bool no_stream = std::getenv("FEMTO_B200_NO_STREAM") != nullptr;
-  if (in_order && npats >= 2 * kChunk && ix->stream2 && ix->stream3 && ix->stream_ok && !no_stream) {
+  const bool streamed = in_order && npats >= 2 * kChunk && ix->stream2 && ix->stream3 && ix->stream_ok && !no_stream;
+  if (lazy && !streamed) return kRetryValidated;
+  if (streamed) {
     const int m = uniform_len;
     // the second kernel takes the last quarter: its results are the only transfer nothing overlaps
     const int64_t mid = (npats - npats / 4) & ~int64_t(31);
@@ -416,7 +427,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     int64_t nmarks = 0;
     for (int h = 0; h < 2; h++)
       for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo)) nmarks++;
-    unsigned long long* marks = static_cast<unsigned long long*>(ix->h_marks.get(size_t(nmarks) * 8));
+    unsigned long long* marks = static_cast<unsigned long long*>(ix->h_marks.get(size_t(nmarks + 2) * 8));
     unsigned long long* d_avail = ix->d_work + 12;
     cudaStream_t sk = ix->stream, sc = ix->stream2, sr = ix->stream3;
     // FEMTO_B200_TRACE=1: print when (ms after the start) the copies, each kernel and the results finish
@@ -427,14 +438,17 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     if (trace) CK(cudaEventRecord(tev[0], sk));
     CK(cudaEventRecord(ix->ev[0], sk));
     CK(cudaStreamWaitEvent(sc, ix->ev[0], 0));
-    // kernels first: they spin on their arrival counters until the copies below land
+    CK(cudaStreamWaitEvent(sr, ix->ev[0], 0));
+    // kernels first: they spin on their arrival counters until the copies below land.  The second
+    // kernel sits on its own stream: its CTAs take the SM slots the first kernel's CTAs free one by
+    // one, so the first kernel's tail is not idle time.
     for (int h = 0; h < 2; h++) {
       const int64_t lo = half_lo[h], n = half_hi[h] - lo;
+      cudaStream_t ks = h == 0 ? sk : sr;
       CountArgs a{n, d_plen + lo, m ? d_flat + lo * m : d_flat, d_offs + lo, d_first + lo,
                   d_last ? d_last + lo : nullptr, d_avail + h, ix->d_status + 1, m};
-      CK(launch_count(ix->im, a, ix->d_work + 8 + h, ix->count_sched, ix->sm_count, sk, &ix->launches));
-      CK(cudaEventRecord(ix->ev[1 + h], sk));
-      if (trace) CK(cudaEventRecord(tev[1 + h], sk));
+      CK(launch_count(ix->im, a, ix->d_work + 8 + h, ix->count_sched, ix->sm_count, ks, &ix->launches));
+      if (trace) CK(cudaEventRecord(tev[1 + h], ks));
     }
     // copies: chunk after chunk, each followed by its arrival mark.  Symbol ranges are cut at
     // 128-byte boundaries of the device buffer so that no cache line is shared by two chunks (a
@@ -445,11 +459,33 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     for (int h = 0; h < 2; h++) {
       for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo), k++) {
         const int64_t hi = std::min(half_hi[h], lo + chunk_at(lo));
+        if (lazy) {  // does this chunk keep the claim?  (uniform: length m at i * m; else: densely packed)
+          bool ok = true;
+          if (m) {
+            for (int64_t i = lo; i < hi; i++) ok &= (plen[i] == m) & (offs[i] == i * int64_t(m));
+          } else {
+            if (lo == 0) ok = plen[0] >= 0 && offs[0] >= 0;
+            for (int64_t i = std::max<int64_t>(lo, 1); i < hi; i++)
+              ok &= (plen[i] >= 0) & (offs[i] == offs[i - 1] + plen[i - 1]);
+          }
+          if (!ok) {  // stop the kernels (they give up on the flag), drain, hand the batch back
+            int32_t* one = reinterpret_cast<int32_t*>(marks + nmarks);
+            *one = 1;
+            CK(cudaMemcpyAsync(ix->d_status + 1, one, sizeof(int32_t), cudaMemcpyHostToDevice, sc));
+            CK(cudaStreamSynchronize(sc));
+            CK(cudaStreamSynchronize(sk));
+            CK(cudaStreamSynchronize(sr));
+            CK(cudaMemsetAsync(ix->d_status + 1, 0, sizeof(int32_t), sk));
+            CK(cudaStreamSynchronize(sk));
+            if (trace) for (cudaEvent_t e : tev) cudaEventDestroy(e);
+            return kRetryValidated;
+          }
+        }
         if (!m) {
           CK(cudaMemcpyAsync(d_plen + lo, plen + lo, size_t(hi - lo) * 4, cudaMemcpyHostToDevice, sc));
           CK(cudaMemcpyAsync(d_offs + lo, offs + lo, size_t(hi - lo) * 8, cudaMemcpyHostToDevice, sc));
         }
-        int64_t fend = hi < npats ? offs[hi] : flat_len;     // patterns [0, hi) end at or before this symbol
+        int64_t fend = offs[hi - 1] + plen[hi - 1];          // in-order batch: patterns [0, hi) end here
         fend = std::min(flat_len, (fend + 63) & ~int64_t(63));
         if (hi == npats) fend = flat_len;
         if (fend > fdone) {
@@ -461,28 +497,32 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
       }
     }
     if (trace) CK(cudaEventRecord(tev[3], sc));
-    // results: first half on its own stream as soon as its kernel is done, second half behind its kernel
-    CK(cudaStreamWaitEvent(sr, ix->ev[1], 0));
+    // results: each part behind its kernel, on that kernel's stream
     if (to_host) {
-      CK(cudaMemcpyAsync(first, d_first, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
-      if (last) CK(cudaMemcpyAsync(last, d_last, size_t(mid) * 8, cudaMemcpyDeviceToHost, sr));
-      CK(cudaMemcpyAsync(first + mid, d_first + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
-      if (last) CK(cudaMemcpyAsync(last + mid, d_last + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sk));
+      CK(cudaMemcpyAsync(first, d_first, size_t(mid) * 8, cudaMemcpyDeviceToHost, sk));
+      if (last) CK(cudaMemcpyAsync(last, d_last, size_t(mid) * 8, cudaMemcpyDeviceToHost, sk));
+      CK(cudaMemcpyAsync(first + mid, d_first + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sr));
+      if (last) CK(cudaMemcpyAsync(last + mid, d_last + mid, size_t(npats - mid) * 8, cudaMemcpyDeviceToHost, sr));
     }
     if (trace) {
-      CK(cudaEventRecord(tev[4], sr));
-      CK(cudaEventRecord(tev[5], sk));
+      CK(cudaEventRecord(tev[4], sk));
+      CK(cudaEventRecord(tev[5], sr));
     }
-    int32_t stalled = 0;
-    CK(cudaMemcpyAsync(&stalled, ix->d_status + 1, sizeof(stalled), cudaMemcpyDeviceToHost, sk));
+    int32_t* h_stalled = reinterpret_cast<int32_t*>(marks + nmarks + 1);
+    const auto t_enq = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(sc));
-    CK(cudaStreamSynchronize(sr));
     CK(cudaStreamSynchronize(sk));
+    CK(cudaMemcpyAsync(h_stalled, ix->d_status + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, sr));  // after both kernels
+    CK(cudaStreamSynchronize(sr));
+    const int32_t stalled = *h_stalled;
     if (trace) {
       float t[6] = {0, 0, 0, 0, 0, 0};
       for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+      const double enq_ms = std::chrono::duration<double, std::milli>(t_enq - t_call).count();
+      const double all_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
       std::fprintf(stderr, "[femto_b200 trace] count %lld patterns: kernel A done %.3f ms, kernel B done %.3f, copies in done "
-                   "%.3f, results A out %.3f, results B out %.3f\n", (long long)npats, t[1], t[2], t[3], t[4], t[5]);
+                   "%.3f, results A out %.3f, results B out %.3f | host: enqueue %.3f ms, whole call %.3f\n",
+                   (long long)npats, t[1], t[2], t[3], t[4], t[5], enq_ms, all_ms);
       for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     if (!stalled) return FM_OK;
@@ -490,6 +530,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     // stream that made no progress for 0.1 s): repeat the batch the plain way, and stay there.
     CK(cudaMemsetAsync(ix->d_status + 1, 0, sizeof(int32_t), sk));
     ix->stream_ok = false;
+    if (lazy) return kRetryValidated;  // the plain path below needs a validated batch
   }
   ix->last_h2d = npats * 12 + flat_len * 2;
   ix->last_d2h = npats * (last ? 16 : 8);
@@ -643,7 +684,25 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
     if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
     int64_t flat_len = 0;
     bool ordered = false;
+    if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
+      return fail(FM_ERR_MISSING, "fm_count_flat: index is a shard; use the sharded driver");
+    if (npats >= (1 << 17) && flat) {
+      // Large batch: take its shape from the first and the last pattern, start searching at once
+      // and validate chunk by chunk behind the running kernel (count_host, lazy).
+      const int64_t claim_len = offs[npats - 1] + int64_t(plen[npats - 1]);
+      int m = (plen[0] > 0 && offs[0] == 0 && plen[1] == plen[0] && offs[1] == plen[0]) ? plen[0] : 0;
+      if (m && claim_len != npats * int64_t(m)) m = 0;
+      if (claim_len >= 0 && offs[npats - 1] >= 0 && plen[npats - 1] >= 0 && claim_len <= (int64_t(1) << 33)) {
+        const int rc = count_host(ix, npats, plen, flat, claim_len, offs, first, last, /*in_order=*/true, m,
+                                  /*to_host=*/true, /*lazy=*/true);
+        if (rc != kRetryValidated) return rc;
+      }
+    }
+    const auto t_scan = std::chrono::steady_clock::now();
     const BatchShape shape = scan_batch(npats, plen, offs);
+    if (std::getenv("FEMTO_B200_TRACE"))
+      std::fprintf(stderr, "[femto_b200 trace] batch validation %.3f ms\n",
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_scan).count());
     if (shape.bad) return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
     if (shape.dense) {
       flat_len = shape.flat_len;
@@ -652,8 +711,6 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
       return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
     }
     if (flat_len && !flat) return fail(FM_ERR_PARAM, "fm_count_flat: null pattern buffer");
-    if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
-      return fail(FM_ERR_MISSING, "fm_count_flat: index is a shard; use the sharded driver");
     return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered, shape.uniform);
   });
 }

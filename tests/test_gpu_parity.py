@@ -515,3 +515,46 @@ def test_mixed_length_zipf_on_64mib_english_like_corpus(tmp_path):
             pb = bytes((pats[i] - 5).astype(np.uint8))
             for off in offs_:
                 assert text[off:off + len(pb)] == pb
+
+
+def test_streamed_batch_lazy_validation_falls_back(built_indexes, corpora):
+    """Large batches are validated chunk by chunk behind the running kernel, on the shape their first
+    and last pattern claim.  Batches that break the claim half-way must be caught before anything is
+    read out of bounds and still give the reference's answers (or the reference's error)."""
+    name = "english_100k"
+    docs, _ = corpora[name]
+    n = 200000
+    base = corpus.sample_patterns(docs, 2000, [12], seed=71, random_fraction=0.2)
+    rng = np.random.default_rng(72)
+    pick = rng.integers(0, len(base), n)
+    pats = [base[i] for i in pick]
+    with fb.Index(built_indexes[name], device=0) as ix, Oracle(built_indexes[name]) as o:
+        of, ol = o.count(base)
+        want_f, want_l = of[pick].copy(), ol[pick].copy()
+        # (a) claims "all of length 12" (first two patterns, total size) but two patterns in the middle are 11 and 13
+        a_pats = list(pats)
+        a_pats[n // 2] = a_pats[n // 2][:11]
+        a_pats[n // 2 + 1] = np.concatenate([a_pats[n // 2 + 1], a_pats[n // 2 + 1][:1]])
+        plen, flat, offs = fb.flatten_patterns(a_pats)
+        assert int(plen.sum()) == 12 * n
+        f, l = ix.count_flat(plen, flat, offs)
+        af, al = o.count([a_pats[n // 2], a_pats[n // 2 + 1]])
+        want_a_f, want_a_l = want_f.copy(), want_l.copy()
+        want_a_f[n // 2:n // 2 + 2], want_a_l[n // 2:n // 2 + 2] = af, al
+        assert (f == want_a_f).all() and (l == want_a_l).all()
+        # (b) claims "densely packed" but one unused symbol sits between two patterns in the middle
+        plen, flat, offs = fb.flatten_patterns([pats[0][:11]] + pats[1:])   # not uniform: the dense claim is tried
+        cut = int(offs[n // 3])
+        flat_b = np.concatenate([flat[:cut], np.array([77], dtype=np.uint16), flat[cut:]])
+        offs_b = offs.copy()
+        offs_b[n // 3:] += 1
+        f, l = ix.count_flat(plen, flat_b, offs_b)
+        f0, l0 = o.count([pats[0][:11]])
+        assert f[0] == f0[0] and l[0] == l0[0] and (f[1:] == want_f[1:]).all() and (l[1:] == want_l[1:]).all()
+        # (c) a negative length in the middle: the reference's parameter error, nothing else
+        plen_c = plen.copy()
+        plen_c[n - 1000] = -3
+        with pytest.raises(Exception):
+            ix.count_flat(plen_c, flat_b, offs_b)
+        f, l = ix.count_flat(plen, flat_b, offs_b)            # the handle is fine afterwards
+        assert (f[1:] == want_f[1:]).all()
