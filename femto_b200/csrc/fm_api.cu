@@ -93,7 +93,7 @@ struct fm_index {
   int device = 0;
   int sm_count = 148;
   int lanes_per_query = 4;   // walk / occ kernels
-  int count_sched = 1045;    // count kernel: 1000 + 10*lanes + min blocks = merged-pair schedule, 4 / 8 = pair
+  int count_sched = 1024;    // launch_count schedule code; set from default_count_sched() at open
   fm_info_t info{};
   DevImage im;
   // device allocations of the image
@@ -139,9 +139,10 @@ int paired_sched(int block_words, int lanes) {
   return 1000 + 10 * lanes + minb;
 }
 
-// quad-level blocks: 1000 + 10 * k + CTAs per SM; k = 2: two lanes per pattern evaluate both positions
-// of a step together (default; k = 3 adds the one-step-ahead symbol fetch); 60 + v: one lane per
-// Occ ("split" schedule, selectable with fm_set_count_schedule(.., 1))
+// quad-level blocks: 1000 + 10 * 2 + CTAs per SM = sync schedule (two lanes per pattern evaluate both
+// positions of a step together; default); 1000 + 60 + v = split schedule (one lane per Occ, selectable
+// with fm_set_count_schedule(.., 1)); 1000 + 70 + 10 * EXP + CTAs per SM = measurement variants of the
+// sync kernel (fm_kernels.cu, profiles/r01_quad_schedules.md)
 constexpr int kQuadSched = 1000 + 10 * 2 + 4;  // 64 registers, no spills, 4 CTAs x 8 warps per SM
 constexpr int kQuadSchedSplit = 1000 + 67;
 
