@@ -73,6 +73,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pointer-api", action="store_true",
+                    help="also time fm_count (the reference's parallel_count prototype: one pointer per pattern)")
     ap.add_argument("--ref-worker", nargs=3, metavar=("INDEX", "PATS_NPZ", "OUT_NPZ"), help=argparse.SUPPRESS)
     return ap.parse_args()
 
@@ -370,6 +372,28 @@ def main():
     lib.fm_last_transfer(ix.h, C.byref(_h2d), C.byref(_d2h))
     h2d, d2h = int(_h2d.value), int(_d2h.value)
 
+    # ---- optional: the pointer-array prototype of parallel_count (gathers on the host first) ----
+    pointer_api = None
+    if args.pointer_api:
+        addr = (h_flat[0].data_ptr() + np.arange(npats, dtype=np.int64) * (2 * m)).astype(np.uint64)
+        ptrs = (C.c_void_p * npats).from_buffer(addr)
+        plen_c = (C.c_int * npats).from_buffer(h_plen.numpy())
+        lib.fm_count.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+        def step_ptr():
+            rc = lib.fm_count(ix.h, npats, plen_c, ptrs, C.c_void_p(h_first.data_ptr()), C.c_void_p(h_last.data_ptr()))
+            if rc:
+                raise RuntimeError(f"fm_count rc={rc}: {lib.fm_last_error()}")
+
+        step_ptr()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step_ptr()
+        dt = (time.perf_counter() - t0) / 3
+        assert (h_first.numpy() == results_gpu[0]).all() if nbatch == 1 else True
+        pointer_api = {"api": "fm_count (alpha_t** pats, as parallel_count)", "ms_per_batch": round(dt * 1e3, 3),
+                       "value": round(npats / dt, 1), "unit": "patterns/s"}
+
     # ---- locate (BASELINE configs[2]): text-sampled patterns, count + SA-sample walk, host buffers ----
     nloc = min(args.locate_npats, npats)
     loc_flat = h_flat[0].numpy()[:nloc].reshape(-1).view(np.uint16)
@@ -536,6 +560,7 @@ def main():
         "e2e": {"value": round(e2e_value, 1), "unit": "patterns/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms / args.steps, 4),
                 "api": "fm_count_flat (pinned host buffers in/out; kernel streamed behind the copies)"},
+        "e2e_pointer_api": pointer_api,
         "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "parity": parity,
         "locate": {"metric": "patterns/sec (locate, count + SA-sample walk, host buffers in/out)",

@@ -558,3 +558,25 @@ def test_streamed_batch_lazy_validation_falls_back(built_indexes, corpora):
             ix.count_flat(plen_c, flat_b, offs_b)
         f, l = ix.count_flat(plen, flat_b, offs_b)            # the handle is fine afterwards
         assert (f[1:] == want_f[1:]).all()
+
+
+def test_pointer_array_call_gathers_behind_the_kernel(built_indexes, corpora):
+    """fm_count with one pointer per pattern (parallel_count's prototype): the patterns are gathered
+    into pinned staging by background threads while the streamed kernel already runs.  Ragged lengths
+    incl. empty patterns; must equal the flat call and the oracle."""
+    name = "english_100k"
+    docs, _ = corpora[name]
+    base = corpus.sample_patterns(docs, 3000, [1, 2, 3, 5, 8, 13, 21, 34, 70], seed=81, random_fraction=0.2)
+    base += [np.zeros(0, dtype=np.uint16)] * 40
+    rng = np.random.default_rng(82)
+    n = 180000 + 13
+    pick = rng.integers(0, len(base), n)
+    pats = [base[i] for i in pick]
+    plen, flat, offs = fb.flatten_patterns(pats)
+    with fb.Index(built_indexes[name], device=0) as ix, Oracle(built_indexes[name]) as o:
+        of, ol = o.count(base)
+        for _ in range(2):
+            f, l = ix.count(pats)
+            assert (f == of[pick]).all() and (l == ol[pick]).all()
+        f2, l2 = ix.count_flat(plen, flat, offs)
+        assert (f2 == f).all() and (l2 == l).all()
