@@ -934,8 +934,13 @@ int fm_locate_range(fm_index_t* ix, int64_t first, int64_t last, int64_t* offset
   });
 }
 
-int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
-                   int max_occs_each, int32_t* noccs, int64_t* out_start, int64_t* out, int64_t out_cap) {
+namespace {
+// fm_locate_flat / fm_locate: count -> ranges -> rows -> walks.  `provide(total)` is called once the
+// number of offsets is known and returns the buffer they go to (NULL: it cannot hold them, FM_ERR_FULL
+// with noccs / out_start filled) -- fm_locate allocates there, so it needs a single pass.
+int locate_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                     int max_occs_each, int32_t* noccs, int64_t* out_start,
+                     const std::function<int64_t*(int64_t)>& provide) {
   return guarded(ix, "fm_locate_flat", [&]() -> int {
     if (npats < 0 || (npats && (!plen || !offs || !noccs || !out_start)))
       return fail(FM_ERR_PARAM, "fm_locate_flat: bad argument");
@@ -966,9 +971,9 @@ int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
     CK(cudaStreamSynchronize(s));
     const int64_t total = *h_total;
     const auto t1 = std::chrono::steady_clock::now();
-    if (total > out_cap) return fail(FM_ERR_FULL, "fm_locate_flat: output buffer too small");
     if (total == 0) return FM_OK;
-    if (!out) return fail(FM_ERR_PARAM, "fm_locate_flat: null output");
+    int64_t* out = provide(total);
+    if (!out) return fail(FM_ERR_FULL, "fm_locate_flat: output buffer too small");
     // rows first[i] .. first[i] + noccs[i] - 1 of every pattern, then the sampled-SA walks
     int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(total) * 8));
     int64_t* d_off = static_cast<int64_t*>(ix->d_out[2].get(size_t(total) * 8));
@@ -992,6 +997,14 @@ int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
   });
 }
 
+}  // namespace
+
+int fm_locate_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                   int max_occs_each, int32_t* noccs, int64_t* out_start, int64_t* out, int64_t out_cap) {
+  return locate_flat_impl(ix, npats, plen, flat, offs, max_occs_each, noccs, out_start,
+                          [&](int64_t total) -> int64_t* { return (out && total <= out_cap) ? out : nullptr; });
+}
+
 int fm_locate(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* pats, int max_occs_each,
               int* noccs, int64_t** offsets) {
   if (!ix) return fail(FM_ERR_PARAM, "fm_locate: null index");
@@ -1007,19 +1020,21 @@ int fm_locate(fm_index_t* ix, int npats, const int* plen, const uint16_t* const*
   flat.resize(size_t(std::max<int64_t>(total, 1)));
   for (int i = 0; i < npats; i++)
     if (plen[i]) std::memcpy(flat.data() + offs[size_t(i)], pats[i], size_t(plen[i]) * 2);
-  // two passes: sizes first, then results
-  std::vector<int64_t> tmp(1);
-  int rc = fm_locate_flat(ix, npats, reinterpret_cast<const int32_t*>(plen), flat.data(), offs.data(), max_occs_each,
-                          noccs, start.data(), tmp.data(), 0);
-  int64_t need = 0;
-  for (int i = 0; i < npats; i++) need += noccs[i];
-  if (rc != FM_OK && !(rc == FM_ERR_FULL)) return rc;
-  std::vector<int64_t> outv(static_cast<size_t>(std::max<int64_t>(need, 1)));
-  if (need > 0) {
-    rc = fm_locate_flat(ix, npats, reinterpret_cast<const int32_t*>(plen), flat.data(), offs.data(), max_occs_each,
-                        noccs, start.data(), outv.data(), need);
-    if (rc) return rc;
-  }
+  // one pass: the result buffer is allocated when the number of offsets is known
+  std::vector<int64_t> outv;
+  bool oom = false;
+  const int rc = locate_flat_impl(ix, npats, reinterpret_cast<const int32_t*>(plen), flat.data(), offs.data(),
+                                  max_occs_each, noccs, start.data(), [&](int64_t total) -> int64_t* {
+                                    try {
+                                      outv.resize(size_t(total));
+                                    } catch (const std::bad_alloc&) {
+                                      oom = true;
+                                      return nullptr;
+                                    }
+                                    return outv.data();
+                                  });
+  if (oom) return fail(FM_ERR_MEM, "fm_locate: out of memory");
+  if (rc) return rc;
   for (int i = 0; i < npats; i++) {
     offsets[i] = nullptr;
     if (noccs[i] > 0) {
