@@ -476,9 +476,16 @@ __device__ __forceinline__ void retire_and_fetch(PatternState& s, bool can_retir
     s.have = false;
   }
   const bool need = !s.have && !s.exhausted;
+  // ONE atomic per warp for all the groups that need a pattern (equal-length batches retire a warp's
+  // patterns together, and at launch every group of the grid asks at once): the groups take
+  // consecutive queue positions in lane order
+  const unsigned askers = __ballot_sync(kFull, need && lane == gleader);
   unsigned long long idx = 0;
-  if (need && lane == gleader) idx = atomicAdd(work, 1ull);
-  idx = __shfl_sync(kFull, idx, gleader);
+  if (askers) {
+    const int first_asker = __ffs(askers) - 1;
+    if (lane == first_asker) idx = atomicAdd(work, static_cast<unsigned long long>(__popc(askers)));
+    idx = __shfl_sync(kFull, idx, first_asker) + __popc(askers & ((1u << gleader) - 1u));
+  }
   if (need) {
     bool arrived = static_cast<int64_t>(idx) < a.npats;
     if (arrived && a.avail) {  // streamed batch: wait until the copy stream has delivered this pattern
