@@ -23,6 +23,7 @@
 #include "fm_image.hpp"
 #include "fm_kernels.cuh"
 #include "fm_loader.hpp"
+#include "fm_stream_plan.hpp"
 
 using namespace fmb;
 
@@ -417,19 +418,18 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   // counter written after every chunk gates the queue, CountArgs::avail), so the host->device
   // transfer overlaps the search instead of preceding it.  The batch runs as two kernels, one per
   // half, so that the results of the first half travel back while the second half is searched.
-  constexpr int64_t kChunk = 1 << 16;  // patterns per copy chunk; a multiple of 32 keeps every 128-byte
-                                       // line of plen / offs inside one chunk
+  // (chunk sizes, the split and the symbol cuts: fm_stream_plan.hpp)
   static const bool no_stream = std::getenv("FEMTO_B200_NO_STREAM") != nullptr;
-  const bool streamed = in_order && npats >= 2 * kChunk && ix->stream2 && ix->stream3 && ix->stream_ok && !no_stream;
+  const bool streamed = in_order && npats >= kStreamMinBatch && ix->stream2 && ix->stream3 && ix->stream_ok && !no_stream;
   if (lazy && !streamed) return kRetryValidated;
   if (streamed) {
     const int m = uniform_len;
     // the second kernel takes the last quarter: its results are the only transfer nothing overlaps
-    const int64_t mid = (npats - npats / 4) & ~int64_t(31);
+    const int64_t mid = stream_split(npats);
     const int64_t half_lo[2] = {0, mid}, half_hi[2] = {mid, npats};
     // copy chunks grow from 8 Ki to 128 Ki patterns: the first patterns arrive after a few microseconds,
     // the bulk travels in few, large transfers
-    auto chunk_at = [&](int64_t done) { return std::min<int64_t>(kChunk * 2, std::max<int64_t>(kChunk / 8, done)); };
+    auto chunk_at = [](int64_t lo) { return stream_chunk_at(lo); };
     int64_t nmarks = 0;
     for (int h = 0; h < 2; h++)
       for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo)) nmarks++;
@@ -468,7 +468,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
         if (ready_upto) {
           // the symbol copy below is cut at a 128-byte line, i.e. up to 63 symbols into the patterns that
           // follow: wait for every pattern that starts before that cut
-          const int64_t cut = std::min(flat_len, (offs[hi - 1] + plen[hi - 1] + 63) & ~int64_t(63));
+          const int64_t cut = stream_symbol_cut(plen, offs, hi, npats, flat_len);
           const int64_t j = hi == npats ? npats : std::lower_bound(offs + hi, offs + npats, cut) - offs;
           (*ready_upto)(j);
         }
@@ -498,9 +498,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
           CK(cudaMemcpyAsync(d_plen + lo, plen + lo, size_t(hi - lo) * 4, cudaMemcpyHostToDevice, sc));
           CK(cudaMemcpyAsync(d_offs + lo, offs + lo, size_t(hi - lo) * 8, cudaMemcpyHostToDevice, sc));
         }
-        int64_t fend = offs[hi - 1] + plen[hi - 1];          // in-order batch: patterns [0, hi) end here
-        fend = std::min(flat_len, (fend + 63) & ~int64_t(63));
-        if (hi == npats) fend = flat_len;
+        const int64_t fend = stream_symbol_cut(plen, offs, hi, npats, flat_len);
         if (fend > fdone) {
           CK(cudaMemcpyAsync(d_flat + fdone, flat + fdone, size_t(fend - fdone) * 2, cudaMemcpyHostToDevice, sc));
           fdone = fend;

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "fm_loader.hpp"
+#include "fm_stream_plan.hpp"
 
 using namespace fmb;
 
@@ -173,3 +174,27 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
 }
 
 }  // extern "C"
+
+// The chunk plan of a streamed count (fm_stream_plan.hpp) for an in-order batch, as count_host walks
+// it: out receives 5 int64 per chunk {kernel (0/1), first pattern, end pattern, first symbol, end
+// symbol}; returns the number of chunks, -1 when the batch is too small to be streamed, -2 when
+// out_cap (in chunks) is too small.
+extern "C" int64_t fm_debug_stream_plan(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t flat_len,
+                                        int64_t* out, int64_t out_cap) {
+  using namespace fmb;
+  if (npats < kStreamMinBatch) return -1;
+  const int64_t mid = stream_split(npats);
+  const int64_t half_lo[2] = {0, mid}, half_hi[2] = {mid, npats};
+  int64_t k = 0, fdone = 0;
+  for (int h = 0; h < 2; h++) {
+    for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += stream_chunk_at(lo), k++) {
+      const int64_t hi = std::min(half_hi[h], lo + stream_chunk_at(lo));
+      const int64_t fend = std::max(fdone, stream_symbol_cut(plen, offs, hi, npats, flat_len));
+      if (k >= out_cap) return -2;
+      int64_t* o = out + 5 * k;
+      o[0] = h; o[1] = lo; o[2] = hi; o[3] = fdone; o[4] = fend;
+      fdone = fend;
+    }
+  }
+  return k;
+}
