@@ -451,7 +451,9 @@ def main():
     # uses 64 B of bits and an 8 B header entry); per backward-search step: the symbol's 16 B OccRec,
     # shared by the step's two Occ (+ the 16 B BucketRec in the layouts whose root is not addressed
     # by row); per pattern: 2 B/symbol + 4+8 B length/offset + 16 B result
-    per_block = {1: block_bytes + 16, 2: block_bytes + 8, 4: 64 + 8 + 8}[levels]
+    # (quad: 64 B of bits + the 8 B header entry; the exit entry of the root block rides in the symbol
+    # record for codes of up to 8 bits and is not read)
+    per_block = {1: block_bytes + 16, 2: block_bytes + 8, 4: 64 + 8}[levels]
     per_step = 16 if levels == 4 else 32
     alg_bytes = (st["distinct_block_reads"] * per_block + st["steps"] * per_step +
                  npats * (m * 2 + 28))

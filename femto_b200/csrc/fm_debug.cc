@@ -75,7 +75,13 @@ int64_t fm_debug_image_occ(void* h, int ch, int64_t row) {
       const HostQuadRank r = host_quad_rank(im.rank_words, base, idx1, int(path));
       idx1 = r.index1;
       const uint32_t* ex = im.quads[node].exit[path];
-      if (lvl == 0 && ex != &im.quads[0].exit[0][0] + 2 * size_t(o.root_exit)) return -3;
+      if (lvl == 0) {  // the record's shortcut to this entry
+        if (o.root_exit & kRootExitDirect) {
+          if (L <= 4 || L > 8 || (o.root_exit & ~kRootExitDirect) != ex[0]) return -3;
+        } else if (ex != &im.quads[0].exit[0][0] + 2 * size_t(o.root_exit)) {
+          return -3;
+        }
+      }
       if (rem <= 4) {
         if (!(ex[1] & kChildLeaf) || (ex[1] & 0xffffu) != uint32_t(ch)) return -2;
         break;

@@ -110,8 +110,11 @@ struct alignas(16) OccRec {
   int64_t occ_base;  // C[ch] + occurrences of ch before this bucket
   uint32_t leaf;     // wavelet-tree leaf id (1<<len | code) of ch in this bucket, 0 = absent
   uint32_t root_exit;  // quad layout: 16 * (root QuadRec index) + first four path bits of ch, i.e. the
-                       // index of the exit entry {first block, QuadRec} the second block read needs
+                       // index of the exit entry {first block, QuadRec} the second block read needs;
+                       // or kRootExitDirect | first block of that entry, for codes of 5..8 bits (the
+                       // second block is their last, so the QuadRec behind it is never needed)
 };
+constexpr uint32_t kRootExitDirect = 0x80000000u;
 
 struct alignas(8) MarkRec {
   uint32_t mark_base;    // first rank block of the mark bit-vector

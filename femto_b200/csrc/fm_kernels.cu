@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
     // ---- set-up of one backward-search step: this lane's row, record and root block
     bool stepping = s.have && s.f <= s.l && s.i > 0;
     bool act = false;
-    uint32_t idx = 0, base = 0, node = 0, leaf = 0;
+    uint32_t idx = 0, base = 0, node = 0, leaf = 0, rexit = 0;
     int L = 0;
     int64_t ob = 0;
     QuadLine line;
@@ -706,6 +706,7 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
           ob = rec_occ_base(rv);
           leaf = static_cast<uint32_t>(rv.z);
           node = static_cast<uint32_t>(rv.w) >> 4;
+          rexit = static_cast<uint32_t>(rv.w);
           if (STATS) n_occ++;
           if (leaf) {  // else: symbol absent from the bucket, Occ is the bucket base (index.c:2080-2089)
             L = 31 - __clz(leaf);
@@ -732,7 +733,10 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
       if (act) {
         const uint32_t nib = quad_path(leaf, L, lvl);
         uint2 ex = make_uint2(0, 0);
-        if (lvl + 4 < L) ex = ldg_pinned(exits + (static_cast<size_t>(node) * 16 + nib));
+        if (lvl + 4 < L) {
+          if (lvl == 0 && (rexit & kRootExitDirect)) ex = make_uint2(rexit & ~kRootExitDirect, 0u);
+          else ex = ldg_pinned(exits + (static_cast<size_t>(node) * 16 + nib));
+        }
         const uint2 h = ldg_pinned(reinterpret_cast<const uint2*>(im.blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4)) + (nib >> 1));
         if (lvl > 0) line.load(im.blocks, blk);  // the root block was requested during set-up
         idx = line.eval(h, nib, static_cast<int>(p & 127u) + 1);
@@ -815,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
     // ---- set-up of one round (normally a whole backward-search step), all groups together
     bool stepping = s.have && (cross_pending || (s.f <= s.l && s.i > 0));
     bool actA = false, actB = false;
-    uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0;
+    uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0, rexit = 0;
     int L = 0;
     if (stepping) {
       int64_t g;
@@ -843,6 +847,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
         const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
         uint4 br = make_uint4(static_cast<uint32_t>(g * im.root_stride), static_cast<uint32_t>(rv.w) >> 4, 0, 0);
         if (LV != 4) br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+        if (LV == 4) rexit = static_cast<uint32_t>(rv.w);
         const int64_t ob = rec_occ_base(rv);
         leaf = static_cast<uint32_t>(rv.z);
         if (cross_pending) {  // second round of a cross-bucket step: row `last`
@@ -906,7 +911,11 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
             q.load(im.blocks, blkB, sub);
             hq = quad_header(im.blocks, blkB, nib >> 1);
           }
-          if (lvl + 4 < L) ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
+          if (lvl + 4 < L) {
+            // codes of 5..8 bits carry the first block of their second (and last) quad node in the record
+            if (lvl == 0 && (rexit & kRootExitDirect)) ex = make_uint2(rexit & ~kRootExitDirect, 0u);
+            else ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[nib]));
+          }
         }
         if (EXP == 2) {
           uint32_t x = p.d[0] ^ nib;

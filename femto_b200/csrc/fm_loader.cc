@@ -501,7 +501,12 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
     if (im->levels == 4 && o.leaf) {  // index of the root QuadRec's exit entry on this symbol's path
       const int len = 31 - __builtin_clz(o.leaf);
       const uint32_t nib = len >= 4 ? (o.leaf >> (len - 4)) & 15u : (o.leaf << (4 - len)) & 15u;
-      o.root_exit = uint32_t(p.node_base + p.super_of[0]) * 16u + nib;
+      const uint32_t root = uint32_t(p.node_base + p.super_of[0]);
+      o.root_exit = root * 16u + nib;
+      // codes of 5..8 bits need exactly one more block, and of its exit entry only the first block:
+      // store that directly (kRootExitDirect) and the step saves the read of the entry
+      const uint32_t base2 = im->quads[root].exit[nib][0];
+      if (len > 4 && len <= 8 && base2 < kRootExitDirect) o.root_exit = kRootExitDirect | base2;
     }
     MarkRec& m = im->mark[rec0 + size_t(ch)];
     m.mark_base = 0;
