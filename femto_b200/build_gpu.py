@@ -102,6 +102,60 @@ def prepare_text_gpu(docs: List[torch.Tensor]) -> Tuple[torch.Tensor, np.ndarray
     return T, np.array(ends, dtype=np.int64)
 
 
+def english_vocabulary(vocab: int, seed: int) -> Tuple[np.ndarray, np.ndarray]:
+    """A fixed vocabulary for synthetic_english: `vocab` lower-case words, frequent ones short
+    (rank r has 2 + min(8, floor(log2(r+1))) letters, drawn from splitmix64).  Returns (letters
+    concatenated, word offsets [vocab + 1]).  Host side, numpy, device independent."""
+    ranks = np.arange(vocab, dtype=np.int64)
+    wlen = 2 + np.minimum(8, np.floor(np.log2(ranks + 1.0)).astype(np.int64))
+    woff = np.zeros(vocab + 1, dtype=np.int64)
+    woff[1:] = np.cumsum(wlen)
+    total = int(woff[-1])
+    # letters with English-like frequencies (per mille, a..z), by inverse CDF on 16-bit draws
+    permille = np.array([82, 15, 28, 43, 127, 22, 20, 61, 70, 2, 8, 40, 24, 67, 75, 19, 1, 60, 63, 91, 28, 10,
+                         24, 2, 20, 1], dtype=np.float64)
+    cdf = np.cumsum(permille) / permille.sum()
+    raw = synthetic_bytes_numpy(2 * total, seed * 7919 + 13).astype(np.uint32)
+    u = (raw[0::2] * 256 + raw[1::2]) / 65536.0
+    letters = (97 + np.minimum(np.searchsorted(cdf, u, side="right"), 25)).astype(np.uint8)
+    return letters, woff
+
+
+def synthetic_english(n: int, seed: int, device, vocab: int = 50000, words_per_chunk: int = 1 << 22) -> torch.Tensor:
+    """n bytes of English-like text (BASELINE configs[3]): words of a fixed `vocab`-word vocabulary
+    drawn with Zipf(s=1) rank frequencies and separated by single spaces.  Counter-based and integer /
+    exact-float only, so the bytes are identical on any device and torch version.  Byte entropy is
+    ~4.2 bits, so the index gets Huffman codes of 3..15 bits (deep wavelet trees: three quad rounds for
+    the rare letters), and repeats long enough to need several tie-refinement rounds in the sorter."""
+    letters_h, woff_h = english_vocabulary(vocab, seed)
+    ranks = np.arange(1, vocab + 1, dtype=np.float64)
+    cdf_h = np.cumsum(1.0 / ranks)
+    cdf_h /= cdf_h[-1]
+    letters = torch.from_numpy(letters_h).to(device)
+    woff = torch.from_numpy(woff_h).to(device)
+    cdf = torch.from_numpy(cdf_h).to(device)
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    pos, w0 = 0, 0
+    while pos < n:
+        idx = torch.arange(w0, w0 + words_per_chunk, dtype=torch.int64, device=device) + ((int(seed) + 1) << 44)
+        x = _splitmix64(idx)
+        u = ((x >> 11) & ((1 << 53) - 1)).to(torch.float64) * (2.0 ** -53)   # exact in float64
+        wid = torch.clamp(torch.searchsorted(cdf, u, right=True), max=vocab - 1)
+        wl = woff[wid + 1] - woff[wid]
+        ends = torch.cumsum(wl + 1, 0)                      # each word is followed by one space
+        total = int(ends[-1])
+        take = min(total, n - pos)
+        p = torch.arange(take, dtype=torch.int64, device=device)
+        w = torch.searchsorted(ends, p, right=True)         # word that byte p belongs to
+        k = p - (ends[w] - wl[w] - 1)                       # position inside "word + space"
+        inside = k < wl[w]
+        src = woff[wid[w]] + torch.where(inside, k, torch.zeros_like(k))
+        out[pos:pos + take] = torch.where(inside, letters[src], torch.full_like(letters[src], 32))
+        pos += take
+        w0 += words_per_chunk
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # suffix sorting
 

@@ -57,3 +57,41 @@ def test_streamed_build_equals_host_build(tmp_path):
     assert info["rows"] == sum(len(d) + 1 for d in docs)
     for f in sorted(os.listdir(a)):
         assert open(os.path.join(a, f), "rb").read() == open(os.path.join(b, f), "rb").read(), f
+
+
+def test_english_like_generator_properties():
+    """synthetic_english (the corpus of BASELINE configs[3]; prepared for the 16 GiB run of round 2):
+    deterministic, independent of the chunking, words from the fixed vocabulary with Zipf-like
+    frequencies, a skewed byte distribution (deep Huffman codes)."""
+    a = build_gpu.synthetic_english(300001, 5, "cpu", vocab=2000, words_per_chunk=1 << 14).numpy()
+    b = build_gpu.synthetic_english(300001, 5, "cpu", vocab=2000, words_per_chunk=1 << 14).numpy()
+    assert len(a) == 300001 and (a == b).all()
+    c = build_gpu.synthetic_english(100000, 5, "cpu", vocab=2000, words_per_chunk=1 << 14).numpy()
+    assert (c == a[:100000]).all()                           # a prefix of the longer text
+    assert (build_gpu.synthetic_english(1000, 6, "cpu", vocab=2000).numpy() != a[:1000]).any()
+    letters, woff = build_gpu.english_vocabulary(2000, 5)
+    vocab = {bytes(letters[woff[i]:woff[i + 1]]) for i in range(2000)}
+    words = bytes(a).split(b" ")
+    assert all(w in vocab for w in words[:-1])               # the last word may be cut
+    assert set(np.unique(a).tolist()) <= set(range(97, 123)) | {32}
+    # Zipf: the most frequent word is rank 0, and frequencies fall steeply
+    from collections import Counter
+    cnt = Counter(words[:-1])
+    top = cnt.most_common(3)
+    assert top[0][0] == bytes(letters[woff[0]:woff[1]]) and top[0][1] > 2.5 * top[2][1] * 0.5
+    # skewed bytes: space is by far the most frequent, some letters are rare
+    freq = np.bincount(a, minlength=256) / len(a)
+    assert freq[32] > 0.08 and freq[freq > 0].min() < 0.005 and freq[ord("e")] > 0.06
+
+
+def test_english_like_corpus_sorts_and_indexes(tmp_path):
+    """The GPU pipeline (on CPU tensors here) handles the English-like corpus: repeats force several
+    tie-refinement rounds; the streamed index equals the host-built one."""
+    text = build_gpu.synthetic_english(60000, 9, "cpu", vocab=500, words_per_chunk=1 << 12)
+    docs = [bytes(text[:25000].numpy()), bytes(text[25000:].numpy())]
+    params = dict(block_size=16384, bucket_size=4096, chunk_size=1024, mark_period=20)
+    a, b = str(tmp_path / "host"), str(tmp_path / "stream")
+    fb.build_index_host(docs, a, **params)
+    build_gpu.build_index_gpu([torch.frombuffer(bytearray(d), dtype=torch.uint8) for d in docs], b, batch=9000, **params)
+    for f in sorted(os.listdir(a)):
+        assert open(os.path.join(a, f), "rb").read() == open(os.path.join(b, f), "rb").read(), f
