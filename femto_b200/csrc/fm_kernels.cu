@@ -11,18 +11,26 @@
 //                    (do_extract_document_query, server.c:6364-6437).
 //   occ_kernel     : a batch of single C[ch]+Occ(ch,row) evaluations (leaf interface cross-check).
 //
-// Execution model.  A rank block (BW 32-bit words: word 0 = ones before the block, then (BW-1)*32
-// payload bits) is read by a group of LPQ adjacent lanes, each lane loading BW/LPQ words with one or
-// more 128-bit (or 64-bit) ld.global.nc, popcounting them under a position mask built with a funnel
-// shift, and combining with __shfl_xor_sync.  Warps are persistent: a lane group that finishes its
-// pattern pulls the next one from a global atomic queue, so dead patterns and mixed lengths do not
-// idle lanes for the rest of the batch.  No tensor cores: this is HBM-latency / issue-bound integer work.
+// Execution model.  A rank block is read by a group of LPQ adjacent lanes through the read-only path
+// and popcounted under position masks, lane partials combined with __shfl_xor_sync.  Three block
+// layouts (fm_image.hpp): plain (word 0 = ones before the block, then (BW-1)*32 payload bits: one
+// wavelet-tree level per read), paired (two levels per read) and quad (four levels per 128-byte
+// read, the default: a lane holds one 32-byte sector, fetched with ONE 256-bit load, and builds
+// both words' masks from one 64-bit shift).  Warps are persistent: a lane group that finishes its
+// pattern pulls the next one from a global atomic queue (one atomic per warp for all the groups that
+// ask together), so dead patterns and mixed lengths do not idle lanes for the rest of the batch; a
+// queue position may be gated by an arrival counter (streamed host-buffer batches).  No tensor cores:
+// the work is bound by the RATE of dependent random HBM reads (profiles/r01_quad_schedules.md).
 //
-// Two schedules of the count kernel:
-//   pair : a pattern owns 2*LPQ lanes; one sub-group evaluates Occ(c, first-1), the other Occ(c, last).
-//   sync : a pattern owns LPQ lanes that advance BOTH ranks together, warp-synchronously per
-//          backward-search step; when both positions fall into the same rank block (93% of the
-//          levels on the 4 GiB byte corpus) the block is read once and popcounted under two masks.
+// Schedules of the count kernel:
+//   sync  : a pattern owns LPQ lanes that advance BOTH ranks together, warp-synchronously per
+//           backward-search step; when both positions fall into the same rank block (93% of the
+//           iterations on the 4 GiB byte corpus) the block is read once and evaluated for both.
+//           Default for every layout.
+//   split : quad blocks only; one lane per Occ, the two lanes of a pattern meet once per step.
+//   pair  : plain blocks only; a pattern owns 2*LPQ lanes, one sub-group per Occ (the first kernel).
+// After the count of a locate call: clip_kernel / cub scan / expand_rows_kernel turn the ranges into
+// rows on the device.
 #include "fm_kernels.cuh"
 
 #include <algorithm>
