@@ -441,6 +441,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (trace) for (cudaEvent_t& e : tev) CK(cudaEventCreate(&e));
     CK(cudaMemsetAsync(d_avail, 0, 2 * sizeof(unsigned long long), sk));
+    CK(cudaMemsetAsync(ix->d_status + 1, 0, sizeof(int32_t), sk));  // a call that failed half-way may have left it set
     if (trace) CK(cudaEventRecord(tev[0], sk));
     CK(cudaEventRecord(ix->ev[0], sk));
     CK(cudaStreamWaitEvent(sc, ix->ev[0], 0));
@@ -746,7 +747,9 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
       const int64_t claim_len = offs[npats - 1] + int64_t(plen[npats - 1]);
       int m = (plen[0] > 0 && offs[0] == 0 && plen[1] == plen[0] && offs[1] == plen[0]) ? plen[0] : 0;
       if (m && claim_len != npats * int64_t(m)) m = 0;
-      if (claim_len >= 0 && offs[npats - 1] >= 0 && plen[npats - 1] >= 0 && claim_len <= (int64_t(1) << 33)) {
+      // (a claim of more than 4 Ki symbols per pattern on average is not believed without a full check:
+      // the device buffers are sized from it)
+      if (claim_len >= 0 && offs[npats - 1] >= 0 && plen[npats - 1] >= 0 && claim_len <= npats * int64_t(4096)) {
         const int rc = count_host(ix, npats, plen, flat, claim_len, offs, first, last, /*in_order=*/true, m,
                                   /*to_host=*/true, /*lazy=*/true);
         if (rc != kRetryValidated) return rc;
