@@ -270,6 +270,15 @@ class Index:
                "fm_range_documents")
         return docs[:n.value]
 
+    def chunk_documents(self, row: int):
+        """(first row, last row, ascending documents) of the document chunk holding `row` (block_chunk_request)."""
+        a, b, n = C.c_int64(), C.c_int64(), C.c_int64()
+        cap = max(int(self.info.num_documents), 1)
+        docs = np.zeros(cap, dtype=np.int64)
+        _check(self.lib.fm_chunk_documents(self.h, row, C.byref(a), C.byref(b), _ptr(docs, C.c_int64), cap, C.byref(n)),
+               "fm_chunk_documents")
+        return a.value, b.value, docs[:n.value]
+
     def extract(self, doc: int) -> np.ndarray:
         ln, _ = self.doc_info(doc)
         out = np.zeros(max(ln, 1), dtype=np.uint16)

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "fm_last_transfer": (C.c_int, [vp, P(i64), P(i64)]),
     "fm_doc_name": (C.c_int, [vp, i64, vp, i64, P(i64)]),
     "fm_range_documents": (C.c_int, [vp, i64, i64, P(i64), i64, P(i64)]),
+    "fm_chunk_documents": (C.c_int, [vp, i64, P(i64), P(i64), P(i64), i64, P(i64)]),
     "fm_locate": (C.c_int, [vp, C.c_int, P(C.c_int), P(P(u16)), C.c_int, P(C.c_int), P(P(i64))]),
     "fm_locate_flat": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), C.c_int, P(i32), P(i64), P(i64), i64]),
     "fm_locate_range": (C.c_int, [vp, i64, i64, P(i64)]),

@@ -112,6 +112,12 @@ struct fm_index {
   // host-side header tables
   std::vector<int64_t> doc_ends, doc_eof_rows, C_host, doc_info_off;
   std::vector<uint8_t> doc_info_bytes;
+  // document chunks as stored (HostImage::chunk_*), decoded on demand
+  std::vector<uint8_t> chunk_bytes;
+  std::vector<int64_t> chunk_off;
+  std::vector<int32_t> chunk_count;
+  std::vector<uint32_t> chunk_dir_rel;
+  BlockHeader hdr;
   // per-call scratch, serialised by mu
   std::mutex mu;
   cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
@@ -282,6 +288,11 @@ int open_impl(const char* path, int device, int shard, int nshards, fm_index_t**
     ix->doc_eof_rows = std::move(host->doc_eof_rows);
     ix->doc_info_off = std::move(host->doc_info_off);
     ix->doc_info_bytes = std::move(host->doc_info_bytes);
+    ix->chunk_bytes = std::move(host->chunk_bytes);
+    ix->chunk_off = std::move(host->chunk_off);
+    ix->chunk_count = std::move(host->chunk_count);
+    ix->chunk_dir_rel = std::move(host->chunk_dir_rel);
+    ix->hdr = host->hdr;
   } catch (const CudaFail& e) {
     destroy(ix);
     return fail(FM_ERR_IO, std::string("fm_open: ") + e.what());
@@ -1164,6 +1175,26 @@ int fm_doc_name(const fm_index_t* ix, int64_t doc, void* out, int64_t out_cap, i
     std::memcpy(out, ix->doc_info_bytes.data() + lo, size_t(len));
   }
   return FM_OK;
+}
+
+int fm_chunk_documents(const fm_index_t* ix, int64_t row, int64_t* chunk_first, int64_t* chunk_last, int64_t* docs,
+                       int64_t docs_cap, int64_t* ndocs) {
+  if (!ix || !chunk_first || !chunk_last || !ndocs) return fail(FM_ERR_PARAM, "fm_chunk_documents: null argument");
+  *ndocs = 0;
+  try {
+    std::vector<int64_t> d;
+    chunk_documents(ix->hdr, ix->info.first_row, ix->info.end_row, ix->im.first_bucket, ix->chunk_bytes, ix->chunk_off,
+                    ix->chunk_count, ix->chunk_dir_rel, row, chunk_first, chunk_last, &d);
+    *ndocs = int64_t(d.size());
+    if (*ndocs > docs_cap) return fail(FM_ERR_FULL, "fm_chunk_documents: output buffer too small");
+    if (*ndocs && !docs) return fail(FM_ERR_PARAM, "fm_chunk_documents: null output");
+    std::copy(d.begin(), d.end(), docs);
+    return FM_OK;
+  } catch (const Error& e) {
+    return fail(e.code, std::string("fm_chunk_documents: ") + e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(FM_ERR_MEM, "fm_chunk_documents: out of memory");
+  }
 }
 
 int fm_range_documents(fm_index_t* ix, int64_t first, int64_t last, int64_t* docs, int64_t docs_cap, int64_t* ndocs) {

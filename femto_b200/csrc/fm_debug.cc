@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "fm_loader.hpp"
 #include "fm_stream_plan.hpp"
@@ -180,6 +181,22 @@ int fm_debug_image_back_step(void* h, int64_t row, int32_t* ch_out, int64_t* nex
 }
 
 }  // extern "C"
+
+// Documents of the chunk holding `row` (HostImage tables; fmb::chunk_documents).  Returns the number
+// of documents (docs filled up to cap), or -(error code).
+extern "C" int64_t fm_debug_image_chunk(void* h, int64_t row, int64_t* first, int64_t* last, int64_t* docs,
+                                        int64_t cap) {
+  const fmb::HostImage& im = *static_cast<DebugImage*>(h)->im;
+  try {
+    std::vector<int64_t> d;
+    fmb::chunk_documents(im.hdr, im.first_row, im.end_row, im.first_bucket, im.chunk_bytes, im.chunk_off,
+                         im.chunk_count, im.chunk_dir_rel, row, first, last, &d);
+    for (size_t i = 0; i < d.size() && int64_t(i) < cap; i++) docs[i] = d[i];
+    return int64_t(d.size());
+  } catch (const fmb::Error& e) {
+    return -int64_t(e.code);
+  }
+}
 
 // The chunk plan of a streamed count (fm_stream_plan.hpp) for an in-order batch, as count_host walks
 // it: out receives 5 int64 per chunk {kernel (0/1), first pattern, end pattern, first symbol, end

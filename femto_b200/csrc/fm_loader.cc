@@ -28,6 +28,9 @@ struct BucketPlan {
   std::vector<uint32_t> markarr_offs;
   int64_t n_blocks = 0, n_wtree_blocks = 0;
   int64_t n_root_blocks = 0;  // quad layout: blocks of the root node, placed outside [block_base, +n_blocks)
+  uint32_t chunk_dir = 0;     // absolute offset of the chunk directory in the block (0 = no chunks)
+  int32_t n_chunks = 0;
+  int64_t chunk_len = 0, chunk_base = 0;  // bytes of the chunk section; where they go in HostImage::chunk_bytes
   // paired-level layout: internal nodes at even depth own the blocks ("super nodes")
   std::vector<int32_t> super_of;    // per internal node: its index among the bucket's super nodes, or -1
   int64_t n_records = 0;            // NodeRec (plain) or SuperRec (paired) entries of this bucket
@@ -56,6 +59,19 @@ void plan_bucket(const Blob& blk, const BlockHeader& bh, int bpb, int bucket, Bu
   t_block_words = bw;
   parse_bucket_tables(blk, bh, bpb, bucket, &p->tab);
   const BucketTables& t = p->tab;
+  {  // document chunks: bucket header word 5 = number of chunks, directory right after the header
+    const int64_t nch = int64_t(be32(blk.at(size_t(t.off_bucket) + 20, 4)));
+    if (nch < 0 || nch > (int64_t(1) << 24)) throw Error(FM_ERR_FORMAT, "bad chunk count");
+    p->n_chunks = int32_t(nch);
+    if (nch > 0) {
+      p->chunk_dir = t.off_bucket + 24;
+      const uint8_t* dir = blk.at(p->chunk_dir, 4 * size_t(nch + 1));
+      const uint32_t lo = be32(dir), hi = be32(dir + 4 * size_t(nch));
+      if (lo != 24 + 4 * uint32_t(nch + 1) || hi < lo) throw Error(FM_ERR_FORMAT, "bad chunk directory");
+      blk.at(size_t(t.off_bucket) + hi - 1, 1);
+      p->chunk_len = int64_t(hi) - 24;  // directory + chunks
+    }
+  }
   // wavelet tree directory
   const uint8_t* wt = blk.at(t.off_wtree, 4);
   const size_t wt_avail = size_t(t.off_marktab) - size_t(t.off_wtree);
@@ -444,6 +460,9 @@ void fill_bucket(const IndexFiles& files, const Blob& blk, const BlockHeader& bh
   const size_t wt_avail = size_t(t.off_marktab) - size_t(t.off_wtree);
   const size_t n_int = p.node_ids.size();
 
+  if (p.chunk_len > 0)  // chunk directory + chunks, as stored
+    std::memcpy(im->chunk_bytes.data() + p.chunk_base, blk.at(p.chunk_dir, size_t(p.chunk_len)), size_t(p.chunk_len));
+
   // leaf id -> symbol
   std::unordered_map<uint32_t, uint32_t> leaf_sym;
   leaf_sym.reserve(size_t(t.n_in_use) * 2 + 2);
@@ -794,6 +813,20 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
     vals += p.n_markvals;
     max_len = std::max(max_len, p.tab.max_len);
   }
+  {  // document chunks: one byte range per bucket
+    im->chunk_off.assign(size_t(nb) + 1, 0);
+    im->chunk_count.assign(size_t(nb), 0);
+    im->chunk_dir_rel.assign(size_t(nb), 24);
+    int64_t at = 0;
+    for (int64_t g = 0; g < nb; g++) {
+      plans[size_t(g)].chunk_base = at;
+      im->chunk_off[size_t(g)] = at;
+      im->chunk_count[size_t(g)] = plans[size_t(g)].n_chunks;
+      at += plans[size_t(g)].chunk_len;
+    }
+    im->chunk_off[size_t(nb)] = at;
+    im->chunk_bytes.resize(size_t(at));
+  }
   if (blocks >= (int64_t(1) << 32) || nodes >= (int64_t(1) << (levels == 4 ? 27 : 31)))
     throw Error(FM_ERR_FULL, "shard too large for 32-bit rank block indices; use more shards");
   im->max_code_len = max_len;
@@ -818,6 +851,58 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
                 &scratch[size_t(tid)], &used);
   });
   return im;
+}
+
+void chunk_documents(const BlockHeader& hdr, int64_t first_row, int64_t end_row, int64_t first_bucket,
+                     const std::vector<uint8_t>& chunk_bytes, const std::vector<int64_t>& chunk_off,
+                     const std::vector<int32_t>& chunk_count, const std::vector<uint32_t>& chunk_dir_rel,
+                     int64_t row, int64_t* first, int64_t* last, std::vector<int64_t>* docs) {
+  docs->clear();
+  if (hdr.chunk_size <= 0) throw Error(FM_ERR_MISSING, "index was built without document chunks");
+  if (row < first_row || row >= end_row) throw Error(FM_ERR_PARAM, "row not resident");
+  // chunk number inside the data block, then bucket and chunk in bucket (index.c:2156-2160, 2205-2212)
+  const int64_t blk = row / hdr.block_size, row0 = blk * int64_t(hdr.block_size);
+  const int64_t blk_rows = std::min<int64_t>(hdr.block_size, hdr.total_length - row0);
+  const int64_t cn = (row - row0) / hdr.chunk_size;
+  const int64_t per_bucket = hdr.bucket_size / hdr.chunk_size;
+  const int64_t bpb = (int64_t(hdr.block_size) + hdr.bucket_size - 1) / hdr.bucket_size;
+  const int64_t g = blk * bpb + cn / per_bucket - first_bucket;
+  const int64_t c = cn % per_bucket;
+  *first = row0 + cn * hdr.chunk_size;
+  *last = std::min(*first + hdr.chunk_size - 1, row0 + blk_rows - 1);
+  if (g < 0 || g >= int64_t(chunk_count.size()) || c >= chunk_count[size_t(g)])
+    throw Error(FM_ERR_FORMAT, "chunk missing from its bucket");
+  const uint8_t* sec = chunk_bytes.data() + chunk_off[size_t(g)];
+  const int64_t sec_len = chunk_off[size_t(g) + 1] - chunk_off[size_t(g)];
+  const uint32_t rel = chunk_dir_rel[size_t(g)];  // directory entries are relative to the bucket start
+  const int64_t lo = int64_t(be32(sec + 4 * c)) - rel, hi = int64_t(be32(sec + 4 * (c + 1))) - rel;
+  if (lo < 0 || hi < lo || hi > sec_len) throw Error(FM_ERR_FORMAT, "bad chunk bounds");
+  // number of documents: chunk_num_docs_bits = num_bits64(chunk_size) bits, MSB-first, then flush
+  const int nbits = num_bits64(uint64_t(hdr.chunk_size));
+  size_t bit = size_t(lo) * 8;
+  const size_t end_bit = size_t(hi) * 8;
+  auto get = [&](int n) -> uint64_t {
+    uint64_t v = 0;
+    for (int i = 0; i < n; i++, bit++) {
+      if (bit >= end_bit) throw Error(FM_ERR_FORMAT, "chunk truncated");
+      v = (v << 1) | ((sec[bit >> 3] >> (7 - (bit & 7))) & 1u);
+    }
+    return v;
+  };
+  const uint64_t ndocs = get(nbits);
+  bit = (bit + 7) & ~size_t(7);
+  // gamma-coded deltas of (document + 1) (results.c:133-152, 356-371)
+  int64_t lastdoc = 0;
+  docs->reserve(size_t(ndocs));
+  for (uint64_t i = 0; i < ndocs; i++) {
+    int zeros = 0;
+    while (get(1) == 0) {
+      if (++zeros > 62) throw Error(FM_ERR_FORMAT, "bad gamma code in chunk");
+    }
+    const uint64_t v = (uint64_t(1) << zeros) | get(zeros);
+    lastdoc += int64_t(v);
+    docs->push_back(lastdoc - 1);
+  }
 }
 
 }  // namespace fmb

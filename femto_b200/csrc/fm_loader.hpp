@@ -36,6 +36,14 @@ struct HostImage {
   std::vector<int64_t> doc_ends, doc_eof_rows;
   std::vector<int64_t> doc_info_off;  // ndocs + 1 offsets into doc_info_bytes
   std::vector<uint8_t> doc_info_bytes;
+  // document chunks (block_get_chunk, index.c:2147-2197): per resident bucket the bytes of its chunk
+  // section as stored -- directory of (nchunks + 1) BE u32 offsets relative to the bucket start,
+  // then per chunk the number of documents (chunk_docs_bits bits, MSB-first, byte-flushed) and the
+  // gamma-coded ascending (document + 1) deltas.  Decoded on demand (chunk_documents).
+  std::vector<uint8_t> chunk_bytes;
+  std::vector<int64_t> chunk_off;     // nbuckets + 1 offsets into chunk_bytes
+  std::vector<int32_t> chunk_count;   // chunks per bucket
+  std::vector<uint32_t> chunk_dir_rel;  // offset of the directory from its bucket's start (to rebase entries)
   HostImage() = default;
   HostImage(const HostImage&) = delete;
   HostImage& operator=(const HostImage&) = delete;
@@ -55,6 +63,16 @@ int default_block_words(int levels);
 bool set_default_block_words(int words);          // 0 = back to the built-in default
 int default_levels_per_block();
 bool set_default_levels_per_block(int levels);    // 0 = back to the built-in default
+
+// Documents of one chunk: `row` (global) selects the chunk as block_chunk_request with
+// BLOCK_CHUNK_FIND_NUMBER does (index.c:2200-2215); *first / *last receive the chunk's global row
+// range, docs its ascending document numbers.  Works on the tables above (host side; the same
+// function serves the C ABI and the CPU tests).  Throws Error (FM_ERR_MISSING: index built without
+// chunks; FM_ERR_PARAM: row not resident; FM_ERR_FORMAT: malformed chunk).
+void chunk_documents(const BlockHeader& hdr, int64_t first_row, int64_t end_row, int64_t first_bucket,
+                     const std::vector<uint8_t>& chunk_bytes, const std::vector<int64_t>& chunk_off,
+                     const std::vector<int32_t>& chunk_count, const std::vector<uint32_t>& chunk_dir_rel,
+                     int64_t row, int64_t* first, int64_t* last, std::vector<int64_t>* docs);
 
 // Host-side rank over the image (used by the loader's self-check and by unit tests of the
 // image layout; NOT a query fallback -- the C ABI never calls it).

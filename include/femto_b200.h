@@ -194,6 +194,14 @@ int fm_resolve(const fm_index_t* ix, int64_t n, const int64_t* offsets, int64_t*
  * src/main/index.c:1767-1784 (header_loc_request with HDR_LOC_REQUEST_DOC_INFO).  *out_len receives
  * the length; FM_ERR_FULL when it exceeds out_cap. */
 int fm_doc_name(const fm_index_t* ix, int64_t doc, void* out, int64_t out_cap, int64_t* out_len);
+/* The document chunk that holds BWT row `row`: block_chunk_request with BLOCK_CHUNK_FIND_NUMBER |
+ * BLOCK_CHUNK_REQUEST_DOCUMENTS (src/main/index.c:2147-2236).  chunk_first / chunk_last receive the
+ * rows the chunk covers (chunk_size rows, fewer at the end of a data block), docs the ascending
+ * numbers of the documents that hold the suffix of at least one of them -- read from the index's
+ * own chunk section, decoded on the host, no kernel involved.  FM_ERR_MISSING when the index was
+ * built without chunks, FM_ERR_FULL when there are more than docs_cap documents (*ndocs says how many). */
+int fm_chunk_documents(const fm_index_t* ix, int64_t row, int64_t* chunk_first, int64_t* chunk_last, int64_t* docs,
+                       int64_t docs_cap, int64_t* ndocs);
 /* Documents that contain the suffixes of BWT rows first..last, ascending and unique: what the
  * reference's range_to_results query delivers for RESULT_TYPE_DOCUMENTS (src/main/server.c:4549-4889;
  * it unions the per-chunk document lists and locates the ragged ends, this call locates every row

@@ -131,6 +131,17 @@ class _Base:
             raise RuntimeError(f"locate_range rc={rc}")
         return out[:max(last - first + 1, 0)]
 
+    def chunk_documents(self, row: int, cap: int = 1 << 16):
+        """(first row, last row, ascending documents) of the chunk holding `row` -- the live reference only
+        (block_chunk_request); the plain-C oracle does not restate chunks."""
+        a, b, n = C.c_int64(), C.c_int64(), C.c_int64()
+        docs = np.zeros(cap, dtype=np.int64)
+        rc = self._fn("chunk_documents")(self.h, C.c_int64(row), C.byref(a), C.byref(b), _p(docs, C.c_int64),
+                                         C.c_int64(cap), C.byref(n))
+        if rc:
+            raise RuntimeError(f"chunk_documents rc={rc}")
+        return a.value, b.value, docs[:n.value]
+
     def doc_info(self, doc: int) -> Tuple[int, int]:
         a, b = C.c_int64(), C.c_int64()
         rc = self._fn("doc_info")(self.h, C.c_int64(doc), C.byref(a), C.byref(b))

@@ -253,6 +253,44 @@ int ref_back_step(void* hv, int64_t row, int* ch, int64_t* next_row, int64_t* of
 }
 
 /* doc tables from the header: out_end = doc_ends[doc], out_eof_row = doc_eof_rows[doc] */
+/* The document chunk that holds `row`: block_chunk_request with BLOCK_CHUNK_FIND_NUMBER |
+ * BLOCK_CHUNK_REQUEST_DOCUMENTS (src/main/index.c:2200-2236), its results read back with
+ * results_reader_next (src/main/results.c:356-371).  first/last = global rows of the chunk. */
+int ref_chunk_documents(void* hv, int64_t row, int64_t* first, int64_t* last, int64_t* docs, int64_t cap,
+                        int64_t* ndocs)
+{
+  ref_handle_t* h = hv;
+  header_occs_request_t r;
+  block_chunk_request_t c;
+  results_reader_t rd;
+  int64_t doc, off, n = 0;
+  int rc = leaf_get(h, -1);
+  if (rc) return rc;
+  memset(&r, 0, sizeof(r));
+  r.row = row;
+  rc = code_of(header_occs_request(&h->hdr, HDR_BSEARCH_BLOCK_ROWS, &r));
+  if (rc) return rc;
+  rc = leaf_get(h, r.block_num);
+  if (rc) return rc;
+  memset(&c, 0, sizeof(c));
+  c.first = (int) (row - r.row);
+  rc = code_of(block_chunk_request(&h->blk, BLOCK_CHUNK_FIND_NUMBER | BLOCK_CHUNK_REQUEST_DOCUMENTS, &c));
+  if (rc) return rc;
+  *first = r.row + c.first;
+  *last = r.row + c.last;
+  rc = code_of(results_reader_create(&rd, &c.results));
+  if (!rc) {
+    while (results_reader_next(&rd, &doc, &off)) {
+      if (n < cap) docs[n] = doc;
+      n++;
+    }
+    results_reader_destroy(&rd);
+  }
+  results_destroy(&c.results);
+  *ndocs = n;
+  return rc;
+}
+
 int ref_doc_info(void* hv, int64_t doc, int64_t* out_len, int64_t* out_eof_row)
 {
   ref_handle_t* h = hv;
