@@ -114,3 +114,20 @@ def test_sharded_locate_on_gpus(name, built_indexes, corpora, tmp_path):
     for k, w in enumerate(want):
         got = offsets[ends[k] - cnt[k]:ends[k]]
         assert len(got) == len(w) and (got == w).all(), k
+
+
+def test_chunk_documents_through_the_c_abi(built_indexes, corpora):
+    """fm_chunk_documents on an opened index (host-side decode of the stored chunk lists; the decode
+    itself is pinned on CPU against the live reference in tests/test_chunk_documents.py)."""
+    from oracle.bindings import Oracle
+    name = "multi_doc_mixed"
+    path = built_indexes[name]
+    cs = corpora[name][1]["chunk_size"]
+    with fb.Index(path, device=0) as ix, Oracle(path) as o:
+        n = o.header_info()["total_length"]
+        sa = o.locate_range(0, n - 1)
+        doc_of = np.array([o.resolve(int(x))[0] for x in sa], dtype=np.int64)
+        for row in list(range(0, n, max(1, cs // 2)))[:40] + [n - 1]:
+            first, last, docs = ix.chunk_documents(row)
+            assert first <= row <= last
+            assert (docs == np.unique(doc_of[first:last + 1])).all()
