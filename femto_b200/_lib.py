@@ -37,6 +37,16 @@ PROTOTYPES = {
     "fm_count_device": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
     "fm_count_shard_step": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp]),
     "fm_locate_shard_step": (C.c_int, [vp, i64, vp, vp, C.c_int, vp]),
+    "fm_take_status": (C.c_int, [vp, vp, P(C.c_int)]),
+    "fm_mesh_create": (C.c_int, [vp, C.c_int, C.c_int, i64, C.c_int, P(vp)]),
+    "fm_mesh_destroy": (None, [vp]),
+    "fm_mesh_export": (C.c_int, [vp, vp, i64]),
+    "fm_mesh_connect": (C.c_int, [vp, vp, i64]),
+    "fm_mesh_connect_local": (C.c_int, [vp, P(vp)]),
+    "fm_mesh_set_limits": (C.c_int, [vp, C.c_int, C.c_double]),
+    "fm_mesh_count": (C.c_int, [vp, vp, vp, vp, C.c_int, i64, i64, vp, vp, vp]),
+    "fm_mesh_locate_rows": (C.c_int, [vp, i64, vp, vp, vp]),
+    "fm_mesh_finish": (C.c_int, [vp, vp, P(C.c_int), P(C.c_uint64)]),
     "fm_last_transfer": (C.c_int, [vp, P(i64), P(i64)]),
     "fm_doc_name": (C.c_int, [vp, i64, vp, i64, P(i64)]),
     "fm_range_documents": (C.c_int, [vp, i64, i64, P(i64), i64, P(i64)]),

@@ -23,6 +23,7 @@
 #include "fm_image.hpp"
 #include "fm_kernels.cuh"
 #include "fm_loader.hpp"
+#include "fm_mesh.cuh"
 #include "fm_stream_plan.hpp"
 
 using namespace fmb;
@@ -128,6 +129,22 @@ struct fm_index {
   int64_t last_h2d = 0, last_d2h = 0;  // bytes copied by the most recent host-buffer count call
   bool stream_ok = true;               // cleared when a streamed batch stalled (e.g. under a serialising profiler)
   int dev_slot = 0;
+};
+
+// One rank's end of the device-initiated exchange (fm_mesh.cuh).
+struct fm_mesh {
+  fm_index* ix = nullptr;
+  int rank = 0, world = 1, cap_shift = 0;
+  unsigned long long window = 0;
+  size_t region_bytes = 0;
+  void* region = nullptr;                    // MeshCtl + inbox rings, one cudaMalloc (exported through cudaIpc)
+  void* peer_region[kMeshMaxRanks] = {};     // every rank's region in this process's address space
+  bool peer_ipc[kMeshMaxRanks] = {};         // opened with cudaIpcOpenMemHandle
+  bool connected = false;
+  unsigned long long epoch = 0;
+  int max_ctas = 0;
+  double timeout_s = 10.0;
+  int clock_khz = 1000000;
 };
 
 namespace {
@@ -399,6 +416,25 @@ int walk_status(fm_index* ix) {
   return st;
 }
 
+// Arrival marks of a streamed batch are written with the driver's stream memory operation
+// (cuStreamWriteValue64: ordered behind the stream's earlier copies, and the operation CUDA defines
+// for signalling a kernel that polls device memory); resolved at run time so that the library has no
+// link-time dependency on libcuda and still loads on hosts without a driver.  NULL: not available,
+// the mark then travels as an 8-byte copy on the same stream.
+using StreamWrite64 = int (*)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+StreamWrite64 stream_write64() {
+  static const StreamWrite64 fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (std::getenv("FEMTO_B200_MARK_MEMCPY") ||
+        cudaGetDriverEntryPoint("cuStreamWriteValue64", &f, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<StreamWrite64>(f);
+  }();
+  return fn;
+}
+
 constexpr int kRetryValidated = -1000;  // count_host(lazy): the batch is not what its first / last pattern claimed
 
 // count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
@@ -489,9 +525,12 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
           if (m) {
             for (int64_t i = lo; i < hi; i++) ok &= (plen[i] == m) & (offs[i] == i * int64_t(m));
           } else {
-            if (lo == 0) ok = plen[0] >= 0 && offs[0] >= 0;
+            // every pattern must also END inside the claimed buffer: the claim comes from the last
+            // pattern alone, which may point back into a dense prefix (the kernel would otherwise read
+            // symbols the device buffer, sized from the claim, does not hold)
+            if (lo == 0) ok = plen[0] >= 0 && offs[0] >= 0 && offs[0] + int64_t(plen[0]) <= flat_len;
             for (int64_t i = std::max<int64_t>(lo, 1); i < hi; i++)
-              ok &= (plen[i] >= 0) & (offs[i] == offs[i - 1] + plen[i - 1]);
+              ok &= (plen[i] >= 0) & (offs[i] == offs[i - 1] + plen[i - 1]) & (offs[i] + int64_t(plen[i]) <= flat_len);
           }
           if (!ok) {  // stop the kernels (they give up on the flag), drain, hand the batch back
             int32_t* one = reinterpret_cast<int32_t*>(marks + nmarks);
@@ -516,7 +555,12 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
           fdone = fend;
         }
         marks[k] = static_cast<unsigned long long>(hi - half_lo[h]);
-        CK(cudaMemcpyAsync(d_avail + h, marks + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc));
+        if (StreamWrite64 wv = stream_write64()) {
+          if (wv(sc, reinterpret_cast<unsigned long long>(d_avail + h), marks[k], 0) != 0)
+            throw CudaFail("cuStreamWriteValue64 failed");
+        } else {
+          CK(cudaMemcpyAsync(d_avail + h, marks + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc));
+        }
       }
     }
     if (trace) CK(cudaEventRecord(tev[3], sc));
@@ -584,6 +628,7 @@ int locate_rows_host(fm_index* ix, int64_t nrows, const int64_t* rows, int64_t* 
   w.rows = d_rows;
   w.out_offset = d_off;
   w.status = ix->d_status;
+  CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), s));  // word 0 belongs to the host-buffer calls (serialised by mu)
   CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
   CK(cudaMemcpyAsync(offsets, d_off, size_t(nrows) * 8, cudaMemcpyDeviceToHost, s));
   const int st = walk_status(ix);
@@ -905,7 +950,7 @@ int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, 
     w.nrows = nrows;
     w.rows = d_rows;
     w.out_offset = d_offsets;
-    w.status = ix->d_status;
+    w.status = ix->d_status + 2;  // caller-stream launches: read and cleared by fm_take_status
     ix->dev_slot = ix->dev_slot % 7 + 1;
     CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
                    static_cast<cudaStream_t>(stream), &ix->launches));
@@ -921,7 +966,7 @@ int fm_locate_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, int3
     if (nstates == 0) return FM_OK;
     WalkArgs w{};
     w.nrows = nstates;
-    w.status = ix->d_status;
+    w.status = ix->d_status + 2;
     w.state = d_state;
     w.dest = d_dest;
     w.nshards = nshards;
@@ -930,6 +975,212 @@ int fm_locate_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, int3
     ix->dev_slot = ix->dev_slot % 7 + 1;
     CK(launch_walk(ix->im, w, kWalkShard, ix->d_work + ix->dev_slot, ix->lanes_per_query, ix->sm_count,
                    static_cast<cudaStream_t>(stream), &ix->launches));
+    return FM_OK;
+  });
+}
+
+int fm_take_status(fm_index_t* ix, void* stream, int* status) {
+  return guarded(ix, "fm_take_status", [&]() -> int {
+    if (!status) return fail(FM_ERR_PARAM, "fm_take_status: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int32_t st = 0;
+    CK(cudaMemcpyAsync(&st, ix->d_status + 2, sizeof(st), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (st) CK(cudaMemsetAsync(ix->d_status + 2, 0, sizeof(int32_t), s));
+    *status = st;
+    return FM_OK;
+  });
+}
+
+// ---- device-initiated exchange over a BWT-range-sharded index (fm_mesh.cuh) --------------------------
+int fm_mesh_create(fm_index_t* ix, int rank, int world, int64_t window, int cap_log2, fm_mesh_t** out) {
+  if (!out) return fail(FM_ERR_PARAM, "fm_mesh_create: null argument");
+  *out = nullptr;
+  return guarded(ix, "fm_mesh_create", [&]() -> int {
+    if (world < 1 || world > kMeshMaxRanks || rank < 0 || rank >= world || window < 0)
+      return fail(FM_ERR_PARAM, "fm_mesh_create: bad rank / world / window");
+    if (ix->im.levels != 4) return fail(FM_ERR_PARAM, "fm_mesh_create: needs the quad-level image (the default)");
+    if (window == 0) window = 128 << 10;
+    // a ring must hold every state in flight: world * (window + what the warps of one rank may claim
+    // beyond the window between its check and their claims)
+    const int64_t slack = int64_t(ix->sm_count) * 8 * 8 * 16;  // SMs x CTAs x warps x groups
+    int shift = 10;
+    while ((int64_t(1) << shift) < int64_t(world) * (window + slack)) shift++;
+    if (cap_log2 > 0) {  // tests: a small ring that wraps many times (the caller also bounds the grid: fm_mesh_set_limits)
+      if (cap_log2 < 8 || cap_log2 > 30) return fail(FM_ERR_PARAM, "fm_mesh_create: cap_log2 out of range");
+      shift = cap_log2;
+    }
+    if (shift > 30) return fail(FM_ERR_PARAM, "fm_mesh_create: window too large");
+    std::unique_ptr<fm_mesh> m(new fm_mesh());
+    m->ix = ix;
+    m->rank = rank;
+    m->world = world;
+    m->cap_shift = shift;
+    m->window = static_cast<unsigned long long>(window);
+    m->region_bytes = sizeof(MeshCtl) + (size_t(world) << shift) * 32;
+    CK(cudaMalloc(&m->region, m->region_bytes));
+    CK(cudaMemset(m->region, 0, m->region_bytes));
+    CK(cudaDeviceSynchronize());
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ix->device) == cudaSuccess && khz > 0) m->clock_khz = khz;
+    m->peer_region[rank] = m->region;
+    if (world == 1) m->connected = true;
+    *out = m.release();
+    return FM_OK;
+  });
+}
+
+void fm_mesh_destroy(fm_mesh_t* m) {
+  if (!m) return;
+  cudaSetDevice(m->ix->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < m->world; r++)
+    if (m->peer_ipc[r] && m->peer_region[r]) cudaIpcCloseMemHandle(m->peer_region[r]);
+  if (m->region) cudaFree(m->region);
+  delete m;
+}
+
+int fm_mesh_export(fm_mesh_t* m, void* handle, int64_t handle_bytes) {
+  if (!m || !handle || handle_bytes < int64_t(sizeof(cudaIpcMemHandle_t)))
+    return fail(FM_ERR_PARAM, "fm_mesh_export: needs FM_MESH_HANDLE_BYTES bytes");
+  return guarded(m->ix, "fm_mesh_export", [&]() -> int {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, m->region));
+    std::memcpy(handle, &h, sizeof(h));
+    return FM_OK;
+  });
+}
+
+int fm_mesh_connect(fm_mesh_t* m, const void* handles, int64_t handle_stride) {
+  if (!m || !handles || handle_stride < int64_t(sizeof(cudaIpcMemHandle_t)))
+    return fail(FM_ERR_PARAM, "fm_mesh_connect: bad argument");
+  return guarded(m->ix, "fm_mesh_connect", [&]() -> int {
+    for (int r = 0; r < m->world; r++) {
+      if (r == m->rank || m->peer_region[r]) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const char*>(handles) + size_t(r) * size_t(handle_stride), sizeof(h));
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      m->peer_region[r] = p;
+      m->peer_ipc[r] = true;
+    }
+    m->connected = true;
+    return FM_OK;
+  });
+}
+
+int fm_mesh_connect_local(fm_mesh_t* m, fm_mesh_t* const* peers) {
+  if (!m || !peers) return fail(FM_ERR_PARAM, "fm_mesh_connect_local: bad argument");
+  return guarded(m->ix, "fm_mesh_connect_local", [&]() -> int {
+    for (int r = 0; r < m->world; r++) {
+      if (r == m->rank) continue;
+      const fm_mesh* p = peers[r];
+      if (!p || p->world != m->world || p->rank != r || p->cap_shift != m->cap_shift)
+        return fail(FM_ERR_PARAM, "fm_mesh_connect_local: peer list does not match");
+      if (p->ix->device != m->ix->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, m->ix->device, p->ix->device));
+        if (!can) return fail(FM_ERR_IO, "fm_mesh_connect_local: no peer access between the devices");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(p->ix->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        (void)cudaGetLastError();
+      }
+      m->peer_region[r] = p->region;
+    }
+    m->connected = true;
+    return FM_OK;
+  });
+}
+
+int fm_mesh_set_limits(fm_mesh_t* m, int max_ctas, double timeout_seconds) {
+  if (!m || max_ctas < 0 || timeout_seconds < 0) return fail(FM_ERR_PARAM, "fm_mesh_set_limits: bad argument");
+  m->max_ctas = max_ctas;
+  if (timeout_seconds > 0) m->timeout_s = timeout_seconds;
+  return FM_OK;
+}
+
+namespace {
+int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* d_flat, const int64_t* d_offs,
+                int uniform_len, int64_t pid_lo, int64_t n_mine, int64_t* d_first, int64_t* d_last,
+                const int64_t* d_rows, int64_t* d_offsets, void* stream) {
+  if (!m) return fail(FM_ERR_PARAM, "fm_mesh: null mesh");
+  fm_index* ix = m->ix;
+  return guarded(ix, "fm_mesh", [&]() -> int {
+    if (!m->connected) return fail(FM_ERR_PARAM, "fm_mesh: not connected");
+    if (n_mine < 0 || pid_lo < 0 || pid_lo + n_mine > (int64_t(1) << 32))
+      return fail(FM_ERR_PARAM, "fm_mesh: pattern ids must fit 32 bits");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {  // the ring must hold every state in flight (fm_mesh.cuh): world * (window + one claim per group of the grid)
+      const int64_t ctas = m->max_ctas > 0 ? m->max_ctas : int64_t(ix->sm_count) * 8;
+      if ((int64_t(1) << m->cap_shift) < int64_t(m->world) * (int64_t(m->window) + ctas * 8 * 16))
+        return fail(FM_ERR_PARAM, "fm_mesh: ring too small for this window and grid (cap_log2 / fm_mesh_set_limits)");
+    }
+    m->epoch++;
+    MeshArgs a{};
+    char* base = static_cast<char*>(m->region);
+    a.ctl = reinterpret_cast<MeshCtl*>(base);
+    a.ring = reinterpret_cast<uint4*>(base + sizeof(MeshCtl));
+    for (int r = 0; r < m->world; r++) {
+      char* pb = static_cast<char*>(m->peer_region[r]);
+      a.peer_ctl[r] = reinterpret_cast<MeshCtl*>(pb);
+      a.peer_ring[r] = reinterpret_cast<uint4*>(pb + sizeof(MeshCtl));
+    }
+    a.rank = m->rank;
+    a.world = m->world;
+    a.cap_shift = m->cap_shift;
+    // 16 bits of the batch number travel in every message's tag (never 0: a cleared slot is never valid);
+    // when they wrap the rings are cleared so that nothing 65535 batches old can look current
+    a.epoch = m->epoch;
+    if (m->epoch % 65535 == 0) CK(cudaMemsetAsync(base + sizeof(MeshCtl), 0, m->region_bytes - sizeof(MeshCtl), s));
+    a.window = m->window;
+    a.timeout_cycles = static_cast<long long>(m->timeout_s * 1e3 * double(m->clock_khz));
+    a.plen = d_plen;
+    a.flat = d_flat;
+    a.offs = d_offs;
+    a.uniform_len = uniform_len;
+    a.pid_lo = pid_lo;
+    a.n_mine = n_mine;
+    a.first = d_first;
+    a.last = d_last;
+    a.rows = d_rows;
+    a.out_offset = d_offsets;
+    a.block_size = ix->info.block_size;
+    a.nblocks = ix->info.num_blocks;
+    // the kernel's own counters start from zero; rank_done (written by the peers) is never reset
+    CK(cudaMemsetAsync(base, 0, offsetof(MeshCtl, rank_done), s));
+    if (walk) CK(launch_mesh_walk(ix->im, a, ix->sm_count, m->max_ctas, s, &ix->launches));
+    else CK(launch_mesh_count(ix->im, a, ix->sm_count, m->max_ctas, s, &ix->launches));
+    return FM_OK;
+  });
+}
+}  // namespace
+
+int fm_mesh_count(fm_mesh_t* m, const int32_t* d_plen, const uint16_t* d_flat, const int64_t* d_offs, int uniform_len,
+                  int64_t pid_lo, int64_t n_mine, int64_t* d_first, int64_t* d_last, void* stream) {
+  if (n_mine > 0 && (!d_flat || !d_first || (uniform_len <= 0 && (!d_plen || !d_offs))))
+    return fail(FM_ERR_PARAM, "fm_mesh_count: null argument");
+  return mesh_launch(m, false, d_plen, d_flat, d_offs, uniform_len, pid_lo, n_mine, d_first, d_last, nullptr, nullptr,
+                     stream);
+}
+
+int fm_mesh_locate_rows(fm_mesh_t* m, int64_t nrows, const int64_t* d_rows, int64_t* d_offsets, void* stream) {
+  if (nrows > 0 && (!d_rows || !d_offsets)) return fail(FM_ERR_PARAM, "fm_mesh_locate_rows: null argument");
+  return mesh_launch(m, true, nullptr, nullptr, nullptr, 0, 0, nrows, nullptr, nullptr, d_rows, d_offsets, stream);
+}
+
+int fm_mesh_finish(fm_mesh_t* m, void* stream, int* status, uint64_t* stats8) {
+  if (!m) return fail(FM_ERR_PARAM, "fm_mesh_finish: null mesh");
+  return guarded(m->ix, "fm_mesh_finish", [&]() -> int {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MeshCtl h;
+    CK(cudaMemcpyAsync(&h, m->region, sizeof(MeshCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (status) *status = h.status;
+    if (stats8) std::memcpy(stats8, h.stats, sizeof(h.stats));
+    if (h.status)
+      return fail(h.status == 1 ? FM_ERR_CANCELED : FM_ERR_INVALID,
+                  h.status == 1 ? "fm_mesh: a kernel waited too long for the other ranks (timed out)"
+                                : "fm_mesh: malformed state");
     return FM_OK;
   });
 }
@@ -995,6 +1246,7 @@ int locate_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const u
     w.rows = d_rows;
     w.out_offset = d_off;
     w.status = ix->d_status;
+    CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), s));
     CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
     CK(cudaMemcpyAsync(out, d_off, size_t(total) * 8, cudaMemcpyDeviceToHost, s));
     const int st = walk_status(ix);
@@ -1078,6 +1330,7 @@ int fm_back_step(fm_index_t* ix, int64_t nrows, const int64_t* rows, int32_t* ch
     w.out_next = d_next;
     w.out_ch = d_ch;
     w.status = ix->d_status;
+    CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), s));
     CK(launch_walk(ix->im, w, kWalkStep, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
     CK(cudaMemcpyAsync(offset, d_off, size_t(nrows) * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(next, d_next, size_t(nrows) * 8, cudaMemcpyDeviceToHost, s));
@@ -1135,7 +1388,8 @@ int fm_backward_step(fm_index_t* ix, int64_t n, const int64_t* first, const int6
     CK(cudaMemcpyAsync(res.data(), d_out, size_t(2 * n) * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (int64_t i = 0; i < n; i++) {
-      if (res[size_t(2 * i + 1)] < 0) return fail(FM_ERR_MISSING, "fm_backward_step: row not resident (sharded index)");
+      if (res[size_t(2 * i + 1)] < 0 || (first[i] > 0 && res[size_t(2 * i)] < 0))
+        return fail(FM_ERR_MISSING, "fm_backward_step: row not resident (sharded index)");
       new_first[i] = first[i] > 0 ? res[size_t(2 * i)] : ix->C_host[ch[i]];
       new_last[i] = res[size_t(2 * i + 1)] - 1;
     }
@@ -1246,6 +1500,7 @@ int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int6
     w.sym_off = d_par + 2;
     w.out_sym = d_sym;
     w.status = ix->d_status;
+    CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), s));
     CK(launch_walk(ix->im, w, kWalkExtract, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
     CK(cudaMemcpyAsync(out, d_sym, size_t(len) * 2, cudaMemcpyDeviceToHost, s));
     const int st = walk_status(ix);

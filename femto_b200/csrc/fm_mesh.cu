@@ -1,0 +1,432 @@
+// fm_mesh.cu -- persistent kernels of the BWT-range-sharded query path (design: fm_mesh.cuh).
+//
+//   mesh_count_kernel : do_string_query's backward search (src/main/server.c:713-946) over an index
+//                       split by data block (src/main/index.h:83-100); a pattern's state
+//                       {id, first | C+Occ(c,first-1), last, i, phase, home} moves to the GPU that
+//                       owns the row its next Occ needs and comes home with [first, last].
+//   mesh_walk_kernel  : the sampled-SA walk of do_back_query / do_context_query
+//                       (server.c:2228-2359, 2627-2795); state {slot, row, LF steps, home}.
+//
+// Both evaluate rank over quad-level blocks exactly as the single-GPU kernels do (fm_rank.cuh), so a
+// state computes the same numbers wherever it is.  A round of a warp: take states (inbox first, then
+// new patterns of the own batch), decide per state -- deliver, send, or evaluate here --, store the
+// departing ones into their owners' inboxes, evaluate the others warp-synchronously.
+#include "fm_mesh.cuh"
+
+#include <cstdlib>
+
+#include "fm_rank.cuh"
+
+namespace fmb {
+namespace {
+
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// A state in flight: 2 x 16 bytes, each half led by the tag.
+//   half 0: tag, id, A bits 0..31, A bits 32..47 | meta << 16     meta = phase | home << 2
+//   half 1: tag, i,  B bits 0..31, B bits 32..47
+// A, B are rows or C+Occ values (< 2^47 in magnitude, B may be -1): sign-extended from 48 bits.
+struct MeshState {
+  int64_t A = 0, B = 0;
+  uint32_t id = 0;
+  int32_t i = 0;
+  int phase = 0, home = 0;
+};
+constexpr int kPhaseA = 0;     // count: needs Occ(c, first-1) then Occ(c, last); A = first, B = last.  walk: walking
+constexpr int kPhaseB = 1;     // count: A = C[c]+Occ(c,first-1) is known, needs Occ(c, last)
+constexpr int kPhaseDone = 2;  // finished: travels home; count: A = first, B = last; walk: A = offset
+
+__device__ __forceinline__ int64_t sext48(uint32_t lo, uint32_t hi16) {
+  const uint64_t v = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi16 & 0xffffu) << 32);
+  return static_cast<int64_t>(v << 16) >> 16;
+}
+__device__ __forceinline__ void pack_state(const MeshState& s, uint32_t tag, uint4& m0, uint4& m1) {
+  const uint64_t a = static_cast<uint64_t>(s.A), b = static_cast<uint64_t>(s.B);
+  const uint32_t meta = static_cast<uint32_t>(s.phase) | (static_cast<uint32_t>(s.home) << 2);
+  m0 = make_uint4(tag, s.id, static_cast<uint32_t>(a), (static_cast<uint32_t>(a >> 32) & 0xffffu) | (meta << 16));
+  m1 = make_uint4(tag, static_cast<uint32_t>(s.i), static_cast<uint32_t>(b), static_cast<uint32_t>(b >> 32) & 0xffffu);
+}
+
+struct MeshWarp {
+  int lane, sub, gleader, wic;
+  unsigned long long W, wid;
+  uint32_t cap_mask, ep16;
+  unsigned long long n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;
+};
+
+__device__ __forceinline__ uint32_t mesh_tag(const MeshWarp& w, const MeshArgs& a, unsigned long long idx) {
+  return w.ep16 | (static_cast<uint32_t>((idx >> a.cap_shift) + 1) & 0xffffu);
+}
+
+// Fill idle groups from this warp's share of the inbox.  needers: ballot of the leader lanes of the
+// groups without a state; updated.  Returns states through s / have.  Warp-collective.
+__device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, unsigned long long (*s_cur)[kMeshMaxRanks],
+                                                unsigned rot, unsigned& needers, MeshState& s, bool& have) {
+  int want = __popc(needers);
+  // which rings hold a message at this warp's cursor (one lane per ring)
+  bool ready = false;
+  if (w.lane < a.world) {
+    const unsigned long long cur = s_cur[w.wic][w.lane];
+    const uint4* slot = a.ring + ((static_cast<size_t>(w.lane) << a.cap_shift) + (cur & w.cap_mask)) * 2;
+    ready = ld_volatile_v4(slot).x == mesh_tag(w, a, cur);
+  }
+  unsigned rings = __ballot_sync(kFull, ready);
+  if (!rings) w.n_empty++;
+  while (rings && want > 0) {
+    // lowest ring at or after `rot` (rotating start: no ring is favoured)
+    const unsigned rr = ((rings >> rot) | (rings << (a.world - rot))) & ((1u << a.world) - 1u);
+    const int r = static_cast<int>((__ffs(rr) - 1 + rot) % a.world);
+    const unsigned long long cur = s_cur[w.wic][r];
+    const int navail = kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1));
+    bool valid = false;
+    uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+    if (w.lane < navail) {
+      const unsigned long long idx = cur + w.lane;
+      const uint4* slot = a.ring + ((static_cast<size_t>(r) << a.cap_shift) + (idx & w.cap_mask)) * 2;
+      m0 = ld_volatile_v4(slot);
+      m1 = ld_volatile_v4(slot + 1);
+      const uint32_t tag = mesh_tag(w, a, idx);
+      valid = m0.x == tag && m1.x == tag;  // both halves of THIS message have landed
+    }
+    const unsigned vm = __ballot_sync(kFull, valid);
+    const int v = __ffs(~vm) - 1;  // messages in order from the cursor
+    const int take = min(v, want);
+    if (take > 0) {
+      // the k-th idle group takes the k-th message
+      const int k = __popc(needers & ((1u << w.gleader) - 1u));
+      const int src = min(k, 31);
+      const uint32_t id = __shfl_sync(kFull, m0.y, src), alo = __shfl_sync(kFull, m0.z, src),
+                     ahi = __shfl_sync(kFull, m0.w, src), ii = __shfl_sync(kFull, m1.y, src),
+                     blo = __shfl_sync(kFull, m1.z, src), bhi = __shfl_sync(kFull, m1.w, src);
+      if (!have && k < take) {
+        s.id = id;
+        s.A = sext48(alo, ahi);
+        s.B = sext48(blo, bhi);
+        s.i = static_cast<int32_t>(ii);
+        s.phase = static_cast<int>((ahi >> 16) & 3u);
+        s.home = static_cast<int>((ahi >> 18) & 0xffu);
+        have = true;
+      }
+      for (int t = 0; t < take; t++) needers &= needers - 1;
+      want -= take;
+      w.n_recv += take;
+      if (w.lane == 0) {
+        unsigned long long nx = cur + take;
+        if ((nx & (kMeshBlock - 1)) == 0) nx += (w.W - 1) * kMeshBlock;  // this warp's next block of the ring
+        s_cur[w.wic][r] = nx;
+      }
+      __syncwarp();
+    }
+    rings &= ~(1u << r);
+  }
+}
+
+// Store the departing states into their owners' inboxes.  Warp-collective.
+__device__ __forceinline__ void mesh_send(MeshWarp& w, const MeshArgs& a, bool send, int dest, const MeshState& s) {
+  const bool mine = send && w.sub == 0;
+  unsigned todo = __ballot_sync(kFull, mine);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    const int d = __shfl_sync(kFull, dest, src);
+    const unsigned same = __ballot_sync(kFull, mine && dest == d);
+    unsigned long long base = 0;
+    if (w.lane == src) base = atomicAdd(&a.ctl->out_tail[d], static_cast<unsigned long long>(__popc(same)));
+    base = __shfl_sync(kFull, base, src);
+    if (mine && dest == d) {
+      const unsigned long long idx = base + __popc(same & lanemask_lt());
+      uint4 m0, m1;
+      pack_state(s, mesh_tag(w, a, idx), m0, m1);
+      uint4* slot = a.peer_ring[d] + ((static_cast<size_t>(a.rank) << a.cap_shift) + (idx & w.cap_mask)) * 2;
+      st_volatile_v4(slot, m0);
+      st_volatile_v4(slot + 1, m1);
+    }
+    w.n_sent += __popc(same);
+    todo &= ~same;
+  }
+}
+
+// `cnt` results were delivered: the rank that completes its batch tells everybody.
+__device__ __forceinline__ void mesh_delivered(const MeshWarp& w, const MeshArgs& a, unsigned delivered_mask) {
+  if (delivered_mask && w.lane == 0) {
+    const unsigned long long cnt = __popc(delivered_mask);
+    const unsigned long long old = atomicAdd(&a.ctl->done_count, cnt);
+    if (old + cnt == static_cast<unsigned long long>(a.n_mine)) {
+      __threadfence();
+      for (int r = 0; r < a.world; r++) st_volatile_u64(&a.peer_ctl[r]->rank_done[a.rank], a.epoch);
+    }
+  }
+}
+
+__device__ __forceinline__ int mesh_owner(const MeshArgs& a, int64_t row) {
+  return static_cast<int>(((row / a.block_size) * a.world) / a.nblocks);
+}
+
+// Idle warp: true when the batch is over everywhere (or has failed).
+__device__ __forceinline__ bool mesh_idle_exit(const MeshWarp& w, const MeshArgs& a, long long& idle_start, unsigned& backoff) {
+  const bool ok = w.lane >= a.world || ld_volatile_u64(&a.ctl->rank_done[w.lane]) >= a.epoch;
+  if (__all_sync(kFull, ok)) return true;
+  int st = 0;
+  if (w.lane == 0) st = *reinterpret_cast<volatile int*>(&a.ctl->status);
+  if (__shfl_sync(kFull, st, 0)) return true;
+  const long long now = clock64();
+  if (!idle_start) idle_start = now;
+  else if (now - idle_start > a.timeout_cycles) {
+    if (w.lane == 0) atomicExch(&a.ctl->status, 1);
+    return true;
+  }
+  __nanosleep(backoff);
+  backoff = min(backoff * 2, 2000u);
+  return false;
+}
+
+__device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshArgs& a, unsigned long long rounds,
+                                                 unsigned long long pairs, unsigned long long singles) {
+  if (w.lane == 0) {
+    atomicAdd(&a.ctl->stats[0], w.n_sent);
+    atomicAdd(&a.ctl->stats[1], w.n_recv);
+    atomicAdd(&a.ctl->stats[2], rounds);
+    atomicAdd(&a.ctl->stats[3], pairs);
+    atomicAdd(&a.ctl->stats[4], singles);
+    atomicAdd(&a.ctl->stats[5], w.n_empty);
+    atomicAdd(&a.ctl->stats[6], w.n_inject);
+  }
+}
+
+__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, unsigned long long (*s_cur)[kMeshMaxRanks]) {
+  MeshWarp w;
+  w.lane = threadIdx.x & 31;
+  w.sub = w.lane & 1;
+  w.gleader = w.lane & ~1;
+  w.wic = threadIdx.x >> 5;
+  w.W = static_cast<unsigned long long>(gridDim.x) * (kThreads / 32);
+  w.wid = static_cast<unsigned long long>(blockIdx.x) * (kThreads / 32) + w.wic;
+  w.cap_mask = (1u << a.cap_shift) - 1u;
+  w.ep16 = static_cast<uint32_t>(a.epoch & 0xffffu) << 16;
+  if (w.lane < kMeshMaxRanks) s_cur[w.wic][w.lane] = w.wid * kMeshBlock;
+  __syncwarp();
+  // a rank without patterns of its own has nothing to wait for
+  if (a.n_mine == 0 && blockIdx.x == 0 && threadIdx.x < a.world)
+    st_volatile_u64(&a.peer_ctl[threadIdx.x]->rank_done[a.rank], a.epoch);
+  return w;
+}
+
+// Claim new patterns of the own batch for the idle groups the inbox could not serve.  Returns the
+// batch-local index for this group or -1.  Warp-collective.
+__device__ __forceinline__ int64_t mesh_inject(MeshWarp& w, const MeshArgs& a, unsigned needers, bool have, bool& exhausted) {
+  const int want = __popc(needers);
+  unsigned long long base = ~0ull;
+  if (w.lane == 0) {
+    const unsigned long long inj = ld_volatile_u64(&a.ctl->injected), done = ld_volatile_u64(&a.ctl->done_count);
+    if (inj >= static_cast<unsigned long long>(a.n_mine)) base = ~0ull - 1;
+    else if (inj - done < a.window) base = atomicAdd(&a.ctl->injected, static_cast<unsigned long long>(want));
+  }
+  base = __shfl_sync(kFull, base, 0);
+  if (base == ~0ull - 1) { exhausted = true; return -1; }
+  if (base == ~0ull) return -1;
+  const unsigned long long idx = base + __popc(needers & ((1u << w.gleader) - 1u));
+  if (base + want >= static_cast<unsigned long long>(a.n_mine)) exhausted = true;
+  if (have || idx >= static_cast<unsigned long long>(a.n_mine)) return -1;
+  w.n_inject += (w.sub == 0);
+  return static_cast<int64_t>(idx);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im, const MeshArgs a) {
+  __shared__ unsigned long long s_cur[kThreads / 32][kMeshMaxRanks];
+  MeshWarp w = mesh_warp_init(a, s_cur);
+  MeshState s;
+  bool have = false, exhausted = a.n_mine == 0;
+  long long idle_start = 0;
+  unsigned backoff = 100, iter = 0;
+  unsigned long long n_rounds = 0, n_pairs = 0, n_singles = 0;
+
+  for (;; iter++) {
+    // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch
+    unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
+    if (needers) {
+      mesh_take_inbox(w, a, s_cur, static_cast<unsigned>((w.wid + iter) % a.world), needers, s, have);
+      if (needers && !exhausted) {
+        const int64_t k = mesh_inject(w, a, needers, have, exhausted);
+        if (k >= 0) {
+          s.id = static_cast<uint32_t>(a.pid_lo + k);
+          const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.id];
+          const uint16_t* pat = a.flat + (a.uniform_len > 0 ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
+          if (m <= 0) {  // empty pattern: every row (server.c:782-808)
+            s.A = 0; s.B = im.total_length - 1; s.i = 0;
+          } else {
+            const int c = pat[m - 1];
+            if (c >= kAlphaDev) { s.A = im.total_length; s.B = s.A - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
+            else { s.A = __ldg(im.C + c); s.B = __ldg(im.C + c + 1) - 1; }
+            s.i = m - 1;
+          }
+          s.phase = kPhaseA;
+          s.home = a.rank;
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(kFull, have)) {
+      if (mesh_idle_exit(w, a, idle_start, backoff)) break;
+      continue;
+    }
+    idle_start = 0;
+    backoff = 100;
+
+    // ---- 2. what happens to each state in this round
+    bool send = false, deliver = false, doA = false, doB = false;
+    int dest = 0, c = 0;
+    int64_t rowA = 0, rowB = 0;
+    if (have) {
+      if (s.phase == kPhaseDone) {
+        deliver = true;
+      } else if (s.phase == kPhaseA && (s.A > s.B || s.i == 0)) {  // ends the reference's loop (server.c:832-841)
+        if (s.home == a.rank) deliver = true;
+        else { s.phase = kPhaseDone; send = true; dest = s.home; }
+      } else {
+        const int m = a.uniform_len > 0 ? a.uniform_len : 0;
+        const uint16_t* pat = a.flat + (m ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
+        c = pat[s.i - 1];
+        if (s.phase == kPhaseA && c >= kAlphaDev) {  // symbol outside the alphabet: empty range
+          s.A = im.total_length; s.B = s.A - 1; s.i--;
+        } else {
+          if (s.phase == kPhaseA) {
+            if (s.A == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
+              s.A = __ldg(im.C + c);
+              s.phase = kPhaseB;
+            } else {
+              rowA = s.A - 1;
+              if (rowA >= im.first_row && rowA < im.end_row) doA = true;
+              else { send = true; dest = mesh_owner(a, rowA); }
+            }
+          }
+          if (!send) {
+            rowB = s.B;
+            const bool resB = rowB >= im.first_row && rowB < im.end_row;
+            if (s.phase == kPhaseB) {
+              if (resB) doB = true;
+              else { send = true; dest = mesh_owner(a, rowB); }
+            } else if (resB) {  // both rows here: one round when they share a bucket, else A now and B next
+              int64_t gA, gB;
+              uint32_t ra, rb;
+              split_row(im, rowA, gA, ra);
+              split_row(im, rowB, gB, rb);
+              doB = gA == gB;
+            }
+          }
+        }
+      }
+    }
+
+    // ---- 3. results that are home
+    if (deliver) {
+      if (w.sub == 0) {
+        const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
+        if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
+        else a.first[slot] = s.B - s.A + 1;  // parallel_count with last==NULL (femto.c:313-318)
+      }
+      have = false;
+    }
+    mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
+
+    // ---- 4. states whose next row lives elsewhere
+    mesh_send(w, a, send, dest, s);
+    if (send) have = false;
+
+    // ---- 5. the Occ evaluations that can be done here, all groups together
+    const bool any = doA || doB;
+    if (__any_sync(kFull, any)) {
+      uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0, rexit = 0;
+      int L = 0;
+      int64_t ob = 0;
+      bool actA = false, actB = false;
+      if (any) {
+        int64_t g = 0, g2;
+        uint32_t ra = 0, rb = 0;
+        if (doA) split_row(im, rowA, g, ra);
+        if (doB) split_row(im, rowB, doA ? g2 : g, rb);
+        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
+        ob = rec_occ_base(rv);
+        leaf = static_cast<uint32_t>(rv.z);
+        rexit = static_cast<uint32_t>(rv.w);
+        base = static_cast<uint32_t>(g * im.root_stride);
+        node = rexit >> 4;
+        idxA = ra + 1;
+        idxB = rb + 1;
+        if (leaf) {  // else: symbol absent from the bucket, Occ is the bucket base (index.c:2080-2089)
+          L = 31 - __clz(leaf);
+          actA = doA;
+          actB = doB;
+        }
+        if (w.sub == 0) {
+          n_rounds++;
+          if (doA && doB) n_pairs++; else n_singles++;
+        }
+      }
+      quad_descend_pair(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub);
+      if (any) {
+        const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
+        if (doA && doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; }
+        else if (doA) { s.A = resA; s.phase = kPhaseB; }
+        else { s.B = resB - 1; s.i--; s.phase = kPhaseA; }  // A already holds C[c]+Occ(c,first-1)
+      }
+    }
+  }
+  mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles);
+}
+
+cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas,
+                        cudaStream_t stream, int64_t* launch_counter) {
+  if (im.levels != 4) return cudaErrorInvalidValue;  // quad-level image only
+  if (a.world < 1 || a.world > kMeshMaxRanks || a.cap_shift < 4 || a.cap_shift > 30) return cudaErrorInvalidValue;
+  int bps = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, kThreads, 0);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) bps = 1;
+  int grid = sm_count * bps;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  // cooperative launch: every CTA of the grid is resident at once -- each warp owns a share of the
+  // inbox, so a CTA that is not running would leave its share unread
+  DevImage im_copy = im;
+  MeshArgs a_copy = a;
+  void* args[2] = {&im_copy, &a_copy};
+  static const bool plain = [] { const char* v = std::getenv("FEMTO_B200_MESH_COOP"); return v && v[0] == '0'; }();
+  if (plain) e = cudaLaunchKernel(kernel, dim3(grid), dim3(kThreads), args, 0, stream);  // debugging aid
+  else e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), args, 0, stream);
+  if (e != cudaSuccess) return e;
+  if (launch_counter) ++*launch_counter;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_mesh_count(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
+                              int64_t* launch_counter) {
+  return launch_mesh(reinterpret_cast<const void*>(&mesh_count_kernel), im, a, sm_count, max_ctas, stream,
+                     launch_counter);
+}
+
+cudaError_t launch_mesh_walk(const DevImage&, const MeshArgs&, int, int, cudaStream_t, int64_t*) {
+  return cudaErrorNotSupported;
+}
+
+}  // namespace fmb

@@ -158,6 +158,16 @@ def sharded_locate_rows(walk_fn: WalkFn, rows: torch.Tensor, rank: int, world: i
     return out[:n], rounds
 
 
+def take_walk_status(ix) -> int:
+    """Status word of the caller-stream walk launches enqueued so far (fm_take_status): 0, or the code
+    of a malformed walk.  sharded_locate checks it after its exchange loop."""
+    import ctypes as C
+    from . import _check
+    st = C.c_int(0)
+    _check(ix.lib.fm_take_status(ix.h, torch.cuda.current_stream().cuda_stream, C.byref(st)), "fm_take_status")
+    return int(st.value)
+
+
 def expand_ranges(first: torch.Tensor, last: torch.Tensor, max_occs: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Rows first..last of every non-empty range, clipped the way parallel_locate clips them
     (src/main/server.c:4411-4415: ``last - first > max_occs`` cuts to max_occs rows, so a range
@@ -193,3 +203,123 @@ def cuda_walk_fn(ix, nshards: int) -> WalkFn:
                "fm_locate_shard_step")
 
     return walk
+
+
+# ---- device-initiated exchange ("mesh", femto_b200/csrc/fm_mesh.cuh) ----------------------------------
+class Mesh:
+    """One rank's end of the device-initiated exchange (``fm_mesh_*``): a persistent kernel per GPU
+    stores pattern states straight into the inbox of the GPU owning the row they need next, over
+    NVLink peer memory.  Nothing here touches the data path: this class creates the inbox, hands its
+    CUDA IPC handle to the other ranks (``torch.distributed``), and launches one kernel per batch.
+
+    Several ranks living in ONE process (tests on a single GPU) are wired with ``Mesh.connect_local``.
+    """
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ix, rank: int, world: int, window: int = 0, cap_log2: int = 0, group=None,
+                 connect: bool = True):
+        import ctypes as C
+        from . import _check
+        self.ix, self.rank, self.world, self.group = ix, rank, world, group
+        self.lib = ix.lib
+        h = C.c_void_p()
+        _check(self.lib.fm_mesh_create(ix.h, rank, world, window, cap_log2, C.byref(h)), "fm_mesh_create")
+        self.h = h
+        if connect and world > 1:
+            buf = C.create_string_buffer(self.HANDLE_BYTES)
+            _check(self.lib.fm_mesh_export(self.h, buf, self.HANDLE_BYTES), "fm_mesh_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(buf.raw), group=group)
+            blob = b"".join(handles)
+            _check(self.lib.fm_mesh_connect(self.h, blob, self.HANDLE_BYTES), "fm_mesh_connect")
+
+    @staticmethod
+    def connect_local(meshes) -> None:
+        """Wire the meshes of all ranks of ONE process to each other (no IPC)."""
+        import ctypes as C
+        from . import _check
+        arr = (C.c_void_p * len(meshes))(*[m.h for m in meshes])
+        for m in meshes:
+            _check(m.lib.fm_mesh_connect_local(m.h, arr), "fm_mesh_connect_local")
+
+    def set_limits(self, max_ctas: int = 0, timeout_seconds: float = 0.0) -> None:
+        from . import _check
+        _check(self.lib.fm_mesh_set_limits(self.h, max_ctas, timeout_seconds), "fm_mesh_set_limits")
+
+    def launch_count(self, d_plen, d_flat, d_offs, uniform_len: int, pid_lo: int, n_mine: int, d_first, d_last,
+                     stream: Optional[int] = None) -> None:
+        """Asynchronous: this rank's share of the batch (global pattern ids [pid_lo, pid_lo+n_mine))."""
+        from . import _check
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        _check(self.lib.fm_mesh_count(self.h, ptr(d_plen), ptr(d_flat), ptr(d_offs), uniform_len, pid_lo, n_mine,
+                                      ptr(d_first), ptr(d_last), st), "fm_mesh_count")
+
+    def launch_locate_rows(self, d_rows, d_offsets, stream: Optional[int] = None) -> None:
+        from . import _check
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _check(self.lib.fm_mesh_locate_rows(self.h, int(d_rows.shape[0]), d_rows.data_ptr(), d_offsets.data_ptr(), st),
+               "fm_mesh_locate_rows")
+
+    def finish(self, stream: Optional[int] = None) -> dict:
+        """Wait for the batch; raises if the kernel gave up.  Returns its counters."""
+        import ctypes as C
+        from . import _check
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        status = C.c_int(0)
+        stats = (C.c_uint64 * 8)()
+        _check(self.lib.fm_mesh_finish(self.h, st, C.byref(status), stats), "fm_mesh_finish")
+        names = ["sent", "received", "rounds", "occ_pairs", "occ_singles", "empty_polls", "injected"]
+        return {k: int(stats[i]) for i, k in enumerate(names)}
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.fm_mesh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gather_uniform_batch(my_pats: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """Replicate a batch of equal-length patterns: every rank contributes my_pats [n, m] (same n on
+    every rank) and receives [world * n, m]; rank r's patterns are ids [r*n, (r+1)*n).  This
+    all-gather is the only collective of a mesh batch (NCCL over NVLink; gloo in the CPU tests)."""
+    if world == 1:
+        return my_pats
+    out = torch.empty((world * my_pats.shape[0], my_pats.shape[1]), dtype=my_pats.dtype, device=my_pats.device)
+    dist.all_gather_into_tensor(out, my_pats.contiguous(), group=group)
+    return out
+
+
+def gather_ragged_batch(plen: torch.Tensor, flat: torch.Tensor, world: int, group=None):
+    """Replicate a batch of patterns of any lengths.  Every rank contributes its plen [n_r] and flat
+    symbols; returns (plen_all, flat_all, offs_all, pid_lo) with rank r's patterns at ids
+    [pid_lo_r, pid_lo_r + n_r).  Two small all-gathers size the exchange, two padded ones move it."""
+    dev = plen.device
+    if world == 1:
+        offs = torch.cumsum(plen.to(torch.int64), 0) - plen.to(torch.int64)
+        return plen, flat, offs, 0
+    rank = dist.get_rank(group)
+    sizes = torch.tensor([plen.shape[0], flat.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes.view(-1), sizes, group=group)
+    all_sizes = all_sizes.cpu()
+    max_n, max_f = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    pl = torch.zeros(max_n, dtype=plen.dtype, device=dev)
+    pl[:plen.shape[0]] = plen
+    fl = torch.zeros(max_f, dtype=flat.dtype, device=dev)
+    fl[:flat.shape[0]] = flat
+    pl_all = torch.empty((world, max_n), dtype=plen.dtype, device=dev)
+    fl_all = torch.empty((world, max_f), dtype=flat.dtype, device=dev)
+    dist.all_gather_into_tensor(pl_all.view(-1), pl, group=group)
+    dist.all_gather_into_tensor(fl_all.view(-1), fl, group=group)
+    plen_all = torch.cat([pl_all[r, :int(all_sizes[r, 0])] for r in range(world)])
+    flat_all = torch.cat([fl_all[r, :int(all_sizes[r, 1])] for r in range(world)])
+    offs_all = torch.cumsum(plen_all.to(torch.int64), 0) - plen_all.to(torch.int64)
+    pid_lo = int(all_sizes[:rank, 0].sum())
+    return plen_all, flat_all, offs_all, pid_lo

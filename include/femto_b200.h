@@ -138,6 +138,49 @@ int fm_locate_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, int3
                          void* stream);
 
 /* --------------------------------------------------------------------------
+ * Device-initiated exchange for the range-sharded index ("mesh").  One fm_mesh_t per rank (GPU),
+ * bound to an index opened with fm_open_shard(path, dev, rank, world).  Every rank runs ONE
+ * persistent kernel per batch; a pattern's 32-byte state is stored straight into the inbox of the
+ * GPU owning the BWT row its next Occ needs, over NVLink peer memory, and returns to its home
+ * rank with [first, last] -- no host round trip and no collective inside a batch
+ * (femto_b200/csrc/fm_mesh.cuh).  Partition unit = the reference's data block
+ * (src/main/index.h:83-100); the computation per state is do_string_query's (src/main/server.c:713-946).
+ *
+ * Set-up (collective): fm_mesh_create on every rank with the same world / window / cap_log2;
+ * exchange the FM_MESH_HANDLE_BYTES handles of fm_mesh_export between the processes (any transport;
+ * femto_b200/sharded.py uses torch.distributed) and pass all of them, in rank order, to
+ * fm_mesh_connect -- or, for ranks living in ONE process, fm_mesh_connect_local with the peers'
+ * fm_mesh_t.  window = patterns of its own batch a rank keeps in flight (0 = default); cap_log2 = 0
+ * sizes the inbox rings from it.
+ *
+ * Per batch (collective, asynchronous on `stream`): the pattern batch of ALL ranks is replicated on
+ * every rank (d_plen / d_flat / d_offs indexed by global pattern id; uniform_len > 0: pattern p is
+ * d_flat[p * uniform_len ...) and d_plen / d_offs are not read); this rank's patterns are ids
+ * [pid_lo, pid_lo + n_mine), their results go to d_first / d_last [0, n_mine) (d_last NULL: counts).
+ * A rank must not launch batch k+1 before every rank has finished batch k-1 (the all-gather that
+ * replicates the patterns provides that).  fm_mesh_finish waits for the stream and reports the
+ * kernel's status (FM_ERR_CANCELED: it gave up waiting for the other ranks) and counters
+ * {states sent, received, evaluation rounds, Occ pairs, single Occ, empty inbox polls, patterns
+ * injected, 0}. */
+typedef struct fm_mesh fm_mesh_t;
+#define FM_MESH_HANDLE_BYTES 64
+int fm_mesh_create(fm_index_t* ix, int rank, int world, int64_t window, int cap_log2, fm_mesh_t** out);
+void fm_mesh_destroy(fm_mesh_t* m);
+int fm_mesh_export(fm_mesh_t* m, void* handle, int64_t handle_bytes);
+int fm_mesh_connect(fm_mesh_t* m, const void* handles, int64_t handle_stride);
+int fm_mesh_connect_local(fm_mesh_t* m, fm_mesh_t* const* peers);
+/* max_ctas > 0 bounds the kernel's grid (several meshes sharing one GPU must all be resident at
+ * once); timeout_seconds > 0 replaces the 10 s a kernel waits for the other ranks before giving up. */
+int fm_mesh_set_limits(fm_mesh_t* m, int max_ctas, double timeout_seconds);
+int fm_mesh_count(fm_mesh_t* m, const int32_t* d_plen, const uint16_t* d_flat, const int64_t* d_offs,
+                  int uniform_len, int64_t pid_lo, int64_t n_mine, int64_t* d_first, int64_t* d_last,
+                  void* stream);
+/* Sampled-SA walks (parallel_locate_range's per-row work, src/main/femto.c:481-536) for this rank's
+ * nrows global BWT rows; d_offsets[k] = SA[d_rows[k]].  Collective like fm_mesh_count. */
+int fm_mesh_locate_rows(fm_mesh_t* m, int64_t nrows, const int64_t* d_rows, int64_t* d_offsets, void* stream);
+int fm_mesh_finish(fm_mesh_t* m, void* stream, int* status, uint64_t* stats8);
+
+/* --------------------------------------------------------------------------
  * locate.  Mirrors parallel_locate (src/main/femto.c:331-399): for pattern i,
  * noccs[i] offsets are returned in BWT row order first..; offsets[i] is malloc()ed
  * by the callee and freed by the caller with free() (NULL when noccs[i]==0).
@@ -160,6 +203,13 @@ int fm_locate_range(fm_index_t* ix, int64_t first, int64_t last, int64_t* offset
 int fm_locate_rows(fm_index_t* ix, int64_t nrows, const int64_t* rows, int64_t* offsets);
 int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, int64_t* d_offsets,
                           void* stream);
+
+/* Status of the caller-stream walk launches (fm_locate_rows_device, fm_locate_shard_step) enqueued on
+ * `stream` so far: waits for the stream, returns 0 or the code of a malformed walk (1 row not
+ * resident / out of range, 2 symbol or occurrence number out of range, 3 unmarked document start)
+ * and clears it.  The host-buffer calls keep their own status word and report through their return
+ * value. */
+int fm_take_status(fm_index_t* ix, void* stream, int* status);
 
 /* --------------------------------------------------------------------------
  * Single LF step with mark test = do_back_query (src/main/server.c:2228-2359):
