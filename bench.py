@@ -73,6 +73,10 @@ def parse_args():
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-big-locate", action="store_true", help="skip the locate leg over the whole batch")
+    ap.add_argument("--no-sharded-leg", action="store_true",
+                    help="N>1: skip the leg that runs the same batches on the index range-sharded over the N GPUs")
+    ap.add_argument("--mesh-window", type=int, default=0, help="sharded leg: own patterns in flight per rank (0 = default)")
     ap.add_argument("--pointer-api", action="store_true",
                     help="also time fm_count (the reference's parallel_count prototype: one pointer per pattern)")
     ap.add_argument("--ref-worker", nargs=3, metavar=("INDEX", "PATS_NPZ", "OUT_NPZ"), help=argparse.SUPPRESS)
@@ -395,35 +399,64 @@ def main():
                        "value": round(npats / dt, 1), "unit": "patterns/s"}
 
     # ---- locate (BASELINE configs[2]): text-sampled patterns, count + SA-sample walk, host buffers ----
+    from femto_b200 import sharded as _sh
+
+    def locate_leg(nloc, reps):
+        """fm_locate_flat on the first nloc patterns of batch 0 (pinned buffers in and out), then the walk
+        kernel alone on the same rows (device-resident, CUDA events) with its counters for the roofline."""
+        loc_cap = nloc * 8
+        h_noccs = torch.zeros(nloc, dtype=torch.int32).pin_memory()
+        h_lstart = torch.zeros(nloc, dtype=torch.int64).pin_memory()
+        h_lout = torch.zeros(loc_cap, dtype=torch.int64).pin_memory()
+
+        def step_locate():
+            rc = lib.fm_locate_flat(ix.h, nloc, C.cast(h_plen.data_ptr(), C.POINTER(C.c_int32)),
+                                    C.cast(h_flat[0].data_ptr(), C.POINTER(C.c_uint16)),
+                                    C.cast(h_offs.data_ptr(), C.POINTER(C.c_int64)), 2**31 - 1,
+                                    C.cast(h_noccs.data_ptr(), C.POINTER(C.c_int32)),
+                                    C.cast(h_lstart.data_ptr(), C.POINTER(C.c_int64)),
+                                    C.cast(h_lout.data_ptr(), C.POINTER(C.c_int64)), loc_cap)
+            if rc:
+                raise RuntimeError(f"fm_locate_flat rc={rc}: {lib.fm_last_error()}")
+
+        step_locate()                                                                             # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step_locate()
+        barrier()
+        locate_s = (time.perf_counter() - t0) / reps
+        # the walk kernel alone: rows of the same patterns, resident in HBM
+        ix.count_device(nloc, d_plen.data_ptr(), batches[0].data_ptr(), d_offs.data_ptr(),
+                        d_first.data_ptr(), d_last.data_ptr(), stream)
+        rows, _cnt = _sh.expand_ranges(d_first[:nloc], d_last[:nloc], 2**31 - 1)
+        rows = rows.contiguous()
+        d_woff = torch.empty_like(rows)
+        wev0, wev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(reps + 1):
+            if it == 1:
+                wev0.record()
+            rc = lib.fm_locate_rows_device(ix.h, rows.numel(), rows.data_ptr(), d_woff.data_ptr(), stream)
+            assert rc == 0
+        wev1.record()
+        torch.cuda.synchronize()
+        walk_ms = wev0.elapsed_time(wev1) / reps
+        assert (d_woff.cpu().numpy() == h_lout.numpy()[:rows.numel()]).all(), "walk kernel and fm_locate_flat disagree"
+        return {"nloc": nloc, "locate_s": locate_s, "walk_ms": walk_ms, "rows": rows.cpu().numpy(),
+                "noccs": h_noccs.numpy(), "lstart": h_lstart.numpy(), "lout": h_lout.numpy()}
+
     nloc = min(args.locate_npats, npats)
-    loc_flat = h_flat[0].numpy()[:nloc].reshape(-1).view(np.uint16)
-    loc_plen, loc_offs = h_plen.numpy()[:nloc], h_offs.numpy()[:nloc]
-    loc_cap = nloc * 8
-    # results land in pinned, preallocated host buffers, as for the count leg (the ctypes convenience
-    # wrapper Index.locate_flat allocates and zero-fills pageable arrays per call: not part of the path)
-    h_noccs = torch.zeros(nloc, dtype=torch.int32).pin_memory()
-    h_lstart = torch.zeros(nloc, dtype=torch.int64).pin_memory()
-    h_lout = torch.zeros(loc_cap, dtype=torch.int64).pin_memory()
-
-    def step_locate():
-        rc = lib.fm_locate_flat(ix.h, nloc, C.cast(h_plen.data_ptr(), C.POINTER(C.c_int32)),
-                                C.cast(h_flat[0].data_ptr(), C.POINTER(C.c_uint16)),
-                                C.cast(h_offs.data_ptr(), C.POINTER(C.c_int64)), 2**31 - 1,
-                                C.cast(h_noccs.data_ptr(), C.POINTER(C.c_int32)),
-                                C.cast(h_lstart.data_ptr(), C.POINTER(C.c_int64)),
-                                C.cast(h_lout.data_ptr(), C.POINTER(C.c_int64)), loc_cap)
-        if rc:
-            raise RuntimeError(f"fm_locate_flat rc={rc}: {lib.fm_last_error()}")
-
-    step_locate()                                                                             # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        step_locate()
-    barrier()
-    locate_s = (time.perf_counter() - t0) / 5
-    noccs, lstart, lout = h_noccs.numpy(), h_lstart.numpy(), h_lout.numpy()
+    leg = locate_leg(nloc, 5)
+    locate_s, noccs, lstart, lout = leg["locate_s"], leg["noccs"], leg["lstart"], leg["lout"]
     locate_results = int(noccs.sum())
+    big = locate_leg(npats, 3) if npats > nloc and not args.no_big_locate else None
+
+    # ---- sharded leg (N > 1): the same index split by BWT row range over the N GPUs, pattern states
+    # exchanged by the GPUs themselves (fm_mesh_*), results compared with the replica leg's -----------
+    sharded_leg = None
+    if world > 1 and not args.no_sharded_leg:
+        sharded_leg = run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, d_last,
+                                   rank, world, local, device)
 
     # ---- max over ranks ---------------------------------------------------------------------
     times = torch.tensor([kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
@@ -493,6 +526,35 @@ def main():
             "peak_source": "fm_probe_random_reads: dependent uniform random reads over the same image, all SMs"}
     except Exception as e:  # noqa: BLE001
         roofline["random_access"] = {"error": str(e)}
+
+    # ---- locate roofline: the walk kernel's counters (instrumented replay) over its CUDA-event time ----
+    def locate_roofline(lg):
+        ws = ix.walk_stats(lg["rows"])
+        nrows = int(lg["rows"].shape[0])
+        # per wavelet-tree block: 64 B of bits + 12 B of header entries + the 8 B exit entry; per mark block
+        # the 128 B line + the symbol's 8 B mark record and 16 B occ record; per LF step the 16 B bucket
+        # record; 8 B per SA sample; 16 B per row in and out
+        alg = (ws["wtree_blocks"] * (64 + 12 + 8) + ws["mark_blocks"] * (128 + 8 + 16) + ws["lf_steps"] * 16 +
+               ws["sa_samples"] * 8 + nrows * 16)
+        t = lg["walk_ms"] / 1e3
+        acc = ws["wtree_blocks"] + ws["mark_blocks"] + ws["sa_samples"]
+        r = {"bound": "hbm", "kernel": "walk_kernel (locate)", "kernel_ms": round(lg["walk_ms"], 4), "rows": nrows,
+             "achieved": round(alg / t / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(alg / t / 1e9 / peak, 4),
+             "algorithmic_bytes_per_launch": int(alg), "traffic": None, **ws,
+             "lf_steps_per_row": round(ws["lf_steps"] / max(nrows, 1), 2)}
+        ra = roofline.get("random_access", {})
+        if "peak_gaccess_s" in ra:
+            r["random_access"] = {"achieved_gaccess_s": round(acc / t / 1e9, 2), "peak_gaccess_s": ra["peak_gaccess_s"],
+                                  "frac": round(acc / t / 1e9 / ra["peak_gaccess_s"], 4)}
+        return r
+
+    locate_roof = locate_roofline(leg)
+    big_locate = None
+    if big is not None:
+        big_locate = {"patterns": big["nloc"], "occurrences": int(big["noccs"].sum()),
+                      "value": round(big["nloc"] / big["locate_s"], 1), "unit": "patterns/s",
+                      "ms_per_batch": round(big["locate_s"] * 1e3, 3), "api": "fm_locate_flat",
+                      "roofline": locate_roofline(big)}
 
     # ---- cpu_baseline + in-run parity: the unmodified reference on a bounded sample ----------
     cpu = None
@@ -568,14 +630,87 @@ def main():
         "locate": {"metric": "patterns/sec (locate, count + SA-sample walk, host buffers in/out)",
                    "value": round(nloc / locate_s, 1), "unit": "patterns/s", "patterns": nloc,
                    "occurrences": locate_results, "ms_per_batch": round(locate_s * 1e3, 3),
-                   "api": "fm_locate_flat", "cpu_baseline": locate_cpu},
+                   "api": "fm_locate_flat", "cpu_baseline": locate_cpu, "roofline": locate_roof,
+                   "whole_batch": big_locate},
     }
+    if sharded_leg is not None:
+        sharded_leg["per_gpu_vs_replica"] = round(sharded_leg["value"] / value, 4)
+        out["sharded"] = sharded_leg
     print(json.dumps(out), flush=True)
     ix.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, d_last, rank, world, local, device):
+    """The batches of the replica leg counted on the index split in `world` BWT row ranges (one per GPU):
+    per step one NCCL all-gather replicates the ranks' patterns, then ONE persistent kernel per GPU runs
+    the whole batch, states hopping between the GPUs through peer memory.  Timed like the main leg
+    (CUDA events, barrier + synchronize on both sides, max over ranks); the last step's results must be
+    bit-identical to the replica leg's for the same batch."""
+    import torch
+    import torch.distributed as dist
+    from femto_b200 import sharded
+    npats, m = args.npats, args.plen
+    t0 = time.time()
+    ixs = fb.Index(index_path, device=local, shard=rank, nshards=world)
+    load_s = time.time() - t0
+    mesh = sharded.Mesh(ixs, rank, world, window=args.mesh_window)
+    s_first = torch.empty(npats, dtype=torch.int64, device=device)
+    s_last = torch.empty(npats, dtype=torch.int64, device=device)
+
+    def step(b):
+        allp = sharded.gather_uniform_batch(batches[b % nbatch], world)
+        mesh.launch_count(None, allp, None, m, rank * npats, npats, s_first, s_last)
+        return allp          # keep the gathered batch alive until the kernel has run
+
+    keep = []
+    for w in range(args.warmup):
+        keep.append(step(w))
+    stats = mesh.finish()
+    keep.clear()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ixs.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(args.steps):
+        keep.append(step(args.warmup + s))
+    ev1.record()
+    stats = mesh.finish()
+    dist.barrier()
+    torch.cuda.synchronize()
+    keep.clear()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = ixs.kernel_launches() - launches0
+    # parity: the replica kernel on the batch of the last sharded step
+    step_resident(args.warmup + args.steps - 1)
+    torch.cuda.synchronize()
+    ok = torch.tensor([int(bool((s_first == d_first).all() and (s_last == d_last).all()))], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    tot = torch.tensor([stats["sent"], stats["received"], stats["rounds"], stats["occ_pairs"], stats["occ_singles"],
+                        stats["empty_polls"]], dtype=torch.float64, device=device)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    info = ixs.info
+    leg = {"metric": "patterns/sec (count), index range-sharded by data block over the GPUs",
+           "value": round(npats * world / (float(ms[0]) / args.steps / 1e3), 1), "unit": "patterns/s",
+           "ms_per_step": round(float(ms[0]) / args.steps, 4), "bit_exact_vs_replica": bool(int(ok[0])),
+           "exchange": "device-initiated: persistent kernel per GPU, 32-byte states stored into the owner's inbox over "
+                       "NVLink peer memory; one NCCL all-gather of the patterns per step inside the timed region",
+           "gpu_launches_per_step": launches / args.steps,
+           "states_sent_per_pattern": round(float(tot[0]) / (npats * world), 2),
+           "occ_pairs": int(tot[3]), "occ_singles": int(tot[4]), "eval_rounds": int(tot[2]),
+           "empty_polls": int(tot[5]),
+           "shard_rows_rank0": [int(info.first_row), int(info.end_row)],
+           "shard_hbm_gib": round(info.hbm_bytes / 2**30, 2), "shard_load_s": round(load_s, 1)}
+    mesh.close()
+    ixs.close()
+    if not leg["bit_exact_vs_replica"]:
+        raise SystemExit("PARITY FAILURE: sharded results differ from the replica leg's")
+    return leg
 
 
 def run_sharded(args, index_path, text, workload, rank, world, local, device):

@@ -143,6 +143,13 @@ class Index:
         return {"block_reads": int(st[0]), "distinct_block_reads": int(st[1]), "occ_evals": int(st[2]),
                 "steps": int(st[3])}
 
+    def walk_stats(self, rows: np.ndarray) -> dict:
+        """Counters of one instrumented locate walk launch over `rows` (see fm_walk_stats)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        st = (C.c_uint64 * 4)()
+        _check(self.lib.fm_walk_stats(self.h, len(rows), _ptr(rows, C.c_int64), st), "fm_walk_stats")
+        return {"lf_steps": int(st[0]), "wtree_blocks": int(st[1]), "mark_blocks": int(st[2]), "sa_samples": int(st[3])}
+
     def probe_random_reads(self, bytes_per_access: int, steps: int = 400) -> dict:
         """Dependent random reads over the resident rank blocks (fm_probe_random_reads): the
         access-rate ceiling of this GPU's memory system for the count kernel's access shape."""

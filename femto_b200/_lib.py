@@ -70,6 +70,7 @@ PROTOTYPES = {
     "fm_set_default_block_bytes": (C.c_int, [C.c_int]),
     "fm_set_default_levels_per_block": (C.c_int, [C.c_int]),
     "fm_count_stats": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), P(C.c_uint64)]),
+    "fm_walk_stats": (C.c_int, [vp, i64, P(i64), P(C.c_uint64)]),
     "fm_probe_random_reads": (C.c_int, [vp, C.c_int, C.c_int, P(i64), P(C.c_double)]),
     "fm_builder_create": (C.c_int, [C.c_char_p, i64, i64, P(i64), i32, i32, i32, i32, C.c_int, P(vp)]),
     "fm_builder_append": (C.c_int, [vp, i64, P(u16), P(i64)]),

@@ -943,6 +943,32 @@ int fm_locate_rows(fm_index_t* ix, int64_t nrows, const int64_t* rows, int64_t* 
   });
 }
 
+int fm_walk_stats(fm_index_t* ix, int64_t nrows, const int64_t* rows, uint64_t* stats4) {
+  return guarded(ix, "fm_walk_stats", [&]() -> int {
+    if (nrows < 0 || !stats4 || (nrows && !rows)) return fail(FM_ERR_PARAM, "fm_walk_stats: bad argument");
+    std::memset(stats4, 0, 4 * sizeof(uint64_t));
+    if (nrows == 0) return FM_OK;
+    cudaStream_t s = ix->stream;
+    int64_t* d_rows = static_cast<int64_t*>(ix->d_in[3].get(size_t(nrows) * 8));
+    int64_t* d_off = static_cast<int64_t*>(ix->d_out[2].get(size_t(nrows) * 8));
+    unsigned long long* d_stats = static_cast<unsigned long long*>(ix->d_out[3].get(64));
+    CK(cudaMemcpyAsync(d_rows, rows, size_t(nrows) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_stats, 0, 64, s));
+    WalkArgs w{};
+    w.nrows = nrows;
+    w.rows = d_rows;
+    w.out_offset = d_off;
+    w.status = ix->d_status;
+    w.stats = d_stats;
+    CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), s));
+    CK(launch_walk(ix->im, w, kWalkLocate, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(stats4, d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    const int st = walk_status(ix);
+    if (st) return fail(st == 1 ? FM_ERR_PARAM : FM_ERR_INVALID, "fm_walk_stats: malformed walk (status " + std::to_string(st) + ")");
+    return FM_OK;
+  });
+}
+
 int fm_locate_rows_device(fm_index_t* ix, int64_t nrows, const int64_t* d_rows, int64_t* d_offsets, void* stream) {
   return guarded(ix, "fm_locate_rows_device", [&]() -> int {
     if (nrows < 0) return fail(FM_ERR_PARAM, "fm_locate_rows_device: negative nrows");

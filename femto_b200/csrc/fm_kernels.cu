@@ -615,6 +615,8 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
 
   int64_t row = 0, rid = -1, steps = 0, nsteps = 0, sym_off = 0, meta = 0;
   bool have = false, exhausted = false;
+  // counters of the instrumented launches (WalkArgs::stats): LF steps, wavelet-tree blocks, mark blocks, SA samples
+  unsigned long long n_steps = 0, n_quad = 0, n_mark = 0, n_sample = 0;
   // kWalkShard: park the state for the rank that must see it next
   auto park = [&](int64_t value, int64_t phase, int dest) {
     if (lane == gleader) {
@@ -628,9 +630,14 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
 
   for (;;) {
     const bool need = !have && !exhausted;
+    // ONE atomic per warp for all the groups that need a row: consecutive queue positions in lane order
+    const unsigned askers = __ballot_sync(kFull, need && lane == gleader);
     unsigned long long idx = 0;
-    if (need && lane == gleader) idx = atomicAdd(work, 1ull);
-    idx = __shfl_sync(kFull, idx, gleader);
+    if (askers) {
+      const int first_asker = __ffs(askers) - 1;
+      if (lane == first_asker) idx = atomicAdd(work, static_cast<unsigned long long>(__popc(askers)));
+      idx = __shfl_sync(kFull, idx, first_asker) + __popc(askers & ((1u << gleader) - 1u));
+    }
     if (need) {
       if (static_cast<int64_t>(idx) < a.nrows) {
         rid = static_cast<int64_t>(idx);
@@ -681,63 +688,20 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
     uint64_t markval_base = 0;
     if (act) {
       split_row(im, row, g, rb);
-      const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
-      base = br.x;
-      node = br.y;
-      markval_base = static_cast<uint64_t>(br.z) | (static_cast<uint64_t>(br.w) << 32);
+      if (LV != 4) {  // (quad: the root block is addressed by the row; quad_wtree_rank reads the record beside it)
+        const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+        base = br.x;
+        node = br.y;
+        markval_base = static_cast<uint64_t>(br.z) | (static_cast<uint64_t>(br.w) << 32);
+      }
       idx1 = rb + 1;
     }
     bool desc = act;
+    (void)desc; (void)base; (void)node;
+    if (act && lane == gleader) n_steps++;
     if constexpr (LV == 4) {
       static_assert(LV != 4 || (LPQ == 2 && BW == kQuadBlockWords), "quad-level blocks: 2 lanes, 128 bytes");
-      const uint32_t* words = reinterpret_cast<const uint32_t*>(im.blocks);
-      while (__any_sync(kFull, desc)) {
-        const uint32_t p = desc ? idx1 - 1 : 0u;
-        const uint32_t blk = base + (p >> 7);
-        const uint32_t* hw = words + static_cast<size_t>(blk) * kQuadBlockWords;
-        QuadWords w;
-        w.clear();
-        if (desc) w.load(im.blocks, blk, sub);
-        const int lb = 64 * sub;
-        int j = static_cast<int>(p & 127u) + 1;
-        // level 0: follow the bit at our position; j stays >= 1 all the way down
-        uint32_t c = group_sum<2>(popc_top(w.d[0], j - lb) + popc_top(w.d[1], j - lb - 32));
-        uint32_t b = w.bit<0>(static_cast<uint32_t>(j - 1));
-        uint32_t path = b;
-        j = b ? c : j - c;
-        // level 1
-        int a = b ? kQuadPos - j : 0;
-        c = group_sum<2>(w.range<1>(a - lb, a + j - lb));
-        uint32_t nb = w.bit<1>(static_cast<uint32_t>(b ? a : a + j - 1));
-        j = nb ? c : j - c;
-        b = nb;
-        path = (path << 1) | b;
-        // level 2: anchor in the top byte of H[4 * (b1 b2)] (an L1 hit: the line was just read)
-        a = static_cast<int>((desc ? __ldg(hw + (path << 2)) : 0u) >> 24) - (b ? j : 0);
-        c = group_sum<2>(w.range<2>(a - lb, a + j - lb));
-        nb = w.bit<2>(static_cast<uint32_t>(b ? a : a + j - 1));
-        j = nb ? c : j - c;
-        b = nb;
-        path = (path << 1) | b;
-        // level 3: anchor in the top byte of H[2 * (b1 b2 b3) + 1]; the exits' counts below it
-        const uint2 h = desc ? __ldg(reinterpret_cast<const uint2*>(hw) + path) : make_uint2(0, 0);
-        a = static_cast<int>(h.y >> 24) - (b ? j : 0);
-        c = group_sum<2>(w.range<3>(a - lb, a + j - lb));
-        nb = w.bit<3>(static_cast<uint32_t>(b ? a : a + j - 1));
-        j = nb ? c : j - c;
-        path = (path << 1) | nb;
-        if (desc) {
-          const uint2 ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[path]));
-          idx1 = ((nb ? h.y : h.x) & 0xffffffu) + static_cast<uint32_t>(j);
-          if (ex.y & kChildLeaf) {
-            ch = ex.y & 0xffffu;
-            desc = false;
-          } else {
-            base = ex.x;
-            node = ex.y;
-          }
-        }
-      }
+      quad_wtree_rank(im, act, g, rb, sub, ch, idx1, markval_base, n_quad);
     } else if constexpr (LV == 2) {
       constexpr uint32_t B = kPairedSlicePos * (BW / kPairedSliceWords);
       while (__any_sync(kFull, desc)) {
@@ -809,22 +773,8 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
 
     // mark test: rank over the symbol's mark bit-vector at its occurrence number (index.c:2102-2140)
     const bool ok = act && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
-    uint32_t mark_base = 0, markval_off = 0;
-    int64_t occ_base = 0;
-    if (ok) {
-      const size_t rec = static_cast<size_t>(g) * kAlphaStride + ch;
-      const uint2 mr = __ldg(reinterpret_cast<const uint2*>(im.mark + rec));
-      mark_base = mr.x;
-      markval_off = mr.y;
-      occ_base = rec_occ_base(__ldg(reinterpret_cast<const int4*>(im.occ + rec)));
-    }
-    const uint32_t mp = ok ? count - 1 : 0u;
-    const uint32_t mk = mp / BITS;
-    const uint32_t moff = mp - mk * BITS;
-    uint32_t mones, mbit;
-    block_rank<LPQ, BW, true>(im.blocks, mark_base + mk, moff, ok, sub, mones, mbit);
-    int64_t offset = -1;
-    if (ok && mbit) offset = __ldg(im.markvals + markval_base + markval_off + (mones - 1));
+    int64_t occ_base = 0, offset = -1;
+    mark_lookup<LPQ, BW>(im, ok, g, ch, count, markval_base, sub, offset, occ_base, n_mark, n_sample);
     // LF: row' = C[ch] + occs before the bucket + count - 1; stop at a document boundary
     // (ch <= ESCAPE_CODE_SEOF, server.c:2341-2346)
     const int64_t next = (ch <= static_cast<uint32_t>(kEscSeofDev)) ? -1 : occ_base + count - 1;
@@ -879,6 +829,7 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
       }
     }
   }
+  if (a.stats) flush_stats(a.stats, lane, n_steps, n_quad, n_mark, n_sample);
 }
 
 // ---------------------------------------------------------------------------------------------

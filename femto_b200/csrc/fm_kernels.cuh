@@ -21,7 +21,7 @@ struct CountArgs {
   // copied in; *avail (device memory, written by the copy stream after each chunk) = number of
   // leading patterns whose plen / offs / symbols have arrived.  NULL = everything is there.
   const unsigned long long* avail;
-  int32_t* stalled;  // set to 1 if a pattern did not arrive within ~10 s (the launch then ends; results invalid)
+  int32_t* stalled;  // set to 1 if a pattern did not arrive within ~0.1 s (the launch then ends; results invalid)
   // > 0: every pattern has this length and pattern i starts at flat + i * uniform_len; plen and offs
   // are not read (and need not be copied in).
   int32_t uniform_len;
@@ -54,6 +54,9 @@ struct WalkArgs {
   int32_t nshards;
   int32_t block_size;    // rows per data block; owner(row) = (row / block_size) * nshards / nblocks
   int64_t nblocks;
+  // optional (4 x uint64, zeroed by the caller): LF steps, wavelet-tree rank blocks read (quad image),
+  // mark bit-vector blocks read, SA samples read -- what the locate roofline is computed from
+  unsigned long long* stats;
 };
 constexpr int kWalkStateWords = 4;
 

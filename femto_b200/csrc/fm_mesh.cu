@@ -244,9 +244,10 @@ __device__ __forceinline__ int64_t mesh_inject(MeshWarp& w, const MeshArgs& a, u
   if (base == ~0ull - 1) { exhausted = true; return -1; }
   if (base == ~0ull) return -1;
   const unsigned long long idx = base + __popc(needers & ((1u << w.gleader) - 1u));
-  if (base + want >= static_cast<unsigned long long>(a.n_mine)) exhausted = true;
-  if (have || idx >= static_cast<unsigned long long>(a.n_mine)) return -1;
-  w.n_inject += (w.sub == 0);
+  const unsigned long long n = static_cast<unsigned long long>(a.n_mine);
+  if (base + want >= n) exhausted = true;
+  if (base < n) w.n_inject += min(static_cast<unsigned long long>(want), n - base);
+  if (have || idx >= n) return -1;
   return static_cast<int64_t>(idx);
 }
 
@@ -394,6 +395,103 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
   mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sampled-SA walks over the range-sharded index.  State: id = result slot at the home rank, A = BWT
+// row (the text offset once finished, -1 for a malformed walk), i = LF steps taken so far.
+__global__ void __launch_bounds__(kThreads) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
+  __shared__ unsigned long long s_cur[kThreads / 32][kMeshMaxRanks];
+  MeshWarp w = mesh_warp_init(a, s_cur);
+  MeshState s;
+  bool have = false, exhausted = a.n_mine == 0;
+  long long idle_start = 0;
+  unsigned backoff = 100, iter = 0;
+  unsigned long long n_rounds = 0, n_quad = 0, n_mark = 0, n_sample = 0;
+
+  for (;; iter++) {
+    unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
+    if (needers) {
+      mesh_take_inbox(w, a, s_cur, static_cast<unsigned>((w.wid + iter) % a.world), needers, s, have);
+      if (needers && !exhausted) {
+        const int64_t k = mesh_inject(w, a, needers, have, exhausted);
+        if (k >= 0) {
+          s.id = static_cast<uint32_t>(k);
+          s.A = a.rows[k];
+          s.B = 0;
+          s.i = 0;
+          s.phase = kPhaseA;
+          s.home = a.rank;
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(kFull, have)) {
+      if (mesh_idle_exit(w, a, idle_start, backoff)) break;
+      continue;
+    }
+    idle_start = 0;
+    backoff = 100;
+
+    bool send = false, deliver = false, step = false;
+    int dest = 0;
+    if (have) {
+      if (s.phase != kPhaseDone && (s.A < 0 || s.A >= im.total_length)) {  // not a row of this index
+        if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+        s.A = -1;
+        s.phase = kPhaseDone;
+      }
+      if (s.phase == kPhaseDone) {
+        if (s.home == a.rank) deliver = true;
+        else { send = true; dest = s.home; }
+      } else if (s.A >= im.first_row && s.A < im.end_row) {
+        step = true;
+      } else {
+        send = true;
+        dest = mesh_owner(a, s.A);
+      }
+    }
+    if (deliver) {
+      if (w.sub == 0) a.out_offset[s.id] = s.A;
+      have = false;
+    }
+    mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
+    mesh_send(w, a, send, dest, s);
+    if (send) have = false;
+
+    // one LF step with mark test for every resident row (do_back_query, server.c:2228-2359)
+    if (__any_sync(kFull, step)) {
+      int64_t g = 0;
+      uint32_t rb = 0, ch = 0, count = 0;
+      uint64_t markval_base = 0;
+      if (step) {
+        split_row(im, s.A, g, rb);
+        if (w.sub == 0) n_rounds++;
+      }
+      quad_wtree_rank(im, step, g, rb, w.sub, ch, count, markval_base, n_quad);
+      const bool ok = step && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
+      int64_t occ_base = 0, offset = -1;
+      mark_lookup<2, kQuadBlockWords>(im, ok, g, ch, count, markval_base, w.sub, offset, occ_base, n_mark, n_sample);
+      if (step) {
+        if (!ok) {
+          if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+          s.A = -1;
+          s.phase = kPhaseDone;
+        } else if (offset >= 0) {
+          s.A = offset + s.i;
+          s.phase = kPhaseDone;
+        } else if (ch <= static_cast<uint32_t>(kEscSeofDev) || s.i > (1 << 30)) {  // unmarked document start
+          if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+          s.A = -1;
+          s.phase = kPhaseDone;
+        } else {
+          s.A = occ_base + count - 1;  // LF
+          s.i++;
+        }
+      }
+    }
+  }
+  mesh_flush_stats(w, a, n_rounds, n_quad, n_mark + n_sample);
+}
+
 cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas,
                         cudaStream_t stream, int64_t* launch_counter) {
   if (im.levels != 4) return cudaErrorInvalidValue;  // quad-level image only
@@ -425,8 +523,10 @@ cudaError_t launch_mesh_count(const DevImage& im, const MeshArgs& a, int sm_coun
                      launch_counter);
 }
 
-cudaError_t launch_mesh_walk(const DevImage&, const MeshArgs&, int, int, cudaStream_t, int64_t*) {
-  return cudaErrorNotSupported;
+cudaError_t launch_mesh_walk(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
+                             int64_t* launch_counter) {
+  return launch_mesh(reinterpret_cast<const void*>(&mesh_walk_kernel), im, a, sm_count, max_ctas, stream,
+                     launch_counter);
 }
 
 }  // namespace fmb

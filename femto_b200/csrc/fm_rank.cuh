@@ -550,5 +550,121 @@ __device__ __forceinline__ void quad_descend_pair(const DevImage& im, bool actA,
   }
 }
 
+// wtree_rank over quad-level blocks (wtree.c:1117-1148): follows the bits found at row rb of local
+// bucket g down to a leaf.  Returns the symbol there and `count` = this row holds the count-th
+// occurrence of it in the bucket.  Warp-collective; 2 lanes per group.
+//   * the root block is addressed by the row alone (root area, fm_image.hpp) and requested FIRST;
+//     the bucket record (root QuadRec, base of the SA samples) is read beside it, not before it;
+//   * both header sectors of a block are requested together with its bit regions, so that the
+//     anchors and exit counts, whose position depends on the bits found, are L1 hits by the time
+//     they are needed instead of a second trip to memory.
+__device__ __forceinline__ void quad_wtree_rank(const DevImage& im, bool act, int64_t g, uint32_t rb, int sub,
+                                                uint32_t& ch, uint32_t& count, uint64_t& markval_base,
+                                                unsigned long long& n_blocks) {
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(im.blocks);
+  uint32_t base = 0, node = 0, idx1 = 0;
+  bool desc = act;
+  bool root = true;
+  ch = 0;
+  markval_base = 0;
+  if (act) {
+    base = static_cast<uint32_t>(g * im.root_stride);
+    idx1 = rb + 1;
+  }
+  while (__any_sync(kFull, desc)) {
+    const uint32_t p = desc ? idx1 - 1 : 0u;
+    const uint32_t blk = base + (p >> 7);
+    const uint32_t* hw = words + static_cast<size_t>(blk) * kQuadBlockWords;
+    QuadWords w;
+    w.clear();
+    if (desc) {
+      w.load(im.blocks, blk, sub);
+      // touch both header sectors now (lane `sub` takes sector `sub`)
+      uint32_t t0, t1, t2, t3;
+      asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "l"(hw + 8 * sub));
+      n_blocks += (sub == 0);
+    }
+    if (root) {  // first block of the walk step: the bucket record travels beside it
+      if (desc) {
+        const uint4 br = __ldg(reinterpret_cast<const uint4*>(im.buckets + g));
+        node = br.y;
+        markval_base = static_cast<uint64_t>(br.z) | (static_cast<uint64_t>(br.w) << 32);
+      }
+      root = false;
+    }
+    const int lb = 64 * sub;
+    int j = static_cast<int>(p & 127u) + 1;
+    // level 0: follow the bit at our position; j stays >= 1 all the way down
+    uint32_t c = group_sum<2>(popc_top(w.d[0], j - lb) + popc_top(w.d[1], j - lb - 32));
+    uint32_t b = w.bit<0>(static_cast<uint32_t>(j - 1));
+    uint32_t path = b;
+    j = b ? c : j - c;
+    // level 1
+    int a = b ? kQuadPos - j : 0;
+    c = group_sum<2>(w.range<1>(a - lb, a + j - lb));
+    uint32_t nb = w.bit<1>(static_cast<uint32_t>(b ? a : a + j - 1));
+    j = nb ? c : j - c;
+    b = nb;
+    path = (path << 1) | b;
+    // level 2: anchor in the top byte of H[4 * (b1 b2)]
+    a = static_cast<int>((desc ? __ldg(hw + (path << 2)) : 0u) >> 24) - (b ? j : 0);
+    c = group_sum<2>(w.range<2>(a - lb, a + j - lb));
+    nb = w.bit<2>(static_cast<uint32_t>(b ? a : a + j - 1));
+    j = nb ? c : j - c;
+    b = nb;
+    path = (path << 1) | b;
+    // level 3: anchor in the top byte of H[2 * (b1 b2 b3) + 1]; the exits' counts below it
+    const uint2 h = desc ? __ldg(reinterpret_cast<const uint2*>(hw) + path) : make_uint2(0, 0);
+    a = static_cast<int>(h.y >> 24) - (b ? j : 0);
+    c = group_sum<2>(w.range<3>(a - lb, a + j - lb));
+    nb = w.bit<3>(static_cast<uint32_t>(b ? a : a + j - 1));
+    j = nb ? c : j - c;
+    path = (path << 1) | nb;
+    if (desc) {
+      const uint2 ex = __ldg(reinterpret_cast<const uint2*>(im.quads[node].exit[path]));
+      idx1 = ((nb ? h.y : h.x) & 0xffffffu) + static_cast<uint32_t>(j);
+      if (ex.y & kChildLeaf) {
+        ch = ex.y & 0xffffu;
+        desc = false;
+      } else {
+        base = ex.x;
+        node = ex.y;
+      }
+    }
+  }
+  count = idx1;
+}
+
+// The mark test and SA sample of a row that holds the count-th occurrence of ch in local bucket g
+// (block_request LOCATION branch, src/main/index.c:2102-2140), and what LF needs: returns
+// offset = SA[row] or -1 when the row is not marked, occ_base = C[ch] + occurrences of ch before the
+// bucket.  Mark bit-vectors are plain one-level blocks in every image.  Warp-collective.
+template <int LPQ, int BW>
+__device__ __forceinline__ void mark_lookup(const DevImage& im, bool ok, int64_t g, uint32_t ch, uint32_t count,
+                                            uint64_t markval_base, int sub, int64_t& offset, int64_t& occ_base,
+                                            unsigned long long& n_mark_blocks, unsigned long long& n_samples) {
+  constexpr uint32_t BITS = (BW - 1) * 32;
+  uint32_t mark_base = 0, markval_off = 0;
+  occ_base = 0;
+  if (ok) {
+    const size_t rec = static_cast<size_t>(g) * kAlphaStride + ch;
+    const uint2 mr = __ldg(reinterpret_cast<const uint2*>(im.mark + rec));
+    mark_base = mr.x;
+    markval_off = mr.y;
+    occ_base = rec_occ_base(__ldg(reinterpret_cast<const int4*>(im.occ + rec)));
+    n_mark_blocks += (sub == 0);
+  }
+  const uint32_t mp = ok ? count - 1 : 0u;
+  const uint32_t mk = mp / BITS;
+  const uint32_t moff = mp - mk * BITS;
+  uint32_t mones, mbit;
+  block_rank<LPQ, BW, true>(im.blocks, mark_base + mk, moff, ok, sub, mones, mbit);
+  offset = -1;
+  if (ok && mbit) {
+    offset = __ldg(im.markvals + markval_base + markval_off + (mones - 1));
+    n_samples += (sub == 0);
+  }
+}
+
 }  // namespace
 }  // namespace fmb

@@ -323,3 +323,14 @@ def gather_ragged_batch(plen: torch.Tensor, flat: torch.Tensor, world: int, grou
     offs_all = torch.cumsum(plen_all.to(torch.int64), 0) - plen_all.to(torch.int64)
     pid_lo = int(all_sizes[:rank, 0].sum())
     return plen_all, flat_all, offs_all, pid_lo
+
+
+def mesh_locate(mesh: "Mesh", first: torch.Tensor, last: torch.Tensor, max_occs: int):
+    """parallel_locate's second half over the mesh: the ranges of this rank's patterns (from a mesh
+    count) expanded into rows with the reference's clip rule, every row walked to a sampled-SA mark by
+    the persistent walk kernels.  Collective.  Returns (rows per pattern, offsets in pattern order)."""
+    rows, cnt = expand_ranges(first, last, max_occs)
+    out = torch.empty(max(int(rows.shape[0]), 1), dtype=torch.int64, device=first.device)
+    mesh.launch_locate_rows(rows.contiguous(), out)
+    mesh.finish()
+    return cnt, out[:rows.shape[0]]

@@ -278,6 +278,11 @@ int fm_last_transfer(const fm_index_t* ix, int64_t* h2d_bytes, int64_t* d2h_byte
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
                    const int64_t* offs, uint64_t* stats4);
 
+/* Instrumented sampled-SA walks (not a timed path): SA[rows[i]] for nrows host rows through the walk
+ * kernel with its counters on; stats4 = { LF steps, wavelet-tree rank blocks read, mark bit-vector
+ * blocks read, SA samples read }.  bench.py derives the locate leg's roofline from these. */
+int fm_walk_stats(fm_index_t* ix, int64_t nrows, const int64_t* rows, uint64_t* stats4);
+
 /* Measurement aid: the ceiling the count kernel is compared with in bench.py.  Runs `steps`
  * rounds of dependent, uniformly random, naturally aligned reads of bytes_per_access (32, 64 or
  * 128) bytes over the resident rank blocks with every SM filled, and reports how many reads were

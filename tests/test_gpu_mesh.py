@@ -63,8 +63,8 @@ def test_mesh_count_shards_on_one_gpu(name, nshards, built_indexes, corpora):
     docs, _ = corpora[name]
     path = built_indexes[name]
     pats = corpus.sample_patterns(docs, 4000, [1, 2, 3, 5, 8, 12, 20, 32], seed=193)
-    pats += [np.zeros(0, dtype=np.uint16), np.array([2], dtype=np.uint16), np.array([300, 70], dtype=np.uint16),
-             np.array([70, 300], dtype=np.uint16)]
+    pats += [np.zeros(0, dtype=np.uint16), np.array([2], dtype=np.uint16), np.array([1], dtype=np.uint16),
+             np.array([3, 4], dtype=np.uint16), np.array([260, 260], dtype=np.uint16), np.array([5, 5, 5], dtype=np.uint16)]
     with Oracle(path) as o:
         of, ol = o.count(pats)
     first, last, stats = _run_local(path, pats, nshards, window=0, cap_log2=0, max_ctas=64)
@@ -114,6 +114,43 @@ def test_mesh_rejects_a_ring_too_small_for_its_window(built_indexes):
     ix.close()
 
 
+@pytest.mark.parametrize("name,nshards", [("acgt_64k", 2), ("english_100k", 2), ("multi_doc_mixed", 3),
+                                          ("gen400_small_blocks", 3)])
+def test_mesh_locate_rows_on_one_gpu(name, nshards, built_indexes, corpora):
+    """SA[row] for every row of the index, each shard walking its share of the rows; a walk hops to the
+    shard owning LF(row) until it meets a mark (fm_mesh_locate_rows)."""
+    from oracle.bindings import Oracle
+    path = built_indexes[name]
+    dev = torch.device("cuda", 0)
+    with Oracle(path) as o:
+        n = o.header_info()["total_length"]
+        want = o.locate_range(0, n - 1)
+    ixs = [fb.Index(path, device=0, shard=r, nshards=nshards) for r in range(nshards)]
+    meshes = [sharded.Mesh(ix, r, nshards, connect=False) for r, ix in enumerate(ixs)]
+    sharded.Mesh.connect_local(meshes)
+    for m in meshes:
+        m.set_limits(max_ctas=64, timeout_seconds=5.0)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(n)                       # every rank gets rows from everywhere
+    bounds = [n * r // nshards for r in range(nshards + 1)]
+    rows = [torch.from_numpy(perm[bounds[r]:bounds[r + 1]].astype(np.int64)).to(dev) for r in range(nshards)]
+    outs = [torch.full((max(len(x), 1),), -9, dtype=torch.int64, device=dev) for x in rows]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nshards)]
+    torch.cuda.synchronize()
+    for r, m in enumerate(meshes):
+        m.launch_locate_rows(rows[r], outs[r], stream=streams[r].cuda_stream)
+    stats = [m.finish(stream=streams[r].cuda_stream) for r, m in enumerate(meshes)]
+    got = np.empty(n, dtype=np.int64)
+    for r in range(nshards):
+        got[perm[bounds[r]:bounds[r + 1]]] = outs[r].cpu().numpy()[:bounds[r + 1] - bounds[r]]
+    assert (got == want).all()
+    assert sum(s["sent"] for s in stats) == sum(s["received"] for s in stats) > 0
+    for m in meshes:
+        m.close()
+    for ix in ixs:
+        ix.close()
+
+
 # ---- one process per GPU, inboxes mapped through CUDA IPC -------------------------------------------
 def _free_port():
     s = socket.socket()
@@ -146,8 +183,9 @@ def _worker(rank, world, port, index_path, pats, out_dir):
         mesh.launch_count(plen_all, flat_all, offs_all, 0, pid_lo, hi - lo, first, last)
         stats = mesh.finish()
         dist.barrier()
+    cnt, offs_out = sharded.mesh_locate(mesh, first[:hi - lo], last[:hi - lo], 25)
     np.savez(os.path.join(out_dir, f"m{rank}.npz"), first=first.cpu().numpy()[:hi - lo], last=last.cpu().numpy()[:hi - lo],
-             sent=stats["sent"])
+             sent=stats["sent"], cnt=cnt.cpu().numpy(), offsets=offs_out.cpu().numpy())
     mesh.close()
     ix.close()
     dist.destroy_process_group()
@@ -170,3 +208,11 @@ def test_mesh_count_across_gpus(name, built_indexes, corpora, tmp_path):
     assert (np.concatenate([p["first"] for p in parts]) == of).all()
     assert (np.concatenate([p["last"] for p in parts]) == ol).all()
     assert sum(int(p["sent"]) for p in parts) > 0
+    with Oracle(path) as o:
+        want = o.locate(pats, 25)
+    cnt = np.concatenate([p["cnt"] for p in parts])
+    offsets = np.concatenate([p["offsets"] for p in parts])
+    ends = np.cumsum(cnt)
+    for k, w in enumerate(want):
+        got = offsets[ends[k] - cnt[k]:ends[k]]
+        assert len(got) == len(w) and (got == w).all(), k
