@@ -292,7 +292,8 @@ def gather_uniform_batch(my_pats: torch.Tensor, world: int, group=None) -> torch
     if world == 1:
         return my_pats
     out = torch.empty((world * my_pats.shape[0], my_pats.shape[1]), dtype=my_pats.dtype, device=my_pats.device)
-    dist.all_gather_into_tensor(out, my_pats.contiguous(), group=group)
+    # as bytes: NCCL has no 16-bit integer type
+    dist.all_gather_into_tensor(out.view(torch.uint8), my_pats.contiguous().view(torch.uint8), group=group)
     return out
 
 
@@ -316,8 +317,8 @@ def gather_ragged_batch(plen: torch.Tensor, flat: torch.Tensor, world: int, grou
     fl[:flat.shape[0]] = flat
     pl_all = torch.empty((world, max_n), dtype=plen.dtype, device=dev)
     fl_all = torch.empty((world, max_f), dtype=flat.dtype, device=dev)
-    dist.all_gather_into_tensor(pl_all.view(-1), pl, group=group)
-    dist.all_gather_into_tensor(fl_all.view(-1), fl, group=group)
+    dist.all_gather_into_tensor(pl_all.view(-1).view(torch.uint8), pl.view(torch.uint8), group=group)
+    dist.all_gather_into_tensor(fl_all.view(-1).view(torch.uint8), fl.view(torch.uint8), group=group)
     plen_all = torch.cat([pl_all[r, :int(all_sizes[r, 0])] for r in range(world)])
     flat_all = torch.cat([fl_all[r, :int(all_sizes[r, 1])] for r in range(world)])
     offs_all = torch.cumsum(plen_all.to(torch.int64), 0) - plen_all.to(torch.int64)

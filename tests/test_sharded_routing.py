@@ -208,3 +208,37 @@ def test_expand_ranges_clip_rule():
     # last - first > max_occs cuts to max_occs rows: 5 rows (one over) are kept, 6 rows become 4
     assert cnt.tolist() == [0, 3, 5, 4, 1]
     assert rows.tolist() == [10, 11, 12, 20, 21, 22, 23, 24, 30, 31, 32, 33, 7]
+
+
+# ---- host side of the device-initiated exchange: replicating the batch (the only collective of a mesh batch)
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    # equal-length batch: int16 symbols (alpha_t) [n, m]
+    mine = torch.from_numpy(rng.integers(1, 261, (5, 7)).astype(np.int16))
+    allp = sharded.gather_uniform_batch(mine, world)
+    # ragged batch: this rank has rank+3 patterns
+    lens = rng.integers(0, 9, rank + 3).astype(np.int32)
+    flat = rng.integers(1, 261, int(lens.sum())).astype(np.int16)
+    plen_all, flat_all, offs_all, pid_lo = sharded.gather_ragged_batch(torch.from_numpy(lens), torch.from_numpy(flat), world)
+    np.savez(os.path.join(out_dir, f"g{rank}.npz"), mine=mine.numpy(), allp=allp.numpy(), lens=lens, flat=flat,
+             plen_all=plen_all.numpy(), flat_all=flat_all.numpy(), offs_all=offs_all.numpy(), pid_lo=pid_lo)
+    dist.destroy_process_group()
+
+
+def test_batch_gather_two_ranks(tmp_path):
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"g{r}.npz") for r in range(world)]
+    want_uniform = np.concatenate([p["mine"] for p in parts])
+    want_lens = np.concatenate([p["lens"] for p in parts])
+    want_flat = np.concatenate([p["flat"] for p in parts])
+    lo = 0
+    for r, p in enumerate(parts):
+        assert (p["allp"] == want_uniform).all()
+        assert (p["plen_all"] == want_lens).all() and (p["flat_all"] == want_flat).all()
+        assert (p["offs_all"] == np.cumsum(want_lens) - want_lens).all()
+        assert int(p["pid_lo"]) == lo
+        lo += len(p["lens"])
