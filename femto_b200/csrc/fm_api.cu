@@ -1154,10 +1154,11 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
     a.rank = m->rank;
     a.world = m->world;
     a.cap_shift = m->cap_shift;
-    // 16 bits of the batch number travel in every message's tag (never 0: a cleared slot is never valid);
-    // when they wrap the rings are cleared so that nothing 65535 batches old can look current
+    // 8 bits of the batch number (1..255) travel in the tag of every message word; the rings are cleared
+    // before that field repeats, so nothing 255 batches old can look current (callers keep batches apart:
+    // see fm_mesh_count in the header)
     a.epoch = m->epoch;
-    if (m->epoch % 65535 == 0) CK(cudaMemsetAsync(base + sizeof(MeshCtl), 0, m->region_bytes - sizeof(MeshCtl), s));
+    if (m->epoch % 255 == 0) CK(cudaMemsetAsync(base + sizeof(MeshCtl), 0, m->region_bytes - sizeof(MeshCtl), s));
     a.window = m->window;
     a.timeout_cycles = static_cast<long long>(m->timeout_s * 1e3 * double(m->clock_khz));
     a.plen = d_plen;

@@ -20,13 +20,16 @@
 namespace fmb {
 namespace {
 
-__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+// Two 64-bit words with one instruction.  A vector access is a set of scalar accesses: each 64-bit
+// word is read / written whole (single-copy atomic), the pair is not -- which is why EVERY word of a
+// message carries the tag.
+__device__ __forceinline__ ulonglong2 ld_volatile_v2(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4 v) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void st_volatile_v2(ulonglong2* p, const ulonglong2 v) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -42,10 +45,12 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
-// A state in flight: 2 x 16 bytes, each half led by the tag.
-//   half 0: tag, id, A bits 0..31, A bits 32..47 | meta << 16     meta = phase | home << 2
-//   half 1: tag, i,  B bits 0..31, B bits 32..47
-// A, B are rows or C+Occ values (< 2^47 in magnitude, B may be -1): sign-extended from 48 bits.
+// A state in flight: four 64-bit words, each = tag (16 bits) << 48 | 48 bits of payload:
+//   word 0: id (32 bits) | meta << 32      meta = phase | home << 2
+//   word 1: A    word 2: B     rows or C+Occ values, two's complement in 48 bits (B may be -1)
+//   word 3: i
+// A word is written and read whole, so a message is complete exactly when all four tags are the
+// expected one -- whatever order the words arrive in over NVLink.
 struct MeshState {
   int64_t A = 0, B = 0;
   uint32_t id = 0;
@@ -55,27 +60,36 @@ struct MeshState {
 constexpr int kPhaseA = 0;     // count: needs Occ(c, first-1) then Occ(c, last); A = first, B = last.  walk: walking
 constexpr int kPhaseB = 1;     // count: A = C[c]+Occ(c,first-1) is known, needs Occ(c, last)
 constexpr int kPhaseDone = 2;  // finished: travels home; count: A = first, B = last; walk: A = offset
+constexpr unsigned long long kPayloadMask = (1ull << 48) - 1;
 
-__device__ __forceinline__ int64_t sext48(uint32_t lo, uint32_t hi16) {
-  const uint64_t v = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi16 & 0xffffu) << 32);
+__device__ __forceinline__ int64_t sext48(unsigned long long v) {
   return static_cast<int64_t>(v << 16) >> 16;
 }
-__device__ __forceinline__ void pack_state(const MeshState& s, uint32_t tag, uint4& m0, uint4& m1) {
-  const uint64_t a = static_cast<uint64_t>(s.A), b = static_cast<uint64_t>(s.B);
-  const uint32_t meta = static_cast<uint32_t>(s.phase) | (static_cast<uint32_t>(s.home) << 2);
-  m0 = make_uint4(tag, s.id, static_cast<uint32_t>(a), (static_cast<uint32_t>(a >> 32) & 0xffffu) | (meta << 16));
-  m1 = make_uint4(tag, static_cast<uint32_t>(s.i), static_cast<uint32_t>(b), static_cast<uint32_t>(b >> 32) & 0xffffu);
+__device__ __forceinline__ void pack_state(const MeshState& s, unsigned long long tag, ulonglong2& m0, ulonglong2& m1) {
+  const unsigned long long meta = static_cast<unsigned long long>(s.phase) | (static_cast<unsigned long long>(s.home) << 2);
+  m0.x = tag | static_cast<unsigned long long>(s.id) | (meta << 32);
+  m0.y = tag | (static_cast<unsigned long long>(s.A) & kPayloadMask);
+  m1.x = tag | (static_cast<unsigned long long>(s.B) & kPayloadMask);
+  m1.y = tag | static_cast<unsigned long long>(static_cast<uint32_t>(s.i));
 }
 
 struct MeshWarp {
   int lane, sub, gleader, wic;
   unsigned long long W, wid;
-  uint32_t cap_mask, ep16;
+  uint32_t cap_mask;
+  unsigned long long eptag;  // the batch's part of the tag, in place (bits 56..63)
   unsigned long long n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;
 };
 
-__device__ __forceinline__ uint32_t mesh_tag(const MeshWarp& w, const MeshArgs& a, unsigned long long idx) {
-  return w.ep16 | (static_cast<uint32_t>((idx >> a.cap_shift) + 1) & 0xffffu);
+// tag of ring index idx: batch field (1..255) << 8 | lap field (1..255), in the top 16 bits.  Never 0, so a
+// cleared slot is never valid; a slot is rewritten every lap, and the rings are cleared before the batch
+// field repeats (fm_api.cu), so a stale word never carries the expected tag.
+__device__ __forceinline__ unsigned long long mesh_tag(const MeshWarp& w, const MeshArgs& a, unsigned long long idx) {
+  return w.eptag | (((idx >> a.cap_shift) % 255ull + 1ull) << 48);
+}
+__device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int src, unsigned long long idx, const MeshWarp& w,
+                                                       const MeshArgs& a) {
+  return reinterpret_cast<const ulonglong2*>(ring + ((static_cast<size_t>(src) << a.cap_shift) + (idx & w.cap_mask)) * 2);
 }
 
 // Fill idle groups from this warp's share of the inbox.  needers: ballot of the leader lanes of the
@@ -84,11 +98,11 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
                                                 unsigned rot, unsigned& needers, MeshState& s, bool& have) {
   int want = __popc(needers);
   // which rings hold a message at this warp's cursor (one lane per ring)
+  constexpr unsigned long long kTagMask = ~kPayloadMask;
   bool ready = false;
   if (w.lane < a.world) {
     const unsigned long long cur = s_cur[w.wic][w.lane];
-    const uint4* slot = a.ring + ((static_cast<size_t>(w.lane) << a.cap_shift) + (cur & w.cap_mask)) * 2;
-    ready = ld_volatile_v4(slot).x == mesh_tag(w, a, cur);
+    ready = (ld_volatile_v2(mesh_slot(a.ring, w.lane, cur, w, a)).x & kTagMask) == mesh_tag(w, a, cur);
   }
   unsigned rings = __ballot_sync(kFull, ready);
   if (!rings) w.n_empty++;
@@ -99,14 +113,15 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
     const unsigned long long cur = s_cur[w.wic][r];
     const int navail = kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1));
     bool valid = false;
-    uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+    ulonglong2 m0 = make_ulonglong2(0, 0), m1 = m0;
     if (w.lane < navail) {
       const unsigned long long idx = cur + w.lane;
-      const uint4* slot = a.ring + ((static_cast<size_t>(r) << a.cap_shift) + (idx & w.cap_mask)) * 2;
-      m0 = ld_volatile_v4(slot);
-      m1 = ld_volatile_v4(slot + 1);
-      const uint32_t tag = mesh_tag(w, a, idx);
-      valid = m0.x == tag && m1.x == tag;  // both halves of THIS message have landed
+      const ulonglong2* slot = mesh_slot(a.ring, r, idx, w, a);
+      m0 = ld_volatile_v2(slot);
+      m1 = ld_volatile_v2(slot + 1);
+      const unsigned long long tag = mesh_tag(w, a, idx);
+      valid = (m0.x & kTagMask) == tag && (m0.y & kTagMask) == tag && (m1.x & kTagMask) == tag &&
+              (m1.y & kTagMask) == tag;  // all four words of THIS message have landed
     }
     const unsigned vm = __ballot_sync(kFull, valid);
     const int v = __ffs(~vm) - 1;  // messages in order from the cursor
@@ -115,16 +130,15 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
       // the k-th idle group takes the k-th message
       const int k = __popc(needers & ((1u << w.gleader) - 1u));
       const int src = min(k, 31);
-      const uint32_t id = __shfl_sync(kFull, m0.y, src), alo = __shfl_sync(kFull, m0.z, src),
-                     ahi = __shfl_sync(kFull, m0.w, src), ii = __shfl_sync(kFull, m1.y, src),
-                     blo = __shfl_sync(kFull, m1.z, src), bhi = __shfl_sync(kFull, m1.w, src);
+      const unsigned long long w0 = __shfl_sync(kFull, m0.x, src), w1 = __shfl_sync(kFull, m0.y, src),
+                               w2 = __shfl_sync(kFull, m1.x, src), w3 = __shfl_sync(kFull, m1.y, src);
       if (!have && k < take) {
-        s.id = id;
-        s.A = sext48(alo, ahi);
-        s.B = sext48(blo, bhi);
-        s.i = static_cast<int32_t>(ii);
-        s.phase = static_cast<int>((ahi >> 16) & 3u);
-        s.home = static_cast<int>((ahi >> 18) & 0xffu);
+        s.id = static_cast<uint32_t>(w0);
+        s.phase = static_cast<int>((w0 >> 32) & 3u);
+        s.home = static_cast<int>((w0 >> 34) & 0xffu);
+        s.A = sext48(w1);
+        s.B = sext48(w2);
+        s.i = static_cast<int32_t>(static_cast<uint32_t>(w3));
         have = true;
       }
       for (int t = 0; t < take; t++) needers &= needers - 1;
@@ -143,7 +157,11 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
 
 // Store the departing states into their owners' inboxes.  Warp-collective.
 __device__ __forceinline__ void mesh_send(MeshWarp& w, const MeshArgs& a, bool send, int dest, const MeshState& s) {
-  const bool mine = send && w.sub == 0;
+  bool mine = send && w.sub == 0;
+  if (mine && (dest < 0 || dest >= a.world)) {  // cannot happen with a well-formed index; never store out of bounds
+    atomicExch(&a.ctl->status, 2);
+    mine = false;
+  }
   unsigned todo = __ballot_sync(kFull, mine);
   while (todo) {
     const int src = __ffs(todo) - 1;
@@ -154,11 +172,11 @@ __device__ __forceinline__ void mesh_send(MeshWarp& w, const MeshArgs& a, bool s
     base = __shfl_sync(kFull, base, src);
     if (mine && dest == d) {
       const unsigned long long idx = base + __popc(same & lanemask_lt());
-      uint4 m0, m1;
+      ulonglong2 m0, m1;
       pack_state(s, mesh_tag(w, a, idx), m0, m1);
-      uint4* slot = a.peer_ring[d] + ((static_cast<size_t>(a.rank) << a.cap_shift) + (idx & w.cap_mask)) * 2;
-      st_volatile_v4(slot, m0);
-      st_volatile_v4(slot + 1, m1);
+      ulonglong2* slot = const_cast<ulonglong2*>(mesh_slot(a.peer_ring[d], a.rank, idx, w, a));
+      st_volatile_v2(slot, m0);
+      st_volatile_v2(slot + 1, m1);
     }
     w.n_sent += __popc(same);
     todo &= ~same;
@@ -221,7 +239,7 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, unsigned l
   w.W = static_cast<unsigned long long>(gridDim.x) * (kThreads / 32);
   w.wid = static_cast<unsigned long long>(blockIdx.x) * (kThreads / 32) + w.wic;
   w.cap_mask = (1u << a.cap_shift) - 1u;
-  w.ep16 = static_cast<uint32_t>(a.epoch & 0xffffu) << 16;
+  w.eptag = (a.epoch % 255ull + 1ull) << 56;
   if (w.lane < kMeshMaxRanks) s_cur[w.wic][w.lane] = w.wid * kMeshBlock;
   __syncwarp();
   // a rank without patterns of its own has nothing to wait for

@@ -269,9 +269,15 @@ class Mesh:
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         status = C.c_int(0)
         stats = (C.c_uint64 * 8)()
-        _check(self.lib.fm_mesh_finish(self.h, st, C.byref(status), stats), "fm_mesh_finish")
+        rc = self.lib.fm_mesh_finish(self.h, st, C.byref(status), stats)
         names = ["sent", "received", "rounds", "occ_pairs", "occ_singles", "empty_polls", "injected"]
-        return {k: int(stats[i]) for i, k in enumerate(names)}
+        out = {k: int(stats[i]) for i, k in enumerate(names)}
+        if rc:
+            from . import FemtoError
+            msg = self.lib.fm_last_error()
+            raise FemtoError(rc, "fm_mesh_finish", f"{msg.decode(errors='replace') if msg else ''} "
+                                                   f"[rank {self.rank}: {out}]")
+        return out
 
     def close(self) -> None:
         if getattr(self, "h", None):
