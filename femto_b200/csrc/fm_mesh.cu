@@ -97,13 +97,27 @@ __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int sr
 __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, unsigned long long (*s_cur)[kMeshMaxRanks],
                                                 unsigned rot, unsigned& needers, MeshState& s, bool& have) {
   int want = __popc(needers);
-  // which rings hold a message at this warp's cursor (one lane per ring)
+  // One lane per ring.  A warp owns at most ONE block of 16 consecutive indices per ring at a time; when it
+  // has none it looks at the ring's next unowned block and, if a message has landed there, takes the next
+  // block ticket (one atomic per 16 messages, on a counter in this rank's own memory).  Blocks are handed out
+  // in arrival order to whichever warp is free, so no part of the ring waits for one particular busy warp
+  // and the unconsumed span of a ring stays within (states in flight + one block per warp).
   constexpr unsigned long long kTagMask = ~kPayloadMask;
+  constexpr unsigned long long kNoBlock = ~0ull;
   bool ready = false;
   if (w.lane < a.world) {
-    const unsigned long long cur = s_cur[w.wic][w.lane];
-    ready = (ld_volatile_v2(mesh_slot(a.ring, w.lane, cur, w, a)).x & kTagMask) == mesh_tag(w, a, cur);
+    unsigned long long cur = s_cur[w.wic][w.lane];
+    if (cur == kNoBlock) {
+      const unsigned long long hb = ld_volatile_u64(&a.ctl->head_block[w.lane]) * kMeshBlock;
+      if ((ld_volatile_v2(mesh_slot(a.ring, w.lane, hb, w, a)).x & kTagMask) == mesh_tag(w, a, hb)) {
+        cur = atomicAdd(&a.ctl->head_block[w.lane], 1ull) * kMeshBlock;  // may be a later block than the one seen
+        s_cur[w.wic][w.lane] = cur;
+      }
+    }
+    if (cur != kNoBlock)
+      ready = (ld_volatile_v2(mesh_slot(a.ring, w.lane, cur, w, a)).x & kTagMask) == mesh_tag(w, a, cur);
   }
+  __syncwarp();
   unsigned rings = __ballot_sync(kFull, ready);
   if (!rings) w.n_empty++;
   while (rings && want > 0) {
@@ -145,9 +159,8 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
       want -= take;
       w.n_recv += take;
       if (w.lane == 0) {
-        unsigned long long nx = cur + take;
-        if ((nx & (kMeshBlock - 1)) == 0) nx += (w.W - 1) * kMeshBlock;  // this warp's next block of the ring
-        s_cur[w.wic][r] = nx;
+        const unsigned long long nx = cur + take;
+        s_cur[w.wic][r] = (nx & (kMeshBlock - 1)) == 0 ? kNoBlock : nx;  // block finished: take a new ticket next time
       }
       __syncwarp();
     }
@@ -240,7 +253,7 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, unsigned l
   w.wid = static_cast<unsigned long long>(blockIdx.x) * (kThreads / 32) + w.wic;
   w.cap_mask = (1u << a.cap_shift) - 1u;
   w.eptag = (a.epoch % 255ull + 1ull) << 56;
-  if (w.lane < kMeshMaxRanks) s_cur[w.wic][w.lane] = w.wid * kMeshBlock;
+  if (w.lane < kMeshMaxRanks) s_cur[w.wic][w.lane] = ~0ull;  // no block owned yet
   __syncwarp();
   // a rank without patterns of its own has nothing to wait for
   if (a.n_mine == 0 && blockIdx.x == 0 && threadIdx.x < a.world)

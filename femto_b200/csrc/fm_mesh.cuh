@@ -9,16 +9,21 @@
 // inbox over NVLink peer memory and takes the next state from its own inbox.  No host round trip,
 // no collective inside a batch; termination by counters the kernels exchange the same way.
 //
-// Inbox of a rank: one ring per SOURCE rank (so a slot index is claimed with an atomic in the
-// sender's own memory -- the transfer itself is a posted 32-byte store, nothing comes back over the
-// link).  Slots are consumed without atomics too: ring slots are owned STATICALLY by the consumer's
-// warps (block k of 16 consecutive indices belongs to warp k mod W), each warp keeps its own cursor
-// per ring.  A message carries its own validity: both 16-byte halves hold a tag = (batch epoch, lap
-// of the ring), so a slot is taken when both tags are the expected one -- no flag, no fence.
+// Inbox of a rank: one ring per SOURCE rank, so a slot index is claimed with an atomic in the
+// sender's own memory -- the transfer itself is a posted store, nothing comes back over the link.
+// On the consumer side a warp takes a BLOCK of 16 consecutive indices with one atomic on a counter
+// in its own memory, when it sees that the ring's next unowned block has received its first
+// message; it then owns that block until it has consumed all 16 (it never waits for it: a warp
+// polls its blocks, one per ring at most, whenever it has idle lane groups).  A message is four
+// 64-bit words that each carry a tag = (batch, lap of the ring) next to 48 bits of payload; a slot
+// is consumed when all four tags are the expected one -- no flag, no fence, no assumption about
+// the order in which NVLink delivers the words.
 //
-// Capacity: a state is in exactly one place, so a ring never holds more unconsumed messages than
-// there are states in flight; every rank injects new patterns only while fewer than `window` of its
-// own are unfinished, and cap >= world * (window + slack) slots per ring make an overrun impossible.
+// Capacity: a state is in exactly one place, so the unconsumed messages of a ring are at most the
+// states in flight; blocks are handed out in index order to whichever warp is free, so they span
+// at most that many indices plus one (partly filled) block per warp.  Every rank injects new
+// patterns only while fewer than `window` of its own are unfinished, and the rings hold
+// world * (window + slack) slots, so a producer can never lap an unconsumed slot.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -36,6 +41,7 @@ constexpr int kMeshBlock = 16;  // consecutive ring indices owned by one consume
 struct MeshCtl {
   // written by the owner's kernel only
   unsigned long long out_tail[kMeshMaxRanks];  // next index in the ring (me -> dst) at dst
+  unsigned long long head_block[kMeshMaxRanks];  // next block of 16 indices of my ring src that no warp owns yet
   unsigned long long injected;                 // patterns of my batch taken so far
   unsigned long long done_count;               // patterns of my batch delivered
   unsigned long long stats[8];                 // sent, received, rounds, occ pairs, occ singles, empty polls, injected, -
