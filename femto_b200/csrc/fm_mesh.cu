@@ -48,7 +48,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 // A state in flight: four 64-bit words, each = tag (16 bits) << 48 | 48 bits of payload:
 //   word 0: id (32 bits) | meta << 32      meta = phase | home << 2
 //   word 1: A    word 2: B     rows or C+Occ values, two's complement in 48 bits (B may be -1)
-//   word 3: i
+//   word 3: i (32 bits) | symbol of the pending step << 32
 // A word is written and read whole, so a message is complete exactly when all four tags are the
 // expected one -- whatever order the words arrive in over NVLink.
 struct MeshState {
@@ -56,6 +56,8 @@ struct MeshState {
   uint32_t id = 0;
   int32_t i = 0;
   int phase = 0, home = 0;
+  int c = 0;  // count: the symbol of the pending step, pattern[i-1] (travels with the state: the rank that
+              // finishes a step reads the next symbol WHILE it evaluates, so no rank waits for a pattern read)
 };
 constexpr int kPhaseA = 0;     // count: needs Occ(c, first-1) then Occ(c, last); A = first, B = last.  walk: walking
 constexpr int kPhaseB = 1;     // count: A = C[c]+Occ(c,first-1) is known, needs Occ(c, last)
@@ -70,7 +72,8 @@ __device__ __forceinline__ void pack_state(const MeshState& s, unsigned long lon
   m0.x = tag | static_cast<unsigned long long>(s.id) | (meta << 32);
   m0.y = tag | (static_cast<unsigned long long>(s.A) & kPayloadMask);
   m1.x = tag | (static_cast<unsigned long long>(s.B) & kPayloadMask);
-  m1.y = tag | static_cast<unsigned long long>(static_cast<uint32_t>(s.i));
+  m1.y = tag | static_cast<unsigned long long>(static_cast<uint32_t>(s.i)) |
+         (static_cast<unsigned long long>(static_cast<uint32_t>(s.c) & 0xffffu) << 32);
 }
 
 struct MeshWarp {
@@ -78,7 +81,7 @@ struct MeshWarp {
   unsigned long long W, wid;
   uint32_t cap_mask;
   unsigned long long eptag;  // the batch's part of the tag, in place (bits 56..63)
-  unsigned long long n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;
+  unsigned n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;  // per warp: 32 bits are plenty
 };
 
 // tag of ring index idx: batch field (1..255) << 8 | lap field (1..255), in the top 16 bits.  Never 0, so a
@@ -153,6 +156,7 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
         s.A = sext48(w1);
         s.B = sext48(w2);
         s.i = static_cast<int32_t>(static_cast<uint32_t>(w3));
+        s.c = static_cast<int>((w3 >> 32) & 0xffffu);
         have = true;
       }
       for (int t = 0; t < take; t++) needers &= needers - 1;
@@ -168,14 +172,17 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
   }
 }
 
-// Store the departing states into their owners' inboxes.  Warp-collective.
-__device__ __forceinline__ void mesh_send(MeshWarp& w, const MeshArgs& a, bool send, int dest, const MeshState& s) {
-  bool mine = send && w.sub == 0;
-  if (mine && (dest < 0 || dest >= a.world)) {  // cannot happen with a well-formed index; never store out of bounds
-    atomicExch(&a.ctl->status, 2);
-    mine = false;
+// Departing states, step 1: claim their ring indices (one atomic per destination and warp, on counters in
+// this rank's own memory).  Returns this lane's index (valid when it sends).  The stores follow in
+// mesh_send_store -- after the round's evaluations have been issued, so the atomics' latency overlaps them.
+__device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const MeshArgs& a, bool& send, int dest) {
+  if (send && (dest < 0 || dest >= a.world)) {  // cannot happen with a well-formed index; never store out of bounds
+    if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+    send = false;
   }
+  const bool mine = send && w.sub == 0;
   unsigned todo = __ballot_sync(kFull, mine);
+  unsigned long long idx = 0;
   while (todo) {
     const int src = __ffs(todo) - 1;
     const int d = __shfl_sync(kFull, dest, src);
@@ -183,16 +190,20 @@ __device__ __forceinline__ void mesh_send(MeshWarp& w, const MeshArgs& a, bool s
     unsigned long long base = 0;
     if (w.lane == src) base = atomicAdd(&a.ctl->out_tail[d], static_cast<unsigned long long>(__popc(same)));
     base = __shfl_sync(kFull, base, src);
-    if (mine && dest == d) {
-      const unsigned long long idx = base + __popc(same & lanemask_lt());
-      ulonglong2 m0, m1;
-      pack_state(s, mesh_tag(w, a, idx), m0, m1);
-      ulonglong2* slot = const_cast<ulonglong2*>(mesh_slot(a.peer_ring[d], a.rank, idx, w, a));
-      st_volatile_v2(slot, m0);
-      st_volatile_v2(slot + 1, m1);
-    }
+    if (mine && dest == d) idx = base + __popc(same & lanemask_lt());
     w.n_sent += __popc(same);
     todo &= ~same;
+  }
+  return idx;
+}
+__device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArgs& a, bool send, int dest,
+                                                unsigned long long idx, const MeshState& s) {
+  if (send && w.sub == 0) {
+    ulonglong2 m0, m1;
+    pack_state(s, mesh_tag(w, a, idx), m0, m1);
+    ulonglong2* slot = const_cast<ulonglong2*>(mesh_slot(a.peer_ring[dest], a.rank, idx, w, a));
+    st_volatile_v2(slot, m0);
+    st_volatile_v2(slot + 1, m1);
   }
 }
 
@@ -233,13 +244,13 @@ __device__ __forceinline__ bool mesh_idle_exit(const MeshWarp& w, const MeshArgs
 __device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshArgs& a, unsigned long long rounds,
                                                  unsigned long long pairs, unsigned long long singles) {
   if (w.lane == 0) {
-    atomicAdd(&a.ctl->stats[0], w.n_sent);
-    atomicAdd(&a.ctl->stats[1], w.n_recv);
+    atomicAdd(&a.ctl->stats[0], static_cast<unsigned long long>(w.n_sent));
+    atomicAdd(&a.ctl->stats[1], static_cast<unsigned long long>(w.n_recv));
     atomicAdd(&a.ctl->stats[2], rounds);
     atomicAdd(&a.ctl->stats[3], pairs);
     atomicAdd(&a.ctl->stats[4], singles);
-    atomicAdd(&a.ctl->stats[5], w.n_empty);
-    atomicAdd(&a.ctl->stats[6], w.n_inject);
+    atomicAdd(&a.ctl->stats[5], static_cast<unsigned long long>(w.n_empty));
+    atomicAdd(&a.ctl->stats[6], static_cast<unsigned long long>(w.n_inject));
   }
 }
 
@@ -277,20 +288,20 @@ __device__ __forceinline__ int64_t mesh_inject(MeshWarp& w, const MeshArgs& a, u
   const unsigned long long idx = base + __popc(needers & ((1u << w.gleader) - 1u));
   const unsigned long long n = static_cast<unsigned long long>(a.n_mine);
   if (base + want >= n) exhausted = true;
-  if (base < n) w.n_inject += min(static_cast<unsigned long long>(want), n - base);
+  if (base < n) w.n_inject += static_cast<unsigned>(min(static_cast<unsigned long long>(want), n - base));
   if (have || idx >= n) return -1;
   return static_cast<int64_t>(idx);
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im, const MeshArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage im, const MeshArgs a) {
   __shared__ unsigned long long s_cur[kThreads / 32][kMeshMaxRanks];
   MeshWarp w = mesh_warp_init(a, s_cur);
   MeshState s;
   bool have = false, exhausted = a.n_mine == 0;
   long long idle_start = 0;
   unsigned backoff = 100, iter = 0;
-  unsigned long long n_rounds = 0, n_pairs = 0, n_singles = 0;
+  unsigned n_rounds = 0, n_pairs = 0, n_singles = 0;
 
   for (;; iter++) {
     // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch
@@ -311,6 +322,7 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
             else { s.A = __ldg(im.C + c); s.B = __ldg(im.C + c + 1) - 1; }
             s.i = m - 1;
           }
+          s.c = s.i > 0 ? pat[s.i - 1] : 0;
           s.phase = kPhaseA;
           s.home = a.rank;
           have = true;
@@ -335,9 +347,7 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
         if (s.home == a.rank) deliver = true;
         else { s.phase = kPhaseDone; send = true; dest = s.home; }
       } else {
-        const int m = a.uniform_len > 0 ? a.uniform_len : 0;
-        const uint16_t* pat = a.flat + (m ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
-        c = pat[s.i - 1];
+        c = s.c;
         if (s.phase == kPhaseA && c >= kAlphaDev) {  // symbol outside the alphabet: empty range
           s.A = im.total_length; s.B = s.A - 1; s.i--;
         } else {
@@ -380,8 +390,10 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
     }
     mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
 
-    // ---- 4. states whose next row lives elsewhere
-    mesh_send(w, a, send, dest, s);
+    // ---- 4. states whose next row lives elsewhere: claim their inbox slots now, store them after the
+    // evaluations below have been issued
+    const MeshState out = s;
+    const unsigned long long out_idx = mesh_send_claim(w, a, send, dest);
     if (send) have = false;
 
     // ---- 5. the Occ evaluations that can be done here, all groups together
@@ -391,6 +403,12 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
       int L = 0;
       int64_t ob = 0;
       bool actA = false, actB = false;
+      int cn = 0;  // the symbol of the step after this one, read while this one is evaluated
+      if (doB && s.i >= 2) {
+        const int m = a.uniform_len > 0 ? a.uniform_len : 0;
+        const uint16_t* pat = a.flat + (m ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
+        cn = pat[s.i - 2];
+      }
       if (any) {
         int64_t g = 0, g2;
         uint32_t ra = 0, rb = 0;
@@ -417,11 +435,12 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
       quad_descend_pair(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub);
       if (any) {
         const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
-        if (doA && doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; }
+        if (doA && doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }
         else if (doA) { s.A = resA; s.phase = kPhaseB; }
-        else { s.B = resB - 1; s.i--; s.phase = kPhaseA; }  // A already holds C[c]+Occ(c,first-1)
+        else { s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }  // A already holds C[c]+Occ(c,first-1)
       }
     }
+    mesh_send_store(w, a, send, dest, out_idx, out);
   }
   mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles);
 }
@@ -429,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) mesh_count_kernel(const DevImage im,
 // ---------------------------------------------------------------------------------------------
 // Sampled-SA walks over the range-sharded index.  State: id = result slot at the home rank, A = BWT
 // row (the text offset once finished, -1 for a malformed walk), i = LF steps taken so far.
-__global__ void __launch_bounds__(kThreads) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
   __shared__ unsigned long long s_cur[kThreads / 32][kMeshMaxRanks];
   MeshWarp w = mesh_warp_init(a, s_cur);
   MeshState s;
@@ -485,7 +504,8 @@ __global__ void __launch_bounds__(kThreads) mesh_walk_kernel(const DevImage im, 
       have = false;
     }
     mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
-    mesh_send(w, a, send, dest, s);
+    const MeshState out = s;
+    const unsigned long long out_idx = mesh_send_claim(w, a, send, dest);
     if (send) have = false;
 
     // one LF step with mark test for every resident row (do_back_query, server.c:2228-2359)
@@ -519,6 +539,7 @@ __global__ void __launch_bounds__(kThreads) mesh_walk_kernel(const DevImage im, 
         }
       }
     }
+    mesh_send_store(w, a, send, dest, out_idx, out);
   }
   mesh_flush_stats(w, a, n_rounds, n_quad, n_mark + n_sample);
 }
