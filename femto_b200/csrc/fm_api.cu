@@ -1029,8 +1029,8 @@ int fm_mesh_create(fm_index_t* ix, int rank, int world, int64_t window, int cap_
     if (window == 0) window = 128 << 10;
     // a ring must hold every state in flight: world * (window + what the warps of one rank may claim
     // beyond the window between its check and their claims)
-    // (SMs x CTAs x warps x 16: once for the claims, once for the one partly filled block a warp may own per ring)
-    const int64_t slack = int64_t(ix->sm_count) * 8 * 8 * 16 * 2;
+    // (SMs x CTAs x warps x 16: once for the claims, twice for the two blocks a warp owns per ring)
+    const int64_t slack = int64_t(ix->sm_count) * 8 * 8 * 16 * 3;
     int shift = 10;
     while ((int64_t(1) << shift) < int64_t(world) * (window + slack)) shift++;
     if (cap_log2 > 0) {  // tests: a small ring that wraps many times (the caller also bounds the grid: fm_mesh_set_limits)
@@ -1139,7 +1139,7 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {  // the ring must hold every state in flight (fm_mesh.cuh): world * (window + one claim per group of the grid)
       const int64_t ctas = m->max_ctas > 0 ? m->max_ctas : int64_t(ix->sm_count) * 8;
-      if ((int64_t(1) << m->cap_shift) < int64_t(m->world) * (int64_t(m->window) + ctas * 8 * 16 * 2))
+      if ((int64_t(1) << m->cap_shift) < int64_t(m->world) * (int64_t(m->window) + ctas * 8 * 16 * 3))
         return fail(FM_ERR_PARAM, "fm_mesh: ring too small for this window and grid (cap_log2 / fm_mesh_set_limits)");
     }
     m->epoch++;

@@ -95,58 +95,88 @@ __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int sr
   return reinterpret_cast<const ulonglong2*>(ring + ((static_cast<size_t>(src) << a.cap_shift) + (idx & w.cap_mask)) * 2);
 }
 
-// Fill idle groups from this warp's share of the inbox.  needers: ballot of the leader lanes of the
-// groups without a state; updated.  Returns states through s / have.  Warp-collective.
-__device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, unsigned long long (*s_cur)[kMeshMaxRanks],
-                                                unsigned rot, unsigned& needers, MeshState& s, bool& have) {
-  int want = __popc(needers);
-  // One lane per ring.  A warp owns at most ONE block of 16 consecutive indices per ring at a time; when it
-  // has none it looks at the ring's next unowned block and, if a message has landed there, takes the next
-  // block ticket (one atomic per 16 messages, on a counter in this rank's own memory).  Blocks are handed out
-  // in arrival order to whichever warp is free, so no part of the ring waits for one particular busy warp
-  // and the unconsumed span of a ring stays within (states in flight + one block per warp).
-  constexpr unsigned long long kTagMask = ~kPayloadMask;
-  constexpr unsigned long long kNoBlock = ~0ull;
-  bool ready = false;
-  if (w.lane < a.world) {
-    unsigned long long cur = s_cur[w.wic][w.lane];
-    if (cur == kNoBlock) {
-      const unsigned long long hb = ld_volatile_u64(&a.ctl->head_block[w.lane]) * kMeshBlock;
-      if ((ld_volatile_v2(mesh_slot(a.ring, w.lane, hb, w, a)).x & kTagMask) == mesh_tag(w, a, hb)) {
-        cur = atomicAdd(&a.ctl->head_block[w.lane], 1ull) * kMeshBlock;  // may be a later block than the one seen
-        s_cur[w.wic][w.lane] = cur;
-      }
-    }
-    if (cur != kNoBlock)
-      ready = (ld_volatile_v2(mesh_slot(a.ring, w.lane, cur, w, a)).x & kTagMask) == mesh_tag(w, a, cur);
+// ---- consuming the inbox -----------------------------------------------------------------------
+// A warp owns, at all times, TWO blocks of 16 consecutive indices on every ring (lane r keeps ring r's in
+// registers: the index of the next unconsumed slot of each).  Blocks are handed out by a ticket counter in
+// this rank's own memory, in index order, to whichever warp has just finished one -- a warp that is busy
+// takes tickets more slowly, so the load follows the warps' speed, and the unconsumed span of a ring never
+// exceeds the states in flight plus two blocks per warp.  The new ticket is requested when a block is used
+// up; its value is needed only when the warp's other block on that ring is used up too, many rounds later.
+//
+// Reading is decoupled from consuming: at the END of its fetch a warp copies the remaining slots of two of
+// its blocks (one per half warp, rotating over its 2 x world blocks) into shared memory with cp.async (L2
+// only: the slots are written by other GPUs); it looks at them at the START of its next fetch, after a whole
+// round of evaluations, so taking states from the inbox costs no memory round trip on the round's critical
+// path.  A slot whose four tags are not (yet) the expected ones is simply not there yet.
+struct MeshInbox {
+  unsigned long long blk[2];  // lane r < world: next unconsumed index in each of the two blocks owned on ring r
+  unsigned rot;               // which two blocks are staged (warp-uniform)
+  bool staged;
+};
+using MeshStage = ulonglong2[kThreads / 32][32][2];  // per warp: one 32-byte slot per lane
+
+__device__ __forceinline__ unsigned long long mesh_ticket(const MeshArgs& a, int ring) {
+  return atomicAdd(&a.ctl->head_block[ring], 1ull) * kMeshBlock;
+}
+
+// the block staged by half h in rotation step `rot`: ring (skipping this rank's own, which is never written) and which of the two
+__device__ __forceinline__ void mesh_stage_source(const MeshArgs& a, unsigned rot, int h, int& ring, int& which) {
+  const unsigned nsrc = 2u * static_cast<unsigned>(a.world - 1);
+  const unsigned k = (rot + static_cast<unsigned>(h)) % nsrc;
+  ring = static_cast<int>(k >> 1);
+  if (ring >= a.rank) ring++;
+  which = static_cast<int>(k & 1u);
+}
+
+__device__ __forceinline__ void mesh_stage_issue(const MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage) {
+  const int h = w.lane >> 4, j = w.lane & 15;
+  int ring, which;
+  mesh_stage_source(a, in.rot, h, ring, which);
+  const unsigned long long b0 = __shfl_sync(kFull, in.blk[0], ring), b1 = __shfl_sync(kFull, in.blk[1], ring);
+  const unsigned long long cur = which ? b1 : b0;
+  if (j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
+    const ulonglong2* src = mesh_slot(a.ring, ring, cur + j, w, a);
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&stage[w.wic][w.lane][0]));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 1) : "memory");
   }
-  __syncwarp();
-  unsigned rings = __ballot_sync(kFull, ready);
-  if (!rings) w.n_empty++;
-  while (rings && want > 0) {
-    // lowest ring at or after `rot` (rotating start: no ring is favoured)
-    const unsigned rr = ((rings >> rot) | (rings << (a.world - rot))) & ((1u << a.world) - 1u);
-    const int r = static_cast<int>((__ffs(rr) - 1 + rot) % a.world);
-    const unsigned long long cur = s_cur[w.wic][r];
-    const int navail = kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1));
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  in.staged = true;
+}
+
+// Fill idle groups from the slots staged by the previous fetch, then stage the next ones.  needers: ballot
+// of the leader lanes of the groups without a state; updated.  Warp-collective.
+__device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage,
+                                                unsigned& needers, MeshState& s, bool& have) {
+  constexpr unsigned long long kTagMask = ~kPayloadMask;
+  if (a.world == 1) return;
+  if (in.staged) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    const int h = w.lane >> 4, j = w.lane & 15;
+    int ring, which;
+    mesh_stage_source(a, in.rot, h, ring, which);
+    const unsigned long long b0 = __shfl_sync(kFull, in.blk[0], ring), b1 = __shfl_sync(kFull, in.blk[1], ring);
+    const unsigned long long cur = which ? b1 : b0;
     bool valid = false;
     ulonglong2 m0 = make_ulonglong2(0, 0), m1 = m0;
-    if (w.lane < navail) {
-      const unsigned long long idx = cur + w.lane;
-      const ulonglong2* slot = mesh_slot(a.ring, r, idx, w, a);
-      m0 = ld_volatile_v2(slot);
-      m1 = ld_volatile_v2(slot + 1);
-      const unsigned long long tag = mesh_tag(w, a, idx);
+    if (j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
+      m0 = stage[w.wic][w.lane][0];
+      m1 = stage[w.wic][w.lane][1];
+      const unsigned long long tag = mesh_tag(w, a, cur + j);
       valid = (m0.x & kTagMask) == tag && (m0.y & kTagMask) == tag && (m1.x & kTagMask) == tag &&
               (m1.y & kTagMask) == tag;  // all four words of THIS message have landed
     }
     const unsigned vm = __ballot_sync(kFull, valid);
-    const int v = __ffs(~vm) - 1;  // messages in order from the cursor
-    const int take = min(v, want);
+    // messages in order from each half's cursor; the two halves never stage the same block (world > 1)
+    const int v0 = __ffs(~(vm & 0xffffu)) - 1, v1 = __ffs(~(vm >> 16)) - 1;
+    const int want = __popc(needers);
+    const int take0 = min(v0, want), take1 = min(v1, want - take0);
+    const int take = take0 + take1;
     if (take > 0) {
-      // the k-th idle group takes the k-th message
+      // the k-th idle group takes the k-th message: first half 0's, then half 1's
       const int k = __popc(needers & ((1u << w.gleader) - 1u));
-      const int src = min(k, 31);
+      const int src = k < take0 ? k : min(16 + (k - take0), 31);
       const unsigned long long w0 = __shfl_sync(kFull, m0.x, src), w1 = __shfl_sync(kFull, m0.y, src),
                                w2 = __shfl_sync(kFull, m1.x, src), w3 = __shfl_sync(kFull, m1.y, src);
       if (!have && k < take) {
@@ -160,16 +190,25 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
         have = true;
       }
       for (int t = 0; t < take; t++) needers &= needers - 1;
-      want -= take;
       w.n_recv += take;
-      if (w.lane == 0) {
-        const unsigned long long nx = cur + take;
-        s_cur[w.wic][r] = (nx & (kMeshBlock - 1)) == 0 ? kNoBlock : nx;  // block finished: take a new ticket next time
+      // advance the cursors (the lane of each ring holds them); a finished block is replaced by a new ticket
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        int rg, wh;
+        mesh_stage_source(a, in.rot, hh, rg, wh);
+        const int tk = hh ? take1 : take0;
+        if (tk > 0 && w.lane == rg) {
+          unsigned long long nx = (wh ? in.blk[1] : in.blk[0]) + tk;
+          if ((nx & (kMeshBlock - 1)) == 0) nx = mesh_ticket(a, rg);
+          if (wh) in.blk[1] = nx; else in.blk[0] = nx;
+        }
       }
-      __syncwarp();
+    } else {
+      w.n_empty++;
     }
-    rings &= ~(1u << r);
+    if (take0 == v0 && take1 == v1) in.rot += 2;  // both staged blocks drained as far as they were filled: move on
   }
+  mesh_stage_issue(w, a, in, stage);
 }
 
 // Departing states, step 1: claim their ring indices (one atomic per destination and warp, on counters in
@@ -254,7 +293,7 @@ __device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshAr
   }
 }
 
-__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, unsigned long long (*s_cur)[kMeshMaxRanks]) {
+__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox& in) {
   MeshWarp w;
   w.lane = threadIdx.x & 31;
   w.sub = w.lane & 1;
@@ -264,8 +303,14 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, unsigned l
   w.wid = static_cast<unsigned long long>(blockIdx.x) * (kThreads / 32) + w.wic;
   w.cap_mask = (1u << a.cap_shift) - 1u;
   w.eptag = (a.epoch % 255ull + 1ull) << 56;
-  if (w.lane < kMeshMaxRanks) s_cur[w.wic][w.lane] = ~0ull;  // no block owned yet
-  __syncwarp();
+  // two blocks on every ring (one lane per ring), then different warps start their rotation at different blocks
+  in.blk[0] = in.blk[1] = 0;
+  if (w.lane < a.world && w.lane != a.rank) {
+    in.blk[0] = mesh_ticket(a, w.lane);
+    in.blk[1] = mesh_ticket(a, w.lane);
+  }
+  in.rot = static_cast<unsigned>(w.wid) * 2u;
+  in.staged = false;
   // a rank without patterns of its own has nothing to wait for
   if (a.n_mine == 0 && blockIdx.x == 0 && threadIdx.x < a.world)
     st_volatile_u64(&a.peer_ctl[threadIdx.x]->rank_done[a.rank], a.epoch);
@@ -295,8 +340,9 @@ __device__ __forceinline__ int64_t mesh_inject(MeshWarp& w, const MeshArgs& a, u
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage im, const MeshArgs a) {
-  __shared__ unsigned long long s_cur[kThreads / 32][kMeshMaxRanks];
-  MeshWarp w = mesh_warp_init(a, s_cur);
+  __shared__ __align__(16) MeshStage stage;
+  MeshInbox inbox;
+  MeshWarp w = mesh_warp_init(a, inbox);
   MeshState s;
   bool have = false, exhausted = a.n_mine == 0;
   long long idle_start = 0;
@@ -307,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage 
     // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
     if (needers) {
-      mesh_take_inbox(w, a, s_cur, static_cast<unsigned>((w.wid + iter) % a.world), needers, s, have);
+      mesh_take_inbox(w, a, inbox, stage, needers, s, have);
       if (needers && !exhausted) {
         const int64_t k = mesh_inject(w, a, needers, have, exhausted);
         if (k >= 0) {
@@ -449,8 +495,9 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage 
 // Sampled-SA walks over the range-sharded index.  State: id = result slot at the home rank, A = BWT
 // row (the text offset once finished, -1 for a malformed walk), i = LF steps taken so far.
 __global__ void __launch_bounds__(kThreads, 4) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
-  __shared__ unsigned long long s_cur[kThreads / 32][kMeshMaxRanks];
-  MeshWarp w = mesh_warp_init(a, s_cur);
+  __shared__ __align__(16) MeshStage stage;
+  MeshInbox inbox;
+  MeshWarp w = mesh_warp_init(a, inbox);
   MeshState s;
   bool have = false, exhausted = a.n_mine == 0;
   long long idle_start = 0;
@@ -460,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_walk_kernel(const DevImage i
   for (;; iter++) {
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
     if (needers) {
-      mesh_take_inbox(w, a, s_cur, static_cast<unsigned>((w.wid + iter) % a.world), needers, s, have);
+      mesh_take_inbox(w, a, inbox, stage, needers, s, have);
       if (needers && !exhausted) {
         const int64_t k = mesh_inject(w, a, needers, have, exhausted);
         if (k >= 0) {
