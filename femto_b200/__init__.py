@@ -124,6 +124,19 @@ class Index:
         _check(rc, "fm_count_flat")
         return first[:n], last[:n]
 
+    def count_bytes(self, plen: np.ndarray, text: np.ndarray, offs: np.ndarray,
+                    first: Optional[np.ndarray] = None, last: Optional[np.ndarray] = None):
+        """fm_count_bytes: patterns as raw text bytes (uint8), symbols = CHARACTER_OFFSET + byte."""
+        n = len(plen)
+        if first is None:
+            first = np.empty(max(n, 1), dtype=np.int64)
+        if last is None:
+            last = np.empty(max(n, 1), dtype=np.int64)
+        rc = self.lib.fm_count_bytes(self.h, n, _ptr(plen, C.c_int32), _ptr(text, C.c_uint8), _ptr(offs, C.c_int64),
+                                     _ptr(first, C.c_int64), _ptr(last, C.c_int64))
+        _check(rc, "fm_count_bytes")
+        return first[:n], last[:n]
+
     def count(self, pats: Sequence[np.ndarray]):
         """[first,last] BWT row range per pattern, through the reference-shaped pointer-array call."""
         n = len(pats)

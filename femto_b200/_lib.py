@@ -34,6 +34,7 @@ PROTOTYPES = {
     "fm_last_error": (C.c_char_p, []),
     "fm_count": (C.c_int, [vp, C.c_int, P(C.c_int), P(P(u16)), P(i64), P(i64)]),
     "fm_count_flat": (C.c_int, [vp, i64, P(i32), P(u16), P(i64), P(i64), P(i64)]),
+    "fm_count_bytes": (C.c_int, [vp, i64, P(i32), P(u8), P(i64), P(i64), P(i64)]),
     "fm_count_device": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
     "fm_count_shard_step": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp]),
     "fm_locate_shard_step": (C.c_int, [vp, i64, vp, vp, C.c_int, vp]),

@@ -438,10 +438,13 @@ StreamWrite64 stream_write64() {
 constexpr int kRetryValidated = -1000;  // count_host(lazy): the batch is not what its first / last pattern claimed
 
 // count on host buffers; leaves first/last on the host.  flat_len symbols in flat.
-int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, int64_t flat_len,
+// sym_bytes: 2 = alpha_t symbols, 1 = raw text bytes (fm_count_bytes; flat is then a byte buffer).
+int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t* flat16, int64_t flat_len,
                const int64_t* offs, int64_t* first, int64_t* last, bool in_order = false, int uniform_len = 0,
                bool to_host = true, bool lazy = false,
-               const std::function<void(int64_t)>* ready_upto = nullptr) {
+               const std::function<void(int64_t)>* ready_upto = nullptr, int sym_bytes = 2) {
+  const unsigned char* flat = reinterpret_cast<const unsigned char*>(flat16);
+  const size_t sb = size_t(sym_bytes);
   // ready_upto (fm_count): the flat buffer is being filled by gather threads while this function
   //   runs; (*ready_upto)(hi) returns once the symbols of patterns [0, hi) are in place.
   // to_host == false: first/last stay in ix->d_out[0] / d_out[1] for a kernel that follows (locate)
@@ -455,7 +458,8 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
   const auto t_call = std::chrono::steady_clock::now();
   cudaStream_t s = ix->stream;
   int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
-  uint16_t* d_flat = static_cast<uint16_t*>(ix->d_in[1].get(size_t(std::max<int64_t>(flat_len, 1)) * 2));
+  unsigned char* d_flat = static_cast<unsigned char*>(ix->d_in[1].get(size_t(std::max<int64_t>(flat_len, 1)) * sb));
+  auto dflat16 = [&](int64_t sym) { return reinterpret_cast<const uint16_t*>(d_flat + size_t(sym) * sb); };
   int64_t* d_offs = static_cast<int64_t*>(ix->d_in[2].get(size_t(npats) * 8));
   int64_t* d_first = static_cast<int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
   int64_t* d_last = (last || !to_host) ? static_cast<int64_t*>(ix->d_out[1].get(size_t(npats) * 8)) : nullptr;
@@ -499,8 +503,8 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     for (int h = 0; h < 2; h++) {
       const int64_t lo = half_lo[h], n = half_hi[h] - lo;
       cudaStream_t ks = h == 0 ? sk : sr;
-      CountArgs a{n, d_plen + lo, m ? d_flat + lo * m : d_flat, d_offs + lo, d_first + lo,
-                  d_last ? d_last + lo : nullptr, d_avail + h, ix->d_status + 1, m};
+      CountArgs a{n, d_plen + lo, dflat16(m ? lo * m : 0), d_offs + lo, d_first + lo,
+                  d_last ? d_last + lo : nullptr, d_avail + h, ix->d_status + 1, m, sym_bytes == 1};
       CK(launch_count(ix->im, a, ix->d_work + 8 + h, ix->count_sched, ix->sm_count, ks, &ix->launches));
       if (trace) CK(cudaEventRecord(tev[1 + h], ks));
     }
@@ -508,7 +512,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     // 128-byte boundaries of the device buffer so that no cache line is shared by two chunks (a
     // line read for an early pattern must not hold not-yet-copied symbols of a later one).
     int64_t k = 0, fdone = 0;
-    ix->last_h2d = (m ? 0 : npats * 12) + flat_len * 2 + nmarks * 8;
+    ix->last_h2d = (m ? 0 : npats * 12) + flat_len * int64_t(sb) + nmarks * 8;
     ix->last_d2h = to_host ? npats * (last ? 16 : 8) : 0;
     for (int h = 0; h < 2; h++) {
       for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += chunk_at(lo), k++) {
@@ -516,7 +520,7 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
         if (ready_upto) {
           // the symbol copy below is cut at a 128-byte line, i.e. up to 63 symbols into the patterns that
           // follow: wait for every pattern that starts before that cut
-          const int64_t cut = stream_symbol_cut(plen, offs, hi, npats, flat_len);
+          const int64_t cut = stream_symbol_cut(plen, offs, hi, npats, flat_len, sym_bytes);
           const int64_t j = hi == npats ? npats : std::lower_bound(offs + hi, offs + npats, cut) - offs;
           (*ready_upto)(j);
         }
@@ -549,9 +553,10 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
           CK(cudaMemcpyAsync(d_plen + lo, plen + lo, size_t(hi - lo) * 4, cudaMemcpyHostToDevice, sc));
           CK(cudaMemcpyAsync(d_offs + lo, offs + lo, size_t(hi - lo) * 8, cudaMemcpyHostToDevice, sc));
         }
-        const int64_t fend = stream_symbol_cut(plen, offs, hi, npats, flat_len);
+        const int64_t fend = stream_symbol_cut(plen, offs, hi, npats, flat_len, sym_bytes);
         if (fend > fdone) {
-          CK(cudaMemcpyAsync(d_flat + fdone, flat + fdone, size_t(fend - fdone) * 2, cudaMemcpyHostToDevice, sc));
+          CK(cudaMemcpyAsync(d_flat + size_t(fdone) * sb, flat + size_t(fdone) * sb, size_t(fend - fdone) * sb,
+                             cudaMemcpyHostToDevice, sc));
           fdone = fend;
         }
         marks[k] = static_cast<unsigned long long>(hi - half_lo[h]);
@@ -600,12 +605,13 @@ int count_host(fm_index* ix, int64_t npats, const int32_t* plen, const uint16_t*
     if (lazy) return kRetryValidated;  // the plain path below needs a validated batch
   }
   if (ready_upto) (*ready_upto)(npats);
-  ix->last_h2d = npats * 12 + flat_len * 2;
+  ix->last_h2d = npats * 12 + flat_len * int64_t(sb);
   ix->last_d2h = npats * (last ? 16 : 8);
   CK(cudaMemcpyAsync(d_plen, plen, size_t(npats) * 4, cudaMemcpyHostToDevice, s));
-  if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * 2, cudaMemcpyHostToDevice, s));
+  if (flat_len) CK(cudaMemcpyAsync(d_flat, flat, size_t(flat_len) * sb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_offs, offs, size_t(npats) * 8, cudaMemcpyHostToDevice, s));
-  CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
+  CountArgs a{npats, d_plen, dflat16(0), d_offs, d_first, d_last};
+  a.sym8 = sym_bytes == 1;
   CK(launch_count(ix->im, a, ix->d_work, ix->count_sched, ix->sm_count, s, &ix->launches));
   if (!to_host) {  // results stay on the device; the caller's next kernel runs on the same stream
     ix->last_d2h = 0;
@@ -789,8 +795,9 @@ void fm_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
-                  int64_t* first, int64_t* last) {
+namespace {
+int count_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                    int64_t* first, int64_t* last, int sym_bytes) {
   return guarded(ix, "fm_count_flat", [&]() -> int {
     if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
     int64_t flat_len = 0;
@@ -807,7 +814,7 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
       // the device buffers are sized from it)
       if (claim_len >= 0 && offs[npats - 1] >= 0 && plen[npats - 1] >= 0 && claim_len <= npats * int64_t(4096)) {
         const int rc = count_host(ix, npats, plen, flat, claim_len, offs, first, last, /*in_order=*/true, m,
-                                  /*to_host=*/true, /*lazy=*/true);
+                                  /*to_host=*/true, /*lazy=*/true, nullptr, sym_bytes);
         if (rc != kRetryValidated) return rc;
       }
     }
@@ -824,8 +831,30 @@ int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint
       return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
     }
     if (flat_len && !flat) return fail(FM_ERR_PARAM, "fm_count_flat: null pattern buffer");
-    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered, shape.uniform);
+    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered, shape.uniform, true, false, nullptr,
+                      sym_bytes);
   });
+}
+}  // namespace
+
+int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                  int64_t* first, int64_t* last) {
+  return count_flat_impl(ix, npats, plen, flat, offs, first, last, 2);
+}
+
+int fm_count_bytes(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint8_t* text, const int64_t* offs,
+                   int64_t* first, int64_t* last) {
+  if (!ix) return fail(FM_ERR_PARAM, "fm_count_bytes: null index");
+  if (ix->im.levels == 4 && ix->count_sched == kQuadSched)  // the kernel reads the bytes itself
+    return count_flat_impl(ix, npats, plen, reinterpret_cast<const uint16_t*>(text), offs, first, last, 1);
+  // other layouts / schedules: widen on the host (strtoalpha, src/main/index_types.h:85-97)
+  if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_bytes: bad argument");
+  int64_t flat_len = 0;
+  if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_count_bytes: negative length/offset");
+  if (flat_len && !text) return fail(FM_ERR_PARAM, "fm_count_bytes: null pattern buffer");
+  std::vector<uint16_t> wide(size_t(std::max<int64_t>(flat_len, 1)));
+  for (int64_t i = 0; i < flat_len; i++) wide[size_t(i)] = uint16_t(text[i]) + FM_CHARACTER_OFFSET;
+  return count_flat_impl(ix, npats, plen, wide.data(), offs, first, last, 2);
 }
 
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,

@@ -51,6 +51,15 @@ struct PatternState {
   bool have = false, exhausted = false;
 };
 
+// Symbol k of a pattern.  SYM8: the batch holds raw text bytes (CountArgs::sym8), symbol = byte +
+// CHARACTER_OFFSET (strtoalpha, src/main/index_types.h:85-97); s.pat is then a byte address.
+template <bool SYM8>
+__device__ __forceinline__ int pat_sym(const uint16_t* pat, int k) {
+  if constexpr (SYM8) return static_cast<int>(reinterpret_cast<const uint8_t*>(pat)[k]) + 5;
+  else return pat[k];
+}
+
+template <bool SYM8 = false>
 __device__ __forceinline__ void retire_and_fetch(PatternState& s, bool can_retire, const DevImage& im,
                                                  const CountArgs& a, unsigned long long* work, int lane,
                                                  int gleader) {
@@ -94,11 +103,12 @@ __device__ __forceinline__ void retire_and_fetch(PatternState& s, bool can_retir
     if (arrived) {
       s.pid = static_cast<int64_t>(idx);
       const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.pid];
-      s.pat = a.flat + (a.uniform_len > 0 ? s.pid * m : a.offs[s.pid]);
+      const int64_t so = a.uniform_len > 0 ? s.pid * m : a.offs[s.pid];
+      s.pat = SYM8 ? reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(a.flat) + so) : a.flat + so;
       if (m <= 0) {  // empty pattern: every row (server.c:782-808)
         s.f = 0; s.l = im.total_length - 1; s.i = 0;
       } else {
-        const int c = s.pat[m - 1];
+        const int c = pat_sym<SYM8>(s.pat, m - 1);
         if (c >= kAlphaDev) { s.f = im.total_length; s.l = s.f - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
         else { s.f = __ldg(im.C + c); s.l = __ldg(im.C + c + 1) - 1; }
         s.i = m - 1;
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, MINB) count_quad_split_kernel(const D
 // EXP (measurement variants of the quad branch, profiles/r01_quad_schedules.md; results unchanged):
 //   1 = position B always re-reads its line, also when it is A's (an L1 hit; the first version),
 //   2 = 150 extra dependent ALU instructions per iteration (issue / ALU sensitivity).
-template <int LPQ, int BW, int MINB, bool STATS, int LV = 1, int EXP = 0>
+template <int LPQ, int BW, int MINB, bool STATS, int LV = 1, int EXP = 0, bool SYM8 = false>
 __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevImage im, const CountArgs a,
                                                                      unsigned long long* __restrict__ work,
                                                                      unsigned long long* __restrict__ stats) {
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
   int64_t obA = 0, obB = 0;    // Occ bases; become C[c]+Occ(c,first-1) and C[c]+Occ(c,last)
 
   for (;;) {
-    retire_and_fetch(s, !cross_pending, im, a, work, lane, gleader);
+    retire_and_fetch<SYM8>(s, !cross_pending, im, a, work, lane, gleader);
     if (!__any_sync(kFull, s.have)) break;
 
     // ---- set-up of one round (normally a whole backward-search step), all groups together
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
       bool hasA = false, cross = false;
       uint32_t rbA = 0;
       if (!cross_pending) {
-        c = s.pat[s.i - 1];
+        c = pat_sym<SYM8>(s.pat, s.i - 1);
         if (STATS && sub == 0) n_steps++;
         if (c >= kAlphaDev) {  // symbol outside the alphabet: empty range
           s.f = im.total_length; s.l = s.f - 1; s.i--;
@@ -977,6 +987,13 @@ cudaError_t launch_count(const DevImage& im, const CountArgs& a, unsigned long l
     if (d_stats) FM_LAUNCH((count_sync_kernel<2, 32, MINB, true, 4>), 2);                                \
     else FM_LAUNCH((count_sync_kernel<2, 32, MINB, false, 4>), 2);                                       \
     break;
+  // raw text bytes instead of alpha_t symbols: the default schedule of the quad image only
+  if (a.sym8) {
+    if (code != 3000000 + 32 * 10000 + 1000 + 10 * 2 + 4 || d_stats) return cudaErrorNotSupported;
+    FM_LAUNCH((count_sync_kernel<2, 32, 4, false, 4, 0, true>), 2);
+    if (launch_counter) ++*launch_counter;
+    return cudaGetLastError();
+  }
 #define FM_SYNC4EXP(MINB, EXP)                                                                           \
   case 3000000 + 32 * 10000 + 1000 + 70 + 10 * (EXP) + (MINB):                                           \
     if (d_stats) FM_LAUNCH((count_sync_kernel<2, 32, MINB, true, 4, EXP>), 2);                           \

@@ -25,6 +25,9 @@ struct CountArgs {
   // > 0: every pattern has this length and pattern i starts at flat + i * uniform_len; plen and offs
   // are not read (and need not be copied in).
   int32_t uniform_len;
+  // != 0: flat holds raw text bytes, one per symbol (symbol = byte + 5, strtoalpha); offs / uniform_len
+  // count bytes.  Halves the host->device traffic of a batch; default quad schedule only.
+  int32_t sym8;
 };
 
 enum WalkMode : int {

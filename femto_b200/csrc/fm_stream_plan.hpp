@@ -28,11 +28,13 @@ inline int64_t stream_chunk_at(int64_t lo) {
 // end (exclusive, in symbols) of the symbol copy of a chunk whose last pattern is hi - 1, for an
 // in-order batch: the end of that pattern rounded up to a 128-byte line, the whole buffer for the
 // last chunk
+// (sym_bytes: 2 for alpha_t symbols, 1 for raw text bytes -- 64 resp. 128 symbols per line)
 inline int64_t stream_symbol_cut(const int32_t* plen, const int64_t* offs, int64_t hi, int64_t npats,
-                                 int64_t flat_len) {
+                                 int64_t flat_len, int sym_bytes = 2) {
   if (hi >= npats) return flat_len;
   const int64_t end = offs[hi - 1] + plen[hi - 1];
-  return std::min(flat_len, (end + 63) & ~int64_t(63));
+  const int64_t per_line = 128 / sym_bytes;
+  return std::min(flat_len, (end + per_line - 1) & ~(per_line - 1));
 }
 
 }  // namespace fmb

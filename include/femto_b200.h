@@ -106,6 +106,15 @@ int fm_count(fm_index_t* ix, int npats, const int* plen, const uint16_t* const* 
 int fm_count_flat(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
                   const int64_t* offs, int64_t* first, int64_t* last);
 
+/* The same call for patterns given as raw text bytes -- what the reference's batch tool reads from its
+ * pattern file before widening every byte to an alpha_t (read_queries, src/main/query_tool.c:48-98;
+ * strtoalpha, src/main/index_types.h:85-97): pattern i is text[offs[i] .. offs[i]+plen[i]), its symbols
+ * are FM_CHARACTER_OFFSET + byte.  Half the host->device bytes of fm_count_flat; the count kernel adds
+ * the offset as it reads (quad image, default schedule; otherwise the bytes are widened on the host).
+ * Escape codes cannot be expressed in this form -- use fm_count_flat for those. */
+int fm_count_bytes(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint8_t* text, const int64_t* offs,
+                   int64_t* first, int64_t* last);
+
 /* Device-resident form: all pointers are device pointers on ix's device, `stream`
  * is a cudaStream_t (NULL = default stream).  Asynchronous: returns after enqueueing.
  * flat_len = number of symbols in d_flat. */

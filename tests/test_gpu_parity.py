@@ -580,3 +580,79 @@ def test_pointer_array_call_gathers_behind_the_kernel(built_indexes, corpora):
             assert (f == of[pick]).all() and (l == ol[pick]).all()
         f2, l2 = ix.count_flat(plen, flat, offs)
         assert (f2 == f).all() and (l2 == l).all()
+
+
+def test_streamed_batch_back_pointing_last_pattern(built_indexes, corpora):
+    """A dense prefix whose LAST pattern points back to offset 0: the shape claimed from the first and
+    last pattern is a 12-symbol buffer, so every chunk must fail the lazy check (each pattern has to
+    end inside the claimed buffer) before the kernel touches symbols that were never copied; the call
+    then validates the whole batch and answers it the plain way."""
+    name = "english_100k"
+    docs, _ = corpora[name]
+    n = 150000
+    base = corpus.sample_patterns(docs, 1000, [12], seed=81, random_fraction=0.2)
+    rng = np.random.default_rng(82)
+    pick = rng.integers(0, len(base), n)
+    pats = [base[i] for i in pick]
+    plen, flat, offs = fb.flatten_patterns(pats)
+    offs = offs.copy()
+    offs[n - 1] = 0                                           # -> claim_len = 12
+    with fb.Index(built_indexes[name], device=0) as ix, Oracle(built_indexes[name]) as o:
+        of, ol = o.count(base)
+        want_f, want_l = of[pick].copy(), ol[pick].copy()
+        want_f[n - 1], want_l[n - 1] = want_f[0], want_l[0]   # the last pattern now IS the first one
+        f, l = ix.count_flat(plen, flat, offs)
+        assert (f == want_f).all() and (l == want_l).all()
+        f, l = ix.count_flat(plen, flat, offs)                # and the handle still streams fine afterwards
+        assert (f == want_f).all() and (l == want_l).all()
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_count_bytes_equals_count_flat(uniform, built_indexes, corpora):
+    """fm_count_bytes (raw text bytes, widened by the kernel as it reads) against fm_count_flat on the
+    same patterns as alpha_t symbols and against the oracle: a small batch (plain path) and a batch of
+    >= 128 Ki patterns (streamed path: chunk cuts at 128 bytes = 128 symbols)."""
+    name = "english_100k"
+    docs, _ = corpora[name]
+    lengths = [12] if uniform else [1, 2, 3, 5, 8, 13, 21, 34]
+    base = corpus.sample_patterns(docs, 3000, lengths, seed=91, random_fraction=0.2)
+    base = [p for p in base if len(p)]                                        # bytes cannot say "empty" differently
+    with fb.Index(built_indexes[name], device=0) as ix, Oracle(built_indexes[name]) as o:
+        of, ol = o.count(base)
+        for n in (len(base), 200000 + 33):
+            pick = np.arange(n) if n == len(base) else np.random.default_rng(92).integers(0, len(base), n)
+            pats = [base[i] for i in pick]
+            plen, flat, offs = fb.flatten_patterns(pats)
+            text = (flat[:int(plen.sum())] - fb.CHARACTER_OFFSET).astype(np.uint8)
+            f, l = ix.count_bytes(plen, text, offs)
+            assert (f == of[pick]).all() and (l == ol[pick]).all()
+            f2, l2 = ix.count_flat(plen, flat, offs)
+            assert (f2 == f).all() and (l2 == l).all()
+
+
+def test_count_bytes_other_layouts_widen_on_the_host(built_indexes, corpora):
+    name = "acgt_64k"
+    docs, _ = corpora[name]
+    base = [p for p in corpus.sample_patterns(docs, 500, [2, 7, 16], seed=93) if len(p)]
+    plen, flat, offs = fb.flatten_patterns(base)
+    text = (flat[:int(plen.sum())] - fb.CHARACTER_OFFSET).astype(np.uint8)
+    opened = open_with_layout({name: built_indexes[name]}, 128, 1)
+    try:
+        with Oracle(built_indexes[name]) as o:
+            of, ol = o.count(base)
+        f, l = opened[name].count_bytes(plen, text, offs)
+        assert (f == of).all() and (l == ol).all()
+    finally:
+        for ix in opened.values():
+            ix.close()
+
+
+def test_locate_negative_max_occs_gives_no_rows(built_indexes, corpora):
+    """max_occs < 0: the reference's clip leaves last < first, i.e. no rows (server.c:4411-4415)."""
+    name = "acgt_64k"
+    docs, _ = corpora[name]
+    pats = corpus.sample_patterns(docs, 50, [3, 5], seed=94, random_fraction=0.0)
+    plen, flat, offs = fb.flatten_patterns(pats)
+    with fb.Index(built_indexes[name], device=0) as ix:
+        noccs, start, out = ix.locate_flat(plen, flat, offs, -5, 16)
+        assert (noccs == 0).all()
