@@ -1058,8 +1058,9 @@ int fm_mesh_create(fm_index_t* ix, int rank, int world, int64_t window, int cap_
     if (window == 0) window = 128 << 10;
     // a ring must hold every state in flight: world * (window + what the warps of one rank may claim
     // beyond the window between its check and their claims)
-    // (SMs x CTAs x warps x 16: once for the claims, twice for the two blocks a warp owns per ring)
-    const int64_t slack = int64_t(ix->sm_count) * 8 * 8 * 16 * 3;
+    // per warp (SMs x 4 CTAs x 8 warps at most): a chunk of 32 ids it may have claimed past the window, and
+    // the three blocks of 16 ring indices it owns per ring
+    const int64_t slack = int64_t(ix->sm_count) * 4 * 8 * (32 + 48);
     int shift = 10;
     while ((int64_t(1) << shift) < int64_t(world) * (window + slack)) shift++;
     if (cap_log2 > 0) {  // tests: a small ring that wraps many times (the caller also bounds the grid: fm_mesh_set_limits)
@@ -1167,8 +1168,8 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
       return fail(FM_ERR_PARAM, "fm_mesh: pattern ids must fit 32 bits");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {  // the ring must hold every state in flight (fm_mesh.cuh): world * (window + one claim per group of the grid)
-      const int64_t ctas = m->max_ctas > 0 ? m->max_ctas : int64_t(ix->sm_count) * 8;
-      if ((int64_t(1) << m->cap_shift) < int64_t(m->world) * (int64_t(m->window) + ctas * 8 * 16 * 3))
+      const int64_t ctas = m->max_ctas > 0 ? m->max_ctas : int64_t(ix->sm_count) * 4;
+      if ((int64_t(1) << m->cap_shift) < int64_t(m->world) * (int64_t(m->window) + ctas * 8 * (32 + 48)))
         return fail(FM_ERR_PARAM, "fm_mesh: ring too small for this window and grid (cap_log2 / fm_mesh_set_limits)");
     }
     m->epoch++;

@@ -82,6 +82,7 @@ struct MeshWarp {
   uint32_t cap_mask;
   unsigned long long eptag;  // the batch's part of the tag, in place (bits 56..63)
   unsigned n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;  // per warp: 32 bits are plenty
+  bool published = false;
 };
 
 // tag of ring index idx: batch field (1..255) << 8 | lap field (1..255), in the top 16 bits.  Never 0, so a
@@ -110,6 +111,8 @@ __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int sr
 // path.  A slot whose four tags are not (yet) the expected ones is simply not there yet.
 struct MeshInbox {
   unsigned long long blk[2];  // lane r < world: next unconsumed index in each of the two blocks owned on ring r
+  unsigned long long spare;   // lane r: a third block, ticket already taken: replaces the next one that is used up
+                              // (its own replacement is requested then and not looked at before the next time)
   unsigned rot;               // which two blocks are staged (warp-uniform)
   bool staged;
 };
@@ -199,7 +202,10 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
         const int tk = hh ? take1 : take0;
         if (tk > 0 && w.lane == rg) {
           unsigned long long nx = (wh ? in.blk[1] : in.blk[0]) + tk;
-          if ((nx & (kMeshBlock - 1)) == 0) nx = mesh_ticket(a, rg);
+          if ((nx & (kMeshBlock - 1)) == 0) {
+            nx = in.spare;
+            in.spare = mesh_ticket(a, rg);
+          }
           if (wh) in.blk[1] = nx; else in.blk[0] = nx;
         }
       }
@@ -246,16 +252,11 @@ __device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArg
   }
 }
 
-// `cnt` results were delivered: the rank that completes its batch tells everybody.
+// Results were delivered: count them (a reduction: nobody waits for the counter).  The rank's "all my
+// results are home" flag is raised by the first warps that find themselves idle afterwards (mesh_idle_exit).
 __device__ __forceinline__ void mesh_delivered(const MeshWarp& w, const MeshArgs& a, unsigned delivered_mask) {
-  if (delivered_mask && w.lane == 0) {
-    const unsigned long long cnt = __popc(delivered_mask);
-    const unsigned long long old = atomicAdd(&a.ctl->done_count, cnt);
-    if (old + cnt == static_cast<unsigned long long>(a.n_mine)) {
-      __threadfence();
-      for (int r = 0; r < a.world; r++) st_volatile_u64(&a.peer_ctl[r]->rank_done[a.rank], a.epoch);
-    }
-  }
+  if (delivered_mask && w.lane == 0)
+    atomicAdd(&a.ctl->done_count, static_cast<unsigned long long>(__popc(delivered_mask)));
 }
 
 __device__ __forceinline__ int mesh_owner(const MeshArgs& a, int64_t row) {
@@ -263,9 +264,16 @@ __device__ __forceinline__ int mesh_owner(const MeshArgs& a, int64_t row) {
 }
 
 // Idle warp: true when the batch is over everywhere (or has failed).
-__device__ __forceinline__ bool mesh_idle_exit(const MeshWarp& w, const MeshArgs& a, long long& idle_start, unsigned& backoff) {
+__device__ __forceinline__ bool mesh_idle_exit(MeshWarp& w, const MeshArgs& a, long long& idle_start, unsigned& backoff) {
   const bool ok = w.lane >= a.world || ld_volatile_u64(&a.ctl->rank_done[w.lane]) >= a.epoch;
   if (__all_sync(kFull, ok)) return true;
+  if (!w.published) {  // all results of this rank's own patterns are home: tell every rank (any idle warp may, once)
+    const bool all_home = ld_volatile_u64(&a.ctl->done_count) >= static_cast<unsigned long long>(a.n_mine);
+    if (all_home) {
+      if (w.lane < a.world) st_volatile_u64(&a.peer_ctl[w.lane]->rank_done[a.rank], a.epoch);
+      w.published = true;
+    }
+  }
   int st = 0;
   if (w.lane == 0) st = *reinterpret_cast<volatile int*>(&a.ctl->status);
   if (__shfl_sync(kFull, st, 0)) return true;
@@ -304,75 +312,110 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox&
   w.cap_mask = (1u << a.cap_shift) - 1u;
   w.eptag = (a.epoch % 255ull + 1ull) << 56;
   // two blocks on every ring (one lane per ring), then different warps start their rotation at different blocks
-  in.blk[0] = in.blk[1] = 0;
+  in.blk[0] = in.blk[1] = in.spare = 0;
   if (w.lane < a.world && w.lane != a.rank) {
     in.blk[0] = mesh_ticket(a, w.lane);
     in.blk[1] = mesh_ticket(a, w.lane);
+    in.spare = mesh_ticket(a, w.lane);
   }
   in.rot = static_cast<unsigned>(w.wid) * 2u;
   in.staged = false;
-  // a rank without patterns of its own has nothing to wait for
-  if (a.n_mine == 0 && blockIdx.x == 0 && threadIdx.x < a.world)
-    st_volatile_u64(&a.peer_ctl[threadIdx.x]->rank_done[a.rank], a.epoch);
   return w;
 }
 
-// Claim new patterns of the own batch for the idle groups the inbox could not serve.  Returns the
-// batch-local index for this group or -1.  Warp-collective.
-__device__ __forceinline__ int64_t mesh_inject(MeshWarp& w, const MeshArgs& a, unsigned needers, bool have, bool& exhausted) {
-  const int want = __popc(needers);
-  unsigned long long base = ~0ull;
-  if (w.lane == 0) {
-    const unsigned long long inj = ld_volatile_u64(&a.ctl->injected), done = ld_volatile_u64(&a.ctl->done_count);
-    if (inj >= static_cast<unsigned long long>(a.n_mine)) base = ~0ull - 1;
-    else if (inj - done < a.window) base = atomicAdd(&a.ctl->injected, static_cast<unsigned long long>(want));
-  }
-  base = __shfl_sync(kFull, base, 0);
-  if (base == ~0ull - 1) { exhausted = true; return -1; }
-  if (base == ~0ull) return -1;
-  const unsigned long long idx = base + __popc(needers & ((1u << w.gleader) - 1u));
+// ---- new patterns of the own batch --------------------------------------------------------------
+// A warp claims batch-local ids in chunks and hands them to its idle groups over the following rounds.  The
+// claim is a three-stage pipeline, one stage per round, so that no round waits for it: read the rank's
+// counters -> if fewer than `window` own patterns are unfinished, add the chunk to `injected` -> use the ids.
+constexpr unsigned kFeedChunk = 32;
+struct MeshFeed {
+  unsigned pool_next = 0, pool_end = 0;     // batch-local ids this warp may hand out (warp-uniform; ids fit 32 bits)
+  unsigned long long p0 = 0, p1 = 0;        // lane 0: what the previous stage requested (counters, then the claim)
+  int stage = 0;
+  bool exhausted = false;
+};
+
+__device__ __forceinline__ void mesh_feed_advance(const MeshWarp& w, const MeshArgs& a, MeshFeed& f) {
+  if (f.exhausted || f.pool_next < f.pool_end) return;
   const unsigned long long n = static_cast<unsigned long long>(a.n_mine);
-  if (base + want >= n) exhausted = true;
-  if (base < n) w.n_inject += static_cast<unsigned>(min(static_cast<unsigned long long>(want), n - base));
-  if (have || idx >= n) return -1;
-  return static_cast<int64_t>(idx);
+  if (f.stage == 0) {
+    if (w.lane == 0) {
+      f.p0 = ld_volatile_u64(&a.ctl->injected);
+      f.p1 = ld_volatile_u64(&a.ctl->done_count);
+    }
+    f.stage = 1;
+  } else if (f.stage == 1) {
+    int dec = 0;  // 0 window full: look again, 1 chunk requested, 2 nothing left
+    if (w.lane == 0) {
+      if (f.p0 >= n) dec = 2;
+      else if (f.p0 - f.p1 < a.window) {
+        dec = 1;
+        f.p0 = atomicAdd(&a.ctl->injected, static_cast<unsigned long long>(kFeedChunk));
+      }
+    }
+    dec = __shfl_sync(kFull, dec, 0);
+    if (dec == 2) f.exhausted = true;
+    f.stage = dec == 1 ? 2 : 0;
+  } else {
+    const unsigned long long base = __shfl_sync(kFull, f.p0, 0);
+    if (base >= n) f.exhausted = true;
+    else { f.pool_next = static_cast<unsigned>(base); f.pool_end = static_cast<unsigned>(min(base + kFeedChunk, n)); }
+    f.stage = 0;
+  }
 }
 
+// the batch-local id for this group, or -1.  Warp-collective.
+__device__ __forceinline__ int64_t mesh_feed_take(MeshWarp& w, MeshFeed& f, unsigned needers, bool have) {
+  const unsigned avail = f.pool_end - f.pool_next;
+  if (!needers || !avail) return -1;
+  const unsigned take = min(static_cast<unsigned>(__popc(needers)), avail);
+  const unsigned k = __popc(needers & ((1u << w.gleader) - 1u));
+  const unsigned idx = f.pool_next + k;
+  f.pool_next += take;
+  w.n_inject += take;
+  return (!have && k < take) ? static_cast<int64_t>(idx) : -1;
+}
+
+constexpr int kPhaseNew = 3;  // just injected: the pattern's symbols are still on their way from memory
+
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage im, const MeshArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevImage im, const MeshArgs a) {
   __shared__ __align__(16) MeshStage stage;
+  __shared__ int64_t s_C[kAlphaDev + 1];  // C[] of the whole index (replicated header table)
+  for (int t = threadIdx.x; t <= kAlphaDev; t += kThreads) s_C[t] = im.C[t];
+  __syncthreads();
   MeshInbox inbox;
   MeshWarp w = mesh_warp_init(a, inbox);
+  MeshFeed feed;
+  feed.exhausted = a.n_mine == 0;
   MeshState s;
-  bool have = false, exhausted = a.n_mine == 0;
+  bool have = false;
   long long idle_start = 0;
-  unsigned backoff = 100, iter = 0;
+  unsigned backoff = 100;
   unsigned n_rounds = 0, n_pairs = 0, n_singles = 0;
 
-  for (;; iter++) {
-    // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch
+  for (;;) {
+    // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch.  Neither waits for
+    // memory: the inbox slots were copied to shared memory during the previous round, the ids come from the
+    // warp's pool, and a new pattern's symbols are only looked at in the NEXT round (fresh).
+    bool fresh = false;
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
-    if (needers) {
-      mesh_take_inbox(w, a, inbox, stage, needers, s, have);
-      if (needers && !exhausted) {
-        const int64_t k = mesh_inject(w, a, needers, have, exhausted);
-        if (k >= 0) {
-          s.id = static_cast<uint32_t>(a.pid_lo + k);
-          const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.id];
-          const uint16_t* pat = a.flat + (a.uniform_len > 0 ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
-          if (m <= 0) {  // empty pattern: every row (server.c:782-808)
-            s.A = 0; s.B = im.total_length - 1; s.i = 0;
-          } else {
-            const int c = pat[m - 1];
-            if (c >= kAlphaDev) { s.A = im.total_length; s.B = s.A - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
-            else { s.A = __ldg(im.C + c); s.B = __ldg(im.C + c + 1) - 1; }
-            s.i = m - 1;
-          }
-          s.c = s.i > 0 ? pat[s.i - 1] : 0;
-          s.phase = kPhaseA;
-          s.home = a.rank;
-          have = true;
-        }
+    if (needers) mesh_take_inbox(w, a, inbox, stage, needers, s, have);
+    mesh_feed_advance(w, a, feed);
+    {
+      const int64_t k = mesh_feed_take(w, feed, needers, have);
+      if (k >= 0) {
+        s.id = static_cast<uint32_t>(a.pid_lo + k);
+        const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.id];
+        const uint16_t* pat = a.flat + (a.uniform_len > 0 ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
+        s.i = m;
+        s.A = m > 0 ? pat[m - 1] : 0;  // raw symbols until the next round turns them into a range
+        s.B = m > 1 ? pat[m - 2] : 0;
+        s.phase = kPhaseNew;
+        s.home = a.rank;
+        have = true;
+        fresh = true;
       }
     }
     if (!__any_sync(kFull, have)) {
@@ -382,11 +425,24 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage 
     idle_start = 0;
     backoff = 100;
 
+    if (have && !fresh && s.phase == kPhaseNew) {  // [C[c], C[c+1]-1] for the pattern's last symbol (server.c:781-801)
+      const int m = s.i, c0 = static_cast<int>(s.A);
+      s.c = static_cast<int>(s.B);
+      if (m <= 0) {  // empty pattern: every row (server.c:782-808)
+        s.A = 0; s.B = im.total_length - 1; s.i = 0;
+      } else {
+        if (c0 >= kAlphaDev) { s.A = im.total_length; s.B = s.A - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
+        else { s.A = s_C[c0]; s.B = s_C[c0 + 1] - 1; }
+        s.i = m - 1;
+      }
+      s.phase = kPhaseA;
+    }
+
     // ---- 2. what happens to each state in this round
     bool send = false, deliver = false, doA = false, doB = false;
     int dest = 0, c = 0;
     int64_t rowA = 0, rowB = 0;
-    if (have) {
+    if (have && !fresh) {
       if (s.phase == kPhaseDone) {
         deliver = true;
       } else if (s.phase == kPhaseA && (s.A > s.B || s.i == 0)) {  // ends the reference's loop (server.c:832-841)
@@ -399,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage 
         } else {
           if (s.phase == kPhaseA) {
             if (s.A == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
-              s.A = __ldg(im.C + c);
+              s.A = s_C[c];
               s.phase = kPhaseB;
             } else {
               rowA = s.A - 1;
@@ -494,31 +550,36 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_count_kernel(const DevImage 
 // ---------------------------------------------------------------------------------------------
 // Sampled-SA walks over the range-sharded index.  State: id = result slot at the home rank, A = BWT
 // row (the text offset once finished, -1 for a malformed walk), i = LF steps taken so far.
-__global__ void __launch_bounds__(kThreads, 4) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
   __shared__ __align__(16) MeshStage stage;
   MeshInbox inbox;
   MeshWarp w = mesh_warp_init(a, inbox);
+  MeshFeed feed;
+  feed.exhausted = a.n_mine == 0;
   MeshState s;
-  bool have = false, exhausted = a.n_mine == 0;
+  bool have = false;
   long long idle_start = 0;
-  unsigned backoff = 100, iter = 0;
+  unsigned backoff = 100;
   unsigned long long n_rounds = 0, n_quad = 0, n_mark = 0, n_sample = 0;
 
-  for (;; iter++) {
+  for (;;) {
+    bool fresh = false;
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
-    if (needers) {
-      mesh_take_inbox(w, a, inbox, stage, needers, s, have);
-      if (needers && !exhausted) {
-        const int64_t k = mesh_inject(w, a, needers, have, exhausted);
-        if (k >= 0) {
-          s.id = static_cast<uint32_t>(k);
-          s.A = a.rows[k];
-          s.B = 0;
-          s.i = 0;
-          s.phase = kPhaseA;
-          s.home = a.rank;
-          have = true;
-        }
+    if (needers) mesh_take_inbox(w, a, inbox, stage, needers, s, have);
+    mesh_feed_advance(w, a, feed);
+    {
+      const int64_t k = mesh_feed_take(w, feed, needers, have);
+      if (k >= 0) {
+        s.id = static_cast<uint32_t>(k);
+        s.A = a.rows[k];  // looked at in the next round
+        s.B = 0;
+        s.i = 0;
+        s.c = 0;
+        s.phase = kPhaseA;
+        s.home = a.rank;
+        have = true;
+        fresh = true;
       }
     }
     if (!__any_sync(kFull, have)) {
@@ -530,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 4) mesh_walk_kernel(const DevImage i
 
     bool send = false, deliver = false, step = false;
     int dest = 0;
-    if (have) {
+    if (have && !fresh) {
       if (s.phase != kPhaseDone && (s.A < 0 || s.A >= im.total_length)) {  // not a row of this index
         if (w.sub == 0) atomicExch(&a.ctl->status, 2);
         s.A = -1;
@@ -618,14 +679,19 @@ cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& 
 
 cudaError_t launch_mesh_count(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
                               int64_t* launch_counter) {
-  return launch_mesh(reinterpret_cast<const void*>(&mesh_count_kernel), im, a, sm_count, max_ctas, stream,
-                     launch_counter);
+  // resident CTAs per SM the kernel is compiled for: 4 (64 registers; default) or 3 (80)
+  static const int minb = [] { const char* v = std::getenv("FEMTO_B200_MESH_CTAS"); return v && v[0] == '3' ? 3 : 4; }();
+  return launch_mesh(minb == 3 ? reinterpret_cast<const void*>(&mesh_count_kernel<3>)
+                               : reinterpret_cast<const void*>(&mesh_count_kernel<4>),
+                     im, a, sm_count, max_ctas, stream, launch_counter);
 }
 
 cudaError_t launch_mesh_walk(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
                              int64_t* launch_counter) {
-  return launch_mesh(reinterpret_cast<const void*>(&mesh_walk_kernel), im, a, sm_count, max_ctas, stream,
-                     launch_counter);
+  static const int minb = [] { const char* v = std::getenv("FEMTO_B200_MESH_CTAS"); return v && v[0] == '3' ? 3 : 4; }();
+  return launch_mesh(minb == 3 ? reinterpret_cast<const void*>(&mesh_walk_kernel<3>)
+                               : reinterpret_cast<const void*>(&mesh_walk_kernel<4>),
+                     im, a, sm_count, max_ctas, stream, launch_counter);
 }
 
 }  // namespace fmb

@@ -76,7 +76,7 @@ def test_mesh_count_shards_on_one_gpu(name, nshards, built_indexes, corpora):
 
 
 def test_mesh_small_ring_wraps_and_window_throttles(built_indexes, corpora):
-    """An 8192-slot ring and 64 patterns in flight per rank: the ring wraps many times within a batch and
+    """A 16384-slot ring and 64 patterns in flight per rank: the ring wraps many times within a batch and
     the injection window is what keeps it from overrunning; three batches in a row reuse it (epochs)."""
     from oracle.bindings import Oracle
     name = "english_100k"
@@ -85,9 +85,9 @@ def test_mesh_small_ring_wraps_and_window_throttles(built_indexes, corpora):
     pats = corpus.sample_patterns(docs, 20000, [16], seed=7, random_fraction=0.05)   # equal lengths: uniform_len path
     with Oracle(path) as o:
         of, ol = o.count(pats)
-    first, last, stats = _run_local(path, pats, 2, window=64, cap_log2=13, max_ctas=8, batches=3)
+    first, last, stats = _run_local(path, pats, 2, window=64, cap_log2=14, max_ctas=8, batches=3)
     assert (first == of).all() and (last == ol).all()
-    assert sum(s["sent"] for s in stats) > 8192 * 4
+    assert sum(s["sent"] for s in stats) > 16384 * 4
 
 
 def test_mesh_counts_only(built_indexes, corpora):
