@@ -97,73 +97,90 @@ __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int sr
 }
 
 // ---- consuming the inbox -----------------------------------------------------------------------
-// A warp owns, at all times, TWO blocks of 16 consecutive indices on every ring (lane r keeps ring r's in
-// registers: the index of the next unconsumed slot of each).  Blocks are handed out by a ticket counter in
-// this rank's own memory, in index order, to whichever warp has just finished one -- a warp that is busy
-// takes tickets more slowly, so the load follows the warps' speed, and the unconsumed span of a ring never
-// exceeds the states in flight plus two blocks per warp.  The new ticket is requested when a block is used
-// up; its value is needed only when the warp's other block on that ring is used up too, many rounds later.
+// A warp owns TWO blocks of 16 consecutive indices on every ring (the index of the next unconsumed slot of
+// each is kept in shared memory, s_blk).  Blocks are handed out by a ticket counter in this rank's own
+// memory, in index order, to whichever warp has just used one up -- a warp that is busy takes tickets more
+// slowly, so the load follows the warps' speed, and the unconsumed span of a ring never exceeds the states in
+// flight plus the blocks the warps hold.  Every block a warp owns is polled (nothing arrives where nobody
+// looks); a ticket is requested in one round and its block joins the polled set in the next, so the
+// atomic's latency is never waited for.
 //
 // Reading is decoupled from consuming: at the END of its fetch a warp copies the remaining slots of two of
-// its blocks (one per half warp, rotating over its 2 x world blocks) into shared memory with cp.async (L2
-// only: the slots are written by other GPUs); it looks at them at the START of its next fetch, after a whole
-// round of evaluations, so taking states from the inbox costs no memory round trip on the round's critical
-// path.  A slot whose four tags are not (yet) the expected ones is simply not there yet.
+// its blocks (one per half warp, rotating over the rings) into shared memory with cp.async (L2 only: the
+// slots are written by other GPUs); it looks at them at the START of its next fetch, after a whole round of
+// evaluations, so taking states from the inbox costs no memory round trip on the round's critical path.  A
+// slot whose four tags are not (yet) the expected ones is simply not there yet.
+constexpr unsigned long long kNoBlock = ~0ull;
 struct MeshInbox {
-  unsigned long long blk[2];  // lane r < world: next unconsumed index in each of the two blocks owned on ring r
-  unsigned long long spare;   // lane r: a third block, ticket already taken: replaces the next one that is used up
-                              // (its own replacement is requested then and not looked at before the next time)
-  unsigned rot;               // which two blocks are staged (warp-uniform)
+  unsigned long long pend;  // lane r < world: the ticket requested for ring r in the previous round
+  int pend_which;           // which of the ring's two blocks it replaces, -1: none outstanding
+  unsigned todo;            // lane r: blocks of ring r used up and not yet replaced (bit per block)
+  unsigned rot;             // which ring's blocks are staged (warp-uniform)
   bool staged;
 };
-using MeshStage = ulonglong2[kThreads / 32][32][2];  // per warp: one 32-byte slot per lane
+using MeshStage = ulonglong2[kThreads / 32][32][2];                   // per warp: one 32-byte slot per lane
+// per warp and ring: cursors of its two blocks; entry [kMeshMaxRanks] = the two cursors the staged copies were made from
+using MeshBlocks = unsigned long long[kThreads / 32][kMeshMaxRanks + 1][2];
 
 __device__ __forceinline__ unsigned long long mesh_ticket(const MeshArgs& a, int ring) {
   return atomicAdd(&a.ctl->head_block[ring], 1ull) * kMeshBlock;
 }
 
-// the block staged by half h in rotation step `rot`: ring (skipping this rank's own, which is never written) and which of the two
-__device__ __forceinline__ void mesh_stage_source(const MeshArgs& a, unsigned rot, int h, int& ring, int& which) {
-  const unsigned nsrc = 2u * static_cast<unsigned>(a.world - 1);
-  const unsigned k = (rot + static_cast<unsigned>(h)) % nsrc;
-  ring = static_cast<int>(k >> 1);
+// the ring staged in rotation step `rot` (this rank's own ring is never written: skipped)
+__device__ __forceinline__ int mesh_stage_ring(const MeshArgs& a, unsigned rot) {
+  int ring = static_cast<int>(rot % static_cast<unsigned>(a.world - 1));
   if (ring >= a.rank) ring++;
-  which = static_cast<int>(k & 1u);
+  return ring;
 }
 
-__device__ __forceinline__ void mesh_stage_issue(const MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage) {
+__device__ __forceinline__ void mesh_stage_issue(const MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage,
+                                                 MeshBlocks& blk) {
   const int h = w.lane >> 4, j = w.lane & 15;
-  int ring, which;
-  mesh_stage_source(a, in.rot, h, ring, which);
-  const unsigned long long b0 = __shfl_sync(kFull, in.blk[0], ring), b1 = __shfl_sync(kFull, in.blk[1], ring);
-  const unsigned long long cur = which ? b1 : b0;
-  if (j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
+  const int ring = mesh_stage_ring(a, in.rot);
+  const unsigned long long cur = blk[w.wic][ring][h];
+  if (cur != kNoBlock && j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
     const ulonglong2* src = mesh_slot(a.ring, ring, cur + j, w, a);
     const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&stage[w.wic][w.lane][0]));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 1) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  if (j == 0) blk[w.wic][kMeshMaxRanks][h] = cur;  // what the staged slots belong to
   in.staged = true;
 }
 
 // Fill idle groups from the slots staged by the previous fetch, then stage the next ones.  needers: ballot
-// of the leader lanes of the groups without a state; updated.  Warp-collective.
+// of the leader lanes of the groups without a state; updated.  Warp-collective; called every round.
 __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage,
-                                                unsigned& needers, MeshState& s, bool& have) {
+                                                MeshBlocks& blk, unsigned& needers, MeshState& s, bool& have) {
   constexpr unsigned long long kTagMask = ~kPayloadMask;
   if (a.world == 1) return;
-  if (in.staged) {
+  // tickets requested in the previous round have arrived: their blocks join the polled set; blocks still
+  // waiting for a replacement request theirs
+  if (w.lane < a.world && w.lane != a.rank) {
+    if (in.pend_which >= 0) {
+      blk[w.wic][w.lane][in.pend_which] = in.pend;
+      in.pend_which = -1;
+    }
+    if (in.todo) {
+      const int wh = (in.todo & 1u) ? 0 : 1;
+      in.pend = mesh_ticket(a, w.lane);
+      in.pend_which = wh;
+      in.todo &= ~(1u << wh);
+    }
+  }
+  __syncwarp();
+  const int want = __popc(needers);
+  if (in.staged && want > 0) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     const int h = w.lane >> 4, j = w.lane & 15;
-    int ring, which;
-    mesh_stage_source(a, in.rot, h, ring, which);
-    const unsigned long long b0 = __shfl_sync(kFull, in.blk[0], ring), b1 = __shfl_sync(kFull, in.blk[1], ring);
-    const unsigned long long cur = which ? b1 : b0;
+    const int ring = mesh_stage_ring(a, in.rot);
+    const unsigned long long cur = blk[w.wic][ring][h];
+    const bool same = cur == blk[w.wic][kMeshMaxRanks][h];  // (a block that joined the set since was not staged)
     bool valid = false;
     ulonglong2 m0 = make_ulonglong2(0, 0), m1 = m0;
-    if (j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
+    if (same && cur != kNoBlock && j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
       m0 = stage[w.wic][w.lane][0];
       m1 = stage[w.wic][w.lane][1];
       const unsigned long long tag = mesh_tag(w, a, cur + j);
@@ -171,13 +188,12 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
               (m1.y & kTagMask) == tag;  // all four words of THIS message have landed
     }
     const unsigned vm = __ballot_sync(kFull, valid);
-    // messages in order from each half's cursor; the two halves never stage the same block (world > 1)
+    // messages in order from each block's cursor
     const int v0 = __ffs(~(vm & 0xffffu)) - 1, v1 = __ffs(~(vm >> 16)) - 1;
-    const int want = __popc(needers);
     const int take0 = min(v0, want), take1 = min(v1, want - take0);
     const int take = take0 + take1;
     if (take > 0) {
-      // the k-th idle group takes the k-th message: first half 0's, then half 1's
+      // the k-th idle group takes the k-th message: first block 0's, then block 1's
       const int k = __popc(needers & ((1u << w.gleader) - 1u));
       const int src = k < take0 ? k : min(16 + (k - take0), 31);
       const unsigned long long w0 = __shfl_sync(kFull, m0.x, src), w1 = __shfl_sync(kFull, m0.y, src),
@@ -194,27 +210,30 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
       }
       for (int t = 0; t < take; t++) needers &= needers - 1;
       w.n_recv += take;
-      // advance the cursors (the lane of each ring holds them); a finished block is replaced by a new ticket
+      __syncwarp();
+      // advance the cursors; a block that is used up leaves the polled set and is replaced by a new ticket
+      if (w.lane == ring) {
 #pragma unroll
-      for (int hh = 0; hh < 2; hh++) {
-        int rg, wh;
-        mesh_stage_source(a, in.rot, hh, rg, wh);
-        const int tk = hh ? take1 : take0;
-        if (tk > 0 && w.lane == rg) {
-          unsigned long long nx = (wh ? in.blk[1] : in.blk[0]) + tk;
-          if ((nx & (kMeshBlock - 1)) == 0) {
-            nx = in.spare;
-            in.spare = mesh_ticket(a, rg);
+        for (int hh = 0; hh < 2; hh++) {
+          const int tk = hh ? take1 : take0;
+          if (tk > 0) {
+            unsigned long long nx = blk[w.wic][ring][hh] + tk;
+            if ((nx & (kMeshBlock - 1)) == 0) {
+              nx = kNoBlock;
+              in.todo |= 1u << hh;
+            }
+            blk[w.wic][ring][hh] = nx;
           }
-          if (wh) in.blk[1] = nx; else in.blk[0] = nx;
         }
       }
+      __syncwarp();
     } else {
       w.n_empty++;
     }
-    if (take0 == v0 && take1 == v1) in.rot += 2;  // both staged blocks drained as far as they were filled: move on
+    if (take0 == v0 && take1 == v1) in.rot++;  // both blocks drained as far as they were filled: next ring
+    in.staged = false;
   }
-  mesh_stage_issue(w, a, in, stage);
+  if (!in.staged) mesh_stage_issue(w, a, in, stage, blk);
 }
 
 // Departing states, step 1: claim their ring indices (one atomic per destination and warp, on counters in
@@ -301,7 +320,7 @@ __device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshAr
   }
 }
 
-__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox& in) {
+__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox& in, MeshBlocks& blk) {
   MeshWarp w;
   w.lane = threadIdx.x & 31;
   w.sub = w.lane & 1;
@@ -312,13 +331,16 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox&
   w.cap_mask = (1u << a.cap_shift) - 1u;
   w.eptag = (a.epoch % 255ull + 1ull) << 56;
   // two blocks on every ring (one lane per ring), then different warps start their rotation at different blocks
-  in.blk[0] = in.blk[1] = in.spare = 0;
-  if (w.lane < a.world && w.lane != a.rank) {
-    in.blk[0] = mesh_ticket(a, w.lane);
-    in.blk[1] = mesh_ticket(a, w.lane);
-    in.spare = mesh_ticket(a, w.lane);
+  in.pend = 0;
+  in.pend_which = -1;
+  in.todo = 0;
+  if (w.lane < kMeshMaxRanks) {
+    const bool ring = w.lane < a.world && w.lane != a.rank;
+    blk[w.wic][w.lane][0] = ring ? mesh_ticket(a, w.lane) : kNoBlock;
+    blk[w.wic][w.lane][1] = ring ? mesh_ticket(a, w.lane) : kNoBlock;
   }
-  in.rot = static_cast<unsigned>(w.wid) * 2u;
+  __syncwarp();
+  in.rot = static_cast<unsigned>(w.wid);  // different warps start their rotation at different rings
   in.staged = false;
   return w;
 }
@@ -382,11 +404,12 @@ constexpr int kPhaseNew = 3;  // just injected: the pattern's symbols are still 
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevImage im, const MeshArgs a) {
   __shared__ __align__(16) MeshStage stage;
+  __shared__ MeshBlocks blocks;
   __shared__ int64_t s_C[kAlphaDev + 1];  // C[] of the whole index (replicated header table)
   for (int t = threadIdx.x; t <= kAlphaDev; t += kThreads) s_C[t] = im.C[t];
   __syncthreads();
   MeshInbox inbox;
-  MeshWarp w = mesh_warp_init(a, inbox);
+  MeshWarp w = mesh_warp_init(a, inbox, blocks);
   MeshFeed feed;
   feed.exhausted = a.n_mine == 0;
   MeshState s;
@@ -401,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
     // warp's pool, and a new pattern's symbols are only looked at in the NEXT round (fresh).
     bool fresh = false;
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
-    if (needers) mesh_take_inbox(w, a, inbox, stage, needers, s, have);
+    mesh_take_inbox(w, a, inbox, stage, blocks, needers, s, have);
     mesh_feed_advance(w, a, feed);
     {
       const int64_t k = mesh_feed_take(w, feed, needers, have);
@@ -553,8 +576,9 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
   __shared__ __align__(16) MeshStage stage;
+  __shared__ MeshBlocks blocks;
   MeshInbox inbox;
-  MeshWarp w = mesh_warp_init(a, inbox);
+  MeshWarp w = mesh_warp_init(a, inbox, blocks);
   MeshFeed feed;
   feed.exhausted = a.n_mine == 0;
   MeshState s;
@@ -566,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
   for (;;) {
     bool fresh = false;
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
-    if (needers) mesh_take_inbox(w, a, inbox, stage, needers, s, have);
+    mesh_take_inbox(w, a, inbox, stage, blocks, needers, s, have);
     mesh_feed_advance(w, a, feed);
     {
       const int64_t k = mesh_feed_take(w, feed, needers, have);
