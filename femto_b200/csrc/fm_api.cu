@@ -1204,6 +1204,11 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
     a.out_offset = d_offsets;
     a.block_size = ix->info.block_size;
     a.nblocks = ix->info.num_blocks;
+    for (int r = 0; r <= kMeshMaxRanks; r++) {
+      // shard r = blocks b with b * world / nblocks == r, i.e. from block ceil(r * nblocks / world) on (fm_open_shard)
+      const int64_t b = r >= m->world ? a.nblocks : (int64_t(r) * a.nblocks + m->world - 1) / m->world;
+      a.shard_start[r] = std::min<int64_t>(b * a.block_size, ix->info.total_length);
+    }
     // the kernel's own counters start from zero; rank_done (written by the peers) is never reset
     CK(cudaMemsetAsync(base, 0, offsetof(MeshCtl, rank_done), s));
     if (walk) CK(launch_mesh_walk(ix->im, a, ix->sm_count, m->max_ctas, s, &ix->launches));

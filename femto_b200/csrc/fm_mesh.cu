@@ -2,15 +2,21 @@
 //
 //   mesh_count_kernel : do_string_query's backward search (src/main/server.c:713-946) over an index
 //                       split by data block (src/main/index.h:83-100); a pattern's state
-//                       {id, first | C+Occ(c,first-1), last, i, phase, home} moves to the GPU that
-//                       owns the row its next Occ needs and comes home with [first, last].
+//                       {id, first | C+Occ(c,first-1), last, i, pending symbol, phase, home} moves to the
+//                       GPU that owns the row its next Occ needs and comes home with [first, last].
 //   mesh_walk_kernel  : the sampled-SA walk of do_back_query / do_context_query
 //                       (server.c:2228-2359, 2627-2795); state {slot, row, LF steps, home}.
 //
 // Both evaluate rank over quad-level blocks exactly as the single-GPU kernels do (fm_rank.cuh), so a
-// state computes the same numbers wherever it is.  A round of a warp: take states (inbox first, then
-// new patterns of the own batch), decide per state -- deliver, send, or evaluate here --, store the
-// departing ones into their owners' inboxes, evaluate the others warp-synchronously.
+// state computes the same numbers wherever it is.  One round of a warp (16 lane groups, one state each):
+//   1. fill the idle groups -- from the inbox slots copied to shared memory during the previous round, else
+//      with new patterns of the rank's own batch;
+//   2. evaluate, warp-synchronously, every state whose row(s) are resident here;
+//   3. store the states that left in the previous round into their owners' inboxes (their slot indices were
+//      requested then: the atomics' latency lies behind a whole round);
+//   4. route every state: finished and home -> result; next row elsewhere -> leaves (slot index requested
+//      now); next row here -> stays for the next round.
+// Nothing in a round waits for a memory access other than the evaluation's own rank-block reads.
 #include "fm_mesh.cuh"
 
 #include <cstdlib>
@@ -23,11 +29,6 @@ namespace {
 // Two 64-bit words with one instruction.  A vector access is a set of scalar accesses: each 64-bit
 // word is read / written whole (single-copy atomic), the pair is not -- which is why EVERY word of a
 // message carries the tag.
-__device__ __forceinline__ ulonglong2 ld_volatile_v2(const ulonglong2* p) {
-  ulonglong2 v;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_volatile_v2(ulonglong2* p, const ulonglong2 v) {
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
@@ -62,7 +63,10 @@ struct MeshState {
 constexpr int kPhaseA = 0;     // count: needs Occ(c, first-1) then Occ(c, last); A = first, B = last.  walk: walking
 constexpr int kPhaseB = 1;     // count: A = C[c]+Occ(c,first-1) is known, needs Occ(c, last)
 constexpr int kPhaseDone = 2;  // finished: travels home; count: A = first, B = last; walk: A = offset
+constexpr int kPhaseNew = 3;   // just injected (never travels): the pattern's symbols are still on their way from memory
 constexpr unsigned long long kPayloadMask = (1ull << 48) - 1;
+constexpr unsigned long long kTagMask = ~kPayloadMask;
+constexpr unsigned long long kNoBlock = ~0ull;
 
 __device__ __forceinline__ int64_t sext48(unsigned long long v) {
   return static_cast<int64_t>(v << 16) >> 16;
@@ -76,90 +80,100 @@ __device__ __forceinline__ void pack_state(const MeshState& s, unsigned long lon
          (static_cast<unsigned long long>(static_cast<uint32_t>(s.c) & 0xffffu) << 32);
 }
 
+// Per CTA.  stage: one 32-byte inbox slot per lane, copied in with cp.async; blk: per warp and ring the cursors
+// (next unconsumed index) of its two blocks, entry [kMeshMaxRanks] = the cursors the staged copies were made
+// from; peer_ring / start: kernel parameters that are indexed with a run-time value.
+struct MeshShared {
+  ulonglong2 stage[kThreads / 32][32][2];
+  unsigned long long blk[kThreads / 32][kMeshMaxRanks + 1][2];
+  uint4* peer_ring[kMeshMaxRanks];
+  int64_t start[kMeshMaxRanks + 1];
+};
+
 struct MeshWarp {
   int lane, sub, gleader, wic;
-  unsigned long long W, wid;
   uint32_t cap_mask;
   unsigned long long eptag;  // the batch's part of the tag, in place (bits 56..63)
   unsigned n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;  // per warp: 32 bits are plenty
   bool published = false;
 };
 
-// tag of ring index idx: batch field (1..255) << 8 | lap field (1..255), in the top 16 bits.  Never 0, so a
-// cleared slot is never valid; a slot is rewritten every lap, and the rings are cleared before the batch
-// field repeats (fm_api.cu), so a stale word never carries the expected tag.
+// tag of ring index idx: batch field (1..255) << 8 | low 8 bits of the ring's lap, in the top 16 bits.  Never
+// 0, so a cleared slot is never valid; a slot is rewritten every lap, and the rings are cleared before the
+// batch field repeats (fm_api.cu), so a stale word never carries the expected tag.
 __device__ __forceinline__ unsigned long long mesh_tag(const MeshWarp& w, const MeshArgs& a, unsigned long long idx) {
-  return w.eptag | (((idx >> a.cap_shift) % 255ull + 1ull) << 48);
+  return w.eptag | (((idx >> a.cap_shift) & 0xffull) << 48);
 }
 __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int src, unsigned long long idx, const MeshWarp& w,
                                                        const MeshArgs& a) {
   return reinterpret_cast<const ulonglong2*>(ring + ((static_cast<size_t>(src) << a.cap_shift) + (idx & w.cap_mask)) * 2);
 }
 
+// owner(row) = (row / block_size) * world / nblocks (the reference's block -> file map, partitioned): shard r
+// starts at block ceil(r * nblocks / world); start[r] is that block's first row.
+__device__ __forceinline__ int mesh_owner(const MeshArgs& a, const MeshShared& sh, int64_t row) {
+  int o = 0;
+  for (int r = 1; r < a.world; r++) o += row >= sh.start[r] ? 1 : 0;
+  return o;
+}
+
 // ---- consuming the inbox -----------------------------------------------------------------------
 // A warp owns TWO blocks of 16 consecutive indices on every ring (the index of the next unconsumed slot of
-// each is kept in shared memory, s_blk).  Blocks are handed out by a ticket counter in this rank's own
-// memory, in index order, to whichever warp has just used one up -- a warp that is busy takes tickets more
-// slowly, so the load follows the warps' speed, and the unconsumed span of a ring never exceeds the states in
-// flight plus the blocks the warps hold.  Every block a warp owns is polled (nothing arrives where nobody
-// looks); a ticket is requested in one round and its block joins the polled set in the next, so the
-// atomic's latency is never waited for.
+// each is kept in shared memory).  Blocks are handed out by a ticket counter in this rank's own memory, in
+// index order, to whichever warp has just used one up -- a warp that is busy takes tickets more slowly, so
+// the load follows the warps' speed, and the unconsumed span of a ring never exceeds the states in flight
+// plus the blocks the warps hold.  Every block a warp owns is polled (nothing arrives where nobody looks); a
+// ticket is requested in one round and its block joins the polled set in the next, so the atomic's latency is
+// never waited for.
 //
-// Reading is decoupled from consuming: at the END of its fetch a warp copies the remaining slots of two of
-// its blocks (one per half warp, rotating over the rings) into shared memory with cp.async (L2 only: the
-// slots are written by other GPUs); it looks at them at the START of its next fetch, after a whole round of
-// evaluations, so taking states from the inbox costs no memory round trip on the round's critical path.  A
-// slot whose four tags are not (yet) the expected ones is simply not there yet.
-constexpr unsigned long long kNoBlock = ~0ull;
+// Reading is decoupled from consuming: at the END of its fetch a warp copies the remaining slots of the two
+// blocks it owns on one ring (one block per half warp; the rings take turns) into shared memory with
+// cp.async (L2 only: the slots are written by other GPUs); it looks at them at the START of its next fetch,
+// after a whole round of evaluations, so taking states from the inbox costs no memory round trip on the
+// round's critical path.  A slot whose four tags are not (yet) the expected ones is simply not there yet.
 struct MeshInbox {
   unsigned long long pend;  // lane r < world: the ticket requested for ring r in the previous round
   int pend_which;           // which of the ring's two blocks it replaces, -1: none outstanding
   unsigned todo;            // lane r: blocks of ring r used up and not yet replaced (bit per block)
-  unsigned rot;             // which ring's blocks are staged (warp-uniform)
+  int ring;                 // the ring whose blocks are staged (warp-uniform)
   bool staged;
 };
-using MeshStage = ulonglong2[kThreads / 32][32][2];                   // per warp: one 32-byte slot per lane
-// per warp and ring: cursors of its two blocks; entry [kMeshMaxRanks] = the two cursors the staged copies were made from
-using MeshBlocks = unsigned long long[kThreads / 32][kMeshMaxRanks + 1][2];
 
 __device__ __forceinline__ unsigned long long mesh_ticket(const MeshArgs& a, int ring) {
   return atomicAdd(&a.ctl->head_block[ring], 1ull) * kMeshBlock;
 }
 
-// the ring staged in rotation step `rot` (this rank's own ring is never written: skipped)
-__device__ __forceinline__ int mesh_stage_ring(const MeshArgs& a, unsigned rot) {
-  int ring = static_cast<int>(rot % static_cast<unsigned>(a.world - 1));
-  if (ring >= a.rank) ring++;
+__device__ __forceinline__ int mesh_next_ring(const MeshArgs& a, int ring) {  // this rank's own ring is never written
+  ring++;
+  if (ring == a.rank) ring++;
+  if (ring >= a.world) ring = a.rank == 0 ? 1 : 0;
   return ring;
 }
 
-__device__ __forceinline__ void mesh_stage_issue(const MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage,
-                                                 MeshBlocks& blk) {
+__device__ __forceinline__ void mesh_stage_issue(const MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshShared& sh) {
   const int h = w.lane >> 4, j = w.lane & 15;
-  const int ring = mesh_stage_ring(a, in.rot);
-  const unsigned long long cur = blk[w.wic][ring][h];
+  const unsigned long long cur = sh.blk[w.wic][in.ring][h];
   if (cur != kNoBlock && j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
-    const ulonglong2* src = mesh_slot(a.ring, ring, cur + j, w, a);
-    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&stage[w.wic][w.lane][0]));
+    const ulonglong2* src = mesh_slot(a.ring, in.ring, cur + j, w, a);
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&sh.stage[w.wic][w.lane][0]));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 1) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  if (j == 0) blk[w.wic][kMeshMaxRanks][h] = cur;  // what the staged slots belong to
+  if (j == 0) sh.blk[w.wic][kMeshMaxRanks][h] = cur;  // what the staged slots belong to
   in.staged = true;
 }
 
 // Fill idle groups from the slots staged by the previous fetch, then stage the next ones.  needers: ballot
 // of the leader lanes of the groups without a state; updated.  Warp-collective; called every round.
-__device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshStage& stage,
-                                                MeshBlocks& blk, unsigned& needers, MeshState& s, bool& have) {
-  constexpr unsigned long long kTagMask = ~kPayloadMask;
+__device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, MeshInbox& in, MeshShared& sh,
+                                                unsigned& needers, MeshState& s, bool& have) {
   if (a.world == 1) return;
   // tickets requested in the previous round have arrived: their blocks join the polled set; blocks still
   // waiting for a replacement request theirs
   if (w.lane < a.world && w.lane != a.rank) {
     if (in.pend_which >= 0) {
-      blk[w.wic][w.lane][in.pend_which] = in.pend;
+      sh.blk[w.wic][w.lane][in.pend_which] = in.pend;
       in.pend_which = -1;
     }
     if (in.todo) {
@@ -175,14 +189,13 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     const int h = w.lane >> 4, j = w.lane & 15;
-    const int ring = mesh_stage_ring(a, in.rot);
-    const unsigned long long cur = blk[w.wic][ring][h];
-    const bool same = cur == blk[w.wic][kMeshMaxRanks][h];  // (a block that joined the set since was not staged)
+    const unsigned long long cur = sh.blk[w.wic][in.ring][h];
+    const bool same = cur == sh.blk[w.wic][kMeshMaxRanks][h];  // (a block that joined the set since was not staged)
     bool valid = false;
     ulonglong2 m0 = make_ulonglong2(0, 0), m1 = m0;
     if (same && cur != kNoBlock && j < kMeshBlock - static_cast<int>(cur & (kMeshBlock - 1))) {
-      m0 = stage[w.wic][w.lane][0];
-      m1 = stage[w.wic][w.lane][1];
+      m0 = sh.stage[w.wic][w.lane][0];
+      m1 = sh.stage[w.wic][w.lane][1];
       const unsigned long long tag = mesh_tag(w, a, cur + j);
       valid = (m0.x & kTagMask) == tag && (m0.y & kTagMask) == tag && (m1.x & kTagMask) == tag &&
               (m1.y & kTagMask) == tag;  // all four words of THIS message have landed
@@ -212,17 +225,17 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
       w.n_recv += take;
       __syncwarp();
       // advance the cursors; a block that is used up leaves the polled set and is replaced by a new ticket
-      if (w.lane == ring) {
+      if (w.lane == in.ring) {
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
           const int tk = hh ? take1 : take0;
           if (tk > 0) {
-            unsigned long long nx = blk[w.wic][ring][hh] + tk;
+            unsigned long long nx = sh.blk[w.wic][in.ring][hh] + tk;
             if ((nx & (kMeshBlock - 1)) == 0) {
               nx = kNoBlock;
               in.todo |= 1u << hh;
             }
-            blk[w.wic][ring][hh] = nx;
+            sh.blk[w.wic][in.ring][hh] = nx;
           }
         }
       }
@@ -230,15 +243,15 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
     } else {
       w.n_empty++;
     }
-    if (take0 == v0 && take1 == v1) in.rot++;  // both blocks drained as far as they were filled: next ring
+    if (take0 == v0 && take1 == v1) in.ring = mesh_next_ring(a, in.ring);  // drained as far as filled: next ring
     in.staged = false;
   }
-  if (!in.staged) mesh_stage_issue(w, a, in, stage, blk);
+  if (!in.staged) mesh_stage_issue(w, a, in, sh);
 }
 
-// Departing states, step 1: claim their ring indices (one atomic per destination and warp, on counters in
-// this rank's own memory).  Returns this lane's index (valid when it sends).  The stores follow in
-// mesh_send_store -- after the round's evaluations have been issued, so the atomics' latency overlaps them.
+// ---- leaving states ------------------------------------------------------------------------------
+// Step 1: claim their ring indices (one atomic per destination and warp, on counters in this rank's own
+// memory).  Returns this lane's index (valid when it sends).  The stores follow one round later.
 __device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const MeshArgs& a, bool& send, int dest) {
   if (send && (dest < 0 || dest >= a.world)) {  // cannot happen with a well-formed index; never store out of bounds
     if (w.sub == 0) atomicExch(&a.ctl->status, 2);
@@ -260,12 +273,12 @@ __device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const
   }
   return idx;
 }
-__device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArgs& a, bool send, int dest,
-                                                unsigned long long idx, const MeshState& s) {
+__device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArgs& a, const MeshShared& sh, bool send,
+                                                int dest, unsigned long long idx, const MeshState& s) {
   if (send && w.sub == 0) {
     ulonglong2 m0, m1;
     pack_state(s, mesh_tag(w, a, idx), m0, m1);
-    ulonglong2* slot = const_cast<ulonglong2*>(mesh_slot(a.peer_ring[dest], a.rank, idx, w, a));
+    ulonglong2* slot = const_cast<ulonglong2*>(mesh_slot(sh.peer_ring[dest], a.rank, idx, w, a));
     st_volatile_v2(slot, m0);
     st_volatile_v2(slot + 1, m1);
   }
@@ -276,10 +289,6 @@ __device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArg
 __device__ __forceinline__ void mesh_delivered(const MeshWarp& w, const MeshArgs& a, unsigned delivered_mask) {
   if (delivered_mask && w.lane == 0)
     atomicAdd(&a.ctl->done_count, static_cast<unsigned long long>(__popc(delivered_mask)));
-}
-
-__device__ __forceinline__ int mesh_owner(const MeshArgs& a, int64_t row) {
-  return static_cast<int>(((row / a.block_size) * a.world) / a.nblocks);
 }
 
 // Idle warp: true when the batch is over everywhere (or has failed).
@@ -320,28 +329,29 @@ __device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshAr
   }
 }
 
-__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox& in, MeshBlocks& blk) {
+__device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox& in, MeshShared& sh) {
   MeshWarp w;
   w.lane = threadIdx.x & 31;
   w.sub = w.lane & 1;
   w.gleader = w.lane & ~1;
   w.wic = threadIdx.x >> 5;
-  w.W = static_cast<unsigned long long>(gridDim.x) * (kThreads / 32);
-  w.wid = static_cast<unsigned long long>(blockIdx.x) * (kThreads / 32) + w.wic;
   w.cap_mask = (1u << a.cap_shift) - 1u;
   w.eptag = (a.epoch % 255ull + 1ull) << 56;
-  // two blocks on every ring (one lane per ring), then different warps start their rotation at different blocks
+  if (threadIdx.x < kMeshMaxRanks) sh.peer_ring[threadIdx.x] = a.peer_ring[threadIdx.x];
+  if (threadIdx.x <= kMeshMaxRanks) sh.start[threadIdx.x] = a.shard_start[threadIdx.x];
   in.pend = 0;
   in.pend_which = -1;
   in.todo = 0;
   if (w.lane < kMeshMaxRanks) {
     const bool ring = w.lane < a.world && w.lane != a.rank;
-    blk[w.wic][w.lane][0] = ring ? mesh_ticket(a, w.lane) : kNoBlock;
-    blk[w.wic][w.lane][1] = ring ? mesh_ticket(a, w.lane) : kNoBlock;
+    sh.blk[w.wic][w.lane][0] = ring ? mesh_ticket(a, w.lane) : kNoBlock;
+    sh.blk[w.wic][w.lane][1] = ring ? mesh_ticket(a, w.lane) : kNoBlock;
   }
-  __syncwarp();
-  in.rot = static_cast<unsigned>(w.wid);  // different warps start their rotation at different rings
+  // different warps start their rotation at different rings
+  in.ring = a.world > 1 ? static_cast<int>((blockIdx.x * (kThreads / 32) + w.wic) % (a.world - 1)) : 0;
+  if (in.ring >= a.rank) in.ring++;
   in.staged = false;
+  __syncthreads();
   return w;
 }
 
@@ -398,33 +408,87 @@ __device__ __forceinline__ int64_t mesh_feed_take(MeshWarp& w, MeshFeed& f, unsi
   return (!have && k < take) ? static_cast<int64_t>(idx) : -1;
 }
 
-constexpr int kPhaseNew = 3;  // just injected: the pattern's symbols are still on their way from memory
-
 // ---------------------------------------------------------------------------------------------
+// What a state does next.
+struct CountPlan {
+  bool send = false, deliver = false, doA = false, doB = false;
+  int dest = 0;
+  int64_t rowA = 0, rowB = 0;
+};
+
+__device__ __forceinline__ CountPlan mesh_count_plan(const DevImage& im, const MeshArgs& a, const MeshShared& sh,
+                                                     const int64_t* s_C, MeshState& s, bool live) {
+  CountPlan p;
+  if (!live) return p;
+  if (s.phase == kPhaseNew) {  // [C[c], C[c+1]-1] for the pattern's last symbol (server.c:781-801)
+    const int m = s.i, c0 = static_cast<int>(s.A);
+    s.c = static_cast<int>(s.B);
+    if (m <= 0) {  // empty pattern: every row (server.c:782-808)
+      s.A = 0; s.B = im.total_length - 1; s.i = 0;
+    } else {
+      if (c0 >= kAlphaDev) { s.A = im.total_length; s.B = s.A - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
+      else { s.A = s_C[c0]; s.B = s_C[c0 + 1] - 1; }
+      s.i = m - 1;
+    }
+    s.phase = kPhaseA;
+  }
+  if (s.phase == kPhaseA && s.A <= s.B && s.i > 0 && s.c >= kAlphaDev) {  // symbol outside the alphabet: empty range
+    s.A = im.total_length; s.B = s.A - 1; s.i--;
+  }
+  if (s.phase == kPhaseA && (s.A > s.B || s.i == 0)) s.phase = kPhaseDone;  // ends the reference's loop (server.c:832-841)
+  if (s.phase == kPhaseDone) {
+    if (s.home == a.rank) p.deliver = true;
+    else { p.send = true; p.dest = s.home; }
+    return p;
+  }
+  if (s.phase == kPhaseA) {
+    if (s.A == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
+      s.A = s_C[s.c];
+      s.phase = kPhaseB;
+    } else {
+      p.rowA = s.A - 1;
+      if (p.rowA >= im.first_row && p.rowA < im.end_row) p.doA = true;
+      else { p.send = true; p.dest = mesh_owner(a, sh, p.rowA); return p; }
+    }
+  }
+  p.rowB = s.B;
+  const bool resB = p.rowB >= im.first_row && p.rowB < im.end_row;
+  if (s.phase == kPhaseB) {
+    if (resB) p.doB = true;
+    else { p.send = true; p.dest = mesh_owner(a, sh, p.rowB); }
+  } else if (resB) {  // both rows here: one round when they share a bucket, else A now and B in the next round
+    int64_t gA, gB;
+    uint32_t ra, rb;
+    split_row(im, p.rowA, gA, ra);
+    split_row(im, p.rowB, gB, rb);
+    p.doB = gA == gB;
+  }
+  return p;
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevImage im, const MeshArgs a) {
-  __shared__ __align__(16) MeshStage stage;
-  __shared__ MeshBlocks blocks;
+  __shared__ __align__(16) MeshShared sh;
   __shared__ int64_t s_C[kAlphaDev + 1];  // C[] of the whole index (replicated header table)
   for (int t = threadIdx.x; t <= kAlphaDev; t += kThreads) s_C[t] = im.C[t];
-  __syncthreads();
   MeshInbox inbox;
-  MeshWarp w = mesh_warp_init(a, inbox, blocks);
+  MeshWarp w = mesh_warp_init(a, inbox, sh);
   MeshFeed feed;
   feed.exhausted = a.n_mine == 0;
-  MeshState s;
-  bool have = false;
+  MeshState s, out;                  // out: the state that left this group in the previous round
+  bool have = false, out_live = false;
+  int out_dest = 0;
+  unsigned long long out_idx = 0;
   long long idle_start = 0;
   unsigned backoff = 100;
   unsigned n_rounds = 0, n_pairs = 0, n_singles = 0;
 
   for (;;) {
-    // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch.  Neither waits for
-    // memory: the inbox slots were copied to shared memory during the previous round, the ids come from the
-    // warp's pool, and a new pattern's symbols are only looked at in the NEXT round (fresh).
+    // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch.  A new pattern's
+    // symbols are requested here and looked at after the evaluations below (fresh).
     bool fresh = false;
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
-    mesh_take_inbox(w, a, inbox, stage, blocks, needers, s, have);
+    mesh_take_inbox(w, a, inbox, sh, needers, s, have);
     mesh_feed_advance(w, a, feed);
     {
       const int64_t k = mesh_feed_take(w, feed, needers, have);
@@ -433,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
         const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.id];
         const uint16_t* pat = a.flat + (a.uniform_len > 0 ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
         s.i = m;
-        s.A = m > 0 ? pat[m - 1] : 0;  // raw symbols until the next round turns them into a range
+        s.A = m > 0 ? pat[m - 1] : 0;  // raw symbols until the routing step turns them into a range
         s.B = m > 1 ? pat[m - 2] : 0;
         s.phase = kPhaseNew;
         s.home = a.rank;
@@ -441,131 +505,95 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
         fresh = true;
       }
     }
-    if (!__any_sync(kFull, have)) {
+    if (!__any_sync(kFull, have || out_live)) {
       if (mesh_idle_exit(w, a, idle_start, backoff)) break;
       continue;
     }
     idle_start = 0;
     backoff = 100;
 
-    if (have && !fresh && s.phase == kPhaseNew) {  // [C[c], C[c+1]-1] for the pattern's last symbol (server.c:781-801)
-      const int m = s.i, c0 = static_cast<int>(s.A);
-      s.c = static_cast<int>(s.B);
-      if (m <= 0) {  // empty pattern: every row (server.c:782-808)
-        s.A = 0; s.B = im.total_length - 1; s.i = 0;
-      } else {
-        if (c0 >= kAlphaDev) { s.A = im.total_length; s.B = s.A - 1; }  // get_C(ch>=ALPHA_SIZE), index.c:1545
-        else { s.A = s_C[c0]; s.B = s_C[c0 + 1] - 1; }
-        s.i = m - 1;
-      }
-      s.phase = kPhaseA;
-    }
-
-    // ---- 2. what happens to each state in this round
-    bool send = false, deliver = false, doA = false, doB = false;
-    int dest = 0, c = 0;
-    int64_t rowA = 0, rowB = 0;
-    if (have && !fresh) {
-      if (s.phase == kPhaseDone) {
-        deliver = true;
-      } else if (s.phase == kPhaseA && (s.A > s.B || s.i == 0)) {  // ends the reference's loop (server.c:832-841)
-        if (s.home == a.rank) deliver = true;
-        else { s.phase = kPhaseDone; send = true; dest = s.home; }
-      } else {
-        c = s.c;
-        if (s.phase == kPhaseA && c >= kAlphaDev) {  // symbol outside the alphabet: empty range
-          s.A = im.total_length; s.B = s.A - 1; s.i--;
-        } else {
-          if (s.phase == kPhaseA) {
-            if (s.A == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
-              s.A = s_C[c];
-              s.phase = kPhaseB;
-            } else {
-              rowA = s.A - 1;
-              if (rowA >= im.first_row && rowA < im.end_row) doA = true;
-              else { send = true; dest = mesh_owner(a, rowA); }
-            }
-          }
-          if (!send) {
-            rowB = s.B;
-            const bool resB = rowB >= im.first_row && rowB < im.end_row;
-            if (s.phase == kPhaseB) {
-              if (resB) doB = true;
-              else { send = true; dest = mesh_owner(a, rowB); }
-            } else if (resB) {  // both rows here: one round when they share a bucket, else A now and B next
-              int64_t gA, gB;
-              uint32_t ra, rb;
-              split_row(im, rowA, gA, ra);
-              split_row(im, rowB, gB, rb);
-              doB = gA == gB;
-            }
-          }
-        }
-      }
-    }
-
-    // ---- 3. results that are home
-    if (deliver) {
-      if (w.sub == 0) {
-        const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
-        if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
-        else a.first[slot] = s.B - s.A + 1;  // parallel_count with last==NULL (femto.c:313-318)
-      }
-      have = false;
-    }
-    mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
-
-    // ---- 4. states whose next row lives elsewhere: claim their inbox slots now, store them after the
-    // evaluations below have been issued
-    const MeshState out = s;
-    const unsigned long long out_idx = mesh_send_claim(w, a, send, dest);
-    if (send) have = false;
-
-    // ---- 5. the Occ evaluations that can be done here, all groups together
-    const bool any = doA || doB;
-    if (__any_sync(kFull, any)) {
-      uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0, rexit = 0;
-      int L = 0;
-      int64_t ob = 0;
-      bool actA = false, actB = false;
-      int cn = 0;  // the symbol of the step after this one, read while this one is evaluated
-      if (doB && s.i >= 2) {
-        const int m = a.uniform_len > 0 ? a.uniform_len : 0;
-        const uint16_t* pat = a.flat + (m ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
-        cn = pat[s.i - 2];
-      }
-      if (any) {
-        int64_t g = 0, g2;
-        uint32_t ra = 0, rb = 0;
-        if (doA) split_row(im, rowA, g, ra);
-        if (doB) split_row(im, rowB, doA ? g2 : g, rb);
-        const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + c));
-        ob = rec_occ_base(rv);
-        leaf = static_cast<uint32_t>(rv.z);
-        rexit = static_cast<uint32_t>(rv.w);
-        base = static_cast<uint32_t>(g * im.root_stride);
-        node = rexit >> 4;
-        idxA = ra + 1;
-        idxB = rb + 1;
-        if (leaf) {  // else: symbol absent from the bucket, Occ is the bucket base (index.c:2080-2089)
-          L = 31 - __clz(leaf);
-          actA = doA;
-          actB = doB;
-        }
+    // ---- 2. the Occ evaluations that can be done here, all groups together
+    {
+      const CountPlan p = mesh_count_plan(im, a, sh, s_C, s, have && !fresh);
+      if (p.deliver) {  // (a finished state that has just arrived home)
         if (w.sub == 0) {
-          n_rounds++;
-          if (doA && doB) n_pairs++; else n_singles++;
+          const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
+          if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
+          else a.first[slot] = s.B - s.A + 1;  // parallel_count with last==NULL (femto.c:313-318)
+        }
+        have = false;
+      }
+      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
+      const bool any = p.doA || p.doB;
+      if (__any_sync(kFull, any)) {
+        uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0, rexit = 0;
+        int L = 0;
+        int64_t ob = 0;
+        bool actA = false, actB = false;
+        int cn = 0;  // the symbol of the step after this one, read while this one is evaluated
+        if (p.doB && s.i >= 2) {
+          const int m = a.uniform_len > 0 ? a.uniform_len : 0;
+          const uint16_t* pat = a.flat + (m ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
+          cn = pat[s.i - 2];
+        }
+        if (any) {
+          int64_t g = 0, g2;
+          uint32_t ra = 0, rb = 0;
+          if (p.doA) split_row(im, p.rowA, g, ra);
+          if (p.doB) split_row(im, p.rowB, p.doA ? g2 : g, rb);
+          const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + s.c));
+          ob = rec_occ_base(rv);
+          leaf = static_cast<uint32_t>(rv.z);
+          rexit = static_cast<uint32_t>(rv.w);
+          base = static_cast<uint32_t>(g * im.root_stride);
+          node = rexit >> 4;
+          idxA = ra + 1;
+          idxB = rb + 1;
+          if (leaf) {  // else: symbol absent from the bucket, Occ is the bucket base (index.c:2080-2089)
+            L = 31 - __clz(leaf);
+            actA = p.doA;
+            actB = p.doB;
+          }
+          if (w.sub == 0) {
+            n_rounds++;
+            if (p.doA && p.doB) n_pairs++; else n_singles++;
+          }
+        }
+        quad_descend_pair(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub);
+        if (any) {
+          const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
+          if (p.doA && p.doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }
+          else if (p.doA) { s.A = resA; s.phase = kPhaseB; }
+          else { s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }  // A already holds C[c]+Occ(c,first-1)
         }
       }
-      quad_descend_pair(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub);
-      if (any) {
-        const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
-        if (doA && doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }
-        else if (doA) { s.A = resA; s.phase = kPhaseB; }
-        else { s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }  // A already holds C[c]+Occ(c,first-1)
+    }
+
+    // ---- 3. the states that left in the previous round: their slot indices have long arrived
+    mesh_send_store(w, a, sh, out_live, out_dest, out_idx, out);
+    out_live = false;
+
+    // ---- 4. route every state: result, leaves, or stays
+    {
+      const CountPlan p = mesh_count_plan(im, a, sh, s_C, s, have);
+      if (p.deliver) {
+        if (w.sub == 0) {
+          const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
+          if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
+          else a.first[slot] = s.B - s.A + 1;
+        }
+        have = false;
+      }
+      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
+      bool send = p.send;
+      out_idx = mesh_send_claim(w, a, send, p.dest);
+      if (send) {
+        out = s;
+        out_dest = p.dest;
+        out_live = true;
+        have = false;
       }
     }
-    mesh_send_store(w, a, send, dest, out_idx, out);
   }
   mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles);
 }
@@ -573,16 +601,43 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
 // ---------------------------------------------------------------------------------------------
 // Sampled-SA walks over the range-sharded index.  State: id = result slot at the home rank, A = BWT
 // row (the text offset once finished, -1 for a malformed walk), i = LF steps taken so far.
+struct WalkPlan {
+  bool send = false, deliver = false, step = false;
+  int dest = 0;
+};
+
+__device__ __forceinline__ WalkPlan mesh_walk_plan(const DevImage& im, const MeshArgs& a, const MeshShared& sh,
+                                                   const MeshWarp& w, MeshState& s, bool live) {
+  WalkPlan p;
+  if (!live) return p;
+  if (s.phase != kPhaseDone && (s.A < 0 || s.A >= im.total_length)) {  // not a row of this index
+    if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+    s.A = -1;
+    s.phase = kPhaseDone;
+  }
+  if (s.phase == kPhaseDone) {
+    if (s.home == a.rank) p.deliver = true;
+    else { p.send = true; p.dest = s.home; }
+  } else if (s.A >= im.first_row && s.A < im.end_row) {
+    p.step = true;
+  } else {
+    p.send = true;
+    p.dest = mesh_owner(a, sh, s.A);
+  }
+  return p;
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImage im, const MeshArgs a) {
-  __shared__ __align__(16) MeshStage stage;
-  __shared__ MeshBlocks blocks;
+  __shared__ __align__(16) MeshShared sh;
   MeshInbox inbox;
-  MeshWarp w = mesh_warp_init(a, inbox, blocks);
+  MeshWarp w = mesh_warp_init(a, inbox, sh);
   MeshFeed feed;
   feed.exhausted = a.n_mine == 0;
-  MeshState s;
-  bool have = false;
+  MeshState s, out;
+  bool have = false, out_live = false;
+  int out_dest = 0;
+  unsigned long long out_idx = 0;
   long long idle_start = 0;
   unsigned backoff = 100;
   unsigned long long n_rounds = 0, n_quad = 0, n_mark = 0, n_sample = 0;
@@ -590,13 +645,13 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
   for (;;) {
     bool fresh = false;
     unsigned needers = __ballot_sync(kFull, !have && w.sub == 0);
-    mesh_take_inbox(w, a, inbox, stage, blocks, needers, s, have);
+    mesh_take_inbox(w, a, inbox, sh, needers, s, have);
     mesh_feed_advance(w, a, feed);
     {
       const int64_t k = mesh_feed_take(w, feed, needers, have);
       if (k >= 0) {
         s.id = static_cast<uint32_t>(k);
-        s.A = a.rows[k];  // looked at in the next round
+        s.A = a.rows[k];  // looked at after this round's steps
         s.B = 0;
         s.i = 0;
         s.c = 0;
@@ -606,72 +661,72 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
         fresh = true;
       }
     }
-    if (!__any_sync(kFull, have)) {
+    if (!__any_sync(kFull, have || out_live)) {
       if (mesh_idle_exit(w, a, idle_start, backoff)) break;
       continue;
     }
     idle_start = 0;
     backoff = 100;
 
-    bool send = false, deliver = false, step = false;
-    int dest = 0;
-    if (have && !fresh) {
-      if (s.phase != kPhaseDone && (s.A < 0 || s.A >= im.total_length)) {  // not a row of this index
-        if (w.sub == 0) atomicExch(&a.ctl->status, 2);
-        s.A = -1;
-        s.phase = kPhaseDone;
-      }
-      if (s.phase == kPhaseDone) {
-        if (s.home == a.rank) deliver = true;
-        else { send = true; dest = s.home; }
-      } else if (s.A >= im.first_row && s.A < im.end_row) {
-        step = true;
-      } else {
-        send = true;
-        dest = mesh_owner(a, s.A);
-      }
-    }
-    if (deliver) {
-      if (w.sub == 0) a.out_offset[s.id] = s.A;
-      have = false;
-    }
-    mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
-    const MeshState out = s;
-    const unsigned long long out_idx = mesh_send_claim(w, a, send, dest);
-    if (send) have = false;
-
     // one LF step with mark test for every resident row (do_back_query, server.c:2228-2359)
-    if (__any_sync(kFull, step)) {
-      int64_t g = 0;
-      uint32_t rb = 0, ch = 0, count = 0;
-      uint64_t markval_base = 0;
-      if (step) {
-        split_row(im, s.A, g, rb);
-        if (w.sub == 0) n_rounds++;
+    {
+      const WalkPlan p = mesh_walk_plan(im, a, sh, w, s, have && !fresh);
+      if (p.deliver) {
+        if (w.sub == 0) a.out_offset[s.id] = s.A;
+        have = false;
       }
-      quad_wtree_rank(im, step, g, rb, w.sub, ch, count, markval_base, n_quad);
-      const bool ok = step && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
-      int64_t occ_base = 0, offset = -1;
-      mark_lookup<2, kQuadBlockWords>(im, ok, g, ch, count, markval_base, w.sub, offset, occ_base, n_mark, n_sample);
-      if (step) {
-        if (!ok) {
-          if (w.sub == 0) atomicExch(&a.ctl->status, 2);
-          s.A = -1;
-          s.phase = kPhaseDone;
-        } else if (offset >= 0) {
-          s.A = offset + s.i;
-          s.phase = kPhaseDone;
-        } else if (ch <= static_cast<uint32_t>(kEscSeofDev) || s.i > (1 << 30)) {  // unmarked document start
-          if (w.sub == 0) atomicExch(&a.ctl->status, 2);
-          s.A = -1;
-          s.phase = kPhaseDone;
-        } else {
-          s.A = occ_base + count - 1;  // LF
-          s.i++;
+      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
+      if (__any_sync(kFull, p.step)) {
+        int64_t g = 0;
+        uint32_t rb = 0, ch = 0, count = 0;
+        uint64_t markval_base = 0;
+        if (p.step) {
+          split_row(im, s.A, g, rb);
+          if (w.sub == 0) n_rounds++;
+        }
+        quad_wtree_rank(im, p.step, g, rb, w.sub, ch, count, markval_base, n_quad);
+        const bool ok = p.step && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
+        int64_t occ_base = 0, offset = -1;
+        mark_lookup<2, kQuadBlockWords>(im, ok, g, ch, count, markval_base, w.sub, offset, occ_base, n_mark, n_sample);
+        if (p.step) {
+          if (!ok) {
+            if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+            s.A = -1;
+            s.phase = kPhaseDone;
+          } else if (offset >= 0) {
+            s.A = offset + s.i;
+            s.phase = kPhaseDone;
+          } else if (ch <= static_cast<uint32_t>(kEscSeofDev) || s.i > (1 << 30)) {  // unmarked document start
+            if (w.sub == 0) atomicExch(&a.ctl->status, 2);
+            s.A = -1;
+            s.phase = kPhaseDone;
+          } else {
+            s.A = occ_base + count - 1;  // LF
+            s.i++;
+          }
         }
       }
     }
-    mesh_send_store(w, a, send, dest, out_idx, out);
+
+    mesh_send_store(w, a, sh, out_live, out_dest, out_idx, out);
+    out_live = false;
+
+    {
+      const WalkPlan p = mesh_walk_plan(im, a, sh, w, s, have);
+      if (p.deliver) {
+        if (w.sub == 0) a.out_offset[s.id] = s.A;
+        have = false;
+      }
+      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
+      bool send = p.send;
+      out_idx = mesh_send_claim(w, a, send, p.dest);
+      if (send) {
+        out = s;
+        out_dest = p.dest;
+        out_live = true;
+        have = false;
+      }
+    }
   }
   mesh_flush_stats(w, a, n_rounds, n_quad, n_mark + n_sample);
 }
@@ -686,8 +741,8 @@ cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& 
   if (bps < 1) bps = 1;
   int grid = sm_count * bps;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  // cooperative launch: every CTA of the grid is resident at once -- each warp owns a share of the
-  // inbox, so a CTA that is not running would leave its share unread
+  // cooperative launch: every CTA of the grid is resident at once -- each warp owns blocks of the inbox, so a
+  // CTA that is not running would leave its blocks unread
   DevImage im_copy = im;
   MeshArgs a_copy = a;
   void* args[2] = {&im_copy, &a_copy};
@@ -699,22 +754,25 @@ cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& 
   return cudaGetLastError();
 }
 
+// resident CTAs per SM the kernels are compiled for: 4 (64 registers; default) or 3 (80)
+int mesh_ctas_per_sm() {
+  static const int minb = [] { const char* v = std::getenv("FEMTO_B200_MESH_CTAS"); return v && v[0] == '3' ? 3 : 4; }();
+  return minb;
+}
+
 }  // namespace
 
 cudaError_t launch_mesh_count(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
                               int64_t* launch_counter) {
-  // resident CTAs per SM the kernel is compiled for: 4 (64 registers; default) or 3 (80)
-  static const int minb = [] { const char* v = std::getenv("FEMTO_B200_MESH_CTAS"); return v && v[0] == '3' ? 3 : 4; }();
-  return launch_mesh(minb == 3 ? reinterpret_cast<const void*>(&mesh_count_kernel<3>)
-                               : reinterpret_cast<const void*>(&mesh_count_kernel<4>),
+  return launch_mesh(mesh_ctas_per_sm() == 3 ? reinterpret_cast<const void*>(&mesh_count_kernel<3>)
+                                             : reinterpret_cast<const void*>(&mesh_count_kernel<4>),
                      im, a, sm_count, max_ctas, stream, launch_counter);
 }
 
 cudaError_t launch_mesh_walk(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
                              int64_t* launch_counter) {
-  static const int minb = [] { const char* v = std::getenv("FEMTO_B200_MESH_CTAS"); return v && v[0] == '3' ? 3 : 4; }();
-  return launch_mesh(minb == 3 ? reinterpret_cast<const void*>(&mesh_walk_kernel<3>)
-                               : reinterpret_cast<const void*>(&mesh_walk_kernel<4>),
+  return launch_mesh(mesh_ctas_per_sm() == 3 ? reinterpret_cast<const void*>(&mesh_walk_kernel<3>)
+                                             : reinterpret_cast<const void*>(&mesh_walk_kernel<4>),
                      im, a, sm_count, max_ctas, stream, launch_counter);
 }
 

@@ -74,8 +74,10 @@ struct MeshArgs {
   // sampled-SA walks (mesh_walk_kernel): my rows [0, n_mine) and their offsets
   const int64_t* rows;
   int64_t* out_offset;
-  // owner(row) = (row / block_size) * world / nblocks
+  // owner(row) = (row / block_size) * world / nblocks: shard r holds the rows from shard_start[r] on
+  // (first row of block ceil(r * nblocks / world)); shard_start[world] = total_length
   int64_t block_size, nblocks;
+  int64_t shard_start[kMeshMaxRanks + 1];
 };
 
 // max_ctas: 0 = fill the device; else an upper bound (several meshes sharing one GPU in a test).
