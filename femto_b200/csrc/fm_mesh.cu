@@ -466,8 +466,11 @@ __device__ __forceinline__ CountPlan mesh_count_plan(const DevImage& im, const M
   return p;
 }
 
-template <int MINB>
+// HINT: rank blocks are read with the L2 evict-first policy, so that they do not push the inbox rings and the
+// in-flight patterns' symbols (both re-read within microseconds) out of L2.
+template <int MINB, bool HINT>
 __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevImage im, const MeshArgs a) {
+  const uint64_t pol = HINT ? l2_evict_first_policy() : 0;
   __shared__ __align__(16) MeshShared sh;
   __shared__ int64_t s_C[kAlphaDev + 1];  // C[] of the whole index (replicated header table)
   for (int t = threadIdx.x; t <= kAlphaDev; t += kThreads) s_C[t] = im.C[t];
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
             if (p.doA && p.doB) n_pairs++; else n_singles++;
           }
         }
-        quad_descend_pair(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub);
+        quad_descend_pair<HINT>(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub, pol);
         if (any) {
           const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
           if (p.doA && p.doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }
@@ -764,9 +767,12 @@ int mesh_ctas_per_sm() {
 
 cudaError_t launch_mesh_count(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,
                               int64_t* launch_counter) {
-  return launch_mesh(mesh_ctas_per_sm() == 3 ? reinterpret_cast<const void*>(&mesh_count_kernel<3>)
-                                             : reinterpret_cast<const void*>(&mesh_count_kernel<4>),
-                     im, a, sm_count, max_ctas, stream, launch_counter);
+  static const bool hint = [] { const char* v = std::getenv("FEMTO_B200_MESH_EF"); return !(v && v[0] == '0'); }();
+  const void* k3 = hint ? reinterpret_cast<const void*>(&mesh_count_kernel<3, true>)
+                        : reinterpret_cast<const void*>(&mesh_count_kernel<3, false>);
+  const void* k4 = hint ? reinterpret_cast<const void*>(&mesh_count_kernel<4, true>)
+                        : reinterpret_cast<const void*>(&mesh_count_kernel<4, false>);
+  return launch_mesh(mesh_ctas_per_sm() == 3 ? k3 : k4, im, a, sm_count, max_ctas, stream, launch_counter);
 }
 
 cudaError_t launch_mesh_walk(const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas, cudaStream_t stream,

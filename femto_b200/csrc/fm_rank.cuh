@@ -323,6 +323,14 @@ struct QuadWords {
         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
         : "l"(b));
   }
+  // the same load with an L2 eviction hint (pol from l2_evict_first_policy()): a block read once and not
+  // again soon should not push out the lines other parts of a kernel keep coming back to
+  __device__ __forceinline__ void load_hint(const uint4* __restrict__ blocks, uint32_t blk, int sub, uint64_t pol) {
+    const uint4* b = blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4) + 4 + 2 * sub;
+    asm("ld.global.nc.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+        : "l"(b), "l"(pol));
+  }
   // Masks of this lane's 64 bits at positions >= x (x relative to the lane's first bit, any
   // integer): .x for the first word, .y for the second.  ONE 64-bit shift of all-ones serves both
   // words and needs no upper clamp (shr.b64 yields 0 for amounts >= 64); the lower clamp is the
@@ -354,6 +362,19 @@ struct QuadWords {
     return (word >> (31 - (pos & 31))) & 1u;
   }
 };
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint2 quad_header_hint(const uint4* __restrict__ blocks, uint32_t blk, uint32_t path3,
+                                                  uint64_t pol) {
+  uint2 v;
+  const uint2* p = reinterpret_cast<const uint2*>(blocks + static_cast<size_t>(blk) * (kQuadBlockWords / 4)) + path3;
+  asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
 
 // H[2 path3], H[2 path3 + 1]: both exits below the level-3 node and, in their top bytes, the
 // anchors of the level-2 and level-3 nodes on the path
@@ -493,9 +514,11 @@ __device__ __forceinline__ uint32_t quad_eval_pair(const QuadWords& p, const Qua
 // rows asked for (actA / actB say which of them), base / node the root quad node, leaf the symbol's
 // code (1 << L | code), rexit OccRec::root_exit.  On return idxA / idxB are the occurrences of the
 // symbol among the bucket's rows up to and including the row (wtree_occs, wtree.c:1081-1115).
+// HINT: the block reads carry the L2 evict-first policy `pol`.
+template <bool HINT = false>
 __device__ __forceinline__ void quad_descend_pair(const DevImage& im, bool actA, bool actB, uint32_t& idxA,
                                                   uint32_t& idxB, uint32_t base, uint32_t node, uint32_t leaf, int L,
-                                                  uint32_t rexit, int sub) {
+                                                  uint32_t rexit, int sub, uint64_t pol = 0) {
   int lvl = 0;
   while (__any_sync(kFull, actA || actB)) {
     const bool any = actA || actB;
@@ -509,11 +532,20 @@ __device__ __forceinline__ void quad_descend_pair(const DevImage& im, bool actA,
     q.clear();
     uint2 hp = make_uint2(0, 0), hq = hp, ex = hp;
     if (any) {
-      p.load(im.blocks, blkA, sub);
-      hp = quad_header(im.blocks, blkA, nib >> 1);
-      if (two) {
-        q.load(im.blocks, blkB, sub);
-        hq = quad_header(im.blocks, blkB, nib >> 1);
+      if (HINT) {
+        p.load_hint(im.blocks, blkA, sub, pol);
+        hp = quad_header_hint(im.blocks, blkA, nib >> 1, pol);
+        if (two) {
+          q.load_hint(im.blocks, blkB, sub, pol);
+          hq = quad_header_hint(im.blocks, blkB, nib >> 1, pol);
+        }
+      } else {
+        p.load(im.blocks, blkA, sub);
+        hp = quad_header(im.blocks, blkA, nib >> 1);
+        if (two) {
+          q.load(im.blocks, blkB, sub);
+          hq = quad_header(im.blocks, blkB, nib >> 1);
+        }
       }
       if (lvl + 4 < L) {
         if (lvl == 0 && (rexit & kRootExitDirect)) ex = make_uint2(rexit & ~kRootExitDirect, 0u);
