@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
     }
     idle_start = 0;
     backoff = 100;
+    n_rounds++;
 
     // ---- 2. the Occ evaluations that can be done here, all groups together
     {
@@ -557,11 +558,9 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
             actA = p.doA;
             actB = p.doB;
           }
-          if (w.sub == 0) {
-            n_rounds++;
-            if (p.doA && p.doB) n_pairs++; else n_singles++;
-          }
         }
+        n_pairs += __popc(__ballot_sync(kFull, p.doA && p.doB && w.sub == 0));
+        n_singles += __popc(__ballot_sync(kFull, any && !(p.doA && p.doB) && w.sub == 0));
         quad_descend_pair<HINT>(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub, pol);
         if (any) {
           const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);

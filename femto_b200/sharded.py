@@ -270,7 +270,7 @@ class Mesh:
         status = C.c_int(0)
         stats = (C.c_uint64 * 8)()
         rc = self.lib.fm_mesh_finish(self.h, st, C.byref(status), stats)
-        names = ["sent", "received", "rounds", "occ_pairs", "occ_singles", "empty_polls", "injected"]
+        names = ["sent", "received", "rounds", "occ_pairs", "occ_singles", "empty_polls", "injected"]  # rounds = warp rounds
         out = {k: int(stats[i]) for i, k in enumerate(names)}
         if rc:
             from . import FemtoError
