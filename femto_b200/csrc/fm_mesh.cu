@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 }
 
 // A state in flight: four 64-bit words, each = tag (16 bits) << 48 | 48 bits of payload:
-//   word 0: id (32 bits) | meta << 32      meta = phase | home << 2
+//   word 0: id (32 bits) | meta << 32      meta = phase | home << 2 | what to evaluate next << 10
 //   word 1: A    word 2: B     rows or C+Occ values, two's complement in 48 bits (B may be -1)
 //   word 3: i (32 bits) | symbol of the pending step << 32
 // A word is written and read whole, so a message is complete exactly when all four tags are the
@@ -56,9 +56,21 @@ struct MeshState {
   int64_t A = 0, B = 0;
   uint32_t id = 0;
   int32_t i = 0;
-  int phase = 0, home = 0;
-  int c = 0;  // count: the symbol of the pending step, pattern[i-1] (travels with the state: the rank that
-              // finishes a step reads the next symbol WHILE it evaluates, so no rank waits for a pattern read)
+  // bits 0-1 phase, 2-9 home rank, 10 / 11: the next evaluation covers Occ(c, A-1) / Occ(c, B) (decided by the
+  // rank that routed the state: it knows the shard boundaries and the bucket size, the receiver just does it),
+  // 16-31 count: the symbol of the pending step, pattern[i-1] (travels with the state: the rank that finishes a
+  // step reads the next symbol WHILE it evaluates, so no rank waits for a pattern read)
+  uint32_t meta = 0;
+  __device__ __forceinline__ int phase() const { return static_cast<int>(meta & 3u); }
+  __device__ __forceinline__ int home() const { return static_cast<int>((meta >> 2) & 0xffu); }
+  __device__ __forceinline__ bool doA() const { return (meta >> 10) & 1u; }
+  __device__ __forceinline__ bool doB() const { return (meta >> 11) & 1u; }
+  __device__ __forceinline__ int c() const { return static_cast<int>(meta >> 16); }
+  __device__ __forceinline__ void set_phase(int p) { meta = (meta & ~3u) | static_cast<uint32_t>(p); }
+  __device__ __forceinline__ void set_c(int c) { meta = (meta & 0xffffu) | (static_cast<uint32_t>(c) << 16); }
+  __device__ __forceinline__ void set_do(bool a, bool b) {
+    meta = (meta & ~0xc00u) | (a ? 0x400u : 0u) | (b ? 0x800u : 0u);
+  }
 };
 constexpr int kPhaseA = 0;     // count: needs Occ(c, first-1) then Occ(c, last); A = first, B = last.  walk: walking
 constexpr int kPhaseB = 1;     // count: A = C[c]+Occ(c,first-1) is known, needs Occ(c, last)
@@ -71,20 +83,30 @@ constexpr unsigned long long kNoBlock = ~0ull;
 __device__ __forceinline__ int64_t sext48(unsigned long long v) {
   return static_cast<int64_t>(v << 16) >> 16;
 }
-__device__ __forceinline__ void pack_state(const MeshState& s, unsigned long long tag, ulonglong2& m0, ulonglong2& m1) {
-  const unsigned long long meta = static_cast<unsigned long long>(s.phase) | (static_cast<unsigned long long>(s.home) << 2);
-  m0.x = tag | static_cast<unsigned long long>(s.id) | (meta << 32);
-  m0.y = tag | (static_cast<unsigned long long>(s.A) & kPayloadMask);
-  m1.x = tag | (static_cast<unsigned long long>(s.B) & kPayloadMask);
-  m1.y = tag | static_cast<unsigned long long>(static_cast<uint32_t>(s.i)) |
-         (static_cast<unsigned long long>(static_cast<uint32_t>(s.c) & 0xffffu) << 32);
+// the four payload words of a message (the tag is added when the slot index is known)
+__device__ __forceinline__ void pack_state(const MeshState& s, ulonglong2& m0, ulonglong2& m1) {
+  m0.x = static_cast<unsigned long long>(s.id) | (static_cast<unsigned long long>(s.meta & 0xfffu) << 32);
+  m0.y = static_cast<unsigned long long>(s.A) & kPayloadMask;
+  m1.x = static_cast<unsigned long long>(s.B) & kPayloadMask;
+  m1.y = static_cast<unsigned long long>(static_cast<uint32_t>(s.i)) | (static_cast<unsigned long long>(s.meta >> 16) << 32);
+}
+__device__ __forceinline__ void unpack_state(MeshState& s, unsigned long long w0, unsigned long long w1,
+                                             unsigned long long w2, unsigned long long w3) {
+  s.id = static_cast<uint32_t>(w0);
+  s.A = sext48(w1);
+  s.B = sext48(w2);
+  s.i = static_cast<int32_t>(static_cast<uint32_t>(w3));
+  s.meta = (static_cast<uint32_t>(w0 >> 32) & 0xfffu) | (static_cast<uint32_t>(w3 >> 32) << 16);
 }
 
 // Per CTA.  stage: one 32-byte inbox slot per lane, copied in with cp.async; blk: per warp and ring the cursors
 // (next unconsumed index) of its two blocks, entry [kMeshMaxRanks] = the cursors the staged copies were made
 // from; peer_ring / start: kernel parameters that are indexed with a run-time value.
+// out: the payload words of the state that left each lane group in the previous round (it is stored one round
+// after its slot index was requested).
 struct MeshShared {
   ulonglong2 stage[kThreads / 32][32][2];
+  ulonglong2 out[kThreads / 32][32][2];
   unsigned long long blk[kThreads / 32][kMeshMaxRanks + 1][2];
   uint4* peer_ring[kMeshMaxRanks];
   int64_t start[kMeshMaxRanks + 1];
@@ -94,7 +116,7 @@ struct MeshWarp {
   int lane, sub, gleader, wic;
   uint32_t cap_mask;
   unsigned long long eptag;  // the batch's part of the tag, in place (bits 56..63)
-  unsigned n_sent = 0, n_recv = 0, n_empty = 0, n_inject = 0;  // per warp: 32 bits are plenty
+  unsigned n_sent = 0, n_recv = 0;  // per warp: 32 bits are plenty
   bool published = false;
 };
 
@@ -212,13 +234,7 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
       const unsigned long long w0 = __shfl_sync(kFull, m0.x, src), w1 = __shfl_sync(kFull, m0.y, src),
                                w2 = __shfl_sync(kFull, m1.x, src), w3 = __shfl_sync(kFull, m1.y, src);
       if (!have && k < take) {
-        s.id = static_cast<uint32_t>(w0);
-        s.phase = static_cast<int>((w0 >> 32) & 3u);
-        s.home = static_cast<int>((w0 >> 34) & 0xffu);
-        s.A = sext48(w1);
-        s.B = sext48(w2);
-        s.i = static_cast<int32_t>(static_cast<uint32_t>(w3));
-        s.c = static_cast<int>((w3 >> 32) & 0xffffu);
+        unpack_state(s, w0, w1, w2, w3);
         have = true;
       }
       for (int t = 0; t < take; t++) needers &= needers - 1;
@@ -240,8 +256,6 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
         }
       }
       __syncwarp();
-    } else {
-      w.n_empty++;
     }
     if (take0 == v0 && take1 == v1) in.ring = mesh_next_ring(a, in.ring);  // drained as far as filled: next ring
     in.staged = false;
@@ -273,11 +287,12 @@ __device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const
   }
   return idx;
 }
-__device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArgs& a, const MeshShared& sh, bool send,
-                                                int dest, unsigned long long idx, const MeshState& s) {
-  if (send && w.sub == 0) {
-    ulonglong2 m0, m1;
-    pack_state(s, mesh_tag(w, a, idx), m0, m1);
+__device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArgs& a, const MeshShared& sh, int dest,
+                                                unsigned long long idx) {
+  if (dest >= 0 && w.sub == 0) {
+    const unsigned long long tag = mesh_tag(w, a, idx);
+    ulonglong2 m0 = sh.out[w.wic][w.lane][0], m1 = sh.out[w.wic][w.lane][1];
+    m0.x |= tag; m0.y |= tag; m1.x |= tag; m1.y |= tag;
     ulonglong2* slot = const_cast<ulonglong2*>(mesh_slot(sh.peer_ring[dest], a.rank, idx, w, a));
     st_volatile_v2(slot, m0);
     st_volatile_v2(slot + 1, m1);
@@ -317,15 +332,14 @@ __device__ __forceinline__ bool mesh_idle_exit(MeshWarp& w, const MeshArgs& a, l
 }
 
 __device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshArgs& a, unsigned long long rounds,
-                                                 unsigned long long pairs, unsigned long long singles) {
+                                                 unsigned long long pairs, unsigned long long singles, unsigned long long injected) {
   if (w.lane == 0) {
     atomicAdd(&a.ctl->stats[0], static_cast<unsigned long long>(w.n_sent));
     atomicAdd(&a.ctl->stats[1], static_cast<unsigned long long>(w.n_recv));
     atomicAdd(&a.ctl->stats[2], rounds);
     atomicAdd(&a.ctl->stats[3], pairs);
     atomicAdd(&a.ctl->stats[4], singles);
-    atomicAdd(&a.ctl->stats[5], static_cast<unsigned long long>(w.n_empty));
-    atomicAdd(&a.ctl->stats[6], static_cast<unsigned long long>(w.n_inject));
+    atomicAdd(&a.ctl->stats[6], injected);
   }
 }
 
@@ -364,6 +378,7 @@ struct MeshFeed {
   unsigned pool_next = 0, pool_end = 0;     // batch-local ids this warp may hand out (warp-uniform; ids fit 32 bits)
   unsigned long long p0 = 0, p1 = 0;        // lane 0: what the previous stage requested (counters, then the claim)
   int stage = 0;
+  unsigned n_inject = 0;
   bool exhausted = false;
 };
 
@@ -404,25 +419,18 @@ __device__ __forceinline__ int64_t mesh_feed_take(MeshWarp& w, MeshFeed& f, unsi
   const unsigned k = __popc(needers & ((1u << w.gleader) - 1u));
   const unsigned idx = f.pool_next + k;
   f.pool_next += take;
-  w.n_inject += take;
+  f.n_inject += take;
   return (!have && k < take) ? static_cast<int64_t>(idx) : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
-// What a state does next.
-struct CountPlan {
-  bool send = false, deliver = false, doA = false, doB = false;
-  int dest = 0;
-  int64_t rowA = 0, rowB = 0;
-};
-
-__device__ __forceinline__ CountPlan mesh_count_plan(const DevImage& im, const MeshArgs& a, const MeshShared& sh,
-                                                     const int64_t* s_C, MeshState& s, bool live) {
-  CountPlan p;
-  if (!live) return p;
-  if (s.phase == kPhaseNew) {  // [C[c], C[c+1]-1] for the pattern's last symbol (server.c:781-801)
+// Where a state goes next, and what is evaluated there: 0.. = that rank (possibly this one), -1 = its result
+// is home (deliver).  Sets the state's doA / doB bits for the rank that evaluates.
+__device__ __forceinline__ int mesh_count_route(const DevImage& im, const MeshArgs& a, const MeshShared& sh,
+                                                const int64_t* s_C, MeshState& s) {
+  if (s.phase() == kPhaseNew) {  // [C[c], C[c+1]-1] for the pattern's last symbol (server.c:781-801)
     const int m = s.i, c0 = static_cast<int>(s.A);
-    s.c = static_cast<int>(s.B);
+    s.set_c(static_cast<int>(s.B));
     if (m <= 0) {  // empty pattern: every row (server.c:782-808)
       s.A = 0; s.B = im.total_length - 1; s.i = 0;
     } else {
@@ -430,40 +438,37 @@ __device__ __forceinline__ CountPlan mesh_count_plan(const DevImage& im, const M
       else { s.A = s_C[c0]; s.B = s_C[c0 + 1] - 1; }
       s.i = m - 1;
     }
-    s.phase = kPhaseA;
+    s.set_phase(kPhaseA);
   }
-  if (s.phase == kPhaseA && s.A <= s.B && s.i > 0 && s.c >= kAlphaDev) {  // symbol outside the alphabet: empty range
+  if (s.phase() == kPhaseA && s.A <= s.B && s.i > 0 && s.c() >= kAlphaDev) {  // symbol outside the alphabet: empty range
     s.A = im.total_length; s.B = s.A - 1; s.i--;
   }
-  if (s.phase == kPhaseA && (s.A > s.B || s.i == 0)) s.phase = kPhaseDone;  // ends the reference's loop (server.c:832-841)
-  if (s.phase == kPhaseDone) {
-    if (s.home == a.rank) p.deliver = true;
-    else { p.send = true; p.dest = s.home; }
-    return p;
+  if (s.phase() == kPhaseA && (s.A > s.B || s.i == 0)) s.set_phase(kPhaseDone);  // ends the reference's loop (server.c:832-841)
+  s.set_do(false, false);
+  if (s.phase() == kPhaseDone) return s.home() == a.rank ? -1 : s.home();
+  if (s.phase() == kPhaseA && s.A == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
+    s.A = s_C[s.c()];
+    s.set_phase(kPhaseB);
   }
-  if (s.phase == kPhaseA) {
-    if (s.A == 0) {  // Occ(c,-1) = 0 without touching the index (server.c:847-851)
-      s.A = s_C[s.c];
-      s.phase = kPhaseB;
-    } else {
-      p.rowA = s.A - 1;
-      if (p.rowA >= im.first_row && p.rowA < im.end_row) p.doA = true;
-      else { p.send = true; p.dest = mesh_owner(a, sh, p.rowA); return p; }
-    }
+  const int oB = mesh_owner(a, sh, s.B);
+  if (s.phase() == kPhaseB) {
+    s.set_do(false, true);
+    return oB;
   }
-  p.rowB = s.B;
-  const bool resB = p.rowB >= im.first_row && p.rowB < im.end_row;
-  if (s.phase == kPhaseB) {
-    if (resB) p.doB = true;
-    else { p.send = true; p.dest = mesh_owner(a, sh, p.rowB); }
-  } else if (resB) {  // both rows here: one round when they share a bucket, else A now and B in the next round
-    int64_t gA, gB;
-    uint32_t ra, rb;
-    split_row(im, p.rowA, gA, ra);
-    split_row(im, p.rowB, gB, rb);
-    p.doB = gA == gB;
-  }
-  return p;
+  const int64_t rowA = s.A - 1;
+  const int oA = mesh_owner(a, sh, rowA);
+  // both rows in one evaluation when they lie on one rank and in one bucket, else Occ(c, first-1) now and
+  // Occ(c, last) in a round of its own
+  const bool same = im.bucket_shift >= 0 ? (rowA >> im.bucket_shift) == (s.B >> im.bucket_shift)
+                                         : rowA / im.bucket_size == s.B / im.bucket_size;
+  s.set_do(true, oA == oB && same);
+  return oA;
+}
+
+__device__ __forceinline__ void mesh_count_deliver(const MeshArgs& a, const MeshState& s) {
+  const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
+  if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
+  else a.first[slot] = s.B - s.A + 1;  // parallel_count with last==NULL (femto.c:313-318)
 }
 
 // HINT: rank blocks are read with the L2 evict-first policy, so that they do not push the inbox rings and the
@@ -478,10 +483,10 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
   MeshWarp w = mesh_warp_init(a, inbox, sh);
   MeshFeed feed;
   feed.exhausted = a.n_mine == 0;
-  MeshState s, out;                  // out: the state that left this group in the previous round
-  bool have = false, out_live = false;
-  int out_dest = 0;
-  unsigned long long out_idx = 0;
+  MeshState s;
+  bool have = false;
+  int out_dest = -1;                 // >= 0: a state left this group in the previous round (payload in sh.out)
+  unsigned long long out_idx = 0;    // its slot index (requested then)
   long long idle_start = 0;
   unsigned backoff = 100;
   unsigned n_rounds = 0, n_pairs = 0, n_singles = 0;
@@ -502,13 +507,12 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
         s.i = m;
         s.A = m > 0 ? pat[m - 1] : 0;  // raw symbols until the routing step turns them into a range
         s.B = m > 1 ? pat[m - 2] : 0;
-        s.phase = kPhaseNew;
-        s.home = a.rank;
+        s.meta = static_cast<uint32_t>(kPhaseNew) | (static_cast<uint32_t>(a.rank) << 2);
         have = true;
         fresh = true;
       }
     }
-    if (!__any_sync(kFull, have || out_live)) {
+    if (!__any_sync(kFull, have || out_dest >= 0)) {
       if (mesh_idle_exit(w, a, idle_start, backoff)) break;
       continue;
     }
@@ -516,26 +520,17 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
     backoff = 100;
     n_rounds++;
 
-    // ---- 2. the Occ evaluations that can be done here, all groups together
+    // ---- 2. the Occ evaluations the states ask for (their rows are resident: that is why they are here)
     {
-      const CountPlan p = mesh_count_plan(im, a, sh, s_C, s, have && !fresh);
-      if (p.deliver) {  // (a finished state that has just arrived home)
-        if (w.sub == 0) {
-          const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
-          if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
-          else a.first[slot] = s.B - s.A + 1;  // parallel_count with last==NULL (femto.c:313-318)
-        }
-        have = false;
-      }
-      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
-      const bool any = p.doA || p.doB;
+      const bool doA = have && !fresh && s.doA(), doB = have && !fresh && s.doB();
+      const bool any = doA || doB;
       if (__any_sync(kFull, any)) {
         uint32_t idxA = 0, idxB = 0, base = 0, node = 0, leaf = 0, rexit = 0;
         int L = 0;
         int64_t ob = 0;
         bool actA = false, actB = false;
         int cn = 0;  // the symbol of the step after this one, read while this one is evaluated
-        if (p.doB && s.i >= 2) {
+        if (doB && s.i >= 2) {
           const int m = a.uniform_len > 0 ? a.uniform_len : 0;
           const uint16_t* pat = a.flat + (m ? static_cast<int64_t>(s.id) * m : a.offs[s.id]);
           cn = pat[s.i - 2];
@@ -543,9 +538,9 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
         if (any) {
           int64_t g = 0, g2;
           uint32_t ra = 0, rb = 0;
-          if (p.doA) split_row(im, p.rowA, g, ra);
-          if (p.doB) split_row(im, p.rowB, p.doA ? g2 : g, rb);
-          const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + s.c));
+          if (doA) split_row(im, s.A - 1, g, ra);
+          if (doB) split_row(im, s.B, doA ? g2 : g, rb);
+          const int4 rv = __ldg(reinterpret_cast<const int4*>(im.occ + g * kAlphaStride + s.c()));
           ob = rec_occ_base(rv);
           leaf = static_cast<uint32_t>(rv.z);
           rexit = static_cast<uint32_t>(rv.w);
@@ -555,78 +550,61 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
           idxB = rb + 1;
           if (leaf) {  // else: symbol absent from the bucket, Occ is the bucket base (index.c:2080-2089)
             L = 31 - __clz(leaf);
-            actA = p.doA;
-            actB = p.doB;
+            actA = doA;
+            actB = doB;
           }
         }
-        n_pairs += __popc(__ballot_sync(kFull, p.doA && p.doB && w.sub == 0));
-        n_singles += __popc(__ballot_sync(kFull, any && !(p.doA && p.doB) && w.sub == 0));
+        n_pairs += __popc(__ballot_sync(kFull, doA && doB && w.sub == 0));
+        n_singles += __popc(__ballot_sync(kFull, any && !(doA && doB) && w.sub == 0));
         quad_descend_pair<HINT>(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub, pol);
         if (any) {
           const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
-          if (p.doA && p.doB) { s.A = resA; s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }
-          else if (p.doA) { s.A = resA; s.phase = kPhaseB; }
-          else { s.B = resB - 1; s.i--; s.phase = kPhaseA; s.c = cn; }  // A already holds C[c]+Occ(c,first-1)
+          if (doA && doB) { s.A = resA; s.B = resB - 1; s.i--; s.set_phase(kPhaseA); s.set_c(cn); }
+          else if (doA) { s.A = resA; s.set_phase(kPhaseB); }
+          else { s.B = resB - 1; s.i--; s.set_phase(kPhaseA); s.set_c(cn); }  // A already holds C[c]+Occ(c,first-1)
         }
       }
     }
 
     // ---- 3. the states that left in the previous round: their slot indices have long arrived
-    mesh_send_store(w, a, sh, out_live, out_dest, out_idx, out);
-    out_live = false;
+    mesh_send_store(w, a, sh, out_dest, out_idx);
+    out_dest = -1;
 
     // ---- 4. route every state: result, leaves, or stays
     {
-      const CountPlan p = mesh_count_plan(im, a, sh, s_C, s, have);
-      if (p.deliver) {
-        if (w.sub == 0) {
-          const int64_t slot = static_cast<int64_t>(s.id) - a.pid_lo;
-          if (a.last) { a.first[slot] = s.A; a.last[slot] = s.B; }
-          else a.first[slot] = s.B - s.A + 1;
-        }
+      int dest = -2;  // -2: no state
+      if (have) dest = mesh_count_route(im, a, sh, s_C, s);
+      const bool deliver = dest == -1;
+      if (deliver) {
+        if (w.sub == 0) mesh_count_deliver(a, s);
         have = false;
       }
-      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
-      bool send = p.send;
-      out_idx = mesh_send_claim(w, a, send, p.dest);
+      mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
+      bool send = dest >= 0 && dest != a.rank;
+      out_idx = mesh_send_claim(w, a, send, dest);
       if (send) {
-        out = s;
-        out_dest = p.dest;
-        out_live = true;
+        if (w.sub == 0) pack_state(s, sh.out[w.wic][w.lane][0], sh.out[w.wic][w.lane][1]);
+        out_dest = dest;
         have = false;
       }
     }
   }
-  mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles);
+  mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles, feed.n_inject);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Sampled-SA walks over the range-sharded index.  State: id = result slot at the home rank, A = BWT
 // row (the text offset once finished, -1 for a malformed walk), i = LF steps taken so far.
-struct WalkPlan {
-  bool send = false, deliver = false, step = false;
-  int dest = 0;
-};
-
-__device__ __forceinline__ WalkPlan mesh_walk_plan(const DevImage& im, const MeshArgs& a, const MeshShared& sh,
-                                                   const MeshWarp& w, MeshState& s, bool live) {
-  WalkPlan p;
-  if (!live) return p;
-  if (s.phase != kPhaseDone && (s.A < 0 || s.A >= im.total_length)) {  // not a row of this index
+// Route: the rank that must see the state next, or -1 = deliver here.
+__device__ __forceinline__ int mesh_walk_route(const DevImage& im, const MeshArgs& a, const MeshShared& sh,
+                                               const MeshWarp& w, MeshState& s) {
+  if (s.phase() != kPhaseDone && (s.A < 0 || s.A >= im.total_length)) {  // not a row of this index
     if (w.sub == 0) atomicExch(&a.ctl->status, 2);
     s.A = -1;
-    s.phase = kPhaseDone;
+    s.set_phase(kPhaseDone);
   }
-  if (s.phase == kPhaseDone) {
-    if (s.home == a.rank) p.deliver = true;
-    else { p.send = true; p.dest = s.home; }
-  } else if (s.A >= im.first_row && s.A < im.end_row) {
-    p.step = true;
-  } else {
-    p.send = true;
-    p.dest = mesh_owner(a, sh, s.A);
-  }
-  return p;
+  if (s.phase() == kPhaseDone) return s.home() == a.rank ? -1 : s.home();
+  return mesh_owner(a, sh, s.A);
 }
 
 template <int MINB>
@@ -636,9 +614,9 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
   MeshWarp w = mesh_warp_init(a, inbox, sh);
   MeshFeed feed;
   feed.exhausted = a.n_mine == 0;
-  MeshState s, out;
-  bool have = false, out_live = false;
-  int out_dest = 0;
+  MeshState s;
+  bool have = false;
+  int out_dest = -1;
   unsigned long long out_idx = 0;
   long long idle_start = 0;
   unsigned backoff = 100;
@@ -656,52 +634,43 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
         s.A = a.rows[k];  // looked at after this round's steps
         s.B = 0;
         s.i = 0;
-        s.c = 0;
-        s.phase = kPhaseA;
-        s.home = a.rank;
+        s.meta = static_cast<uint32_t>(kPhaseA) | (static_cast<uint32_t>(a.rank) << 2);
         have = true;
         fresh = true;
       }
     }
-    if (!__any_sync(kFull, have || out_live)) {
+    if (!__any_sync(kFull, have || out_dest >= 0)) {
       if (mesh_idle_exit(w, a, idle_start, backoff)) break;
       continue;
     }
     idle_start = 0;
     backoff = 100;
+    n_rounds++;
 
-    // one LF step with mark test for every resident row (do_back_query, server.c:2228-2359)
+    // one LF step with mark test for every walking state whose row is resident (do_back_query, server.c:2228-2359)
     {
-      const WalkPlan p = mesh_walk_plan(im, a, sh, w, s, have && !fresh);
-      if (p.deliver) {
-        if (w.sub == 0) a.out_offset[s.id] = s.A;
-        have = false;
-      }
-      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
-      if (__any_sync(kFull, p.step)) {
+      const bool step = have && !fresh && s.phase() == kPhaseA && s.A >= im.first_row && s.A < im.end_row;
+      if (__any_sync(kFull, step)) {
         int64_t g = 0;
         uint32_t rb = 0, ch = 0, count = 0;
         uint64_t markval_base = 0;
-        if (p.step) {
-          split_row(im, s.A, g, rb);
-          if (w.sub == 0) n_rounds++;
-        }
-        quad_wtree_rank(im, p.step, g, rb, w.sub, ch, count, markval_base, n_quad);
-        const bool ok = p.step && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
+        if (step) split_row(im, s.A, g, rb);
+        quad_wtree_rank(im, step, g, rb, w.sub, ch, count, markval_base, n_quad);
+        const bool ok = step && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
         int64_t occ_base = 0, offset = -1;
         mark_lookup<2, kQuadBlockWords>(im, ok, g, ch, count, markval_base, w.sub, offset, occ_base, n_mark, n_sample);
-        if (p.step) {
+        if (step) {
           if (!ok) {
             if (w.sub == 0) atomicExch(&a.ctl->status, 2);
             s.A = -1;
-            s.phase = kPhaseDone;
+            s.set_phase(kPhaseDone);
           } else if (offset >= 0) {
             s.A = offset + s.i;
-            s.phase = kPhaseDone;
+            s.set_phase(kPhaseDone);
           } else if (ch <= static_cast<uint32_t>(kEscSeofDev) || s.i > (1 << 30)) {  // unmarked document start
             if (w.sub == 0) atomicExch(&a.ctl->status, 2);
             s.A = -1;
-            s.phase = kPhaseDone;
+            s.set_phase(kPhaseDone);
           } else {
             s.A = occ_base + count - 1;  // LF
             s.i++;
@@ -710,27 +679,28 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
       }
     }
 
-    mesh_send_store(w, a, sh, out_live, out_dest, out_idx, out);
-    out_live = false;
+    mesh_send_store(w, a, sh, out_dest, out_idx);
+    out_dest = -1;
 
     {
-      const WalkPlan p = mesh_walk_plan(im, a, sh, w, s, have);
-      if (p.deliver) {
+      int dest = -2;
+      if (have) dest = mesh_walk_route(im, a, sh, w, s);
+      const bool deliver = dest == -1;
+      if (deliver) {
         if (w.sub == 0) a.out_offset[s.id] = s.A;
         have = false;
       }
-      mesh_delivered(w, a, __ballot_sync(kFull, p.deliver && w.sub == 0));
-      bool send = p.send;
-      out_idx = mesh_send_claim(w, a, send, p.dest);
+      mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
+      bool send = dest >= 0 && dest != a.rank;
+      out_idx = mesh_send_claim(w, a, send, dest);
       if (send) {
-        out = s;
-        out_dest = p.dest;
-        out_live = true;
+        if (w.sub == 0) pack_state(s, sh.out[w.wic][w.lane][0], sh.out[w.wic][w.lane][1]);
+        out_dest = dest;
         have = false;
       }
     }
   }
-  mesh_flush_stats(w, a, n_rounds, n_quad, n_mark + n_sample);
+  mesh_flush_stats(w, a, n_rounds, n_quad, n_mark + n_sample, feed.n_inject);
 }
 
 cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas,
