@@ -1191,7 +1191,9 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
     a.epoch = m->epoch;
     if (m->epoch % 255 == 0) CK(cudaMemsetAsync(base + sizeof(MeshCtl), 0, m->region_bytes - sizeof(MeshCtl), s));
     a.window = m->window;
-    a.timeout_cycles = static_cast<long long>(m->timeout_s * 1e3 * double(m->clock_khz));
+    a.cap_mask = (1u << m->cap_shift) - 1u;
+    a.eptag = (m->epoch % 255ull + 1ull) << 56;
+    a.timeout_polls = static_cast<unsigned>(std::min(m->timeout_s * 1e6, 4e9));
     a.plen = d_plen;
     a.flat = d_flat;
     a.offs = d_offs;

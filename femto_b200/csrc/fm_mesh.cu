@@ -110,13 +110,14 @@ struct MeshShared {
   unsigned long long blk[kThreads / 32][kMeshMaxRanks + 1][2];
   uint4* peer_ring[kMeshMaxRanks];
   int64_t start[kMeshMaxRanks + 1];
+  unsigned cnt[kThreads / 32][8];  // per warp: sent, received, rounds, counters 3 and 4 of the kernel, -, injected, -
 };
+__device__ __forceinline__ void mesh_count_up(MeshShared& sh, int wic, int lane, int k, unsigned v) {
+  if (lane == 0 && v) sh.cnt[wic][k] += v;
+}
 
 struct MeshWarp {
   int lane, sub, gleader, wic;
-  uint32_t cap_mask;
-  unsigned long long eptag;  // the batch's part of the tag, in place (bits 56..63)
-  unsigned n_sent = 0, n_recv = 0;  // per warp: 32 bits are plenty
   bool published = false;
 };
 
@@ -124,11 +125,11 @@ struct MeshWarp {
 // 0, so a cleared slot is never valid; a slot is rewritten every lap, and the rings are cleared before the
 // batch field repeats (fm_api.cu), so a stale word never carries the expected tag.
 __device__ __forceinline__ unsigned long long mesh_tag(const MeshWarp& w, const MeshArgs& a, unsigned long long idx) {
-  return w.eptag | (((idx >> a.cap_shift) & 0xffull) << 48);
+  return a.eptag | (((idx >> a.cap_shift) & 0xffull) << 48);
 }
 __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int src, unsigned long long idx, const MeshWarp& w,
                                                        const MeshArgs& a) {
-  return reinterpret_cast<const ulonglong2*>(ring + ((static_cast<size_t>(src) << a.cap_shift) + (idx & w.cap_mask)) * 2);
+  return reinterpret_cast<const ulonglong2*>(ring + ((static_cast<size_t>(src) << a.cap_shift) + (idx & a.cap_mask)) * 2);
 }
 
 // owner(row) = (row / block_size) * world / nblocks (the reference's block -> file map, partitioned): shard r
@@ -238,7 +239,7 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
         have = true;
       }
       for (int t = 0; t < take; t++) needers &= needers - 1;
-      w.n_recv += take;
+      mesh_count_up(sh, w.wic, w.lane, 1, take);
       __syncwarp();
       // advance the cursors; a block that is used up leaves the polled set and is replaced by a new ticket
       if (w.lane == in.ring) {
@@ -266,13 +267,15 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
 // ---- leaving states ------------------------------------------------------------------------------
 // Step 1: claim their ring indices (one atomic per destination and warp, on counters in this rank's own
 // memory).  Returns this lane's index (valid when it sends).  The stores follow one round later.
-__device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const MeshArgs& a, bool& send, int dest) {
+__device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const MeshArgs& a, MeshShared& sh, bool& send,
+                                                             int dest) {
   if (send && (dest < 0 || dest >= a.world)) {  // cannot happen with a well-formed index; never store out of bounds
     if (w.sub == 0) atomicExch(&a.ctl->status, 2);
     send = false;
   }
   const bool mine = send && w.sub == 0;
   unsigned todo = __ballot_sync(kFull, mine);
+  mesh_count_up(sh, w.wic, w.lane, 0, __popc(todo));
   unsigned long long idx = 0;
   while (todo) {
     const int src = __ffs(todo) - 1;
@@ -282,7 +285,6 @@ __device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const
     if (w.lane == src) base = atomicAdd(&a.ctl->out_tail[d], static_cast<unsigned long long>(__popc(same)));
     base = __shfl_sync(kFull, base, src);
     if (mine && dest == d) idx = base + __popc(same & lanemask_lt());
-    w.n_sent += __popc(same);
     todo &= ~same;
   }
   return idx;
@@ -302,12 +304,16 @@ __device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArg
 // Results were delivered: count them (a reduction: nobody waits for the counter).  The rank's "all my
 // results are home" flag is raised by the first warps that find themselves idle afterwards (mesh_idle_exit).
 __device__ __forceinline__ void mesh_delivered(const MeshWarp& w, const MeshArgs& a, unsigned delivered_mask) {
-  if (delivered_mask && w.lane == 0)
-    atomicAdd(&a.ctl->done_count, static_cast<unsigned long long>(__popc(delivered_mask)));
+  if (delivered_mask && w.lane == 0) {
+    const unsigned long long n = __popc(delivered_mask);
+    atomicAdd(&a.ctl->done_count, n);
+    atomicAdd(&a.ctl->inflight, 0ull - n);
+  }
 }
 
-// Idle warp: true when the batch is over everywhere (or has failed).
-__device__ __forceinline__ bool mesh_idle_exit(MeshWarp& w, const MeshArgs& a, long long& idle_start, unsigned& backoff) {
+// Idle warp: true when the batch is over everywhere (or has failed).  idle counts this warp's consecutive idle
+// polls of about a microsecond each.
+__device__ __forceinline__ bool mesh_idle_exit(MeshWarp& w, const MeshArgs& a, unsigned& idle) {
   const bool ok = w.lane >= a.world || ld_volatile_u64(&a.ctl->rank_done[w.lane]) >= a.epoch;
   if (__all_sync(kFull, ok)) return true;
   if (!w.published) {  // all results of this rank's own patterns are home: tell every rank (any idle warp may, once)
@@ -320,27 +326,17 @@ __device__ __forceinline__ bool mesh_idle_exit(MeshWarp& w, const MeshArgs& a, l
   int st = 0;
   if (w.lane == 0) st = *reinterpret_cast<volatile int*>(&a.ctl->status);
   if (__shfl_sync(kFull, st, 0)) return true;
-  const long long now = clock64();
-  if (!idle_start) idle_start = now;
-  else if (now - idle_start > a.timeout_cycles) {
+  if (++idle > a.timeout_polls) {
     if (w.lane == 0) atomicExch(&a.ctl->status, 1);
     return true;
   }
-  __nanosleep(backoff);
-  backoff = min(backoff * 2, 2000u);
+  __nanosleep(idle < 8 ? 100u << (idle >> 1) : 1000u);
   return false;
 }
 
-__device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshArgs& a, unsigned long long rounds,
-                                                 unsigned long long pairs, unsigned long long singles, unsigned long long injected) {
-  if (w.lane == 0) {
-    atomicAdd(&a.ctl->stats[0], static_cast<unsigned long long>(w.n_sent));
-    atomicAdd(&a.ctl->stats[1], static_cast<unsigned long long>(w.n_recv));
-    atomicAdd(&a.ctl->stats[2], rounds);
-    atomicAdd(&a.ctl->stats[3], pairs);
-    atomicAdd(&a.ctl->stats[4], singles);
-    atomicAdd(&a.ctl->stats[6], injected);
-  }
+__device__ __forceinline__ void mesh_flush_stats(const MeshWarp& w, const MeshArgs& a, const MeshShared& sh) {
+  __syncwarp();
+  if (w.lane < 8 && sh.cnt[w.wic][w.lane]) atomicAdd(&a.ctl->stats[w.lane], static_cast<unsigned long long>(sh.cnt[w.wic][w.lane]));
 }
 
 __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox& in, MeshShared& sh) {
@@ -349,8 +345,7 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox&
   w.sub = w.lane & 1;
   w.gleader = w.lane & ~1;
   w.wic = threadIdx.x >> 5;
-  w.cap_mask = (1u << a.cap_shift) - 1u;
-  w.eptag = (a.epoch % 255ull + 1ull) << 56;
+  if (threadIdx.x < (kThreads / 32) * 8) (&sh.cnt[0][0])[threadIdx.x] = 0;
   if (threadIdx.x < kMeshMaxRanks) sh.peer_ring[threadIdx.x] = a.peer_ring[threadIdx.x];
   if (threadIdx.x <= kMeshMaxRanks) sh.start[threadIdx.x] = a.shard_start[threadIdx.x];
   in.pend = 0;
@@ -375,10 +370,9 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox&
 // counters -> if fewer than `window` own patterns are unfinished, add the chunk to `injected` -> use the ids.
 constexpr unsigned kFeedChunk = 32;
 struct MeshFeed {
-  unsigned pool_next = 0, pool_end = 0;     // batch-local ids this warp may hand out (warp-uniform; ids fit 32 bits)
-  unsigned long long p0 = 0, p1 = 0;        // lane 0: what the previous stage requested (counters, then the claim)
+  unsigned pool_next = 0, pool_end = 0;  // batch-local ids this warp may hand out (warp-uniform; ids fit 32 bits)
+  unsigned long long p0 = 0;             // lane 0: what the previous stage requested (in-flight count, then the claim)
   int stage = 0;
-  unsigned n_inject = 0;
   bool exhausted = false;
 };
 
@@ -386,40 +380,36 @@ __device__ __forceinline__ void mesh_feed_advance(const MeshWarp& w, const MeshA
   if (f.exhausted || f.pool_next < f.pool_end) return;
   const unsigned long long n = static_cast<unsigned long long>(a.n_mine);
   if (f.stage == 0) {
-    if (w.lane == 0) {
-      f.p0 = ld_volatile_u64(&a.ctl->injected);
-      f.p1 = ld_volatile_u64(&a.ctl->done_count);
-    }
+    if (w.lane == 0) f.p0 = ld_volatile_u64(&a.ctl->inflight);
     f.stage = 1;
   } else if (f.stage == 1) {
-    int dec = 0;  // 0 window full: look again, 1 chunk requested, 2 nothing left
-    if (w.lane == 0) {
-      if (f.p0 >= n) dec = 2;
-      else if (f.p0 - f.p1 < a.window) {
-        dec = 1;
-        f.p0 = atomicAdd(&a.ctl->injected, static_cast<unsigned long long>(kFeedChunk));
-      }
+    int dec = 0;  // 0 window full: look again, 1 chunk requested
+    if (w.lane == 0 && static_cast<long long>(f.p0) < static_cast<long long>(a.window)) {
+      dec = 1;
+      f.p0 = atomicAdd(&a.ctl->injected, static_cast<unsigned long long>(kFeedChunk));
+      atomicAdd(&a.ctl->inflight, static_cast<unsigned long long>(kFeedChunk));
     }
-    dec = __shfl_sync(kFull, dec, 0);
-    if (dec == 2) f.exhausted = true;
-    f.stage = dec == 1 ? 2 : 0;
+    f.stage = __shfl_sync(kFull, dec, 0) ? 2 : 0;
   } else {
     const unsigned long long base = __shfl_sync(kFull, f.p0, 0);
-    if (base >= n) f.exhausted = true;
-    else { f.pool_next = static_cast<unsigned>(base); f.pool_end = static_cast<unsigned>(min(base + kFeedChunk, n)); }
+    const unsigned long long got = base >= n ? 0ull : min(static_cast<unsigned long long>(kFeedChunk), n - base);
+    if (w.lane == 0 && got < kFeedChunk)  // ids past the end of the batch are not in flight
+      atomicAdd(&a.ctl->inflight, 0ull - (kFeedChunk - got));
+    if (got == 0) f.exhausted = true;
+    else { f.pool_next = static_cast<unsigned>(base); f.pool_end = static_cast<unsigned>(base + got); }
     f.stage = 0;
   }
 }
 
 // the batch-local id for this group, or -1.  Warp-collective.
-__device__ __forceinline__ int64_t mesh_feed_take(MeshWarp& w, MeshFeed& f, unsigned needers, bool have) {
+__device__ __forceinline__ int64_t mesh_feed_take(MeshWarp& w, MeshShared& sh, MeshFeed& f, unsigned needers, bool have) {
   const unsigned avail = f.pool_end - f.pool_next;
   if (!needers || !avail) return -1;
   const unsigned take = min(static_cast<unsigned>(__popc(needers)), avail);
   const unsigned k = __popc(needers & ((1u << w.gleader) - 1u));
   const unsigned idx = f.pool_next + k;
   f.pool_next += take;
-  f.n_inject += take;
+  mesh_count_up(sh, w.wic, w.lane, 6, take);
   return (!have && k < take) ? static_cast<int64_t>(idx) : -1;
 }
 
@@ -487,9 +477,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
   bool have = false;
   int out_dest = -1;                 // >= 0: a state left this group in the previous round (payload in sh.out)
   unsigned long long out_idx = 0;    // its slot index (requested then)
-  long long idle_start = 0;
-  unsigned backoff = 100;
-  unsigned n_rounds = 0, n_pairs = 0, n_singles = 0;
+  unsigned idle = 0;
 
   for (;;) {
     // ---- 1. states for the idle groups: inbox first, then new patterns of the own batch.  A new pattern's
@@ -499,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
     mesh_take_inbox(w, a, inbox, sh, needers, s, have);
     mesh_feed_advance(w, a, feed);
     {
-      const int64_t k = mesh_feed_take(w, feed, needers, have);
+      const int64_t k = mesh_feed_take(w, sh, feed, needers, have);
       if (k >= 0) {
         s.id = static_cast<uint32_t>(a.pid_lo + k);
         const int m = a.uniform_len > 0 ? a.uniform_len : a.plen[s.id];
@@ -513,12 +501,11 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
       }
     }
     if (!__any_sync(kFull, have || out_dest >= 0)) {
-      if (mesh_idle_exit(w, a, idle_start, backoff)) break;
+      if (mesh_idle_exit(w, a, idle)) break;
       continue;
     }
-    idle_start = 0;
-    backoff = 100;
-    n_rounds++;
+    idle = 0;
+    mesh_count_up(sh, w.wic, w.lane, 2, 1);
 
     // ---- 2. the Occ evaluations the states ask for (their rows are resident: that is why they are here)
     {
@@ -554,8 +541,8 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
             actB = doB;
           }
         }
-        n_pairs += __popc(__ballot_sync(kFull, doA && doB && w.sub == 0));
-        n_singles += __popc(__ballot_sync(kFull, any && !(doA && doB) && w.sub == 0));
+        mesh_count_up(sh, w.wic, w.lane, 3, __popc(__ballot_sync(kFull, doA && doB && w.sub == 0)));
+        mesh_count_up(sh, w.wic, w.lane, 4, __popc(__ballot_sync(kFull, any && !(doA && doB) && w.sub == 0)));
         quad_descend_pair<HINT>(im, actA, actB, idxA, idxB, base, node, leaf, L, rexit, w.sub, pol);
         if (any) {
           const int64_t resA = ob + (leaf ? idxA : 0u), resB = ob + (leaf ? idxB : 0u);
@@ -581,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
       }
       mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
       bool send = dest >= 0 && dest != a.rank;
-      out_idx = mesh_send_claim(w, a, send, dest);
+      out_idx = mesh_send_claim(w, a, sh, send, dest);
       if (send) {
         if (w.sub == 0) pack_state(s, sh.out[w.wic][w.lane][0], sh.out[w.wic][w.lane][1]);
         out_dest = dest;
@@ -589,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_count_kernel(const DevIma
       }
     }
   }
-  mesh_flush_stats(w, a, n_rounds, n_pairs, n_singles, feed.n_inject);
+  mesh_flush_stats(w, a, sh);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -618,9 +605,8 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
   bool have = false;
   int out_dest = -1;
   unsigned long long out_idx = 0;
-  long long idle_start = 0;
-  unsigned backoff = 100;
-  unsigned long long n_rounds = 0, n_quad = 0, n_mark = 0, n_sample = 0;
+  unsigned idle = 0;
+  unsigned long long n_quad = 0, n_mark = 0, n_sample = 0;  // (rank_* helpers count in 64 bits)
 
   for (;;) {
     bool fresh = false;
@@ -628,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
     mesh_take_inbox(w, a, inbox, sh, needers, s, have);
     mesh_feed_advance(w, a, feed);
     {
-      const int64_t k = mesh_feed_take(w, feed, needers, have);
+      const int64_t k = mesh_feed_take(w, sh, feed, needers, have);
       if (k >= 0) {
         s.id = static_cast<uint32_t>(k);
         s.A = a.rows[k];  // looked at after this round's steps
@@ -640,12 +626,11 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
       }
     }
     if (!__any_sync(kFull, have || out_dest >= 0)) {
-      if (mesh_idle_exit(w, a, idle_start, backoff)) break;
+      if (mesh_idle_exit(w, a, idle)) break;
       continue;
     }
-    idle_start = 0;
-    backoff = 100;
-    n_rounds++;
+    idle = 0;
+    mesh_count_up(sh, w.wic, w.lane, 2, 1);
 
     // one LF step with mark test for every walking state whose row is resident (do_back_query, server.c:2228-2359)
     {
@@ -692,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
       }
       mesh_delivered(w, a, __ballot_sync(kFull, deliver && w.sub == 0));
       bool send = dest >= 0 && dest != a.rank;
-      out_idx = mesh_send_claim(w, a, send, dest);
+      out_idx = mesh_send_claim(w, a, sh, send, dest);
       if (send) {
         if (w.sub == 0) pack_state(s, sh.out[w.wic][w.lane][0], sh.out[w.wic][w.lane][1]);
         out_dest = dest;
@@ -700,7 +685,9 @@ __global__ void __launch_bounds__(kThreads, MINB) mesh_walk_kernel(const DevImag
       }
     }
   }
-  mesh_flush_stats(w, a, n_rounds, n_quad, n_mark + n_sample, feed.n_inject);
+  mesh_count_up(sh, w.wic, w.lane, 3, static_cast<unsigned>(n_quad));
+  mesh_count_up(sh, w.wic, w.lane, 4, static_cast<unsigned>(n_mark + n_sample));
+  mesh_flush_stats(w, a, sh);
 }
 
 cudaError_t launch_mesh(const void* kernel, const DevImage& im, const MeshArgs& a, int sm_count, int max_ctas,

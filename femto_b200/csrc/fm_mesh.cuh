@@ -44,10 +44,11 @@ struct MeshCtl {
   unsigned long long head_block[kMeshMaxRanks];  // next block of 16 indices of my ring src that no warp owns yet
   unsigned long long injected;                 // patterns of my batch taken so far
   unsigned long long done_count;               // patterns of my batch delivered
+  unsigned long long inflight;                 // of my batch: taken and not yet delivered
   unsigned long long stats[8];                 // sent, received, rounds, occ pairs, occ singles, empty polls, injected, -
   int status;                                  // 0 ok, 1 timed out, 2 malformed message
   int pad0;
-  unsigned long long pad1[5];
+  unsigned long long pad1[4];
   // written by the peers (rank r writes entry r): the last epoch for which rank r holds all its results
   unsigned long long rank_done[kMeshMaxRanks];
 };
@@ -60,9 +61,11 @@ struct MeshArgs {
   uint4* peer_ring[kMeshMaxRanks];     // every rank's inbox
   int rank, world;
   int cap_shift;                       // slots per ring = 1 << cap_shift
+  unsigned cap_mask;                   // (1 << cap_shift) - 1
   unsigned long long epoch;            // batch number, starting at 1
+  unsigned long long eptag;            // the batch's part of every message tag, in place: (epoch % 255 + 1) << 56
   unsigned long long window;           // own patterns in flight at most
-  long long timeout_cycles;            // a warp idle for longer gives up (status 1)
+  unsigned timeout_polls;              // a warp idle for more polls (~1 us each) gives up (status 1)
   // the batch: patterns of ALL ranks (replicated), indexed by global pattern id
   const int32_t* plen;
   const uint16_t* flat;
