@@ -1206,10 +1206,13 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
     a.out_offset = d_offsets;
     a.block_size = ix->info.block_size;
     a.nblocks = ix->info.num_blocks;
-    for (int r = 0; r <= kMeshMaxRanks; r++) {
-      // shard r = blocks b with b * world / nblocks == r, i.e. from block ceil(r * nblocks / world) on (fm_open_shard)
-      const int64_t b = r >= m->world ? a.nblocks : (int64_t(r) * a.nblocks + m->world - 1) / m->world;
-      a.shard_start[r] = std::min<int64_t>(b * a.block_size, ix->info.total_length);
+    {  // shard r holds the rows from shard_start[r] on: the first row of its first block (shard_of_block)
+      int64_t b = 0;
+      for (int r = 0; r <= kMeshMaxRanks; r++) {
+        while (r < m->world && b < a.nblocks && shard_of_block(b, a.block_size, ix->info.total_length, m->world) < r) b++;
+        if (r >= m->world) b = a.nblocks;
+        a.shard_start[r] = std::min<int64_t>(b * a.block_size, ix->info.total_length);
+      }
     }
     // the kernel's own counters start from zero; rank_done (written by the peers) is never reset
     CK(cudaMemsetAsync(base, 0, offsetof(MeshCtl, rank_done), s));

@@ -41,6 +41,17 @@ constexpr int kSegBits = 512;
 constexpr int kMaxCodeLen = 20;
 constexpr uint32_t kEndOfBucketSym = 0x1ff;
 
+// Shard (GPU) of data block b when an index of total_length rows is split over nshards GPUs by BWT row range
+// at data-block granularity (the reference's partition unit, src/main/index.h:83-100): contiguous block
+// ranges, a block going to the shard its MIDDLE row falls into when the rows are cut into nshards equal
+// parts.  Balanced by rows: total_length is normally k * block_size + (a few), i.e. the last block is tiny,
+// and counting blocks would give one GPU a whole block more than the others.
+inline int shard_of_block(int64_t b, int64_t block_size, int64_t total_length, int nshards) {
+  if (nshards <= 1 || total_length <= 0) return 0;
+  const int64_t s = ((2 * b + 1) * block_size * nshards) / (2 * total_length);
+  return static_cast<int>(s < nshards - 1 ? s : nshards - 1);
+}
+
 struct Error : std::runtime_error {
   int code;
   Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}

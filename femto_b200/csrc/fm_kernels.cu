@@ -42,6 +42,12 @@
 namespace fmb {
 namespace {
 
+// the shard holding `row`: shard_of_block (fm_format.hpp) of its data block
+__device__ __forceinline__ int shard_of_row(int64_t row, int64_t block_size, int64_t total_length, int nshards) {
+  const int64_t s = ((2 * (row / block_size) + 1) * block_size * nshards) / (2 * total_length);
+  return static_cast<int>(s < nshards - 1 ? s : nshards - 1);
+}
+
 // Shared by both count schedules: retire a finished pattern, pull the next one from the queue.
 // "first > last || i == 0" ends the reference's while loop (server.c:832-841).
 struct PatternState {
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
     if (act && (row < im.first_row || row >= im.end_row)) {
       if (MODE == kWalkShard && row >= 0 && row < im.total_length) {
         // the row lives on another rank: the state travels there
-        park(row, 0, static_cast<int>(((row / a.block_size) * a.nshards) / a.nblocks));
+        park(row, 0, shard_of_row(row, a.block_size, im.total_length, a.nshards));
       } else if (MODE == kWalkShard) {
         if (lane == gleader) atomicExch(a.status, 1);
         park(-1, 2, static_cast<int>(meta >> 4));
@@ -920,7 +926,7 @@ __global__ void __launch_bounds__(kThreads) count_shard_kernel(const DevImage im
             if (row >= im.first_row && row < im.end_row) {
               q = true;
             } else {
-              dest = static_cast<int>(((row / a.block_size) * a.nshards) / a.nblocks);
+              dest = shard_of_row(row, a.block_size, im.total_length, a.nshards);
               running = false;
             }
           }

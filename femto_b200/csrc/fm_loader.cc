@@ -736,10 +736,10 @@ std::unique_ptr<HostImage> build_host_image(const std::string& path, int shard, 
   im->levels = levels;
   const int kBlockWords = block_words;
 
-  // data blocks of this shard: b with b*nshards/nblocks == shard
+  // data blocks of this shard (shard_of_block, fm_format.hpp: contiguous, balanced by rows)
   int64_t b0 = h.nblocks, b1 = 0;
   for (int64_t b = 0; b < h.nblocks; b++) {
-    if (b * nshards / std::max<int64_t>(1, h.nblocks) == shard) { b0 = std::min(b0, b); b1 = std::max(b1, b + 1); }
+    if (shard_of_block(b, h.block_size, h.total_length, nshards) == shard) { b0 = std::min(b0, b); b1 = std::max(b1, b + 1); }
   }
   if (b0 >= b1) { b0 = b1 = 0; }
   im->first_block = b0;

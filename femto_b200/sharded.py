@@ -34,6 +34,14 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+def shard_of_block(b: int, block_size: int, total_length: int, nshards: int) -> int:
+    """The rank holding data block b (fm_open_shard; fm_format.hpp shard_of_block): contiguous block ranges
+    balanced by rows -- a block goes to the shard its middle row falls into."""
+    if nshards <= 1 or total_length <= 0:
+        return 0
+    return min(nshards - 1, ((2 * b + 1) * block_size * nshards) // (2 * total_length))
+
+
 STATE_WORDS = 6          # pid, first, last, i, obA, meta = phase | home << 4
 PHASE_NEW, PHASE_DONE = 3, 2
 

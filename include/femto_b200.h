@@ -76,8 +76,11 @@ typedef struct {
  * every bucket's map/Huffman tables (b_fault, index.c:1222-1342) and wavelet-tree
  * segments once, and uploads the rank image to `device`'s HBM.
  * fm_close == femto_stop_server (femto.c:77-81).
- * fm_open_shard loads only the data blocks whose index b satisfies
- * b*nshards/num_blocks == shard (BWT row range sharding). */
+ * fm_open_shard loads one of nshards contiguous ranges of data blocks (BWT row range sharding at the
+ * reference's partition unit): block b belongs to the shard its middle row falls
+ * into when the rows are cut into nshards equal parts, i.e. shard = min(nshards - 1,
+ * (2 b + 1) * block_size * nshards / (2 * total_length)) -- balanced by rows, not by block count (the
+ * last block of an index is usually a few rows long). */
 int fm_open(const char* path, int device, fm_index_t** out);
 int fm_open_shard(const char* path, int device, int shard, int nshards, fm_index_t** out);
 void fm_close(fm_index_t* ix);

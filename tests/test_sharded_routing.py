@@ -24,12 +24,12 @@ def oracle_step_fn(index_path, rank, world, plen, flat, offs):
     o = Oracle(index_path)
     info = o.header_info()
     n, bs, nb = info["total_length"], info["block_size"], info["nblocks"]
-    blocks = [b for b in range(nb) if b * world // nb == rank]
+    blocks = [b for b in range(nb) if sharded.shard_of_block(b, bs, n, world) == rank]
     lo_row = blocks[0] * bs if blocks else 0
     hi_row = min(n, (blocks[-1] + 1) * bs) if blocks else 0
 
     def owner(row):
-        return (row // bs) * world // nb
+        return sharded.shard_of_block(row // bs, bs, n, world)
 
     def step(states, dest):
         st = states.numpy()
@@ -91,7 +91,7 @@ def oracle_walk_fn(index_path, rank, world):
     o = Oracle(index_path)
     info = o.header_info()
     n, bs, nb = info["total_length"], info["block_size"], info["nblocks"]
-    blocks = [b for b in range(nb) if b * world // nb == rank]
+    blocks = [b for b in range(nb) if sharded.shard_of_block(b, bs, n, world) == rank]
     lo_row = blocks[0] * bs if blocks else 0
     hi_row = min(n, (blocks[-1] + 1) * bs) if blocks else 0
 
@@ -106,7 +106,7 @@ def oracle_walk_fn(index_path, rank, world):
             while True:
                 if not (lo_row <= row < hi_row):
                     st[k] = (slot, row, steps, home << 4)
-                    dest[k] = (row // bs) * world // nb
+                    dest[k] = sharded.shard_of_block(row // bs, bs, n, world)
                     break
                 ch, nxt, off = o.back_step(row)
                 if off >= 0:
