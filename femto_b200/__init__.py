@@ -150,11 +150,11 @@ class Index:
 
     def count_stats(self, plen: np.ndarray, flat: np.ndarray, offs: np.ndarray) -> dict:
         """Counters of one instrumented count launch (see fm_count_stats)."""
-        st = (C.c_uint64 * 4)()
+        st = (C.c_uint64 * 8)()
         _check(self.lib.fm_count_stats(self.h, len(plen), _ptr(plen, C.c_int32), _ptr(flat, C.c_uint16),
                                        _ptr(offs, C.c_int64), st), "fm_count_stats")
         return {"block_reads": int(st[0]), "distinct_block_reads": int(st[1]), "occ_evals": int(st[2]),
-                "steps": int(st[3])}
+                "steps": int(st[3]), "group_slots": int(st[4]), "groups_active": int(st[5])}
 
     def walk_stats(self, rows: np.ndarray) -> dict:
         """Counters of one instrumented locate walk launch over `rows` (see fm_walk_stats)."""

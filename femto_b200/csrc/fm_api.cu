@@ -858,12 +858,13 @@ int fm_count_bytes(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
 }
 
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
-                   uint64_t* stats4) {
+                   uint64_t* stats8) {
+  uint64_t* stats4 = stats8;
   return guarded(ix, "fm_count_stats", [&]() -> int {
     if (npats < 0 || !stats4 || (npats && (!plen || !offs))) return fail(FM_ERR_PARAM, "fm_count_stats: bad argument");
     int64_t flat_len = 0;
     if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_count_stats: negative length/offset");
-    std::memset(stats4, 0, 4 * sizeof(uint64_t));
+    std::memset(stats4, 0, 8 * sizeof(uint64_t));
     if (npats == 0) return FM_OK;
     cudaStream_t s = ix->stream;
     int32_t* d_plen = static_cast<int32_t*>(ix->d_in[0].get(size_t(npats) * 4));
@@ -878,7 +879,7 @@ int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uin
     CK(cudaMemsetAsync(d_stats, 0, 64, s));
     CountArgs a{npats, d_plen, d_flat, d_offs, d_first, d_last};
     CK(launch_count(ix->im, a, ix->d_work, ix->count_sched, ix->sm_count, s, &ix->launches, d_stats));
-    CK(cudaMemcpyAsync(stats4, d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(stats4, d_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return FM_OK;
   });

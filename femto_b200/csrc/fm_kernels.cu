@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
                                                                      unsigned long long* __restrict__ stats) {
   constexpr uint32_t BITS = (BW - 1) * 32;
   unsigned long long n_ranks = 0, n_blocks = 0, n_occ = 0, n_steps = 0;
+  unsigned long long n_slots = 0, n_active = 0;  // lane groups inside descent iterations: all of them / those with a block to evaluate
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPQ - 1);
   const int gleader = lane & ~(LPQ - 1);
@@ -511,6 +512,10 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
           n_blocks += two ? 2 : 1;
           n_ranks += (actA ? 1 : 0) + (actB ? 1 : 0);
         }
+        if (STATS && sub == 0) {
+          n_slots++;
+          n_active += any ? 1 : 0;
+        }
         lvl += 4;
         if (any) {
           if (actA) {
@@ -617,7 +622,10 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
     if (jobB) obB += idxB;
     if (finish) { s.f = obA; s.l = obB - 1; s.i--; }
   }
-  if (STATS) flush_stats(stats, lane, n_ranks, n_blocks, n_occ, n_steps);
+  if (STATS) {
+    flush_stats(stats, lane, n_ranks, n_blocks, n_occ, n_steps);
+    flush_stats(stats + 4, lane, n_slots, n_active, 0, 0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

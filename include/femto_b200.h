@@ -284,11 +284,13 @@ int64_t fm_kernel_launches(const fm_index_t* ix);
 int fm_last_transfer(const fm_index_t* ix, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* Instrumented count (not a timed path): runs the same batch through a counter-carrying variant
- * of the count kernel and returns stats4 = { rank blocks requested, distinct rank blocks per
+ * of the count kernel and returns stats8 = { rank blocks requested, distinct rank blocks per
  * step and level (the two Occ of a step often share a block), Occ evaluations, backward-search
- * steps }.  bench.py derives the kernel's algorithmic HBM bytes from these. */
+ * steps, lane groups present in descent iterations, of which had a block to evaluate (quad image:
+ * the warp-divergence measure of mixed-length batches and deep codes), 0, 0 }.  bench.py derives the
+ * kernel's algorithmic HBM bytes from these. */
 int fm_count_stats(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat,
-                   const int64_t* offs, uint64_t* stats4);
+                   const int64_t* offs, uint64_t* stats8);
 
 /* Instrumented sampled-SA walks (not a timed path): SA[rows[i]] for nrows host rows through the walk
  * kernel with its counters on; stats4 = { LF steps, wavelet-tree rank blocks read, mark bit-vector

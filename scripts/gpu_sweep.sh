@@ -9,7 +9,7 @@ import json
 try:
     d=json.load(open("gpurun_out/${TAG}_$sched.json"))
     r=d["roofline"]
-    print("sched $sched", round(d["value"]/1e6,1), d["ms_per_step"], "e2e", round(d["e2e"]["value"]/1e6,1), "frac", r["frac"], "blocks", r["rank_blocks_distinct"], "ra", r["random_access"]["frac"], "hbm", d["config"]["index_hbm_gib"], "loc", round(d["locate"]["value"]/1e6,1))
+    print("sched $sched", round(d["value"]/1e6,1), d["ms_per_step"], "e2e", round(d["e2e"]["value"]/1e6,1), "frac", r["frac"], "blocks", r["rank_blocks_distinct"], "ra", r["random_access"]["frac"], "hbm", d["config"]["engine"]["index_hbm_gib"], "loc", round(d["locate"]["value"]/1e6,1))
 except Exception as e:
     print("sched $sched failed", e); print(open("gpurun_out/${TAG}_$sched.log").read()[-800:])
 PY
