@@ -307,6 +307,17 @@ class Index:
         return out[:n.value]
 
 
+    def extract_batch(self, docs: Sequence[int]) -> List[np.ndarray]:
+        """Several documents in one launch (fm_extract_batch)."""
+        d = np.ascontiguousarray(docs, dtype=np.int64)
+        start = np.zeros(len(d) + 1, dtype=np.int64)
+        total = sum(self.doc_info(int(x))[0] - 1 for x in d)
+        out = np.zeros(max(total, 1), dtype=np.uint16)
+        _check(self.lib.fm_extract_batch(self.h, len(d), _ptr(d, C.c_int64), _ptr(out, C.c_uint16), total,
+                                         _ptr(start, C.c_int64)), "fm_extract_batch")
+        return [out[start[k]:start[k + 1]] for k in range(len(d))]
+
+
 # ---------------------------------------------------------------------------------------------
 # index construction (host side)
 

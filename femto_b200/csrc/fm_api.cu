@@ -1524,26 +1524,55 @@ int fm_range_documents(fm_index_t* ix, int64_t first, int64_t last, int64_t* doc
   if (!ix || !ndocs) return fail(FM_ERR_PARAM, "fm_range_documents: null argument");
   *ndocs = 0;
   if (last < first) return FM_OK;
-  const int64_t n = last - first + 1;
-  std::vector<int64_t> offs;
+  if (first < 0 || last >= ix->info.total_length) return fail(FM_ERR_PARAM, "fm_range_documents: rows out of range");
+  std::vector<int64_t> found, rows;
   try {
-    offs.resize(size_t(n));
+    // As range_to_results for documents (src/main/server.c:4549-4889): walk the range chunk by chunk; a chunk
+    // that lies inside the range contributes its stored document list, the rows of a chunk that sticks out
+    // of the range (at most one at each end) are located one by one.  An index built without chunks
+    // locates every row.
+    bool chunks = ix->info.chunk_size > 0 && !ix->chunk_bytes.empty();
+    for (int64_t i = first; i <= last;) {
+      int64_t cf = i, cl = last;
+      std::vector<int64_t> d;
+      if (chunks) {
+        try {
+          chunk_documents(ix->hdr, ix->info.first_row, ix->info.end_row, ix->im.first_bucket, ix->chunk_bytes,
+                          ix->chunk_off, ix->chunk_count, ix->chunk_dir_rel, i, &cf, &cl, &d);
+        } catch (const Error& e) {
+          if (e.code != FM_ERR_MISSING) throw;
+          chunks = false;
+          cf = i;
+          cl = last;
+        }
+      }
+      if (chunks && cf >= first && cl <= last) {
+        found.insert(found.end(), d.begin(), d.end());
+      } else {
+        const int64_t lo = std::max(cf, first), hi = std::min(cl, last);
+        for (int64_t r = lo; r <= hi; r++) rows.push_back(r);
+      }
+      i = std::min(cl, last) + 1;
+    }
+    if (!rows.empty()) {
+      std::vector<int64_t> offs(rows.size());
+      const int rc = fm_locate_rows(ix, int64_t(rows.size()), rows.data(), offs.data());  // SA[row] on the GPU
+      if (rc) return rc;
+      // resolve_location (index.c:1587-1611) per offset
+      for (int64_t o : offs)
+        found.push_back(int64_t(std::upper_bound(ix->doc_ends.begin(), ix->doc_ends.end(), o) - ix->doc_ends.begin()));
+    }
+  } catch (const Error& e) {
+    return fail(e.code, std::string("fm_range_documents: ") + e.what());
   } catch (const std::bad_alloc&) {
     return fail(FM_ERR_MEM, "fm_range_documents: out of memory");
   }
-  int rc = fm_locate_range(ix, first, last, offs.data());  // SA[first..last] on the GPU
-  if (rc) return rc;
-  // resolve_location (index.c:1587-1611) per offset, then the sorted set of documents
-  for (int64_t i = 0; i < n; i++) {
-    const auto it = std::upper_bound(ix->doc_ends.begin(), ix->doc_ends.end(), offs[size_t(i)]);
-    offs[size_t(i)] = int64_t(it - ix->doc_ends.begin());
-  }
-  std::sort(offs.begin(), offs.end());
-  offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
-  *ndocs = int64_t(offs.size());
+  std::sort(found.begin(), found.end());
+  found.erase(std::unique(found.begin(), found.end()), found.end());
+  *ndocs = int64_t(found.size());
   if (*ndocs > docs_cap) return fail(FM_ERR_FULL, "fm_range_documents: output buffer too small");
   if (*ndocs && !docs) return fail(FM_ERR_PARAM, "fm_range_documents: null output");
-  std::copy(offs.begin(), offs.end(), docs);
+  std::copy(found.begin(), found.end(), docs);
   return FM_OK;
 }
 
@@ -1574,6 +1603,49 @@ int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int6
     CK(cudaMemcpyAsync(out, d_sym, size_t(len) * 2, cudaMemcpyDeviceToHost, s));
     const int st = walk_status(ix);
     if (st) return fail(FM_ERR_INVALID, "fm_extract: malformed walk (status " + std::to_string(st) + ")");
+    return FM_OK;
+  });
+}
+
+int fm_extract_batch(fm_index_t* ix, int64_t ndocs, const int64_t* docs, uint16_t* out, int64_t out_cap,
+                     int64_t* out_start) {
+  return guarded(ix, "fm_extract_batch", [&]() -> int {
+    if (ndocs < 0 || !out_start || (ndocs && !docs)) return fail(FM_ERR_PARAM, "fm_extract_batch: bad argument");
+    // per document: its EOF row, doc_len - 1 LF steps, where its symbols go (do_extract_document_query,
+    // src/main/server.c:6364-6437: strictly sequential per document, so the documents run side by side)
+    std::vector<int64_t> par(size_t(3 * std::max<int64_t>(ndocs, 1)));
+    int64_t total = 0;
+    for (int64_t k = 0; k < ndocs; k++) {
+      const int64_t d = docs[k];
+      if (d < 0 || d >= ix->info.num_documents) return fail(FM_ERR_PARAM, "fm_extract_batch: no such document");
+      const int64_t e = ix->doc_ends[size_t(d)];
+      const int64_t len = (d == 0 ? e : e - ix->doc_ends[size_t(d - 1)]) - 1;
+      out_start[k] = total;
+      par[size_t(k)] = ix->doc_eof_rows[size_t(d)];
+      par[size_t(ndocs + k)] = len;
+      par[size_t(2 * ndocs + k)] = total;
+      total += len;
+    }
+    out_start[ndocs] = total;
+    if (total > out_cap) return fail(FM_ERR_FULL, "fm_extract_batch: output buffer too small");
+    if (total == 0) return FM_OK;
+    if (!out) return fail(FM_ERR_PARAM, "fm_extract_batch: null output");
+    cudaStream_t s = ix->stream;
+    int64_t* d_par = static_cast<int64_t*>(ix->d_in[3].get(size_t(3 * ndocs) * 8));
+    uint16_t* d_sym = static_cast<uint16_t*>(ix->d_out[0].get(size_t(total) * 2));
+    CK(cudaMemcpyAsync(d_par, par.data(), size_t(3 * ndocs) * 8, cudaMemcpyHostToDevice, s));
+    WalkArgs w{};
+    w.nrows = ndocs;
+    w.rows = d_par;
+    w.nsteps = d_par + ndocs;
+    w.sym_off = d_par + 2 * ndocs;
+    w.out_sym = d_sym;
+    w.status = ix->d_status;
+    CK(cudaMemsetAsync(ix->d_status, 0, sizeof(int32_t), s));
+    CK(launch_walk(ix->im, w, kWalkExtract, ix->d_work, ix->lanes_per_query, ix->sm_count, s, &ix->launches));
+    CK(cudaMemcpyAsync(out, d_sym, size_t(total) * 2, cudaMemcpyDeviceToHost, s));
+    const int st = walk_status(ix);
+    if (st) return fail(FM_ERR_INVALID, "fm_extract_batch: malformed walk (status " + std::to_string(st) + ")");
     return FM_OK;
   });
 }

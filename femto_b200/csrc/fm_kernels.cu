@@ -798,7 +798,11 @@ __global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const
     // mark test: rank over the symbol's mark bit-vector at its occurrence number (index.c:2102-2140)
     const bool ok = act && ch < static_cast<uint32_t>(kAlphaDev) && count > 0;
     int64_t occ_base = 0, offset = -1;
-    mark_lookup<LPQ, BW>(im, ok, g, ch, count, markval_base, sub, offset, occ_base, n_mark, n_sample);
+    if constexpr (MODE == kWalkExtract) {  // extraction follows LF only: the mark bit-vectors are not read
+      if (ok) occ_base = rec_occ_base(__ldg(reinterpret_cast<const int4*>(im.occ + static_cast<size_t>(g) * kAlphaStride + ch)));
+    } else {
+      mark_lookup<LPQ, BW>(im, ok, g, ch, count, markval_base, sub, offset, occ_base, n_mark, n_sample);
+    }
     // LF: row' = C[ch] + occs before the bucket + count - 1; stop at a document boundary
     // (ch <= ESCAPE_CODE_SEOF, server.c:2341-2346)
     const int64_t next = (ch <= static_cast<uint32_t>(kEscSeofDev)) ? -1 : occ_base + count - 1;

@@ -265,12 +265,19 @@ int fm_doc_name(const fm_index_t* ix, int64_t doc, void* out, int64_t out_cap, i
 int fm_chunk_documents(const fm_index_t* ix, int64_t row, int64_t* chunk_first, int64_t* chunk_last, int64_t* docs,
                        int64_t docs_cap, int64_t* ndocs);
 /* Documents that contain the suffixes of BWT rows first..last, ascending and unique: what the
- * reference's range_to_results query delivers for RESULT_TYPE_DOCUMENTS (src/main/server.c:4549-4889;
- * it unions the per-chunk document lists and locates the ragged ends, this call locates every row
- * on the GPU and resolves the offsets with the header's document table -- same set).  *ndocs
+ * reference's range_to_results query delivers for RESULT_TYPE_DOCUMENTS (src/main/server.c:4549-4889),
+ * computed the same way: the stored document lists of the chunks that lie inside the range, plus the
+ * rows of the (at most two) chunks that stick out of it located on the GPU and resolved with the
+ * header's document table; an index built without chunks locates every row.  *ndocs
  * receives the number of documents; FM_ERR_FULL when it exceeds docs_cap. */
 int fm_range_documents(fm_index_t* ix, int64_t first, int64_t last, int64_t* docs, int64_t docs_cap, int64_t* ndocs);
 int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int64_t* out_len);
+/* Several documents in ONE launch (a document is a strictly sequential chain of LF steps, so throughput
+ * comes from extracting many side by side): the symbols of docs[0], docs[1], ... back to back in out;
+ * out_start (ndocs + 1 entries) receives where each document begins, out_start[ndocs] the total.
+ * FM_ERR_FULL (out_start filled) when the total exceeds out_cap. */
+int fm_extract_batch(fm_index_t* ix, int64_t ndocs, const int64_t* docs, uint16_t* out, int64_t out_cap,
+                     int64_t* out_start);
 
 /* --------------------------------------------------------------------------
  * Pinned host memory for callers that want zero-staging transfers. */

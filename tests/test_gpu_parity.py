@@ -656,3 +656,23 @@ def test_locate_negative_max_occs_gives_no_rows(built_indexes, corpora):
     with fb.Index(built_indexes[name], device=0) as ix:
         noccs, start, out = ix.locate_flat(plen, flat, offs, -5, 16)
         assert (noccs == 0).all()
+
+
+def test_extract_batch_and_chunkless_range_documents(tmp_path):
+    """fm_extract_batch: several documents in one launch equal the documents (and fm_extract one by one);
+    fm_range_documents on an index built WITHOUT document chunks locates every row and gives the same sets."""
+    docs = [corpus.english_like(4000, 500 + d) for d in range(9)] + [b"", b"x", corpus.random_acgt(2500, 9)]
+    for chunk_size in (128, 0):
+        path = str(tmp_path / f"idx{chunk_size}")
+        fb.build_index_host(docs, path, block_size=4096, bucket_size=1024, chunk_size=chunk_size)
+        with fb.Index(path) as ix, Oracle(path) as o:
+            order = [5, 0, 11, 9, 10, 3, 3, 8]
+            got = ix.extract_batch(order)
+            for d, sym in zip(order, got):
+                assert bytes((sym - fb.CHARACTER_OFFSET).astype(np.uint8)) == docs[d]
+                assert (sym == ix.extract(d)).all()
+            n = o.header_info()["total_length"]
+            sa = o.locate_range(0, n - 1)
+            doc_of = np.array([o.resolve(int(x))[0] for x in sa], dtype=np.int64)
+            for first, last in [(0, n - 1), (5, 5), (100, 700), (n - 300, n - 1)]:
+                assert (ix.range_documents(first, last) == np.unique(doc_of[first:last + 1])).all()
