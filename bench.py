@@ -437,7 +437,7 @@ def main():
     def copy_only_ms(nbytes_in, nbytes_out):
         d_in = torch.empty(nbytes_in, dtype=torch.uint8, device=device)
         d_out = torch.empty(nbytes_out, dtype=torch.uint8, device=device)
-        src = h_flat[0].view(torch.uint8).reshape(-1)[:nbytes_in]
+        src = torch.empty(nbytes_in, dtype=torch.uint8).pin_memory()
         dst = torch.empty(nbytes_out, dtype=torch.uint8).pin_memory()
         s_in, s_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
         best = None

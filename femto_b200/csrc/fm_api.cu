@@ -11,6 +11,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -642,37 +643,127 @@ int locate_rows_host(fm_index* ix, int64_t nrows, const int64_t* rows, int64_t* 
   return FM_OK;
 }
 
+// A few long-lived host threads for the pointer-array calls (creating threads per call costs more than the
+// work they do at 2 ms per batch).  run() hands every worker the same job and returns at once; wait() blocks
+// until all of them have returned from it.  One job at a time (callers hold the handle's mutex; the pool
+// itself is shared by all handles and serialises jobs).
+class WorkerPool {
+ public:
+  static WorkerPool& instance() {
+    static WorkerPool pool;
+    return pool;
+  }
+  int size() const { return int(threads_.size()); }
+  void run(std::function<void(int)> job) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return running_ == 0 && !job_; });
+    job_ = std::move(job);
+    running_ = size();
+    generation_++;
+    cv_work_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return running_ == 0; });
+    job_ = nullptr;
+    cv_done_.notify_all();
+  }
+
+ private:
+  WorkerPool() {
+    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    const int n = int(std::min(16u, std::max(2u, hw / 2)));
+    for (int t = 0; t < n; t++) threads_.emplace_back([this, t] { loop(t); });
+    for (auto& th : threads_) th.detach();  // live as long as the process
+  }
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(int)> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        job = job_;
+      }
+      if (job) job(t);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--running_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::function<void(int)> job_;
+  std::vector<std::thread> threads_;
+  uint64_t generation_ = 0;
+  int running_ = 0;
+};
+
 // Gathers the reference-style pointer array (one pointer per pattern) into one pinned flat buffer
-// with a few worker threads, IN ORDER and in the background: the streamed count enqueues the copy
-// of a chunk as soon as its patterns are in place (wait_upto), so the gather -- the most expensive
-// host step of the pointer-array call, ~3.5 ms per Mi patterns -- overlaps the search.
+// with the worker pool, IN ORDER and in the background: the streamed count enqueues the copy of a
+// chunk as soon as its patterns are in place (wait_upto), so the gather -- the most expensive host
+// step of the pointer-array call -- overlaps the search.  The offsets of the patterns in the flat
+// buffer are computed by the same workers: for a batch of equal lengths (probed at three places,
+// verified by every worker on its share) they are i * m and need no serial pass.
 class PatternGatherer {
  public:
   PatternGatherer(fm_index* ix, int64_t npats, const int* plen, const uint16_t* const* pats)
       : npats_(npats), plen_(plen), pats_(pats), offs_(size_t(npats) + 1) {
-    int64_t total = 0;
-    uniform_ = npats > 0 && plen[0] > 0 ? plen[0] : 0;
-    for (int64_t i = 0; i < npats; i++) {
-      if (plen[i] < 0) throw Error(FM_ERR_PARAM, "negative pattern length");
-      offs_[size_t(i)] = total;
-      total += plen[i];
-      if (plen[i] != uniform_) uniform_ = 0;
-    }
-    offs_[size_t(npats)] = total;
-    flat_len_ = total;
-    dst_ = static_cast<uint16_t*>(ix->h_stage[0].get(size_t(std::max<int64_t>(total, 1)) * 2));
     nblocks_ = (npats + kBlock - 1) / kBlock;
     done_.reset(new std::atomic<unsigned char>[size_t(std::max<int64_t>(nblocks_, 1))]);
     for (int64_t b = 0; b < nblocks_; b++) done_[size_t(b)].store(0, std::memory_order_relaxed);
-    const int nthreads = int(std::min<int64_t>(8, std::max<int64_t>(1, npats / 65536)));
-    if (nthreads <= 1) {
-      work();  // small batch: gather inline
+    const int m = npats > 0 ? plen[0] : 0;
+    const bool big = npats >= 8 * kBlock;
+    bool uniform = big && m > 0 && plen[npats / 2] == m && plen[npats - 1] == m;
+    WorkerPool* pool = big ? &WorkerPool::instance() : nullptr;
+    if (uniform) {  // offsets i * m, every worker checking its share of the lengths
+      std::atomic<bool> ok{true};
+      std::atomic<int64_t> next{0};
+      pool->run([&](int) {
+        for (;;) {
+          const int64_t b = next.fetch_add(1);
+          if (b >= nblocks_) return;
+          const int64_t lo = b * kBlock, hi = std::min(npats_, lo + kBlock);
+          bool good = true;
+          for (int64_t i = lo; i < hi; i++) {
+            good &= plen_[i] == m;
+            offs_[size_t(i)] = i * int64_t(m);
+          }
+          if (!good) ok.store(false, std::memory_order_relaxed);
+        }
+      });
+      pool->wait();
+      uniform = ok.load();
+      offs_[size_t(npats)] = npats * int64_t(m);
+    }
+    if (!uniform) {
+      int64_t total = 0;
+      for (int64_t i = 0; i < npats; i++) {
+        if (plen[i] < 0) throw Error(FM_ERR_PARAM, "negative pattern length");
+        offs_[size_t(i)] = total;
+        total += plen[i];
+      }
+      offs_[size_t(npats)] = total;
+    }
+    uniform_ = uniform ? m : 0;
+    if (!uniform && npats > 0) {  // small batches: equal lengths found by the serial pass
+      bool same = plen[0] > 0;
+      for (int64_t i = 1; i < npats && same; i++) same = plen[i] == plen[0];
+      if (same) uniform_ = plen[0];
+    }
+    flat_len_ = offs_[size_t(npats)];
+    dst_ = static_cast<uint16_t*>(ix->h_stage[0].get(size_t(std::max<int64_t>(flat_len_, 1)) * 2));
+    if (pool) {
+      pool_ = pool;
+      pool->run([this](int) { work(); });  // returns at once; joined in the destructor
     } else {
-      for (int t = 0; t < nthreads; t++) threads_.emplace_back([this] { work(); });
+      work();  // small batch: gather inline
     }
   }
   ~PatternGatherer() {
-    for (auto& t : threads_) t.join();
+    if (pool_) pool_->wait();
   }
   // returns once the symbols of patterns [0, hi) are in the flat buffer
   void wait_upto(int64_t hi) {
@@ -706,9 +797,9 @@ class PatternGatherer {
   uint16_t* dst_ = nullptr;
   int64_t flat_len_ = 0, nblocks_ = 0, ready_blocks_ = 0;
   int uniform_ = 0;
+  WorkerPool* pool_ = nullptr;
   std::unique_ptr<std::atomic<unsigned char>[]> done_;
   std::atomic<int64_t> next_{0};
-  std::vector<std::thread> threads_;
 };
 
 }  // namespace
