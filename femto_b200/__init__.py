@@ -307,6 +307,17 @@ class Index:
         return out[:n.value]
 
 
+    def generic_request(self, request: str) -> str:
+        """femto's generic request interface (femto.h:75-149) for the string_rows* requests."""
+        resp = C.c_char_p()
+        _check(self.lib.fm_generic_request(self.h, request.encode(), C.byref(resp)), "fm_generic_request")
+        try:
+            return resp.value.decode()
+        finally:
+            libc = C.CDLL(None)
+            libc.free.argtypes = [C.c_void_p]
+            libc.free(C.cast(resp, C.c_void_p))
+
     def extract_batch(self, docs: Sequence[int]) -> List[np.ndarray]:
         """Several documents in one launch (fm_extract_batch)."""
         d = np.ascontiguousarray(docs, dtype=np.int64)

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "fm_resolve": (C.c_int, [vp, i64, P(i64), P(i64), P(i64)]),
     "fm_extract": (C.c_int, [vp, i64, P(u16), i64, P(i64)]),
     "fm_extract_batch": (C.c_int, [vp, i64, P(i64), P(u16), i64, P(i64)]),
+    "fm_generic_request": (C.c_int, [vp, C.c_char_p, P(C.c_char_p)]),
     "fm_host_alloc": (vp, [C.c_size_t]),
     "fm_host_free": (None, [vp]),
     "fm_kernel_launches": (i64, [vp]),

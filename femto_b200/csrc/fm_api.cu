@@ -1698,6 +1698,98 @@ int fm_extract(fm_index_t* ix, int64_t doc, uint16_t* out, int64_t out_cap, int6
   });
 }
 
+// ---- generic requests (femto.h:75-149) ---------------------------------------------------------------
+int fm_generic_request(fm_index_t* ix, const char* request, char** response) {
+  if (!ix || !request || !response) return fail(FM_ERR_PARAM, "fm_generic_request: null argument");
+  *response = nullptr;
+  // the request word, as femto_create_generic_request_err tells them apart (src/main/femto.c:595-611)
+  enum { kRows = 1, kAll, kLeft, kRight } type;
+  const char* p = request;
+  auto starts = [&](const char* word) {
+    const size_t n = std::strlen(word);
+    if (std::strncmp(request, word, n) != 0) return false;
+    p = request + n;
+    return true;
+  };
+  if (starts("string_rows_left")) type = kLeft;
+  else if (starts("string_rows_right")) type = kRight;
+  else if (starts("string_rows_all")) type = kAll;
+  else if (starts("string_rows")) type = kRows;
+  else if (starts("find_strings") || starts("docs_for_range") || starts("find_docs"))
+    return fail(FM_ERR_INVALID, "fm_generic_request: this request needs femto's query parser / result encoder; "
+                                "only the string_rows* requests run on this engine");
+  else return fail(FM_ERR_INVALID, "Bad request");
+  // the pattern: integers (any base sscanf's %i takes), each a byte value: symbol = CHARACTER_OFFSET + value
+  std::vector<uint16_t> pat;
+  const char* end = request + std::strlen(request);
+  while (p != end) {
+    while (*p == ' ') p++;
+    if (p == end) break;
+    int num = 0, used = 0;
+    if (std::sscanf(p, "%i%n", &num, &used) <= 0) return fail(FM_ERR_INVALID, "Could not scan");
+    const int ch = FM_CHARACTER_OFFSET + num;
+    if (ch >= FM_ALPHA_SIZE || ch < 0) return fail(FM_ERR_INVALID, "Bad request character");
+    pat.push_back(uint16_t(ch));
+    p += used;
+  }
+  // the batch: the pattern itself, or the pattern with every symbol of the alphabet (0 .. ALPHA_SIZE-1, escape
+  // codes included) put in front of it ("left") and / or behind it ("right"): setup_string_rows_*_query,
+  // src/main/server.c:4194-4320
+  const int m = int(pat.size());
+  const int per = FM_ALPHA_SIZE;
+  const int n = type == kRows ? 1 : type == kAll ? 2 * per : per;
+  const int mlen = type == kRows ? m : m + 1;
+  const size_t nn = static_cast<size_t>(n);
+  std::vector<int32_t> plen(nn, mlen);
+  std::vector<int64_t> offs(nn), first(nn), last(nn);
+  std::vector<uint16_t> flat(static_cast<size_t>(std::max(1, n * mlen)));
+  for (int i = 0; i < n; i++) {
+    offs[size_t(i)] = int64_t(i) * mlen;
+    uint16_t* dst = flat.data() + size_t(i) * size_t(mlen);
+    if (type == kRows) {
+      std::copy(pat.begin(), pat.end(), dst);
+    } else {
+      const bool left = type == kLeft || (type == kAll && i < per);
+      const uint16_t c = uint16_t(i % per);
+      if (left) { dst[0] = c; std::copy(pat.begin(), pat.end(), dst + 1); }
+      else { std::copy(pat.begin(), pat.end(), dst); dst[m] = c; }
+    }
+  }
+  const int rc = fm_count_flat(ix, n, plen.data(), flat.data(), offs.data(), first.data(), last.data());
+  if (rc) return rc;
+  // the answer, character for character what femto_response_for_generic_request_err prints (femto.c:919-995)
+  std::string out;
+  char line[128];
+  if (type == kRows) {
+    std::snprintf(line, sizeof(line), "{\"range\":[%lld,%lld]}\n", (long long)first[0], (long long)last[0]);
+    out = line;
+  } else {
+    bool on_right = type == kRight, first_entry = true;
+    out += std::string("{\"") + (on_right ? "right" : "left") + "\":[\n";
+    for (int i = 0; i < n; i++) {
+      if (i == per) {
+        on_right = true;
+        out += "\n ],\n \"right\":[\n";
+        first_entry = true;
+      }
+      const int ch = (i >= per ? i - per : i) - FM_CHARACTER_OFFSET;
+      if (first[size_t(i)] <= last[size_t(i)]) {
+        if (!first_entry) out += ",\n";
+        first_entry = false;
+        std::snprintf(line, sizeof(line), "  {\"ch\":%i, \"range\":[%lld,%lld]}", ch, (long long)first[size_t(i)],
+                      (long long)last[size_t(i)]);
+        out += line;
+      }
+    }
+    out += "\n ]\n}\n";
+  }
+  char* buf = static_cast<char*>(std::malloc(out.size() + 1));
+  if (!buf) return fail(FM_ERR_MEM, "fm_generic_request: out of memory");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  *response = buf;
+  return FM_OK;
+}
+
 int fm_extract_batch(fm_index_t* ix, int64_t ndocs, const int64_t* docs, uint16_t* out, int64_t out_cap,
                      int64_t* out_start) {
   return guarded(ix, "fm_extract_batch", [&]() -> int {

@@ -280,6 +280,20 @@ int fm_extract_batch(fm_index_t* ix, int64_t ndocs, const int64_t* docs, uint16_
                      int64_t* out_start);
 
 /* --------------------------------------------------------------------------
+ * Generic requests: femto_create_generic_request + femto_begin_request + femto_wait_request +
+ * femto_response_for_generic_request (src/main/femto.h:75-149, src/main/femto.c:566-1000) in one blocking
+ * call, for the requests that are batches of backward searches:
+ *   "string_rows B B ..."        -> {"range":[first,last]}
+ *   "string_rows_left B B ..."   -> the ranges of c+pattern for every symbol c of the alphabet
+ *   "string_rows_right B B ..."  -> the ranges of pattern+c
+ *   "string_rows_all B B ..."    -> both
+ * (B = byte values as integers).  *response is malloc()ed, freed by the caller, and byte-identical to the
+ * reference's answer.  find_strings / find_docs / docs_for_range need femto's query parser and result
+ * encoder and are refused with FM_ERR_INVALID.  integration/femto_request_b200.c is the reference's
+ * femto_handle_request tool (src/main/handle_request.c) on top of it. */
+int fm_generic_request(fm_index_t* ix, const char* request, char** response);
+
+/* --------------------------------------------------------------------------
  * Pinned host memory for callers that want zero-staging transfers. */
 void* fm_host_alloc(size_t bytes);
 void fm_host_free(void* p);

@@ -254,6 +254,18 @@ class Reference(_Base):
             raise RuntimeError(f"ref_open({path}) failed")
         self.h = C.c_void_p(self.h)
 
+    def generic_request(self, index_path: str, request: str) -> str:
+        """femto_create_generic_request .. femto_response_for_generic_request (femto.h:75-149)."""
+        resp = C.c_char_p()
+        self.lib.ref_generic_request.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]
+        rc = self.lib.ref_generic_request(self.h, index_path.encode(), request.encode(), C.byref(resp))
+        if rc:
+            raise RuntimeError(f"generic request failed rc={rc}")
+        try:
+            return resp.value.decode()
+        finally:
+            self.lib.ref_free(C.cast(resp, C.c_void_p))
+
     @classmethod
     def build_index(cls, docs: Sequence[bytes], index_path: str, scratch_dir: str, block_size: int = 0,
                     bucket_size: int = 0, chunk_size: int = -1, mark_period: int = -1) -> None:

@@ -404,6 +404,22 @@ void ref_bseq_rank(const unsigned char* zdata, int index1, int* occ0, int* occ1,
   *occ0 = q.occs[0]; *occ1 = q.occs[1]; *bit = q.bit;
 }
 
+/* femto's generic request interface, start to finish (femto.h:75-149): *response is malloc()ed by femto */
+int ref_generic_request(void* hv, const char* index_path, const char* request, char** response)
+{
+  ref_handle_t* h = hv;
+  femto_request_t* req = NULL;
+  int rc;
+  *response = NULL;
+  rc = femto_create_generic_request(&req, &h->srv, index_path, request);
+  if (rc) return rc;
+  rc = femto_begin_request(&h->srv, req);
+  if (!rc) rc = femto_wait_request(&h->srv, req);
+  if (!rc) rc = femto_response_for_generic_request(req, &h->srv, response);
+  femto_destroy_request(req);
+  return rc;
+}
+
 void ref_free(void* p) { free(p); }
 
 int ref_wtree_settings(void) { return wtree_settings_number(); }

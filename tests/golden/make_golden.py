@@ -54,11 +54,17 @@ def main():
             occ = [[int(c), int(row), r.occ(int(c), int(row))[0]]
                    for c, row in zip(rng.integers(0, 261, 400), rng.integers(0, n, 400))]
             sa = r.locate_range(0, n - 1).tolist()
+            # generic requests (femto.h:75-149): the pattern as byte values
+            reqs = {}
+            for p in [q for q in pats if len(q) and (q >= 5).all()][:6]:
+                body = " ".join(str(int(x) - 5) for x in p)
+                for word in ("string_rows", "string_rows_left", "string_rows_right", "string_rows_all"):
+                    reqs[f"{word} {body}"] = r.generic_request(idx, f"{word} {body}")
         json.dump({
             "docs_hex": [d.hex() for d in docs], "params": params, "total_length": n,
             "patterns": [p.tolist() for p in pats], "first": f.tolist(), "last": l.tolist(),
             "max_occs": max_occs, "locate": [x.tolist() for x in loc], "back_step": steps,
-            "occ_samples": occ, "sa": sa,
+            "occ_samples": occ, "sa": sa, "generic_requests": reqs,
         }, open(os.path.join(base, "expected.json"), "w"))
         size = sum(os.path.getsize(os.path.join(idx, f)) for f in os.listdir(idx))
         print(f"{name}: n={n} index bytes={size}")

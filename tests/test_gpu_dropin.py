@@ -50,3 +50,22 @@ def test_femto_multiquery_runs_on_the_gpu_engine(name, length, built_indexes, co
 
     chunk = lambda s: float(re.search(r"Did ([\d.]+) chunk locate results", s).group(1))
     assert chunk(_run(STOCK, index, "-chunklocate", pf, ("50",))) == chunk(_run(DROPIN, index, "-chunklocate", pf, ("50",)))
+
+
+REQUEST_TOOL = os.path.join(REF_DIR, "femto_request_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(REQUEST_TOOL), reason="oracle/_ref tools did not travel (make -C oracle dropin)")
+def test_femto_handle_request_tool_on_the_gpu_engine():
+    """integration/femto_request_b200.c = the reference's femto_handle_request (src/main/handle_request.c) over
+    fm_generic_request: its Response section must be the reference's own answer (golden fixtures)."""
+    import json
+    from conftest import GOLDEN_DIR
+    base = os.path.join(GOLDEN_DIR, "mixed_1500")
+    exp = json.load(open(os.path.join(base, "expected.json")))
+    for req, want in list(exp["generic_requests"].items())[:6]:
+        out = subprocess.run([REQUEST_TOOL, os.path.join(base, "index"), req], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr[-2000:]
+        head, resp = out.stdout.split("Response:\n", 1)
+        assert head == f"Index:{os.path.join(base, 'index')}\nRequest:\n{req}\n"
+        assert resp == want + "\n"

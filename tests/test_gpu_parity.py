@@ -224,6 +224,13 @@ def test_golden_reference_outputs():
             assert ix.locate_range(0, n - 1).tolist() == exp["sa"]
             occ = np.array(exp["occ_samples"])
             assert ix.occ(occ[:, 0], occ[:, 1]).tolist() == occ[:, 2].tolist()
+            # femto's generic requests (femto.h:75-149): the response text, character for character
+            for req, want in exp["generic_requests"].items():
+                assert ix.generic_request(req) == want, req
+            with pytest.raises(fb.FemtoError):
+                ix.generic_request("no_such_request 1 2")
+            with pytest.raises(fb.FemtoError):
+                ix.generic_request("string_rows 1 x")
 
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref did not travel")
