@@ -9,6 +9,7 @@
  * oracle/Makefile builds _ref/femto_multiquery_b200 from the unmodified query_tool.c + this
  * file (tests/test_gpu_dropin.py runs it next to the stock femto_multiquery on the same index).
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -21,27 +22,38 @@
 
 static fm_index_t* handle_for(femto_server_t* srv, index_locator_t loc)
 {
-  /* one fm_index_t per index id, opened on first use; FEMTO_B200_DEVICE selects the GPU */
+  /* one fm_index_t per index id, opened on first use; FEMTO_B200_DEVICE selects the GPU.  The
+   * reference lets several caller threads run batches at once (src/main/server.c:3732-3793), so the
+   * table is guarded; the fm_* calls themselves are thread-safe per handle. */
   static struct { intptr_t id; fm_index_t* ix; } cache[FM_SHIM_MAX_INDEXES];
+  static pthread_mutex_t cache_mu = PTHREAD_MUTEX_INITIALIZER;
   path_translator_t* t = &srv->state->path_to_id;
   const char* path = NULL;
+  fm_index_t* found = NULL;
   int i;
-  for (i = 0; i < FM_SHIM_MAX_INDEXES; i++) if (cache[i].id == loc.id && cache[i].ix) return cache[i].ix;
-  /* id -> path: block_storage.h declares path_translator_path_for_id() but the reference never
-   * defines it (only the static _unlocked helper, block_storage.c:237), so read the table here */
-  pthread_rwlock_rdlock(&t->rwlock);
-  if (loc.id > 0 && loc.id < (intptr_t) t->next_id) path = t->id_to_path[loc.id].path;
-  pthread_rwlock_unlock(&t->rwlock);
-  if (!path) return NULL;
-  for (i = 0; i < FM_SHIM_MAX_INDEXES; i++) {
-    if (!cache[i].ix) {
-      const char* dev = getenv("FEMTO_B200_DEVICE");
-      if (fm_open(path, dev ? atoi(dev) : 0, &cache[i].ix) != FM_OK) return NULL;
-      cache[i].id = loc.id;
-      return cache[i].ix;
+  pthread_mutex_lock(&cache_mu);
+  for (i = 0; i < FM_SHIM_MAX_INDEXES; i++) if (cache[i].id == loc.id && cache[i].ix) { found = cache[i].ix; break; }
+  if (!found) {
+    /* id -> path: block_storage.h declares path_translator_path_for_id() but the reference never
+     * defines it (only the static _unlocked helper, block_storage.c:237), so read the table here */
+    pthread_rwlock_rdlock(&t->rwlock);
+    if (loc.id > 0 && loc.id < (intptr_t) t->next_id) path = t->id_to_path[loc.id].path;
+    pthread_rwlock_unlock(&t->rwlock);
+    for (i = 0; path && i < FM_SHIM_MAX_INDEXES; i++) {
+      if (!cache[i].ix) {
+        const char* dev = getenv("FEMTO_B200_DEVICE");
+        if (fm_open(path, dev ? atoi(dev) : 0, &cache[i].ix) == FM_OK) {
+          cache[i].id = loc.id;
+          found = cache[i].ix;
+        } else {
+          cache[i].ix = NULL;
+        }
+        break;
+      }
     }
   }
-  return NULL;
+  pthread_mutex_unlock(&cache_mu);
+  return found;
 }
 
 static error_t to_error(int rc)
