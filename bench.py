@@ -56,6 +56,10 @@ def parse_args():
     ap.add_argument("--kind", choices=["bytes", "acgt", "english"], default="bytes",
                     help="english: Zipf words over a fixed 50k-word vocabulary, many documents (BASELINE configs[3])")
     ap.add_argument("--doc-mib", type=int, default=1, help="--kind english: document size (MiB)")
+    ap.add_argument("--chunk-size", type=int, default=2048,
+                    help="rows per document chunk of the index (default 2048 as the reference; 0 = build without "
+                         "document chunks: they are not on the count / locate path, and with thousands of documents "
+                         "they outweigh the rest of the index)")
     ap.add_argument("--plen-min", type=int, default=8, help="--patterns zipf: shortest pattern")
     ap.add_argument("--plen-max", type=int, default=256, help="--patterns zipf: longest pattern")
     ap.add_argument("--npats", type=int, default=1 << 20)
@@ -94,6 +98,8 @@ def log(msg):
 
 def index_name(args):
     docs = f"_docs{args.doc_mib}MiB" if args.kind == "english" else ""
+    if args.chunk_size != 2048:
+        docs += f"_chunk{args.chunk_size}"
     return f"{args.kind}_{args.corpus_mib}MiB{docs}_seed{args.seed}_v1"
 
 
@@ -127,7 +133,7 @@ def ensure_index(args, device, rank, world):
         subprocess.run(["rm", "-rf", tmp, path], check=False)
         log(f"building index {index_name(args)} (one-time, cached in {args.cache_dir})")
         text = corpus_tensor(args, device)
-        t = build_gpu.build_index_gpu(corpus_docs(args, text), tmp, log=log)
+        t = build_gpu.build_index_gpu(corpus_docs(args, text), tmp, chunk_size=args.chunk_size, log=log)
         del text
         torch.cuda.empty_cache()
         os.rename(tmp, path)
@@ -892,7 +898,9 @@ def run_ragged(args, fb, lib, index_path, build_info, text, rank, world, local, 
                 raise SystemExit("PARITY FAILURE: GPU first/last differ from the reference on the bench batch")
     workload = (f"count() of {npats} text-sampled patterns, lengths Zipf(s=1) over [{args.plen_min}, {args.plen_max}] "
                 f"(mean {symbols / npats:.1f}), on a {args.corpus_mib} MiB synthetic English-like corpus "
-                f"({ix.info.num_documents} documents of {args.doc_mib} MiB), default index params")
+                f"({ix.info.num_documents} documents of {args.doc_mib} MiB), default index params"
+                + ("" if args.chunk_size == 2048 else f" except chunk_size {args.chunk_size} (no document chunks)" if args.chunk_size <= 0
+                   else f" except chunk_size {args.chunk_size}"))
     out = {
         "metric": "patterns/sec (count)", "value": round(npats * world / (ms_per_step / 1e3), 1), "unit": "patterns/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),

@@ -126,6 +126,7 @@ struct fm_index {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   DevBuf d_in[4], d_out[4];
   HostBuf h_stage[2], h_marks, h_ranges;
+  std::vector<int64_t> gather_offs;   // fm_count (pointer array): offsets of the patterns in the gathered buffer
   int64_t launches = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes copied by the most recent host-buffer count call
   bool stream_ok = true;               // cleared when a streamed batch stalled (e.g. under a serialising profiler)
@@ -650,8 +651,10 @@ int locate_rows_host(fm_index* ix, int64_t nrows, const int64_t* rows, int64_t* 
 class WorkerPool {
  public:
   static WorkerPool& instance() {
-    static WorkerPool pool;
-    return pool;
+    // never destroyed: its threads wait on the condition variables for as long as the process lives, and
+    // destroying a condition variable that has waiters (at exit) blocks forever
+    static WorkerPool* pool = new WorkerPool();
+    return *pool;
   }
   int size() const { return int(threads_.size()); }
   void run(std::function<void(int)> job) {
@@ -710,7 +713,9 @@ class WorkerPool {
 class PatternGatherer {
  public:
   PatternGatherer(fm_index* ix, int64_t npats, const int* plen, const uint16_t* const* pats)
-      : npats_(npats), plen_(plen), pats_(pats), offs_(size_t(npats) + 1) {
+      : npats_(npats), plen_(plen), pats_(pats) {
+    if (ix->gather_offs.size() < size_t(npats) + 1) ix->gather_offs.resize(size_t(npats) + 1 + size_t(npats) / 4);
+    offs_ = ix->gather_offs.data();  // kept with the handle: a fresh 8 MB vector per call costs more than the gather's share
     nblocks_ = (npats + kBlock - 1) / kBlock;
     done_.reset(new std::atomic<unsigned char>[size_t(std::max<int64_t>(nblocks_, 1))]);
     for (int64_t b = 0; b < nblocks_; b++) done_[size_t(b)].store(0, std::memory_order_relaxed);
@@ -775,7 +780,7 @@ class PatternGatherer {
   }
   const uint16_t* flat() const { return dst_; }
   int64_t flat_len() const { return flat_len_; }
-  const int64_t* offs() const { return offs_.data(); }
+  const int64_t* offs() const { return offs_; }
   int uniform() const { return uniform_; }
 
  private:
@@ -793,7 +798,7 @@ class PatternGatherer {
   int64_t npats_;
   const int* plen_;
   const uint16_t* const* pats_;
-  std::vector<int64_t> offs_;
+  int64_t* offs_ = nullptr;
   uint16_t* dst_ = nullptr;
   int64_t flat_len_ = 0, nblocks_ = 0, ready_blocks_ = 0;
   int uniform_ = 0;
@@ -887,10 +892,13 @@ void fm_host_free(void* p) {
 }
 
 namespace {
-int count_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
-                    int64_t* first, int64_t* last, int sym_bytes) {
-  return guarded(ix, "fm_count_flat", [&]() -> int {
-    if (npats < 0 || (npats && (!plen || !offs || !first))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
+// A flat host batch, handle already locked: large ordered batches streamed (shape claimed from the first and
+// last pattern, validated chunk by chunk behind the running kernel), the others validated first.
+// to_host == false: the ranges stay in ix->d_out[0] / d_out[1] (locate).
+int count_batch_locked(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                       int64_t* first, int64_t* last, int sym_bytes, bool to_host) {
+  {
+    if (npats < 0 || (npats && (!plen || !offs || (to_host && !first)))) return fail(FM_ERR_PARAM, "fm_count_flat: bad argument");
     int64_t flat_len = 0;
     bool ordered = false;
     if (ix->info.first_row != 0 || ix->info.end_row != ix->info.total_length)
@@ -905,7 +913,7 @@ int count_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const ui
       // the device buffers are sized from it)
       if (claim_len >= 0 && offs[npats - 1] >= 0 && plen[npats - 1] >= 0 && claim_len <= npats * int64_t(4096)) {
         const int rc = count_host(ix, npats, plen, flat, claim_len, offs, first, last, /*in_order=*/true, m,
-                                  /*to_host=*/true, /*lazy=*/true, nullptr, sym_bytes);
+                                  to_host, /*lazy=*/true, nullptr, sym_bytes);
         if (rc != kRetryValidated) return rc;
       }
     }
@@ -922,8 +930,15 @@ int count_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const ui
       return fail(FM_ERR_PARAM, "fm_count_flat: negative length/offset");
     }
     if (flat_len && !flat) return fail(FM_ERR_PARAM, "fm_count_flat: null pattern buffer");
-    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered, shape.uniform, true, false, nullptr,
+    return count_host(ix, npats, plen, flat, flat_len, offs, first, last, ordered, shape.uniform, to_host, false, nullptr,
                       sym_bytes);
+  }
+}
+
+int count_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const uint16_t* flat, const int64_t* offs,
+                    int64_t* first, int64_t* last, int sym_bytes) {
+  return guarded(ix, "fm_count_flat", [&]() -> int {
+    return count_batch_locked(ix, npats, plen, flat, offs, first, last, sym_bytes, /*to_host=*/true);
   });
 }
 }  // namespace
@@ -1367,14 +1382,12 @@ int locate_flat_impl(fm_index_t* ix, int64_t npats, const int32_t* plen, const u
   return guarded(ix, "fm_locate_flat", [&]() -> int {
     if (npats < 0 || (npats && (!plen || !offs || !noccs || !out_start)))
       return fail(FM_ERR_PARAM, "fm_locate_flat: bad argument");
-    int64_t flat_len = 0;
-    if (check_patterns(npats, plen, offs, &flat_len)) return fail(FM_ERR_PARAM, "fm_locate_flat: negative length/offset");
     if (npats == 0) return FM_OK;
     if (npats > INT32_MAX) return fail(FM_ERR_PARAM, "fm_locate_flat: too many patterns in one call");
     static const bool trace = std::getenv("FEMTO_B200_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    // count; the ranges stay in HBM
-    int rc = count_host(ix, npats, plen, flat, flat_len, offs, nullptr, nullptr, /*in_order=*/false, 0, /*to_host=*/false);
+    // count (streamed like fm_count_flat when the batch is large and in order); the ranges stay in HBM
+    int rc = count_batch_locked(ix, npats, plen, flat, offs, nullptr, nullptr, 2, /*to_host=*/false);
     if (rc) return rc;
     cudaStream_t s = ix->stream;
     const int64_t* d_first = static_cast<const int64_t*>(ix->d_out[0].get(size_t(npats) * 8));
