@@ -36,6 +36,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include <cub/device/device_scan.cuh>
 
@@ -629,8 +630,12 @@ __global__ void __launch_bounds__(kThreads, MINB) count_sync_kernel(const DevIma
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int LPQ, int BW, int MODE, int LV = 1>
-__global__ void __launch_bounds__(kThreads) walk_kernel(const DevImage im, const WalkArgs a,
+// MINB: resident CTAs per SM the kernel is compiled for (0 = the compiler's choice, 64 registers = 4 CTAs).  The
+// walk is a chain of dependent reads with little arithmetic between them: it is bound by how many chains an SM
+// holds (ncu: 82 % of the warp cycles wait for a load, issue slots 24 % busy at 4 CTAs), so the locate kernel
+// trades registers for warps.
+template <int LPQ, int BW, int MODE, int LV = 1, int MINB = 0>
+__global__ void __launch_bounds__(kThreads, MINB) walk_kernel(const DevImage im, const WalkArgs a,
                                                          unsigned long long* __restrict__ work) {
   constexpr uint32_t BITS = (BW - 1) * 32;
   const int lane = threadIdx.x & 31;
@@ -1070,7 +1075,20 @@ template <int LPQ, int BW, int LV = 1>
 static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work,
                                    int sm_count, cudaStream_t stream) {
   const int gpb = kThreads / LPQ;
-  if (mode == kWalkLocate) {
+  if (mode == kWalkLocate && LV == 4) {
+    // CTAs per SM: FEMTO_B200_WALK_CTAS = 4 (64 registers), 6 or 8 (32 registers); tuning experiments only
+    static const int want = [] { const char* v = std::getenv("FEMTO_B200_WALK_CTAS"); return v ? std::atoi(v) : kWalkLocateCtas; }();
+    if (want >= 8) {
+      static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV, 8>);
+      walk_kernel<LPQ, BW, kWalkLocate, LV, 8><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    } else if (want >= 6) {
+      static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV, 6>);
+      walk_kernel<LPQ, BW, kWalkLocate, LV, 6><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    } else {
+      static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV>);
+      walk_kernel<LPQ, BW, kWalkLocate, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
+    }
+  } else if (mode == kWalkLocate) {
     static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV>);
     walk_kernel<LPQ, BW, kWalkLocate, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else if (mode == kWalkStep) {

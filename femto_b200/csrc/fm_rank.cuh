@@ -23,6 +23,7 @@ namespace fmb {
 namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kThreads = 256;
+constexpr int kWalkLocateCtas = 4;  // resident CTAs per SM of the locate walk over the quad image (fm_kernels.cu walk_kernel)
 constexpr int kEscSeofDev = 2;  // ESCAPE_CODE_SEOF, src/main/index_types.h:42-48
 constexpr int kAlphaDev = 261;
 
