@@ -1162,7 +1162,7 @@ int fm_mesh_create(fm_index_t* ix, int rank, int world, int64_t window, int cap_
     if (world < 1 || world > kMeshMaxRanks || rank < 0 || rank >= world || window < 0)
       return fail(FM_ERR_PARAM, "fm_mesh_create: bad rank / world / window");
     if (ix->im.levels != 4) return fail(FM_ERR_PARAM, "fm_mesh_create: needs the quad-level image (the default)");
-    if (window == 0) window = 128 << 10;
+    if (window == 0) window = 256 << 10;  // measured: throughput levels off from about 256 Ki own patterns in flight
     // a ring must hold every state in flight: world * (window + what the warps of one rank may claim
     // beyond the window between its check and their claims)
     // per warp (SMs x 4 CTAs x 8 warps at most): a chunk of 32 ids it may have claimed past the window, and
@@ -1313,6 +1313,8 @@ int mesh_launch(fm_mesh_t* m, bool walk, const int32_t* d_plen, const uint16_t* 
     a.out_offset = d_offsets;
     a.block_size = ix->info.block_size;
     a.nblocks = ix->info.num_blocks;
+    a.block_shift = ((a.block_size & (a.block_size - 1)) == 0 && a.nblocks <= kMeshOwnerTab)
+                        ? __builtin_ctzll(static_cast<unsigned long long>(a.block_size)) : -1;
     {  // shard r holds the rows from shard_start[r] on: the first row of its first block (shard_of_block)
       int64_t b = 0;
       for (int r = 0; r <= kMeshMaxRanks; r++) {

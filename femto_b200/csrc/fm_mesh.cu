@@ -110,6 +110,7 @@ struct MeshShared {
   unsigned long long blk[kThreads / 32][kMeshMaxRanks + 1][2];
   uint4* peer_ring[kMeshMaxRanks];
   int64_t start[kMeshMaxRanks + 1];
+  unsigned char owner_tab[kMeshOwnerTab];  // owner of data block b (when block_size is a power of two and nblocks fits)
   unsigned cnt[kThreads / 32][8];  // per warp: sent, received, rounds, counters 3 and 4 of the kernel, -, injected, -
 };
 __device__ __forceinline__ void mesh_count_up(MeshShared& sh, int wic, int lane, int k, unsigned v) {
@@ -135,6 +136,7 @@ __device__ __forceinline__ const ulonglong2* mesh_slot(const uint4* ring, int sr
 // owner(row) = (row / block_size) * world / nblocks (the reference's block -> file map, partitioned): shard r
 // starts at block ceil(r * nblocks / world); start[r] is that block's first row.
 __device__ __forceinline__ int mesh_owner(const MeshArgs& a, const MeshShared& sh, int64_t row) {
+  if (a.block_shift >= 0) return sh.owner_tab[row >> a.block_shift];
   int o = 0;
   for (int r = 1; r < a.world; r++) o += row >= sh.start[r] ? 1 : 0;
   return o;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
         unpack_state(s, w0, w1, w2, w3);
         have = true;
       }
-      for (int t = 0; t < take; t++) needers &= needers - 1;
+      needers = __ballot_sync(kFull, !have && w.sub == 0);
       mesh_count_up(sh, w.wic, w.lane, 1, take);
       __syncwarp();
       // advance the cursors; a block that is used up leaves the polled set and is replaced by a new ticket
@@ -274,20 +276,9 @@ __device__ __forceinline__ unsigned long long mesh_send_claim(MeshWarp& w, const
     send = false;
   }
   const bool mine = send && w.sub == 0;
-  unsigned todo = __ballot_sync(kFull, mine);
-  mesh_count_up(sh, w.wic, w.lane, 0, __popc(todo));
-  unsigned long long idx = 0;
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    const int d = __shfl_sync(kFull, dest, src);
-    const unsigned same = __ballot_sync(kFull, mine && dest == d);
-    unsigned long long base = 0;
-    if (w.lane == src) base = atomicAdd(&a.ctl->out_tail[d], static_cast<unsigned long long>(__popc(same)));
-    base = __shfl_sync(kFull, base, src);
-    if (mine && dest == d) idx = base + __popc(same & lanemask_lt());
-    todo &= ~same;
-  }
-  return idx;
+  mesh_count_up(sh, w.wic, w.lane, 0, __popc(__ballot_sync(kFull, mine)));
+  // one atomic per leaving state (the lanes of a warp that address the same counter travel in one request)
+  return mine ? atomicAdd(&a.ctl->out_tail[dest], 1ull) : 0ull;
 }
 __device__ __forceinline__ void mesh_send_store(const MeshWarp& w, const MeshArgs& a, const MeshShared& sh, int dest,
                                                 unsigned long long idx) {
@@ -348,6 +339,13 @@ __device__ __forceinline__ MeshWarp mesh_warp_init(const MeshArgs& a, MeshInbox&
   if (threadIdx.x < (kThreads / 32) * 8) (&sh.cnt[0][0])[threadIdx.x] = 0;
   if (threadIdx.x < kMeshMaxRanks) sh.peer_ring[threadIdx.x] = a.peer_ring[threadIdx.x];
   if (threadIdx.x <= kMeshMaxRanks) sh.start[threadIdx.x] = a.shard_start[threadIdx.x];
+  if (a.block_shift >= 0)
+    for (int b = threadIdx.x; b < kMeshOwnerTab; b += kThreads) {
+      const int64_t row = static_cast<int64_t>(b) << a.block_shift;
+      int o = 0;
+      for (int r = 1; r < a.world; r++) o += row >= a.shard_start[r] ? 1 : 0;
+      sh.owner_tab[b] = static_cast<unsigned char>(o);
+    }
   in.pend = 0;
   in.pend_which = -1;
   in.todo = 0;

@@ -36,6 +36,7 @@ namespace fmb {
 
 constexpr int kMeshMaxRanks = 16;
 constexpr int kMeshBlock = 16;  // consecutive ring indices owned by one consumer warp
+constexpr int kMeshOwnerTab = 2048;  // data blocks the kernels' block -> owner table holds
 
 // Control block at the start of every rank's exported region.
 struct MeshCtl {
@@ -81,6 +82,7 @@ struct MeshArgs {
   // (first row of block ceil(r * nblocks / world)); shard_start[world] = total_length
   int64_t block_size, nblocks;
   int64_t shard_start[kMeshMaxRanks + 1];
+  int block_shift;                     // log2(block_size) when it is a power of two and nblocks <= kMeshOwnerTab, else -1
 };
 
 // max_ctas: 0 = fill the device; else an upper bound (several meshes sharing one GPU in a test).
