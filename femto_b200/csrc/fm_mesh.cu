@@ -106,6 +106,7 @@ __device__ __forceinline__ void unpack_state(MeshState& s, unsigned long long w0
 // after its slot index was requested).
 struct MeshShared {
   ulonglong2 stage[kThreads / 32][32][2];
+  ulonglong2 peek[kThreads / 32][32];   // first two words of the slot at the cursor of block (ring = lane >> 1, lane & 1)
   ulonglong2 out[kThreads / 32][32][2];
   unsigned long long blk[kThreads / 32][kMeshMaxRanks + 1][2];
   uint4* peer_ring[kMeshMaxRanks];
@@ -184,6 +185,16 @@ __device__ __forceinline__ void mesh_stage_issue(const MeshWarp& w, const MeshAr
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 1) : "memory");
   }
+  // and a look at the slot under the cursor of EVERY block the warp owns (one lane per block): a block receives
+  // its 16 messages in a burst when the ring's fill frontier passes it, so this tells the next fetch where to go
+  if (a.world > 2 && w.lane < 2 * a.world) {
+    const unsigned long long pc = sh.blk[w.wic][w.lane >> 1][w.lane & 1];
+    if (pc != kNoBlock) {
+      const ulonglong2* src = mesh_slot(a.ring, w.lane >> 1, pc, w, a);
+      const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&sh.peek[w.wic][w.lane]));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
   if (j == 0) sh.blk[w.wic][kMeshMaxRanks][h] = cur;  // what the staged slots belong to
   in.staged = true;
@@ -260,7 +271,24 @@ __device__ __forceinline__ void mesh_take_inbox(MeshWarp& w, const MeshArgs& a, 
       }
       __syncwarp();
     }
-    if (take0 == v0 && take1 == v1) in.ring = mesh_next_ring(a, in.ring);  // drained as far as filled: next ring
+    if (take0 == v0 && take1 == v1) {  // drained as far as filled: another ring
+      int next = mesh_next_ring(a, in.ring);
+      if (a.world > 2) {  // the first one after this whose blocks were seen to hold something, else simply the next
+        bool has = false;
+        if (w.lane < 2 * a.world && (w.lane >> 1) != a.rank && (w.lane >> 1) != in.ring) {
+          const unsigned long long pc = sh.blk[w.wic][w.lane >> 1][w.lane & 1];
+          has = pc != kNoBlock && (sh.peek[w.wic][w.lane].x & kTagMask) == mesh_tag(w, a, pc);
+        }
+        const unsigned lanes = __ballot_sync(kFull, has);
+        if (lanes) {
+          unsigned rings = 0;  // bit r: ring r has a block with data
+          for (int r = 0; r < a.world; r++) rings |= ((lanes >> (2 * r)) & 3u) ? 1u << r : 0u;
+          const unsigned after = rings & ~((2u << in.ring) - 1u);
+          next = __ffs(after ? after : rings) - 1;
+        }
+      }
+      in.ring = next;
+    }
     in.staged = false;
   }
   if (!in.staged) mesh_stage_issue(w, a, in, sh);
