@@ -542,8 +542,14 @@ def main():
     # exchanged by the GPUs themselves (fm_mesh_*), results compared with the replica leg's -----------
     sharded_leg = None
     if world > 1 and not args.no_sharded_leg:
-        sharded_leg = run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, d_last,
-                                   rank, world, local, device)
+        try:
+            sharded_leg = run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, d_last,
+                                       rank, world, local, device)
+        except SystemExit:
+            raise                                  # a parity failure must fail the run
+        except Exception as e:  # noqa: BLE001    (the replica numbers of this line stand on their own)
+            log(f"sharded leg failed: {e}")
+            sharded_leg = {"error": str(e)[:300]}
 
     # ---- max over ranks ---------------------------------------------------------------------
     times = torch.tensor([kernel_ms, e2e_s * 1e3, e2e8_s * 1e3, copy_ms, copy8_ms], dtype=torch.float64, device=device)
@@ -732,7 +738,8 @@ def main():
                    "whole_batch": big_locate},
     }
     if sharded_leg is not None:
-        sharded_leg["per_gpu_vs_replica"] = round(sharded_leg["value"] / value, 4)
+        if "value" in sharded_leg:
+            sharded_leg["per_gpu_vs_replica"] = round(sharded_leg["value"] / value, 4)
         out["sharded"] = sharded_leg
     print(json.dumps(out), flush=True)
     ix.close()

@@ -1075,8 +1075,10 @@ template <int LPQ, int BW, int LV = 1>
 static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMode mode, unsigned long long* d_work,
                                    int sm_count, cudaStream_t stream) {
   const int gpb = kThreads / LPQ;
+#ifdef FM_TUNING_VARIANTS
   if (mode == kWalkLocate && LV == 4) {
-    // CTAs per SM: FEMTO_B200_WALK_CTAS = 4 (64 registers), 6 or 8 (32 registers); tuning experiments only
+    // CTAs per SM: FEMTO_B200_WALK_CTAS = 4 (64 registers), 6 (40) or 8 (32); measured 1.69 / 1.85 / 2.01 ms per
+    // 1 Mi rows (profiles/r02_walk_kernel.md): more warps with spilled registers are slower, 4 stays
     static const int want = [] { const char* v = std::getenv("FEMTO_B200_WALK_CTAS"); return v ? std::atoi(v) : kWalkLocateCtas; }();
     if (want >= 8) {
       static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV, 8>);
@@ -1088,7 +1090,9 @@ static cudaError_t launch_walk_cfg(const DevImage& im, const WalkArgs& a, WalkMo
       static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV>);
       walk_kernel<LPQ, BW, kWalkLocate, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
     }
-  } else if (mode == kWalkLocate) {
+  } else
+#endif
+  if (mode == kWalkLocate) {
     static const int bps = blocks_per_sm(walk_kernel<LPQ, BW, kWalkLocate, LV>);
     walk_kernel<LPQ, BW, kWalkLocate, LV><<<grid_for(a.nrows, gpb, sm_count, bps), kThreads, 0, stream>>>(im, a, d_work);
   } else if (mode == kWalkStep) {
