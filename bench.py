@@ -944,10 +944,14 @@ def run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, 
     s_first = torch.empty(npats, dtype=torch.int64, device=device)
     s_last = torch.empty(npats, dtype=torch.int64, device=device)
 
+    # two buffers for the replicated batch, used in turn: the all-gather of step k+2 is ordered behind the kernel
+    # of step k on the stream
+    gathered = [torch.empty((world * npats, m), dtype=batches[0].dtype, device=device) for _ in range(2)]
+
     def step(b):
-        allp = sharded.gather_uniform_batch(batches[b % nbatch], world)
+        allp = sharded.gather_uniform_batch(batches[b % nbatch], world, out=gathered[b % 2])
         mesh.launch_count(None, allp, None, m, rank * npats, npats, s_first, s_last)
-        return allp          # keep the gathered batch alive until the kernel has run
+        return None
 
     keep = []
     for w in range(args.warmup):

@@ -299,13 +299,15 @@ class Mesh:
             pass
 
 
-def gather_uniform_batch(my_pats: torch.Tensor, world: int, group=None) -> torch.Tensor:
+def gather_uniform_batch(my_pats: torch.Tensor, world: int, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Replicate a batch of equal-length patterns: every rank contributes my_pats [n, m] (same n on
     every rank) and receives [world * n, m]; rank r's patterns are ids [r*n, (r+1)*n).  This
     all-gather is the only collective of a mesh batch (NCCL over NVLink; gloo in the CPU tests)."""
     if world == 1:
         return my_pats
-    out = torch.empty((world * my_pats.shape[0], my_pats.shape[1]), dtype=my_pats.dtype, device=my_pats.device)
+    if out is None:  # (callers in a loop pass a buffer: a fresh device allocation per batch synchronises the device,
+        #              and is slow once peer access is enabled)
+        out = torch.empty((world * my_pats.shape[0], my_pats.shape[1]), dtype=my_pats.dtype, device=my_pats.device)
     # as bytes: NCCL has no 16-bit integer type
     dist.all_gather_into_tensor(out.view(torch.uint8), my_pats.contiguous().view(torch.uint8), group=group)
     return out
