@@ -202,8 +202,15 @@ extern "C" int64_t fm_debug_image_chunk(void* h, int64_t row, int64_t* first, in
 // it: out receives 5 int64 per chunk {kernel (0/1), first pattern, end pattern, first symbol, end
 // symbol}; returns the number of chunks, -1 when the batch is too small to be streamed, -2 when
 // out_cap (in chunks) is too small.
+extern "C" int64_t fm_debug_stream_plan2(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t flat_len,
+                                         int sym_bytes, int64_t* out, int64_t out_cap);
 extern "C" int64_t fm_debug_stream_plan(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t flat_len,
                                         int64_t* out, int64_t out_cap) {
+  return fm_debug_stream_plan2(npats, plen, offs, flat_len, 2, out, out_cap);
+}
+// sym_bytes: 2 = alpha_t symbols (fm_count_flat), 1 = raw text bytes (fm_count_bytes)
+extern "C" int64_t fm_debug_stream_plan2(int64_t npats, const int32_t* plen, const int64_t* offs, int64_t flat_len,
+                                         int sym_bytes, int64_t* out, int64_t out_cap) {
   using namespace fmb;
   if (npats < kStreamMinBatch) return -1;
   const int64_t mid = stream_split(npats);
@@ -212,7 +219,7 @@ extern "C" int64_t fm_debug_stream_plan(int64_t npats, const int32_t* plen, cons
   for (int h = 0; h < 2; h++) {
     for (int64_t lo = half_lo[h]; lo < half_hi[h]; lo += stream_chunk_at(lo), k++) {
       const int64_t hi = std::min(half_hi[h], lo + stream_chunk_at(lo));
-      const int64_t fend = std::max(fdone, stream_symbol_cut(plen, offs, hi, npats, flat_len));
+      const int64_t fend = std::max(fdone, stream_symbol_cut(plen, offs, hi, npats, flat_len, sym_bytes));
       if (k >= out_cap) return -2;
       int64_t* o = out + 5 * k;
       o[0] = h; o[1] = lo; o[2] = hi; o[3] = fdone; o[4] = fend;
@@ -220,4 +227,9 @@ extern "C" int64_t fm_debug_stream_plan(int64_t npats, const int32_t* plen, cons
     }
   }
   return k;
+}
+
+// shard_of_block (fm_format.hpp) for the CPU tests of the shard map
+extern "C" int fm_debug_shard_of_block(int64_t b, int64_t block_size, int64_t total_length, int nshards) {
+  return fmb::shard_of_block(b, block_size, total_length, nshards);
 }

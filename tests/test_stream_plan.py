@@ -57,3 +57,25 @@ def test_plan_tiles_the_batch_on_line_boundaries(n, lengths):
     assert (p[:, 4] >= ends).all()
     # ... and less than one line beyond it
     assert (p[:-1, 4] - ends[:-1] < 64).all()
+
+
+def plan_bytes(plen, offs, flat_len):
+    lib = _lib.load()
+    fn = lib.fm_debug_stream_plan2
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+    out = np.zeros((256, 5), dtype=np.int64)
+    k = fn(len(plen), plen.ctypes.data, offs.ctypes.data, flat_len, 1, out.ctypes.data, 256)
+    return k, out[:max(k, 0)]
+
+
+@pytest.mark.parametrize("n,lengths", [(1 << 20, [32]), (300077, [1, 2, 3, 5, 8, 13, 21, 34]), (200003, [0, 0, 7, 255])])
+def test_plan_for_byte_patterns_cuts_on_128_symbol_lines(n, lengths):
+    """fm_count_bytes: one byte per symbol, so a 128-byte line holds 128 symbols."""
+    plen, offs, flat_len = batch(n, lengths, 9)
+    k, p = plan_bytes(plen, offs, flat_len)
+    assert k > 2
+    assert p[0, 3] == 0 and p[-1, 4] == flat_len and (p[1:, 3] == p[:-1, 4]).all()
+    assert (p[:-1, 4] % 128 == 0).all() or flat_len in p[:-1, 4]
+    ends = offs[p[:, 2] - 1] + plen[p[:, 2] - 1]
+    assert (p[:, 4] >= ends).all() and (p[:-1, 4] - ends[:-1] < 128).all()
