@@ -10,18 +10,19 @@
 // no collective inside a batch; termination by counters the kernels exchange the same way.
 //
 // Inbox of a rank: one ring per SOURCE rank, so a slot index is claimed with an atomic in the
-// sender's own memory -- the transfer itself is a posted store, nothing comes back over the link.
-// On the consumer side a warp takes a BLOCK of 16 consecutive indices with one atomic on a counter
-// in its own memory, when it sees that the ring's next unowned block has received its first
-// message; it then owns that block until it has consumed all 16 (it never waits for it: a warp
-// polls its blocks, one per ring at most, whenever it has idle lane groups).  A message is four
-// 64-bit words that each carry a tag = (batch, lap of the ring) next to 48 bits of payload; a slot
-// is consumed when all four tags are the expected one -- no flag, no fence, no assumption about
-// the order in which NVLink delivers the words.
+// sender's own memory (one atomic per destination and warp) -- the transfer itself is a posted
+// store, nothing comes back over the link.  On the consumer side a warp owns up to two BLOCKS of 16
+// consecutive indices per ring, handed out in index order by a ticket counter in the rank's own
+// memory to whichever warp has just used one up; the ticket is requested in one round and used in
+// the next.  A warp never waits for a block: whenever it has idle lane groups it looks at the blocks
+// it owns, whose slots were copied to shared memory (cp.async, L2 only) at the end of the round
+// before.  A message is four 64-bit words that each carry a tag = (batch, lap of the ring) next to
+// 48 bits of payload; a slot is consumed when all four tags are the expected one -- no flag, no
+// fence, no assumption about the order in which NVLink delivers the words.
 //
 // Capacity: a state is in exactly one place, so the unconsumed messages of a ring are at most the
 // states in flight; blocks are handed out in index order to whichever warp is free, so they span
-// at most that many indices plus one (partly filled) block per warp.  Every rank injects new
+// at most that many indices plus two (partly filled) blocks per warp.  Every rank injects new
 // patterns only while fewer than `window` of its own are unfinished, and the rings hold
 // world * (window + slack) slots, so a producer can never lap an unconsumed slot.
 #pragma once
@@ -46,7 +47,7 @@ struct MeshCtl {
   unsigned long long injected;                 // patterns of my batch taken so far
   unsigned long long done_count;               // patterns of my batch delivered
   unsigned long long inflight;                 // of my batch: taken and not yet delivered
-  unsigned long long stats[8];                 // sent, received, rounds, occ pairs, occ singles, empty polls, injected, -
+  unsigned long long stats[8];                 // sent, received, rounds, occ pairs, occ singles, - , injected, -
   int status;                                  // 0 ok, 1 timed out, 2 malformed message
   int pad0;
   unsigned long long pad1[4];

@@ -172,7 +172,7 @@ int fm_locate_shard_step(fm_index_t* ix, int64_t nstates, int64_t* d_state, int3
  * A rank must not launch batch k+1 before every rank has finished batch k-1 (the all-gather that
  * replicates the patterns provides that).  fm_mesh_finish waits for the stream and reports the
  * kernel's status (FM_ERR_CANCELED: it gave up waiting for the other ranks) and counters
- * {states sent, received, evaluation rounds, Occ pairs, single Occ, empty inbox polls, patterns
+ * {states sent, received, evaluation rounds, Occ pairs, single Occ, 0 (unused), patterns
  * injected, 0}. */
 typedef struct fm_mesh fm_mesh_t;
 #define FM_MESH_HANDLE_BYTES 64
