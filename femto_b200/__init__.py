@@ -364,17 +364,40 @@ def bwt_from_sa(text: np.ndarray, sa: np.ndarray) -> np.ndarray:
 
 
 class IndexBuilder:
-    """Streams BWT rows into femto's on-disk format (``fm_builder_*``)."""
+    """Streams BWT rows into femto's on-disk format (``fm_builder_*``).
+
+    With ``first_block`` / ``range_blocks`` it is a RANGE builder (``fm_builder_create_range``): it writes
+    only those data blocks, is fed their rows, and ends with ``finish_range()``; ``write_index_header``
+    completes the index once all ranges are written."""
 
     def __init__(self, out_dir: str, doc_ends: np.ndarray, block_size: int = 128 << 20, bucket_size: int = 1 << 20,
-                 chunk_size: int = 2048, mark_period: int = 20, nthreads: int = 0):
+                 chunk_size: int = 2048, mark_period: int = 20, nthreads: int = 0,
+                 first_block: Optional[int] = None, range_blocks: int = 0):
         self.lib = _lib.load()
         doc_ends = np.ascontiguousarray(doc_ends, dtype=np.int64)
         b = C.c_void_p()
-        _check(self.lib.fm_builder_create(os.fsencode(out_dir), int(doc_ends[-1]), len(doc_ends),
-                                          _ptr(doc_ends, C.c_int64), block_size, bucket_size, chunk_size,
-                                          mark_period, nthreads, C.byref(b)), "fm_builder_create")
+        self.ndocs = len(doc_ends)
+        self.range_blocks = range_blocks if first_block is not None else None
+        if first_block is None:
+            _check(self.lib.fm_builder_create(os.fsencode(out_dir), int(doc_ends[-1]), len(doc_ends),
+                                              _ptr(doc_ends, C.c_int64), block_size, bucket_size, chunk_size,
+                                              mark_period, nthreads, C.byref(b)), "fm_builder_create")
+        else:
+            _check(self.lib.fm_builder_create_range(os.fsencode(out_dir), int(doc_ends[-1]), len(doc_ends),
+                                                    _ptr(doc_ends, C.c_int64), block_size, bucket_size, chunk_size,
+                                                    mark_period, nthreads, first_block, range_blocks, C.byref(b)),
+                   "fm_builder_create_range")
         self.b = b
+
+    def finish_range(self) -> Tuple[np.ndarray, np.ndarray]:
+        """-> (block_counts [range_blocks, 261], eof_rows [ndocs], -1 where the row is not in this range)."""
+        assert self.range_blocks is not None, "not a range builder"
+        counts = np.zeros((self.range_blocks, ALPHA_SIZE), dtype=np.int64)
+        eof = np.full(self.ndocs, -1, dtype=np.int64)
+        b, self.b = self.b, None
+        _check(self.lib.fm_builder_finish_range(b, _ptr(counts, C.c_int64), _ptr(eof, C.c_int64)),
+               "fm_builder_finish_range")
+        return counts, eof
 
     def set_doc_info(self, doc: int, info: bytes) -> None:
         _check(self.lib.fm_builder_set_doc_info(self.b, doc, info, len(info)), "fm_builder_set_doc_info")
@@ -400,6 +423,37 @@ class IndexBuilder:
             self.abort()
         except Exception:
             pass
+
+
+def write_index_header(out_dir: str, doc_ends: np.ndarray, block_counts: np.ndarray, eof_rows: np.ndarray,
+                       block_size: int = 128 << 20, bucket_size: int = 1 << 20, chunk_size: int = 2048,
+                       mark_period: int = 20, doc_infos: Optional[Sequence[Optional[bytes]]] = None) -> None:
+    """Header block of an index whose data blocks were written by range builders (``fm_builder_write_header``):
+    block_counts [nblocks, 261] in block order, eof_rows [ndocs] merged over the ranges."""
+    lib = _lib.load()
+    doc_ends = np.ascontiguousarray(doc_ends, dtype=np.int64)
+    block_counts = np.ascontiguousarray(block_counts, dtype=np.int64)
+    eof_rows = np.ascontiguousarray(eof_rows, dtype=np.int64)
+    total = int(doc_ends[-1])
+    nblocks = (total + block_size - 1) // block_size
+    if block_counts.shape != (nblocks, ALPHA_SIZE) or eof_rows.shape != (len(doc_ends),):
+        raise ValueError("write_index_header: block_counts must be [nblocks, 261] and eof_rows [ndocs]")
+    info_p = info_n = None
+    keep = []
+    if doc_infos is not None:
+        info_p = (C.c_void_p * len(doc_ends))()
+        info_n = (C.c_int64 * len(doc_ends))()
+        for i, info in enumerate(doc_infos):
+            if info is None:
+                info_p[i], info_n[i] = None, -1
+            else:
+                buf = C.create_string_buffer(bytes(info), len(info))
+                keep.append(buf)
+                info_p[i], info_n[i] = C.cast(buf, C.c_void_p), len(info)
+    _check(lib.fm_builder_write_header(os.fsencode(out_dir), total, len(doc_ends), _ptr(doc_ends, C.c_int64),
+                                       block_size, bucket_size, chunk_size, mark_period,
+                                       _ptr(block_counts, C.c_int64), _ptr(eof_rows, C.c_int64), info_p, info_n),
+           "fm_builder_write_header")
 
 
 def build_index_host(docs: Sequence[bytes], out_dir: str, doc_infos: Optional[Sequence[bytes]] = None,

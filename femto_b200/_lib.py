@@ -80,6 +80,10 @@ PROTOTYPES = {
     "fm_builder_set_doc_info": (C.c_int, [vp, i64, vp, i64]),
     "fm_builder_finish": (C.c_int, [vp]),
     "fm_builder_abort": (None, [vp]),
+    "fm_builder_create_range": (C.c_int, [C.c_char_p, i64, i64, P(i64), i32, i32, i32, i32, C.c_int, i64, i64, P(vp)]),
+    "fm_builder_finish_range": (C.c_int, [vp, P(i64), P(i64)]),
+    "fm_builder_write_header": (C.c_int, [C.c_char_p, i64, i64, P(i64), i32, i32, i32, i32, P(i64), P(i64), P(vp),
+                                          P(i64)]),
     "fm_flatten": (C.c_int, [C.c_char_p, C.c_char_p]),
     "fm_suffix_sort_host": (C.c_int, [P(u16), i64, P(i64)]),
 }

@@ -159,7 +159,9 @@ def synthetic_english(n: int, seed: int, device, vocab: int = 50000, words_per_c
 # --------------------------------------------------------------------------------------------
 # suffix sorting
 
-def _pack_keys(T: torch.Tensor, pos: torch.Tensor, depth: int) -> torch.Tensor:
+def _pack_keys(T, pos: torch.Tensor, depth: int) -> torch.Tensor:
+    if not isinstance(T, torch.Tensor):  # build_dist.ByteText: one byte per position + document ends
+        return T.pack_keys(pos, depth)
     key = torch.zeros_like(pos)
     for k in range(SYMS_PER_KEY):
         key = (key << SYM_BITS) | T[pos + (depth + k)].long()

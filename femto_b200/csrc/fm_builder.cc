@@ -616,8 +616,11 @@ struct fm_builder {
   int64_t cur_block = 0;
   std::vector<uint16_t> L;    // rows of the block being accumulated
   std::vector<int64_t> off, docs;
-  std::vector<int64_t> occs_total;              // [261] before the current block
-  std::vector<std::vector<int64_t>> block_occs; // [block][261]
+  std::vector<int64_t> occs_total;              // [261] before the current block (within this builder's rows)
+  std::vector<std::vector<int64_t>> block_counts; // [block][261]: symbols inside the block
+  // range builders (fm_builder_create_range): data blocks [first_block, first_block + range_blocks) only
+  bool range = false;
+  int64_t first_block = 0, end_row = 0;
   std::vector<int64_t> eof_rows;
   std::vector<std::string> doc_info;
   std::vector<bool> doc_info_set;
@@ -698,7 +701,7 @@ void flush_block(fm_builder* b) {
   }
   write_file(block_path(b->dir, b->cur_block + 1), blk.data(), blk.size());
 
-  b->block_occs.push_back(b->occs_total);
+  b->block_counts.push_back(since);
   for (int c = 0; c < kAlpha; c++) b->occs_total[size_t(c)] += since[size_t(c)];
   b->rows_done += rows;
   b->cur_block++;
@@ -707,23 +710,77 @@ void flush_block(fm_builder* b) {
   b->docs.clear();
 }
 
+// Header block (constructor_construct_header, src/main/construct.c:407-460) from the per-block symbol
+// counts: C[], occurrences before every block, document ends, rows of the document ends, info strings.
+void write_header_block(const std::string& dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                        int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                        int64_t nblocks, const int64_t* block_counts, const int64_t* eof_rows,
+                        const std::vector<std::string>& doc_info, const std::vector<bool>& doc_info_set) {
+  Bytes h;
+  write_block_header_bytes(h, kMagicHeaderBlock, -1, nblocks, total_length, ndocs, 0, 0, block_size, bucket_size,
+                           mark_period, chunk_size > 0 ? chunk_size : -1);
+  std::vector<int64_t> total(kAlpha, 0);
+  for (int64_t k = 0; k < nblocks; k++)
+    for (int c = 0; c < kAlpha; c++) total[size_t(c)] += block_counts[size_t(k) * kAlpha + size_t(c)];
+  int64_t sum = 0;
+  for (int c = 0; c < kAlpha; c++) { put64(h, uint64_t(sum)); sum += total[size_t(c)]; }
+  if (sum != total_length) throw Error(FM_ERR_FORMAT, "block symbol counts do not add up to total_length");
+  for (int c = 0; c < kAlpha; c++) {
+    int64_t before = 0;
+    for (int64_t k = 0; k < nblocks; k++) {
+      put64(h, uint64_t(before));
+      before += block_counts[size_t(k) * kAlpha + size_t(c)];
+    }
+  }
+  for (int64_t d = 0; d < ndocs; d++) put64(h, uint64_t(doc_ends[size_t(d)]));
+  for (int64_t d = 0; d < ndocs; d++) {
+    if (eof_rows[size_t(d)] < 0 || eof_rows[size_t(d)] >= ndocs) throw Error(FM_ERR_FORMAT, "document end row missing");
+    put64(h, uint64_t(eof_rows[size_t(d)]));
+  }
+  const size_t info_dir = h.size();
+  h.resize(info_dir + 8 * (size_t(ndocs) + 1), 0);
+  for (int64_t d = 0; d < ndocs; d++) {
+    std::string info = size_t(d) < doc_info_set.size() && doc_info_set[size_t(d)] ? doc_info[size_t(d)] : ("doc" + std::to_string(d));
+    put_be64(h.data() + info_dir + 8 * size_t(d), uint64_t(h.size()));
+    h.insert(h.end(), info.begin(), info.end());
+    put_be64(h.data() + info_dir + 8 * size_t(d + 1), uint64_t(h.size()));
+  }
+  write_file(block_path(dir, 0), h.data(), h.size());
+  const std::string tag = "This is a FEMTO index constructed by femto_b200\n";
+  write_file(dir + "/_femto_index", reinterpret_cast<const uint8_t*>(tag.data()), tag.size());
+}
+
+int check_build_params(const char* who, const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                       int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period) {
+  const std::string w = who;
+  if (!out_dir || !doc_ends || total_length <= 0 || ndocs <= 0) return bfail(FM_ERR_PARAM, w + ": bad argument");
+  if (block_size <= 0 || bucket_size <= 0 || block_size % bucket_size != 0)
+    return bfail(FM_ERR_PARAM, w + ": block_size must be a positive multiple of bucket_size");
+  if (chunk_size > 0 && bucket_size % chunk_size != 0)
+    return bfail(FM_ERR_PARAM, w + ": bucket_size must be a multiple of chunk_size");
+  if (mark_period < 0) return bfail(FM_ERR_PARAM, w + ": negative mark_period");
+  for (int64_t d = 0; d < ndocs; d++)
+    if (doc_ends[d] <= (d ? doc_ends[d - 1] : 0)) return bfail(FM_ERR_PARAM, w + ": empty or unordered document");
+  if (doc_ends[ndocs - 1] != total_length) return bfail(FM_ERR_PARAM, w + ": document ends do not sum to total_length");
+  if (mkdir(out_dir, 0777) && errno != EEXIST) return bfail(FM_ERR_IO, std::string("cannot create ") + out_dir);
+  return FM_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-int fm_builder_create(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
-                      int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
-                      int nthreads, fm_builder_t** out) {
-  if (!out_dir || !doc_ends || !out || total_length <= 0 || ndocs <= 0) return bfail(FM_ERR_PARAM, "fm_builder_create: bad argument");
-  if (block_size <= 0 || bucket_size <= 0 || block_size % bucket_size != 0)
-    return bfail(FM_ERR_PARAM, "fm_builder_create: block_size must be a positive multiple of bucket_size");
-  if (chunk_size > 0 && bucket_size % chunk_size != 0)
-    return bfail(FM_ERR_PARAM, "fm_builder_create: bucket_size must be a multiple of chunk_size");
-  if (mark_period < 0) return bfail(FM_ERR_PARAM, "fm_builder_create: negative mark_period");
-  for (int64_t d = 0; d < ndocs; d++)
-    if (doc_ends[d] <= (d ? doc_ends[d - 1] : 0)) return bfail(FM_ERR_PARAM, "fm_builder_create: empty or unordered document");
-  if (doc_ends[ndocs - 1] != total_length) return bfail(FM_ERR_PARAM, "fm_builder_create: document ends do not sum to total_length");
-  if (mkdir(out_dir, 0777) && errno != EEXIST) return bfail(FM_ERR_IO, std::string("cannot create ") + out_dir);
+int fm_builder_create_range(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                            int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                            int nthreads, int64_t first_block, int64_t range_blocks, fm_builder_t** out) {
+  if (!out) return bfail(FM_ERR_PARAM, "fm_builder_create: bad argument");
+  const int rc = check_build_params("fm_builder_create", out_dir, total_length, ndocs, doc_ends, block_size, bucket_size,
+                                    chunk_size, mark_period);
+  if (rc) return rc;
+  const int64_t nblocks = (total_length + block_size - 1) / block_size;
+  const bool range = first_block >= 0;
+  if (range && (range_blocks < 0 || first_block + range_blocks > nblocks))
+    return bfail(FM_ERR_PARAM, "fm_builder_create_range: block range outside the index");
   fm_builder* b = new fm_builder();
   b->dir = out_dir;
   b->total_length = total_length;
@@ -734,14 +791,29 @@ int fm_builder_create(const char* out_dir, int64_t total_length, int64_t ndocs, 
   b->chunk_size = chunk_size > 0 ? chunk_size : 0;
   b->mark_period = mark_period;
   b->nthreads = nthreads > 0 ? nthreads : int(std::max(1u, std::thread::hardware_concurrency()));
-  b->nblocks = (total_length + block_size - 1) / block_size;
+  b->nblocks = nblocks;
   b->bpb = block_size / bucket_size;
   b->occs_total.assign(kAlpha, 0);
   b->eof_rows.assign(size_t(ndocs), -1);
   b->doc_info.resize(size_t(ndocs));
   b->doc_info_set.assign(size_t(ndocs), false);
+  b->range = range;
+  b->end_row = total_length;
+  if (range) {
+    b->first_block = first_block;
+    b->cur_block = first_block;
+    b->rows_done = std::min<int64_t>(total_length, first_block * int64_t(block_size));
+    b->end_row = std::min<int64_t>(total_length, (first_block + range_blocks) * int64_t(block_size));
+  }
   *out = b;
   return FM_OK;
+}
+
+int fm_builder_create(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                      int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                      int nthreads, fm_builder_t** out) {
+  return fm_builder_create_range(out_dir, total_length, ndocs, doc_ends, block_size, bucket_size, chunk_size, mark_period,
+                                 nthreads, -1, 0, out);
 }
 
 int fm_builder_set_doc_info(fm_builder_t* b, int64_t doc, const void* info, int64_t len) {
@@ -757,7 +829,7 @@ int fm_builder_append(fm_builder_t* b, int64_t nrows, const uint16_t* L, const i
     int64_t i = 0;
     while (i < nrows) {
       const int64_t row0 = b->rows_done + int64_t(b->L.size());
-      if (row0 >= b->total_length) return bfail(FM_ERR_PARAM, "fm_builder_append: more rows than total_length");
+      if (row0 >= b->end_row) return bfail(FM_ERR_PARAM, "fm_builder_append: more rows than the builder's range holds");
       const int64_t block_rows = std::min<int64_t>(b->block_size, b->total_length - b->rows_done);
       const int64_t take = std::min<int64_t>(nrows - i, block_rows - int64_t(b->L.size()));
       const size_t at = b->L.size();
@@ -814,31 +886,58 @@ void fm_builder_abort(fm_builder_t* b) { delete b; }
 int fm_builder_finish(fm_builder_t* b) {
   if (!b) return bfail(FM_ERR_PARAM, "fm_builder_finish: null builder");
   std::unique_ptr<fm_builder> guard(b);
+  if (b->range) return bfail(FM_ERR_PARAM, "fm_builder_finish: a range builder ends with fm_builder_finish_range");
   if (b->rows_done != b->total_length || !b->L.empty())
     return bfail(FM_ERR_PARAM, "fm_builder_finish: fewer rows appended than total_length");
   try {
-    Bytes h;
-    write_block_header_bytes(h, kMagicHeaderBlock, -1, b->nblocks, b->total_length, b->ndocs, 0, 0, b->block_size,
-                             b->bucket_size, b->mark_period, b->chunk_size > 0 ? b->chunk_size : -1);
-    int64_t sum = 0;
-    for (int c = 0; c < kAlpha; c++) { put64(h, uint64_t(sum)); sum += b->occs_total[size_t(c)]; }
-    for (int c = 0; c < kAlpha; c++)
-      for (int64_t k = 0; k < b->nblocks; k++) put64(h, uint64_t(b->block_occs[size_t(k)][size_t(c)]));
-    for (int64_t d = 0; d < b->ndocs; d++) put64(h, uint64_t(b->doc_ends[size_t(d)]));
-    for (int64_t d = 0; d < b->ndocs; d++) put64(h, uint64_t(b->eof_rows[size_t(d)]));
-    const size_t info_dir = h.size();
-    h.resize(info_dir + 8 * (size_t(b->ndocs) + 1), 0);
-    for (int64_t d = 0; d < b->ndocs; d++) {
-      std::string info = b->doc_info_set[size_t(d)] ? b->doc_info[size_t(d)] : ("doc" + std::to_string(d));
-      put_be64(h.data() + info_dir + 8 * size_t(d), uint64_t(h.size()));
-      h.insert(h.end(), info.begin(), info.end());
-      put_be64(h.data() + info_dir + 8 * size_t(d + 1), uint64_t(h.size()));
-    }
-    write_file(block_path(b->dir, 0), h.data(), h.size());
-    const std::string tag = "This is a FEMTO index constructed by femto_b200\n";
-    write_file(b->dir + "/_femto_index", reinterpret_cast<const uint8_t*>(tag.data()), tag.size());
+    std::vector<int64_t> counts(size_t(b->nblocks) * kAlpha);
+    for (int64_t k = 0; k < b->nblocks; k++)
+      std::copy(b->block_counts[size_t(k)].begin(), b->block_counts[size_t(k)].end(), counts.begin() + k * kAlpha);
+    write_header_block(b->dir, b->total_length, b->ndocs, b->doc_ends.data(), b->block_size, b->bucket_size, b->chunk_size,
+                       b->mark_period, b->nblocks, counts.data(), b->eof_rows.data(), b->doc_info, b->doc_info_set);
   } catch (const Error& e) {
     return bfail(e.code, std::string("fm_builder_finish: ") + e.what());
+  }
+  return FM_OK;
+}
+
+int fm_builder_finish_range(fm_builder_t* b, int64_t* block_counts, int64_t* eof_rows) {
+  if (!b) return bfail(FM_ERR_PARAM, "fm_builder_finish_range: null builder");
+  std::unique_ptr<fm_builder> guard(b);
+  if (!b->range || !block_counts || !eof_rows) return bfail(FM_ERR_PARAM, "fm_builder_finish_range: bad argument");
+  if (b->rows_done != b->end_row || !b->L.empty())
+    return bfail(FM_ERR_PARAM, "fm_builder_finish_range: fewer rows appended than the range holds");
+  for (size_t k = 0; k < b->block_counts.size(); k++)
+    std::copy(b->block_counts[k].begin(), b->block_counts[k].end(), block_counts + k * kAlpha);
+  std::copy(b->eof_rows.begin(), b->eof_rows.end(), eof_rows);
+  return FM_OK;
+}
+
+int fm_builder_write_header(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                            int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                            const int64_t* block_counts, const int64_t* eof_rows, const void* const* doc_info,
+                            const int64_t* doc_info_len) {
+  if (!block_counts || !eof_rows) return bfail(FM_ERR_PARAM, "fm_builder_write_header: bad argument");
+  const int rc = check_build_params("fm_builder_write_header", out_dir, total_length, ndocs, doc_ends, block_size,
+                                    bucket_size, chunk_size, mark_period);
+  if (rc) return rc;
+  try {
+    std::vector<std::string> info;
+    std::vector<bool> info_set;
+    if (doc_info && doc_info_len) {
+      info.resize(size_t(ndocs));
+      info_set.assign(size_t(ndocs), false);
+      for (int64_t d = 0; d < ndocs; d++)
+        if (doc_info[d] && doc_info_len[d] >= 0) {
+          info[size_t(d)].assign(static_cast<const char*>(doc_info[d]), size_t(doc_info_len[d]));
+          info_set[size_t(d)] = true;
+        }
+    }
+    const int64_t nblocks = (total_length + block_size - 1) / block_size;
+    write_header_block(out_dir, total_length, ndocs, doc_ends, block_size, bucket_size, chunk_size > 0 ? chunk_size : 0,
+                       mark_period, nblocks, block_counts, eof_rows, info, info_set);
+  } catch (const Error& e) {
+    return bfail(e.code, std::string("fm_builder_write_header: ") + e.what());
   }
   return FM_OK;
 }

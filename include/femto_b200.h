@@ -378,6 +378,24 @@ int fm_builder_append(fm_builder_t* b, int64_t nrows, const uint16_t* L, const i
 int fm_builder_set_doc_info(fm_builder_t* b, int64_t doc, const void* info, int64_t len);
 int fm_builder_finish(fm_builder_t* b);       /* writes the header block; frees b */
 void fm_builder_abort(fm_builder_t* b);
+/* Builders working side by side (one per GPU / process; the reference's partition unit is the data
+ * block, src/main/index.h:83-100, and its constructor emits blocks one after the other,
+ * src/main/construct.c:293-566): a range builder writes only the data blocks
+ * [first_block, first_block + range_blocks) into out_dir and is fed exactly the BWT rows of those blocks,
+ * first_block * block_size onwards, in order.  fm_builder_finish_range hands back what the header needs from
+ * this range -- block_counts[k * 261 + c] = occurrences of symbol c inside the k-th block of the range, and
+ * eof_rows[d] = row of document d's end when it lies in the range, else -1 -- and frees b.  Once every range
+ * is done, one caller gathers the counts of all blocks in block order, merges eof_rows (max) and writes
+ * the header block with fm_builder_write_header (doc_info / doc_info_len: NULL, or one string per document,
+ * a NULL entry = "doc<i>").  The files are byte-identical to those of one builder fed all rows. */
+int fm_builder_create_range(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                            int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                            int nthreads, int64_t first_block, int64_t range_blocks, fm_builder_t** out);
+int fm_builder_finish_range(fm_builder_t* b, int64_t* block_counts, int64_t* eof_rows);
+int fm_builder_write_header(const char* out_dir, int64_t total_length, int64_t ndocs, const int64_t* doc_ends,
+                            int32_t block_size, int32_t bucket_size, int32_t chunk_size, int32_t mark_period,
+                            const int64_t* block_counts, const int64_t* eof_rows, const void* const* doc_info,
+                            const int64_t* doc_info_len);
 /* Convert a directory index into the flattened single-file form (flatten_index,
  * src/main/index.c:2260-2365). */
 int fm_flatten(const char* index_dir, const char* out_file);
