@@ -75,8 +75,11 @@ def parse_args():
     ap.add_argument("--levels", type=int, default=0,
                     help="wavelet-tree levels per rank block read: 1, 2 (paired) or 4 (quad); default: the library's")
     ap.add_argument("--parallelism", choices=["replica", "sharded"], default="replica",
-                    help="N>1: replicate the index and split patterns (default), or shard the index by BWT "
-                         "row range and route pattern states with NCCL all-to-all")
+                    help="N>1: replicate the index and split patterns (default; the sharded leg runs beside it), or "
+                         "sharded ONLY (BASELINE configs[4], a corpus larger than one GPU): every rank builds and "
+                         "loads just its BWT row range")
+    ap.add_argument("--exchange", choices=["mesh", "nccl"], default="mesh",
+                    help="--parallelism sharded: device-initiated exchange (default) or round 1's host-driven NCCL loop")
     ap.add_argument("--cache-dir", default=os.environ.get("FEMTO_B200_CACHE", "/tmp/femto_b200_cache"))
     ap.add_argument("--locate-npats", type=int, default=100000, help="patterns of the locate leg (configs[2])")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
@@ -300,6 +303,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
+    if args.impl == "b200" and args.parallelism == "sharded":
+        run_sharded(args, rank, world, local, device)    # builds its own index, on all GPUs
+        return
+
     index_path, build_info = ensure_index(args, device, rank, world if args.impl == "b200" else 1)
     text = corpus_tensor(args, device)
     workload = (f"count() of {args.npats} {'text-sampled' if args.patterns == 'text' else 'uniform-random'} "
@@ -315,9 +322,6 @@ def main():
     from femto_b200 import _lib
     lib = _lib.load()
 
-    if args.parallelism == "sharded":
-        run_sharded(args, index_path, text, workload, rank, world, local, device)
-        return
     if args.patterns == "zipf":
         run_ragged(args, fb, lib, index_path, build_info, text, rank, world, local, device)
         return
@@ -1032,34 +1036,91 @@ def run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, 
     return leg
 
 
-def run_sharded(args, index_path, text, workload, rank, world, local, device):
-    """N GPUs each holding a BWT row range of the index; pattern states routed with NCCL all-to-all."""
+def sharded_text(args, device):
+    """The corpus as build_dist.ByteText (one byte per position; 128 GiB of corpus = 137 GB of a B200's HBM)
+    and the plain corpus bytes to sample patterns from.  Every rank generates the same text."""
+    import torch
+    from femto_b200 import build_dist, build_gpu
+    n = args.corpus_mib << 20
+    if args.kind == "english":
+        text = build_gpu.synthetic_english(n, args.seed, device)
+        return build_dist.ByteText.from_docs(corpus_docs(args, text)), text
+    alphabet = b"ACGT" if args.kind == "acgt" else None
+    # counter-based generator: the first n bytes of a longer text are the text of length n
+    data = build_gpu.synthetic_bytes(n + 1 + build_gpu.PAD, args.seed, device, alphabet)
+    data[n:] = 0
+    return build_dist.ByteText(data, np.array([n + 1], dtype=np.int64)), data[:n]
+
+
+def run_sharded(args, rank, world, local, device):
+    """BASELINE configs[4]: an index too large for one GPU.  Every rank builds the data blocks it will serve
+    (femto_b200/build_dist.py; text replicated, suffixes split by BWT row range, no exchange), opens them as
+    its shard, and the batches run through the device-initiated exchange (fm_mesh_count): one NCCL all-gather
+    of the patterns per step, then one persistent kernel per GPU.  No replica exists to compare with at this
+    size: rank 0 counts a bounded sample of its own patterns with the unmodified reference on the index on
+    disk (cpu_baseline + parity).  --exchange nccl runs round 1's host-driven loop instead."""
     import torch
     import torch.distributed as dist
     import femto_b200 as fb
-    from femto_b200 import sharded
+    from femto_b200 import build_dist, sharded
     if world < 2:
         raise SystemExit("--parallelism sharded needs --gpus >= 2 (launch with torchrun)")
+    npats, m = args.npats, args.plen
+    index_path = os.path.join(args.cache_dir, index_name(args))
+    cached = [os.path.exists(os.path.join(index_path, "_femto_index"))]
+    dist.broadcast_object_list(cached, src=0)
+    B, text = sharded_text(args, device)
+    build_info = {"built": False}
+    if not cached[0]:
+        tmp = index_path + ".building"
+        if rank == 0:
+            os.makedirs(args.cache_dir, exist_ok=True)
+            subprocess.run(["rm", "-rf", tmp, index_path], check=False)
+            log(f"building index {index_name(args)} on {world} GPUs")
+        dist.barrier()
+        t = build_dist.build_index_distributed(B, B.doc_ends, tmp, rank, world, chunk_size=args.chunk_size, log=log,
+                                               nthreads=max(1, (os.cpu_count() or 8) // world))
+        if rank == 0:
+            os.rename(tmp, index_path)
+        dist.barrier()
+        build_info = {"built": True, "builder": f"build_dist x{world}", **{k: round(v, 2) for k, v in t.items()}}
+        log(f"index built: {build_info}")
+    del B
+    nbatch = 2
+    batches = [sample_patterns(args, text, b, rank) for b in range(nbatch)]
+    del text
+    torch.cuda.empty_cache()
+
     t0 = time.time()
     ix = fb.Index(index_path, device=local, shard=rank, nshards=world)
     load_s = time.time() - t0
-    npats, m = args.npats, args.plen
-    total = npats * world
-    # the whole batch is replicated: rank r's patterns are rows [r*npats, (r+1)*npats)
-    nbatch = 2
-    batches = [torch.cat([sample_patterns(args, text, b, r) for r in range(world)]) for b in range(nbatch)]
-    del text
-    torch.cuda.empty_cache()
-    d_plen = torch.full((total,), m, dtype=torch.int32, device=device)
-    d_offs = torch.arange(total, dtype=torch.int64, device=device) * m
-    lo, hi = rank * npats, (rank + 1) * npats
+    s_first = torch.empty(npats, dtype=torch.int64, device=device)
+    s_last = torch.empty(npats, dtype=torch.int64, device=device)
+    gathered = [torch.empty((world * npats, m), dtype=batches[0].dtype, device=device) for _ in range(2)]
+    mesh = None
+    rounds = 0
+    if args.exchange == "mesh":
+        mesh = sharded.Mesh(ix, rank, world, window=args.mesh_window)
 
-    def step(b):
-        fn = sharded.cuda_step_fn(ix, d_plen, batches[b % nbatch], d_offs, world)
-        return sharded.sharded_count(fn, lo, hi, rank, world, device)
+        def step(b):
+            allp = sharded.gather_uniform_batch(batches[b % nbatch], world, out=gathered[b % 2])
+            mesh.launch_count(None, allp, None, m, rank * npats, npats, s_first, s_last)
+    else:
+        d_plen = torch.full((world * npats,), m, dtype=torch.int32, device=device)
+        d_offs = torch.arange(world * npats, dtype=torch.int64, device=device) * m
+
+        def step(b):
+            nonlocal rounds
+            allp = sharded.gather_uniform_batch(batches[b % nbatch], world, out=gathered[b % 2])
+            fn = sharded.cuda_step_fn(ix, d_plen, allp, d_offs, world)
+            f, l, rounds = sharded.sharded_count(fn, rank * npats, (rank + 1) * npats, rank, world, device)
+            s_first.copy_(f)
+            s_last.copy_(l)
 
     for w in range(args.warmup):
         step(w)
+    if mesh:
+        mesh.finish()
     dist.barrier()
     torch.cuda.synchronize()
     launches0 = ix.kernel_launches()
@@ -1067,34 +1128,63 @@ def run_sharded(args, index_path, text, workload, rank, world, local, device):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    rounds = 0
     for s in range(args.steps):
-        first, last, rounds = step(args.warmup + s)
+        step(args.warmup + s)
     ev1.record()
+    stats = mesh.finish() if mesh else {}
     dist.barrier()
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop()
     gpu_launches = ix.kernel_launches() - launches0
-    # parity of the last batch against a replica-free check: counts must be >= 1 (text-sampled patterns)
-    ok = bool(((last - first + 1) >= 1).all())
+    sent = torch.tensor([float(stats.get("sent", 0))], dtype=torch.float64, device=device)
+    dist.all_reduce(sent, op=dist.ReduceOp.SUM)
+    found = torch.tensor([int(bool(((s_last - s_first + 1) >= 1).all()))], device=device)
+    dist.all_reduce(found, op=dist.ReduceOp.MIN)
+
+    # cpu_baseline + parity: the unmodified reference on a bounded sample of rank 0's last batch
+    cpu = parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.bindings import have_reference
+        if have_reference():
+            last_b = batches[(args.warmup + args.steps - 1) % nbatch].cpu().numpy()
+            probe = 256
+            _, _, ps = run_reference(index_path, last_b[:probe], 1)
+            sample = int(max(probe, min(npats, probe / max(ps, 1e-6) * args.cpu_sample_seconds)))
+            rf, rl, secs = run_reference(index_path, last_b[:sample], 1)
+            ok = bool((rf == s_first[:sample].cpu().numpy()).all() and (rl == s_last[:sample].cpu().numpy()).all())
+            cpu = {"value": round(sample / secs, 1), "unit": "patterns/s", "cores": 1, "kind": "reference",
+                   "sample": f"{sample} patterns of rank 0's last batch, unmodified reference, 1 server thread"}
+            parity = {"checked_patterns": sample, "bit_exact_vs_reference": ok}
+            if not ok:
+                raise SystemExit("PARITY FAILURE: sharded results differ from the reference's")
     if rank == 0:
         ms_per_step = float(ms[0]) / args.steps
+        total = npats * world
+        how = ("device-initiated: persistent kernel per GPU, 32-byte states stored into the owner's inbox over NVLink "
+               "peer memory" if mesh else f"host-driven: NCCL all-to-all per round, {rounds} rounds per batch")
         out = {
             "metric": "patterns/sec (count)", "value": round(total / (ms_per_step / 1e3), 1), "unit": "patterns/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic", "impl": "b200",
-            "config": {"workload": workload, "patterns_per_gpu_per_step": npats, "pattern_length": m,
-                       "index": index_name(args), "index_load_s": round(load_s, 1),
-                       "parallelism": f"index range-sharded x{world} by data block, pattern states routed with "
-                                      f"NCCL all-to-all ({rounds} exchange rounds per batch)",
-                       "shard_rows": [int(ix.info.first_row), int(ix.info.end_row)],
-                       "shard_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2)},
-            "gpu_launches": int(gpu_launches), "clocks": clocks, "all_patterns_found": ok,
+            "config": {"workload": f"count() of {npats} text-sampled length-{m} patterns per GPU on a "
+                                   f"{args.corpus_mib} MiB synthetic {args.kind} corpus, index range-sharded by data "
+                                   f"block over {world} GPUs",
+                       "patterns_per_gpu_per_step": npats, "pattern_length": m, "index": index_name(args),
+                       "engine": {"parallelism": f"index range-sharded x{world} by data block", "exchange": how,
+                                  "index_build": build_info, "shard_load_s": round(load_s, 1),
+                                  "shard_rows_rank0": [int(ix.info.first_row), int(ix.info.end_row)],
+                                  "shard_hbm_gib": round(ix.info.hbm_bytes / 2**30, 2),
+                                  "states_sent_per_pattern": round(float(sent[0]) / total, 2),
+                                  "l2": "inputs far larger than L2 (no flush)"}},
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "all_patterns_found": bool(int(found[0])),
+            "cpu_baseline": cpu, "parity": parity,
         }
         print(json.dumps(out), flush=True)
+    if mesh:
+        mesh.close()
     ix.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -180,3 +180,20 @@ def test_gloo_ranks_build_one_index(tmp_path, world, use_bytes):
     fb.build_index_host(_docs_for_ranks(), a, **PARAMS)
     mp.spawn(_build_worker, args=(world, _free_port(), b, use_bytes), nprocs=world, join=True)
     _same_files(a, b)
+
+
+@pytest.mark.parametrize("kind", ["bytes", "acgt", "english"])
+def test_bench_sharded_text_is_the_single_gpu_corpus(kind):
+    """bench.py --parallelism sharded builds from ByteText; the symbols must be those of the text the
+    single-GPU path (ensure_index -> build_index_gpu) indexes under the same cache name."""
+    import argparse
+    import bench
+    args = argparse.Namespace(kind=kind, corpus_mib=1, seed=2, doc_mib=1, chunk_size=2048)
+    if kind == "english":
+        args.corpus_mib = 2
+    B, text = bench.sharded_text(args, torch.device("cpu"))
+    plain = bench.corpus_tensor(args, torch.device("cpu"))
+    assert (text == plain).all()
+    T, ends = build_gpu.prepare_text_gpu(bench.corpus_docs(args, plain))
+    assert (B.doc_ends == ends).all() and len(ends) == (2 if kind == "english" else 1)
+    assert (B.slice_symbols(0, B.n + build_gpu.PAD) == T).all()
