@@ -19,11 +19,23 @@ Printed JSON (one line, rank 0):
   e2e        the same through the host-buffer C-ABI call fm_count_flat: pinned host patterns in,
              host first/last out, copies inside the timed region (the call streams: kernel launched
              ahead of the copies, gated by an arrival counter); h2d/d2h bytes = what the call copied
-  locate     BASELINE configs[2] through fm_locate_flat, pinned buffers in and out
-  roofline   algorithmic HBM bytes per launch / kernel time, against MEASURED_PEAKS.json
+             (e2e.copy_only_ms_per_step = the same bytes over the same pinned buffers with no kernel:
+             the ceiling a host-buffer call has on this box; e2e_bytes = the call fed raw text bytes,
+             fm_count_bytes, half the host->device traffic)
+  locate     BASELINE configs[2] through fm_locate_flat, pinned buffers in and out; its own roofline
+             from the walk kernel's counters; locate.whole_batch = the same over all 1 Mi patterns
+  roofline   algorithmic HBM bytes per launch / kernel time, against MEASURED_PEAKS.json;
+             reference_layout = bytes the reference algorithm dereferences on the on-disk layout
+  sharded    N > 1: the same batches on the index split in N BWT row ranges, one per GPU, pattern
+             states exchanged by the kernels themselves over NVLink peer memory; compared bit for
+             bit with the replica leg
   cpu_baseline  the unmodified reference (oracle/_ref) counting a bounded sample of the same
              batch on this box's host cores, 1 server thread as shipped; the sample doubles as
              the in-run parity check (GPU first/last must equal the reference's)
+
+Other workloads: --patterns zipf --kind english --corpus-mib 16384 (BASELINE configs[3], ragged batches);
+--kind acgt --corpus-mib 64 --npats 10000 --plen 16 (configs[0]); --parallelism sharded (configs[4]: an
+index larger than one GPU, built and loaded by BWT row range, no replica leg).
 """
 from __future__ import annotations
 
@@ -60,6 +72,9 @@ def parse_args():
                     help="rows per document chunk of the index (default 2048 as the reference; 0 = build without "
                          "document chunks: they are not on the count / locate path, and with thousands of documents "
                          "they outweigh the rest of the index)")
+    ap.add_argument("--block-rows-log2", type=int, default=27,
+                    help="log2 of the rows per data block of the index (default 27 = 128 Mi as the reference; smaller "
+                         "values give a small corpus several blocks, i.e. something to shard)")
     ap.add_argument("--plen-min", type=int, default=8, help="--patterns zipf: shortest pattern")
     ap.add_argument("--plen-max", type=int, default=256, help="--patterns zipf: longest pattern")
     ap.add_argument("--npats", type=int, default=1 << 20)
@@ -103,6 +118,8 @@ def index_name(args):
     docs = f"_docs{args.doc_mib}MiB" if args.kind == "english" else ""
     if args.chunk_size != 2048:
         docs += f"_chunk{args.chunk_size}"
+    if args.block_rows_log2 != 27:
+        docs += f"_block2p{args.block_rows_log2}"
     return f"{args.kind}_{args.corpus_mib}MiB{docs}_seed{args.seed}_v1"
 
 
@@ -136,7 +153,8 @@ def ensure_index(args, device, rank, world):
         subprocess.run(["rm", "-rf", tmp, path], check=False)
         log(f"building index {index_name(args)} (one-time, cached in {args.cache_dir})")
         text = corpus_tensor(args, device)
-        t = build_gpu.build_index_gpu(corpus_docs(args, text), tmp, chunk_size=args.chunk_size, log=log)
+        t = build_gpu.build_index_gpu(corpus_docs(args, text), tmp, chunk_size=args.chunk_size,
+                                      block_size=1 << args.block_rows_log2, log=log)
         del text
         torch.cuda.empty_cache()
         os.rename(tmp, path)
@@ -1079,6 +1097,7 @@ def run_sharded(args, rank, world, local, device):
             log(f"building index {index_name(args)} on {world} GPUs")
         dist.barrier()
         t = build_dist.build_index_distributed(B, B.doc_ends, tmp, rank, world, chunk_size=args.chunk_size, log=log,
+                                               block_size=1 << args.block_rows_log2,
                                                nthreads=max(1, (os.cpu_count() or 8) // world))
         if rank == 0:
             os.rename(tmp, index_path)

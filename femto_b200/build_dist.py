@@ -20,7 +20,8 @@ Text beyond ~150 GiB would not fit replicated; it would be sharded and the key g
 ``_sort_batch`` would become all-to-all exchanges of (position, key) pairs.  Not built.
 
 Tested on CPU tensors with gloo, world size 2 and 3, byte for byte against the one-process builder
-(tests/test_build_dist.py).  NOT yet run on GPUs (no GPU time was left in the round that wrote it).
+(tests/test_build_dist.py); on GPUs it has run once, 2 ranks on a 64 MiB corpus
+(profiles/r02_bench_sharded_mode_small_n2.json) -- not at the sizes it is meant for.
 """
 from __future__ import annotations
 
