@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--kind", choices=["bytes", "acgt", "english"], default="bytes",
                     help="english: Zipf words over a fixed 50k-word vocabulary, many documents (BASELINE configs[3])")
     ap.add_argument("--doc-mib", type=int, default=1, help="--kind english: document size (MiB)")
+    ap.add_argument("--english-piece-mib", type=int, default=16384,
+                    help="--kind english: the corpus is made of generator streams of this size, seeds seed, seed+1, ...")
     ap.add_argument("--chunk-size", type=int, default=2048,
                     help="rows per document chunk of the index (default 2048 as the reference; 0 = build without "
                          "document chunks: they are not on the count / locate path, and with thousands of documents "
@@ -123,11 +125,23 @@ def index_name(args):
     return f"{args.kind}_{args.corpus_mib}MiB{docs}_seed{args.seed}_v1"
 
 
+def english_pieces(args, device):
+    """The English-like corpus (BASELINE configs[3] / [4]) = streams of --english-piece-mib (16 GiB) of the
+    Zipf-word generator, stream k seeded seed + k ("8 x 16 GiB of the config-4 generator,
+    different seeds"); up to 16 GiB it is one stream."""
+    from femto_b200 import build_gpu
+    n, piece = args.corpus_mib << 20, args.english_piece_mib << 20
+    for k, s in enumerate(range(0, n, piece)):
+        yield build_gpu.synthetic_english(min(piece, n - s), args.seed + k, device)
+
+
 def corpus_tensor(args, device):
+    import torch
     from femto_b200 import build_gpu
     n = args.corpus_mib << 20
     if args.kind == "english":
-        return build_gpu.synthetic_english(n, args.seed, device)
+        pieces = list(english_pieces(args, device))
+        return pieces[0] if len(pieces) == 1 else torch.cat(pieces)
     alphabet = b"ACGT" if args.kind == "acgt" else None
     return build_gpu.synthetic_bytes(n, args.seed, device, alphabet)
 
@@ -1056,18 +1070,60 @@ def run_mesh_leg(args, fb, index_path, batches, nbatch, step_resident, d_first, 
 
 def sharded_text(args, device):
     """The corpus as build_dist.ByteText (one byte per position; 128 GiB of corpus = 137 GB of a B200's HBM)
-    and the plain corpus bytes to sample patterns from.  Every rank generates the same text."""
+    and a function (batch, rank) -> text-sampled patterns.  Every rank generates the same text; nothing here
+    holds the corpus twice (the English-like text is laid out document by document, one 16 GiB stream at a
+    time)."""
     import torch
     from femto_b200 import build_dist, build_gpu
-    n = args.corpus_mib << 20
-    if args.kind == "english":
-        text = build_gpu.synthetic_english(n, args.seed, device)
-        return build_dist.ByteText.from_docs(corpus_docs(args, text)), text
-    alphabet = b"ACGT" if args.kind == "acgt" else None
-    # counter-based generator: the first n bytes of a longer text are the text of length n
-    data = build_gpu.synthetic_bytes(n + 1 + build_gpu.PAD, args.seed, device, alphabet)
-    data[n:] = 0
-    return build_dist.ByteText(data, np.array([n + 1], dtype=np.int64)), data[:n]
+    n, m = args.corpus_mib << 20, args.plen
+    if args.kind != "english":
+        alphabet = b"ACGT" if args.kind == "acgt" else None
+        # counter-based generator: the first n bytes of a longer text are the text of length n
+        data = build_gpu.synthetic_bytes(n + 1 + build_gpu.PAD, args.seed, device, alphabet)
+        data[n:] = 0
+        text = data[:n]
+        return (build_dist.ByteText(data, np.array([n + 1], dtype=np.int64)),
+                lambda b, r: sample_patterns(args, text, b, r))
+    D = args.doc_mib << 20
+    ndocs = (n + D - 1) // D
+    data = torch.zeros(n + ndocs + build_gpu.PAD, dtype=torch.uint8, device=device)
+    ends, pos, carry = [], 0, 0          # carry = bytes of the document being filled that are already in place
+    for t in english_pieces(args, device):
+        off = 0
+        if carry:                         # finish the document the previous stream left open
+            k = min(D - carry, t.numel())
+            data[pos:pos + k] = t[:k]
+            pos, off, carry = pos + k, k, carry + k
+            if carry == D:
+                pos, carry = pos + 1, 0
+                ends.append(pos)
+        q = (t.numel() - off) // D        # whole documents: one strided copy
+        if q:
+            data[pos:pos + q * (D + 1)].view(q, D + 1)[:, :D] = t[off:off + q * D].view(q, D)
+            ends += [pos + (i + 1) * (D + 1) for i in range(q)]
+            pos, off = pos + q * (D + 1), off + q * D
+        k = t.numel() - off
+        if k:
+            data[pos:pos + k] = t[off:]
+            pos, carry = pos + k, k
+        del t
+    if carry:
+        pos += 1
+        ends.append(pos)
+    assert pos == n + ndocs and len(ends) == ndocs
+    B = build_dist.ByteText(data, np.array(ends, dtype=np.int64))
+    full = n // D                          # patterns are taken from inside the whole documents
+
+    def sample(batch_id, rank):
+        g = torch.Generator(device=device)
+        g.manual_seed((args.seed + 1) * 1000003 + batch_id * 9176 + rank * 131)
+        doc = torch.randint(0, max(full, 1), (args.npats,), generator=g, device=device)
+        room = (D if full else n) - m + 1
+        start = doc * (D + 1) + torch.randint(0, room, (args.npats,), generator=g, device=device)
+        idx = start[:, None] + torch.arange(m, device=device)[None, :]
+        return (data[idx].to(torch.int16) + 5).contiguous()
+
+    return B, sample
 
 
 def run_sharded(args, rank, world, local, device):
@@ -1087,7 +1143,7 @@ def run_sharded(args, rank, world, local, device):
     index_path = os.path.join(args.cache_dir, index_name(args))
     cached = [os.path.exists(os.path.join(index_path, "_femto_index"))]
     dist.broadcast_object_list(cached, src=0)
-    B, text = sharded_text(args, device)
+    B, sample = sharded_text(args, device)
     build_info = {"built": False}
     if not cached[0]:
         tmp = index_path + ".building"
@@ -1104,10 +1160,9 @@ def run_sharded(args, rank, world, local, device):
         dist.barrier()
         build_info = {"built": True, "builder": f"build_dist x{world}", **{k: round(v, 2) for k, v in t.items()}}
         log(f"index built: {build_info}")
-    del B
     nbatch = 2
-    batches = [sample_patterns(args, text, b, rank) for b in range(nbatch)]
-    del text
+    batches = [sample(b, rank) for b in range(nbatch)]
+    del B, sample                      # the text must be gone before the shard is loaded (137 GB at configs[4])
     torch.cuda.empty_cache()
 
     t0 = time.time()

@@ -182,18 +182,35 @@ def test_gloo_ranks_build_one_index(tmp_path, world, use_bytes):
     _same_files(a, b)
 
 
-@pytest.mark.parametrize("kind", ["bytes", "acgt", "english"])
-def test_bench_sharded_text_is_the_single_gpu_corpus(kind):
+@pytest.mark.parametrize("kind,corpus_mib,doc_mib,piece_mib", [("bytes", 1, 1, 16384), ("acgt", 1, 1, 16384),
+                                                               ("english", 2, 1, 16384), ("english", 7, 3, 2),
+                                                               ("english", 5, 1, 2), ("english", 3, 4, 2)])
+def test_bench_sharded_text_is_the_single_gpu_corpus(kind, corpus_mib, doc_mib, piece_mib):
     """bench.py --parallelism sharded builds from ByteText; the symbols must be those of the text the
-    single-GPU path (ensure_index -> build_index_gpu) indexes under the same cache name."""
+    single-GPU path (ensure_index -> build_index_gpu) indexes under the same cache name -- also when the
+    English-like corpus is several generator streams and documents straddle them -- and the sampled
+    patterns must come from inside documents."""
     import argparse
     import bench
-    args = argparse.Namespace(kind=kind, corpus_mib=1, seed=2, doc_mib=1, chunk_size=2048)
-    if kind == "english":
-        args.corpus_mib = 2
-    B, text = bench.sharded_text(args, torch.device("cpu"))
+    args = argparse.Namespace(kind=kind, corpus_mib=corpus_mib, seed=2, doc_mib=doc_mib, chunk_size=2048,
+                              english_piece_mib=piece_mib, npats=64, plen=32, patterns="text")
+    B, sample = bench.sharded_text(args, torch.device("cpu"))
     plain = bench.corpus_tensor(args, torch.device("cpu"))
-    assert (text == plain).all()
-    T, ends = build_gpu.prepare_text_gpu(bench.corpus_docs(args, plain))
-    assert (B.doc_ends == ends).all() and len(ends) == (2 if kind == "english" else 1)
+    assert plain.numel() == corpus_mib << 20
+    docs = bench.corpus_docs(args, plain)
+    T, ends = build_gpu.prepare_text_gpu(docs)
+    assert (B.doc_ends == ends).all() and len(ends) == (1 if kind != "english" else -(-corpus_mib // doc_mib))
     assert (B.slice_symbols(0, B.n + build_gpu.PAD) == T).all()
+    if kind == "english" and piece_mib < corpus_mib:      # stream k is seeded seed + k
+        second = build_gpu.synthetic_english(1000, 3, "cpu")
+        assert (plain[piece_mib << 20: (piece_mib << 20) + 1000] == second).all()
+    pats = sample(0, 1)
+    assert pats.shape == (64, 32) and not (pats == sample(1, 1)).all()
+    whole = bytes(plain.numpy())
+    for p in pats[:16]:
+        raw = bytes((p - 5).to(torch.uint8).numpy())
+        at = whole.find(raw)
+        assert at >= 0
+        if kind == "english":                               # inside one document
+            assert any(whole.find(raw, d * (doc_mib << 20), (d + 1) * (doc_mib << 20)) >= 0
+                       for d in range(len(docs)))
