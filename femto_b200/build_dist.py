@@ -11,9 +11,9 @@ own blocks and nothing else.
 What makes that cheap on B200s: the TEXT is replicated (one byte per symbol, 128 GiB of corpus in
 180 GB of HBM), so a rank can sort any set of suffixes with local gathers -- there is no exchange
 step in the sort at all.  The ranks agree on the row range of every first-symbol (and, where
-needed, second-symbol) bucket from histograms each computes by itself; a rank sorts the buckets
-that overlap its rows (the two at its borders are split by their second symbol first, so that what
-it sorts beyond its own rows stays small) and slices.  The only communication is one gather of
+needed, longer-prefix) bucket from histograms each computes by itself; a rank sorts the buckets
+that overlap its rows (those at its borders, and any bucket larger than a batch, are split by the next
+symbol first, so that what it sorts beyond its own rows stays small) and slices.  The only communication is one gather of
 block_counts / eof_rows (KBs) before rank 0 writes the header.
 
 Text beyond ~150 GiB would not fit replicated; it would be sharded and the key gathers of
@@ -121,64 +121,100 @@ def _pair_histogram(T, n: int, step: int = 1 << 27) -> np.ndarray:
     return h.cpu().numpy().reshape(512, 512)
 
 
-def _select(T, n: int, lo: int, hi: int, second: Optional[Tuple[int, int]], step: int = 1 << 28) -> torch.Tensor:
-    """Positions whose symbol is in [lo, hi] (and whose next symbol is in `second`, if given), ascending."""
+MAX_PREFIX = 6   # symbols a bucket's prefix may have; a bucket still too large at that depth is sorted whole
+
+
+def _symbols(T, lo: int, hi: int) -> torch.Tensor:
+    return T.slice_symbols(lo, hi) if isinstance(T, ByteText) else T[lo:hi]
+
+
+def _prefix_mask(t: torch.Tensor, length: int, prefix: Tuple[int, ...]) -> Optional[torch.Tensor]:
+    """mask[p] = the symbols t[p .. p + len(prefix)) equal `prefix`, for p < length (None: empty prefix)."""
+    m = None
+    for j, c in enumerate(prefix):
+        mj = t[j: j + length] == c
+        m = mj if m is None else m & mj
+    return m
+
+
+def _next_histogram(T, n: int, prefix: Tuple[int, ...], step: int = 1 << 28) -> np.ndarray:
+    """Histogram of the symbol that follows `prefix`, over the positions of the text where it occurs."""
+    k = len(prefix)
+    h = torch.zeros(512, dtype=torch.int64, device=T.device)
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        t = _symbols(T, s, e + k)
+        nxt = t[k: k + e - s]
+        m = _prefix_mask(t, e - s, prefix)
+        h += torch.bincount((nxt if m is None else nxt[m]).long(), minlength=512)
+    return h.cpu().numpy()
+
+
+def _select(T, n: int, prefix: Tuple[int, ...], lo: int, hi: int, step: int = 1 << 28) -> torch.Tensor:
+    """Positions where `prefix` occurs followed by a symbol in [lo, hi], ascending."""
+    k = len(prefix)
     parts = []
     for s in range(0, n, step):
         e = min(n, s + step)
-        t = T.slice_symbols(s, e + 1) if isinstance(T, ByteText) else T[s:e + 1]
-        m = (t[: e - s] >= lo) & (t[: e - s] <= hi)
-        if second is not None:
-            m &= (t[1:] >= second[0]) & (t[1:] <= second[1])
+        t = _symbols(T, s, e + k)
+        nxt = t[k: k + e - s]
+        m = (nxt >= lo) & (nxt <= hi)
+        pm = _prefix_mask(t, e - s, prefix)
+        if pm is not None:
+            m &= pm
         parts.append(torch.nonzero(m).squeeze(1) + s)
     return torch.cat(parts) if len(parts) > 1 else parts[0]
 
 
-def plan_groups(hist: np.ndarray, second_hist: Callable[[int], np.ndarray], batch: int, row_lo: int,
-                row_hi: int) -> List[Tuple[int, int, Optional[Tuple[int, int]], int, int]]:
+Job = Tuple[Tuple[int, ...], int, int, int, int]
+
+
+def plan_jobs(count_next: Callable[[Tuple[int, ...]], np.ndarray], batch: int, row_lo: int, row_hi: int,
+              max_prefix: int = MAX_PREFIX) -> List[Job]:
     """Sort jobs that together cover the BWT rows [row_lo, row_hi), in row order.
 
-    A job = (first_lo, first_hi, second or None, row_start, count): the suffixes whose first symbol
-    is in [first_lo, first_hi] (one symbol when `second` = (lo2, hi2) restricts the symbol after it)
-    occupy rows [row_start, row_start + count).  Jobs hold at most `batch` suffixes unless one
-    (first, second) pair alone has more; a first-symbol bucket that sticks out of the row range is
-    split by second symbol so that only the pairs that overlap the range are sorted.  Every rank
-    computes the same buckets from the same histograms."""
-    jobs: List[Tuple[int, int, Optional[Tuple[int, int]], int, int]] = []
-    syms = [int(c) for c in np.nonzero(hist)[0]]
-    start = np.concatenate([[0], np.cumsum(hist)])  # start[c] = first row of the suffixes starting with c
-    i = 0
-    while i < len(syms):
-        c = syms[i]
-        c_lo, c_hi = int(start[c]), int(start[c + 1])
-        if c_hi <= row_lo or c_lo >= row_hi:
-            i += 1
-            continue
-        inside = c_lo >= row_lo and c_hi <= row_hi
-        if int(hist[c]) > batch or not inside:
-            h2 = second_hist(c)
-            seconds = [int(x) for x in np.nonzero(h2)[0]]
-            s2 = c_lo + np.concatenate([[0], np.cumsum(h2)])
-            j = 0
-            while j < len(seconds):
-                d = seconds[j]
-                if int(s2[d + 1]) <= row_lo or int(s2[d]) >= row_hi:
-                    j += 1
-                    continue
-                tot, k = int(h2[d]), j + 1
-                while (k < len(seconds) and tot + int(h2[seconds[k]]) <= batch and int(s2[seconds[k]]) < row_hi):
-                    tot += int(h2[seconds[k]])
-                    k += 1
-                jobs.append((c, c, (d, seconds[k - 1]), int(s2[d]), tot))
-                j = k
-            i += 1
-            continue
-        tot, k = int(hist[c]), i + 1
-        while (k < len(syms) and tot + int(hist[syms[k]]) <= batch and int(start[syms[k] + 1]) <= row_hi):
-            tot += int(hist[syms[k]])
-            k += 1
-        jobs.append((c, syms[k - 1], None, c_lo, tot))
-        i = k
+    A job = (prefix, lo, hi, row_start, count): the suffixes that begin with `prefix` followed by a symbol
+    in [lo, hi] occupy the rows [row_start, row_start + count).  count_next(prefix) = histogram of the
+    symbol following `prefix` in the text (prefix () = the symbols themselves).  A bucket is split by
+    its next symbol while it holds more than `batch` suffixes, or more than batch / 8 and sticks out of the
+    row range (so that a rank sorts little beyond its own rows); neighbouring small buckets of one
+    prefix are merged into one job of at most `batch`.  Every rank derives the same buckets from the same
+    histograms, whatever its row range."""
+    jobs: List[Job] = []
+
+    def visit(prefix: Tuple[int, ...], start: int, hist: np.ndarray) -> None:
+        run: List[int] = []
+        run_start = run_total = 0
+
+        def flush() -> None:
+            nonlocal run, run_total
+            if run:
+                jobs.append((prefix, run[0], run[-1], run_start, run_total))
+            run, run_total = [], 0
+
+        pos = start
+        for c in (int(x) for x in np.nonzero(hist)[0]):
+            cnt = int(hist[c])
+            lo, hi = pos, pos + cnt
+            pos = hi
+            if hi <= row_lo or lo >= row_hi:
+                flush()
+                continue
+            inside = lo >= row_lo and hi <= row_hi
+            too_big = cnt > batch or (not inside and cnt > batch // 8)
+            if too_big and len(prefix) + 1 < max_prefix and c != 0:   # (0 = behind the text: nothing follows)
+                flush()
+                visit(prefix + (c,), lo, count_next(prefix + (c,)))
+                continue
+            if run and run_total + cnt > batch:
+                flush()
+            if not run:
+                run_start = lo
+            run.append(c)
+            run_total += cnt
+        flush()
+
+    visit((), 0, count_next(()))
     return jobs
 
 
@@ -187,9 +223,17 @@ def suffix_batches_range(T, n: int, row_lo: int, row_hi: int, batch: int = 1 << 
     T: ByteText, or the int16 prepared text of ``prepare_text_gpu``."""
     if row_hi <= row_lo:
         return
-    pairs = _pair_histogram(T, n)
-    for c_lo, c_hi, second, start, count in plan_groups(pairs.sum(axis=1), lambda c: pairs[c], batch, row_lo, row_hi):
-        pos = _select(T, n, c_lo, c_hi, second)
+    pairs = _pair_histogram(T, n)       # one pass answers every prefix of length 0 and 1
+
+    def count_next(prefix: Tuple[int, ...]) -> np.ndarray:
+        if len(prefix) == 0:
+            return pairs.sum(axis=1)
+        if len(prefix) == 1:
+            return pairs[prefix[0]]
+        return _next_histogram(T, n, prefix)
+
+    for prefix, lo, hi, start, count in plan_jobs(count_next, batch, row_lo, row_hi):
+        pos = _select(T, n, prefix, lo, hi)
         assert pos.numel() == count, "bucket plan and text disagree"
         sa = _sort_batch(T, n, pos)
         a, b = max(row_lo, start) - start, min(row_hi, start + count) - start

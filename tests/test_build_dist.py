@@ -77,20 +77,56 @@ def test_row_range_of_the_suffix_array(name, batch):
 
 
 def test_plan_sorts_little_beyond_the_rows_it_needs():
-    """A rank whose rows end inside a first-symbol bucket sorts only the second-symbol pairs that overlap."""
+    """A rank whose rows end inside a first-symbol bucket sorts only the finer buckets that overlap."""
     docs = [corpus.random_bytes(200000, 3)]
     B = ByteText.from_docs([_t(d) for d in docs])
     n = B.n
     pairs = build_dist._pair_histogram(B, n)
     assert pairs.sum() == n and pairs[fb.ESCAPE_CODE_SEOF, 0] == 1
+    assert (build_dist._next_histogram(B, n, ()) == pairs.sum(axis=1)).all()
+    assert (build_dist._next_histogram(B, n, (70,)) == pairs[70]).all()
+    h3 = build_dist._next_histogram(B, n, (70, 71))
+    assert h3.sum() == pairs[70, 71] and h3.sum() > 0
+    calls = []
+
+    def count_next(prefix):
+        calls.append(prefix)
+        return pairs.sum(axis=1) if not prefix else pairs[prefix[0]] if len(prefix) == 1 else \
+            build_dist._next_histogram(B, n, prefix)
+
     lo, hi = n // 4 + 13, n // 2 + 7
-    jobs = build_dist.plan_groups(pairs.sum(axis=1), lambda c: pairs[c], 20000, lo, hi)
+    jobs = build_dist.plan_jobs(count_next, 20000, lo, hi)
     sorted_rows = sum(j[4] for j in jobs)
-    assert hi - lo <= sorted_rows <= (hi - lo) + 4 * (n // 65536 + 8)      # at most a pair bucket per border
+    assert hi - lo <= sorted_rows <= (hi - lo) + 2 * (20000 // 8)          # at most a small bucket per border
     assert all(j[4] <= 20000 for j in jobs)
     assert jobs[0][3] <= lo and jobs[-1][3] + jobs[-1][4] >= hi
     for a, b in zip(jobs[:-1], jobs[1:]):
         assert a[3] + a[4] == b[3]                                          # contiguous in row order
+    assert len(calls) <= 4                                                  # the root and the border buckets only
+
+
+def test_plan_splits_big_buckets_as_deep_as_needed():
+    """English-like text: ' ' and ' t' hold far more suffixes than a batch; they are split by longer prefixes."""
+    text = build_gpu.synthetic_english(400000, 9, "cpu", vocab=500, words_per_chunk=1 << 14)
+    B = ByteText.from_docs([text])
+    n = B.n
+    full = fb.suffix_sort_host(fb.prepare_text([bytes(text.numpy())])[0])
+    pairs = build_dist._pair_histogram(B, n)
+    deepest = 0
+
+    def count_next(prefix):
+        nonlocal deepest
+        deepest = max(deepest, len(prefix))
+        return pairs.sum(axis=1) if not prefix else pairs[prefix[0]] if len(prefix) == 1 else \
+            build_dist._next_histogram(B, n, prefix)
+
+    batch = 3000
+    jobs = build_dist.plan_jobs(count_next, batch, 0, n)
+    assert deepest >= 3 and sum(j[4] for j in jobs) == n
+    big = [j for j in jobs if j[4] > batch]
+    assert all(len(j[0]) == build_dist.MAX_PREFIX - 1 and j[1] == j[2] for j in big)   # only at the depth limit
+    got = torch.cat(list(build_dist.suffix_batches_range(B, n, n // 3, n // 2, batch=batch))).numpy()
+    assert (got == full[n // 3: n // 2]).all()
 
 
 PARAMS = dict(block_size=4096, bucket_size=1024, chunk_size=256, mark_period=20)

@@ -22,7 +22,7 @@ def test_two_ranks_shares_on_the_gpu_equal_the_host_build(tmp_path):
     fb.build_index_host(docs, a, **params)
     dev = torch.device("cuda", 0)
     B = build_dist.ByteText.from_docs([torch.frombuffer(bytearray(d), dtype=torch.uint8).to(dev) for d in docs])
-    parts = [build_dist.build_rank_blocks(B, B.doc_ends, b, rank, 2, batch=20000, host_chunk=15000, **params)[0]
+    parts = [build_dist.build_rank_blocks(B, B.doc_ends, b, rank, 2, batch=400, host_chunk=15000, **params)[0]
              for rank in range(2)]
     build_dist.write_header_from_parts(b, B.doc_ends, parts, **params)
     for f in sorted(os.listdir(a)):
