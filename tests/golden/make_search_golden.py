@@ -7,7 +7,7 @@ indexes.  oracle/_ref/femto_search = src/main_cc/search_tool.cc compiled unmodif
 The two small indexes carry document info strings (names with a quote, a '|' and a non-ASCII byte) and
 document chunks; they are written by this repository's emitter, whose files are byte-identical to the
 reference builder's (tests/test_builder_format.py) -- the reference's in-memory test builder cannot set
-info strings.  expected.json holds the documents, the parameters and every command line with the tool's
+info strings.  search_expected.json holds the documents, the parameters and every command line with the tool's
 stdout, so the cases can be replayed anywhere.
 """
 import json
@@ -56,7 +56,7 @@ def main():
     json.dump({"params": PARAMS,
                "indexes": {k: {"docs_hex": [d.hex() for d in v[0]], "infos_hex": [i.hex() for i in v[1]]}
                            for k, v in INDEXES.items()},
-               "cases": cases}, open(os.path.join(base, "expected.json"), "w"), indent=0)
+               "cases": cases}, open(os.path.join(base, "search_expected.json"), "w"), indent=0)
     print(f"search_tool: {len(cases)} cases")
 
 

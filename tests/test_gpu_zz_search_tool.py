@@ -18,7 +18,7 @@ BASE = os.path.join(GOLDEN_DIR, "search_tool")
 
 @pytest.mark.skipif(not os.path.exists(TOOL), reason="oracle/_ref tools did not travel (make -C oracle dropin)")
 def test_femto_search_reports_on_the_gpu_engine(tmp_path):
-    exp = json.load(open(os.path.join(BASE, "expected.json")))
+    exp = json.load(open(os.path.join(BASE, "search_expected.json")))
     cases = exp["cases"]
     picked = cases[::4] + [c for c in cases if c["pattern_hex"] == b"ana".hex()]
     combos = set()

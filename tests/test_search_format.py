@@ -66,7 +66,7 @@ def options_of(case_options):
 
 
 def test_reports_equal_the_reference_tools_golden_output(harness):
-    exp = json.load(open(os.path.join(BASE, "expected.json")))
+    exp = json.load(open(os.path.join(BASE, "search_expected.json")))
     infos = {k: [bytes.fromhex(h) for h in v["infos_hex"]] for k, v in exp["indexes"].items()}
     seen = set()
     for case in exp["cases"]:
@@ -80,8 +80,8 @@ def test_reports_equal_the_reference_tools_golden_output(harness):
 
 
 def test_golden_indexes_are_what_the_documents_give(tmp_path):
-    """The committed search_tool indexes are this emitter's bytes for the documents in expected.json."""
-    exp = json.load(open(os.path.join(BASE, "expected.json")))
+    """The committed search_tool indexes are this emitter's bytes for the documents in search_expected.json."""
+    exp = json.load(open(os.path.join(BASE, "search_expected.json")))
     for name, v in exp["indexes"].items():
         d = str(tmp_path / name)
         fb.build_index_host([bytes.fromhex(h) for h in v["docs_hex"]], d,
