@@ -38,12 +38,14 @@ def test_library_is_built_for_sm_100a():
 
 
 def test_no_oracle_in_product_path():
-    """Nothing under femto_b200/ may reference oracle/ (the oracle is test infrastructure)."""
-    for base, _, files in os.walk(os.path.join(ROOT, "femto_b200")):
+    """Nothing under femto_b200/ or integration/ (the tools and shims a maintainer links) may reference oracle/:
+    the oracle is test infrastructure."""
+    trees = list(os.walk(os.path.join(ROOT, "femto_b200"))) + list(os.walk(os.path.join(ROOT, "integration")))
+    for base, _, files in trees:
         if "build" in base.split(os.sep):
             continue
         for f in files:
-            if f.endswith((".py", ".cc", ".cu", ".hpp", ".cuh", ".h")):
+            if f.endswith((".py", ".c", ".cc", ".cu", ".hpp", ".cuh", ".h")):
                 src = open(os.path.join(base, f), errors="replace").read()
                 assert "fm_oracle" not in src and "libfemto_ref" not in src, f
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
