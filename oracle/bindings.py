@@ -187,7 +187,7 @@ class Oracle(_Base):
             lib.fmo_open.restype = C.c_void_p
             lib.fmo_open.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
             for name in ("close", "header_info", "C", "occ", "back_step", "count", "locate", "locate_range",
-                         "doc_info", "resolve", "extract", "counters", "reset_counters"):
+                         "doc_info", "doc_name", "resolve", "extract", "counters", "reset_counters"):
                 getattr(lib, "fmo_" + name).argtypes = None
             lib.fmo_close.argtypes = [C.c_void_p]
             lib.fmo_close.restype = None

@@ -310,6 +310,21 @@ int fmo_doc_info(const fmo_index* ix, int64_t doc, int64_t* doc_len, int64_t* eo
   return FMO_OK;
 }
 
+/* document_info (index.c:1767-1784): after doc_eof_rows the header block holds ndocs + 1 offsets (from the
+ * start of the block) delimiting every document's info bytes (written at index.c:882-898) */
+int fmo_doc_name(const fmo_index* ix, int64_t doc, const unsigned char** info, int64_t* len)
+{
+  const uint8_t* dir = hdr_doc_ends(ix) + 16 * (size_t)ix->ndocs;
+  int64_t start, end;
+  if (doc < 0 || doc >= ix->ndocs) return FMO_ERR_PARAM;
+  start = (int64_t)be64(dir + 8 * doc);
+  end = (int64_t)be64(dir + 8 * (doc + 1));
+  if (start < 0 || end < start || (size_t)end > ix->header.len) return FMO_ERR_FORMAT;
+  *info = ix->header.data + start;
+  *len = end - start;
+  return FMO_OK;
+}
+
 /* resolve_location (index.c:1587-1611) over bsearch_int64_ntoh_arr (src/utils/util.c:346):
  * prev = last i with doc_ends[i] <= offset, or -1 */
 int fmo_resolve(const fmo_index* ix, int64_t offset, int64_t* doc, int64_t* doc_off)

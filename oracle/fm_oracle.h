@@ -49,6 +49,8 @@ int fmo_locate(fmo_index* ix, int npats, const int32_t* plen, const uint16_t* fl
 int fmo_locate_range(fmo_index* ix, int64_t first, int64_t last, int64_t* offsets);
 int fmo_doc_info(const fmo_index* ix, int64_t doc, int64_t* doc_len, int64_t* eof_row);
 int fmo_resolve(const fmo_index* ix, int64_t offset, int64_t* doc, int64_t* doc_off);
+/* the info bytes stored with a document (its name); *info points into the index, valid until fmo_close */
+int fmo_doc_name(const fmo_index* ix, int64_t doc, const unsigned char** info, int64_t* len);
 /* out must hold doc_len-1 symbols (alphabet values, i.e. 5+byte); see server.c:6364-6437 */
 int fmo_extract(fmo_index* ix, int64_t doc, uint16_t* out, int64_t out_cap, int64_t* out_len);
 

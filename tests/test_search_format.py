@@ -5,7 +5,8 @@ On CPU the results come from the oracle (count, locate_range, resolve) and go th
 code by way of the harness tests/search_format_check.c; the expected bytes are the committed outputs of the
 reference's femto_search (tests/golden/search_tool, generator make_search_golden.py) and, where the
 reference is built here, its live output -- including a pattern with more than 1 Mi occurrences, of which one
-query reports the first 1 Mi rows.  The GPU test of the real tool is tests/test_gpu_zz_search_tool.py.
+query reports the first 1 Mi rows.  The tool's own main() is replayed too, linked with a stand-in engine that
+answers from the oracle.  The GPU test of the real tool is tests/test_gpu_zz_search_tool.py.
 """
 import json
 import os
@@ -77,6 +78,47 @@ def test_reports_equal_the_reference_tools_golden_output(harness):
         assert got == bytes.fromhex(case["stdout_hex"]), (case["indexes"], case["pattern_hex"], case["options"])
         seen.add((len(case["indexes"]), tuple(case["options"])))
     assert len(exp["cases"]) >= 150 and len(seen) == 18
+
+
+def test_the_tools_own_main_replays_the_golden_reports(tmp_path):
+    """integration/femto_search_b200.c itself -- option parsing, the queries it makes, sorting and grouping, the
+    report -- linked with a stand-in engine that answers its fm_* calls from the oracle
+    (tests/search_tool_oracle_engine.c; test infrastructure): every golden command line, byte for byte."""
+    exe = str(tmp_path / "femto_search_oracle_engine")
+    subprocess.run(["gcc", "-O1", "-g", "-Wall", "-Wextra", "-Werror", "-fsanitize=address,undefined",
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "integration"), "-o", exe,
+                    os.path.join(ROOT, "integration", "femto_search_b200.c"),
+                    os.path.join(ROOT, "tests", "search_tool_oracle_engine.c"),
+                    os.path.join(ROOT, "oracle", "fm_oracle.c")], check=True)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")   # a command-line tool: results are freed by exit
+    exp = json.load(open(os.path.join(BASE, "search_expected.json")))
+    pf = tmp_path / "pattern.bin"
+    for case in exp["cases"]:
+        pf.write_bytes(bytes.fromhex(case["pattern_hex"]))
+        args = [os.path.join(BASE, n) for n in case["indexes"]] + ["--raw-pattern-from", str(pf)] + case["options"]
+        out = subprocess.run([exe] + args, capture_output=True, timeout=60, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert out.stdout == bytes.fromhex(case["stdout_hex"]), (case["indexes"], case["pattern_hex"], case["options"])
+    # the pattern on the command line, and the report into a file
+    dest = tmp_path / "report.txt"
+    subprocess.run([exe, os.path.join(BASE, "index1"), "--offsets", "--raw-pattern", "ana", "--output", str(dest)],
+                   check=True, env=env, timeout=60)
+    want = [c for c in exp["cases"] if c["indexes"] == ["index1"] and c["pattern_hex"] == b"ana".hex()
+            and c["options"] == ["--offsets"]][0]
+    assert dest.read_bytes() == bytes.fromhex(want["stdout_hex"])
+
+
+def test_oracle_document_names_are_the_stored_info_strings():
+    exp = json.load(open(os.path.join(BASE, "search_expected.json")))
+    import ctypes as C
+    for name, v in exp["indexes"].items():
+        with Oracle(os.path.join(BASE, name)) as o:
+            for d, h in enumerate(v["infos_hex"]):
+                p, n = C.POINTER(C.c_ubyte)(), C.c_int64()
+                assert o.lib.fmo_doc_name(o.h, C.c_int64(d), C.byref(p), C.byref(n)) == 0
+                assert bytes(p[:n.value]) == bytes.fromhex(h)
+            p, n = C.POINTER(C.c_ubyte)(), C.c_int64()
+            assert o.lib.fmo_doc_name(o.h, C.c_int64(len(v["infos_hex"])), C.byref(p), C.byref(n)) != 0
 
 
 def test_golden_indexes_are_what_the_documents_give(tmp_path):
